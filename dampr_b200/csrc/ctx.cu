@@ -1,0 +1,281 @@
+// ctx.cu — context, streams, timings, pinned memory, text buffers and kv containers.
+// Replaces the process pool / Queue plumbing of StageRunner.run (reference stagerunner.py:15-43)
+// and the on-disk run files of dataset.py with device-resident buffers.
+#include "common.cuh"
+
+extern "C" {
+
+int32_t dampr_abi_version(void) { return 1; }
+
+int32_t dampr_device_count(int32_t *out_n) {
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess) {
+        *out_n = 0;
+        return DAMPR_ERR_CUDA;
+    }
+    *out_n = n;
+    return DAMPR_OK;
+}
+
+int32_t dampr_ctx_create(int32_t device, dampr_ctx **out) {
+    if (!out) return DAMPR_ERR_ARG;
+    *out = nullptr;
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n <= 0) return DAMPR_ERR_CUDA;
+    if (device < 0 || device >= n) return DAMPR_ERR_ARG;
+    if (cudaSetDevice(device) != cudaSuccess) return DAMPR_ERR_CUDA;
+    dampr_ctx *c = new dampr_ctx();
+    c->device = device;
+    c->launches = 0;
+    c->timing_enabled = true;
+    c->upload_pending = false;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) {
+        delete c;
+        return DAMPR_ERR_CUDA;
+    }
+    c->num_sms = prop.multiProcessorCount;
+    if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&c->copy, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreateWithFlags(&c->upload_done, cudaEventDisableTiming) != cudaSuccess ||
+        cudaMalloc(&c->d_scratch, 4096 * sizeof(u64)) != cudaSuccess ||
+        cudaMallocHost(&c->h_scratch, 4096 * sizeof(u64)) != cudaSuccess) {
+        delete c;
+        return DAMPR_ERR_CUDA;
+    }
+    *out = c;
+    return DAMPR_OK;
+}
+
+int32_t dampr_ctx_destroy(dampr_ctx *ctx) {
+    if (!ctx) return DAMPR_ERR_ARG;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    cudaStreamSynchronize(ctx->copy);
+    for (auto &t : ctx->timings) {
+        cudaEventDestroy(t.beg);
+        cudaEventDestroy(t.end);
+    }
+    cudaEventDestroy(ctx->upload_done);
+    cudaFree(ctx->d_scratch);
+    cudaFreeHost(ctx->h_scratch);
+    cudaStreamDestroy(ctx->stream);
+    cudaStreamDestroy(ctx->copy);
+    delete ctx;
+    return DAMPR_OK;
+}
+
+int32_t dampr_ctx_sync(dampr_ctx *ctx) {
+    if (!ctx) return DAMPR_ERR_ARG;
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->copy));
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    return DAMPR_OK;
+}
+
+const char *dampr_last_error(dampr_ctx *ctx) { return ctx ? ctx->err.c_str() : "no context"; }
+
+int32_t dampr_ctx_timings(dampr_ctx *ctx, double *out_ms, int32_t *out_ids, int32_t cap,
+                          int32_t *n) {
+    if (!ctx || !n) return DAMPR_ERR_ARG;
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    int k = 0;
+    for (auto &t : ctx->timings) {
+        if (k >= cap) break;
+        float ms = 0.f;
+        CUDA_TRY(ctx, cudaEventElapsedTime(&ms, t.beg, t.end));
+        out_ms[k] = (double)ms;
+        out_ids[k] = t.id;
+        k++;
+    }
+    *n = k;
+    return DAMPR_OK;
+}
+
+int32_t dampr_ctx_timings_reset(dampr_ctx *ctx) {
+    if (!ctx) return DAMPR_ERR_ARG;
+    cudaStreamSynchronize(ctx->stream);
+    for (auto &t : ctx->timings) {
+        cudaEventDestroy(t.beg);
+        cudaEventDestroy(t.end);
+    }
+    ctx->timings.clear();
+    return DAMPR_OK;
+}
+
+int32_t dampr_ctx_timing_enable(dampr_ctx *ctx, int32_t on) {
+    if (!ctx) return DAMPR_ERR_ARG;
+    ctx->timing_enabled = on != 0;
+    return DAMPR_OK;
+}
+
+int32_t dampr_ctx_launches(dampr_ctx *ctx, uint64_t *out) {
+    if (!ctx || !out) return DAMPR_ERR_ARG;
+    *out = ctx->launches;
+    return DAMPR_OK;
+}
+
+int32_t dampr_ctx_stream(dampr_ctx *ctx, uint64_t *out_stream) {
+    if (!ctx || !out_stream) return DAMPR_ERR_ARG;
+    *out_stream = (uint64_t)(uintptr_t)ctx->stream;
+    return DAMPR_OK;
+}
+
+int32_t dampr_host_alloc(uint64_t nbytes, void **out) {
+    if (!out) return DAMPR_ERR_ARG;
+    *out = nullptr;
+    cudaError_t e = cudaMallocHost(out, nbytes ? nbytes : 1);
+    return e == cudaSuccess ? DAMPR_OK : DAMPR_ERR_NOMEM;
+}
+
+int32_t dampr_host_free(void *p) {
+    if (!p) return DAMPR_OK;
+    return cudaFreeHost(p) == cudaSuccess ? DAMPR_OK : DAMPR_ERR_CUDA;
+}
+
+// ---- text buffers -------------------------------------------------------------------------
+int32_t dampr_textbuf_create(dampr_ctx *ctx, uint64_t capacity, dampr_textbuf **out) {
+    ARG_CHECK(ctx, ctx && out, "null");
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    dampr_textbuf *tb = new dampr_textbuf();
+    u64 cap16 = (capacity + 15) & ~15ULL;
+    tb->alloc_bytes = TEXT_LEAD + cap16 + TEXT_TAIL_PAD;
+    tb->capacity = capacity;
+    tb->n = 0;
+    tb->uploaded_hi = 0;
+    cudaError_t e = cudaMalloc(&tb->alloc, tb->alloc_bytes);
+    if (e != cudaSuccess) {
+        delete tb;
+        ctx->err = std::string("cudaMalloc(textbuf) failed: ") + cudaGetErrorString(e);
+        return DAMPR_ERR_NOMEM;
+    }
+    tb->text = tb->alloc + TEXT_LEAD;
+    // lead-in reads as '\n' so offset 0 is a line start
+    CUDA_TRY(ctx, cudaMemsetAsync(tb->alloc, '\n', TEXT_LEAD, ctx->copy));
+    *out = tb;
+    return DAMPR_OK;
+}
+
+int32_t dampr_textbuf_destroy(dampr_ctx *ctx, dampr_textbuf *tb) {
+    if (!tb) return DAMPR_OK;
+    if (ctx) {
+        cudaSetDevice(ctx->device);
+        cudaStreamSynchronize(ctx->stream);
+        cudaStreamSynchronize(ctx->copy);
+    }
+    cudaFree(tb->alloc);
+    delete tb;
+    return DAMPR_OK;
+}
+
+int32_t dampr_textbuf_set_length(dampr_ctx *ctx, dampr_textbuf *tb, uint64_t n) {
+    ARG_CHECK(ctx, ctx && tb, "null");
+    ARG_CHECK(ctx, n <= tb->capacity, "length exceeds textbuf capacity");
+    tb->n = n;
+    // everything after the text reads as '\n' (virtual terminator of an unterminated last line)
+    u64 pad = tb->alloc_bytes - TEXT_LEAD - n;
+    CUDA_TRY(ctx, cudaMemsetAsync(tb->text + n, '\n', pad, ctx->copy));
+    CUDA_TRY(ctx, cudaEventRecord(ctx->upload_done, ctx->copy));
+    ctx->upload_pending = true;
+    return DAMPR_OK;
+}
+
+int32_t dampr_textbuf_upload(dampr_ctx *ctx, dampr_textbuf *tb, uint64_t off, const void *host,
+                             uint64_t len) {
+    ARG_CHECK(ctx, ctx && tb && (host || len == 0), "null");
+    ARG_CHECK(ctx, off + len <= tb->capacity, "upload exceeds textbuf capacity");
+    if (len) {
+        CUDA_TRY(ctx, cudaMemcpyAsync(tb->text + off, host, len, cudaMemcpyHostToDevice, ctx->copy));
+        if (off + len > tb->uploaded_hi) tb->uploaded_hi = off + len;
+    }
+    CUDA_TRY(ctx, cudaEventRecord(ctx->upload_done, ctx->copy));
+    ctx->upload_pending = true;
+    return DAMPR_OK;
+}
+
+int32_t dampr_textbuf_devptr(dampr_ctx *ctx, dampr_textbuf *tb, uint64_t *out_ptr) {
+    ARG_CHECK(ctx, ctx && tb && out_ptr, "null");
+    *out_ptr = (uint64_t)(uintptr_t)tb->text;
+    return DAMPR_OK;
+}
+
+// ---- kv containers ------------------------------------------------------------------------
+int32_t dampr_kv_create(dampr_ctx *ctx, uint64_t capacity, dampr_kv **out) {
+    ARG_CHECK(ctx, ctx && out, "null");
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    dampr_kv *kv = new dampr_kv();
+    kv->capacity = capacity;
+    kv->n = 0;
+    kv->alt = nullptr;
+    kv->rec = nullptr;
+    u64 bytes = (capacity ? capacity : 1) * sizeof(ulonglong2);
+    cudaError_t e = cudaMalloc(&kv->rec, bytes);
+    if (e != cudaSuccess) {
+        delete kv;
+        ctx->err = std::string("cudaMalloc(kv) failed: ") + cudaGetErrorString(e);
+        return DAMPR_ERR_NOMEM;
+    }
+    *out = kv;
+    return DAMPR_OK;
+}
+
+int32_t dampr_kv_destroy(dampr_ctx *ctx, dampr_kv *kv) {
+    if (!kv) return DAMPR_OK;
+    if (ctx) {
+        cudaSetDevice(ctx->device);
+        cudaStreamSynchronize(ctx->stream);
+        cudaStreamSynchronize(ctx->copy);
+    }
+    cudaFree(kv->rec);
+    if (kv->alt) cudaFree(kv->alt);
+    delete kv;
+    return DAMPR_OK;
+}
+
+int32_t dampr_kv_size(dampr_ctx *ctx, dampr_kv *kv, uint64_t *n) {
+    ARG_CHECK(ctx, ctx && kv && n, "null");
+    *n = kv->n;
+    return DAMPR_OK;
+}
+
+int32_t dampr_kv_set_size(dampr_ctx *ctx, dampr_kv *kv, uint64_t n) {
+    ARG_CHECK(ctx, ctx && kv, "null");
+    ARG_CHECK(ctx, n <= kv->capacity, "size exceeds kv capacity");
+    kv->n = n;
+    return DAMPR_OK;
+}
+
+int32_t dampr_kv_devptr(dampr_ctx *ctx, dampr_kv *kv, uint64_t *out_ptr) {
+    ARG_CHECK(ctx, ctx && kv && out_ptr, "null");
+    *out_ptr = (uint64_t)(uintptr_t)kv->rec;
+    return DAMPR_OK;
+}
+
+int32_t dampr_kv_upload(dampr_ctx *ctx, dampr_kv *kv, uint64_t off, const void *host_records,
+                        uint64_t count) {
+    ARG_CHECK(ctx, ctx && kv && (host_records || count == 0), "null");
+    ARG_CHECK(ctx, off + count <= kv->capacity, "upload exceeds kv capacity");
+    // uploads must not overtake compute that still reads the buffer
+    if (count)
+        CUDA_TRY(ctx, cudaMemcpyAsync(kv->rec + off, host_records, count * sizeof(ulonglong2),
+                                      cudaMemcpyHostToDevice, ctx->copy));
+    if (off + count > kv->n) kv->n = off + count;
+    CUDA_TRY(ctx, cudaEventRecord(ctx->upload_done, ctx->copy));
+    ctx->upload_pending = true;
+    return DAMPR_OK;
+}
+
+int32_t dampr_kv_download(dampr_ctx *ctx, dampr_kv *kv, uint64_t off, void *host_records,
+                          uint64_t count) {
+    ARG_CHECK(ctx, ctx && kv && (host_records || count == 0), "null");
+    ARG_CHECK(ctx, off + count <= kv->n, "download exceeds kv size");
+    wait_uploads(ctx);
+    if (count)
+        CUDA_TRY(ctx, cudaMemcpyAsync(host_records, kv->rec + off, count * sizeof(ulonglong2),
+                                      cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    return DAMPR_OK;
+}
+
+}  // extern "C"

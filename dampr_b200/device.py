@@ -1,0 +1,445 @@
+"""ctypes binding of libdampr_b200.so (the C-ABI declared in include/dampr_b200.h).
+
+This is the only door between the Python host side and the device: every shuffle / sort /
+combine / reduce of the engine goes through these calls.  There is no CPU fallback — if the
+library or a CUDA device is missing the calls raise.
+
+Reference interfaces replaced (see the header for per-function citations): the process pool of
+``StageRunner.run`` (stagerunner.py:15-43), the writers/datasets of dataset.py and the combiner of
+``ReducedWriter`` (dataset.py:84-117).
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libdampr_b200.so")
+
+# tokeniser modes
+TOK_WS = 0
+TOK_NONWORD_LOWER_SET = 1
+TOK_NONWORD_LOWER = 2
+# key transforms
+KEY_RAW, KEY_MIX, KEY_I64, KEY_F64 = 0, 1, 2, 3
+# reduce ops
+OP_SUM_I64, OP_SUM_F64, OP_COUNT, OP_MIN_I64, OP_MAX_I64, OP_MIN_F64, OP_MAX_F64, OP_FIRST, OP_LAST = range(9)
+# table flags
+TF_NONASCII, TF_CR, TF_LONGLINE, TF_TABLEFULL, TF_LONGTOKEN, TF_COLLISION = 1, 2, 4, 8, 16, 32
+
+KERNEL_NAMES = {
+    1: "text_count", 2: "table_extract", 3: "text_verify", 4: "part_hist", 5: "part_scatter",
+    6: "leaf_sort", 7: "seg_reduce", 8: "merge", 9: "join", 10: "probe", 11: "synth", 12: "misc",
+}
+
+
+class DeviceError(RuntimeError):
+    pass
+
+
+_lib = None
+
+
+def _sig(lib, name, *argtypes, restype=C.c_int32):
+    fn = getattr(lib, name)
+    fn.argtypes = list(argtypes)
+    fn.restype = restype
+    return fn
+
+
+def load_library():
+    """Load the shared library (raises if it has not been built)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise DeviceError(
+            "libdampr_b200.so is not built: run `python -m dampr_b200.build` (needs nvcc); "
+            "the engine has no CPU fallback")
+    lib = C.CDLL(LIB_PATH)
+    vp, u64, i32, u32 = C.c_void_p, C.c_uint64, C.c_int32, C.c_uint32
+    pvp, pu64 = C.POINTER(C.c_void_p), C.POINTER(C.c_uint64)
+    _sig(lib, "dampr_abi_version")
+    _sig(lib, "dampr_device_count", C.POINTER(i32))
+    _sig(lib, "dampr_set_option", C.c_char_p, C.c_int64)
+    _sig(lib, "dampr_ctx_create", i32, pvp)
+    _sig(lib, "dampr_ctx_destroy", vp)
+    _sig(lib, "dampr_ctx_sync", vp)
+    _sig(lib, "dampr_last_error", vp, restype=C.c_char_p)
+    _sig(lib, "dampr_ctx_timings", vp, C.POINTER(C.c_double), C.POINTER(i32), i32, C.POINTER(i32))
+    _sig(lib, "dampr_ctx_timings_reset", vp)
+    _sig(lib, "dampr_ctx_timing_enable", vp, i32)
+    _sig(lib, "dampr_ctx_launches", vp, pu64)
+    _sig(lib, "dampr_ctx_stream", vp, pu64)
+    _sig(lib, "dampr_host_alloc", u64, pvp)
+    _sig(lib, "dampr_host_free", vp)
+    _sig(lib, "dampr_textbuf_create", vp, u64, pvp)
+    _sig(lib, "dampr_textbuf_destroy", vp, vp)
+    _sig(lib, "dampr_textbuf_set_length", vp, vp, u64)
+    _sig(lib, "dampr_textbuf_upload", vp, vp, u64, vp, u64)
+    _sig(lib, "dampr_textbuf_download", vp, vp, u64, vp, u64)
+    _sig(lib, "dampr_textbuf_devptr", vp, vp, pu64)
+    _sig(lib, "dampr_table_create", vp, u32, pvp)
+    _sig(lib, "dampr_table_destroy", vp, vp)
+    _sig(lib, "dampr_table_clear", vp, vp)
+    _sig(lib, "dampr_text_count", vp, vp, vp, u64, u64, i32)
+    _sig(lib, "dampr_text_verify", vp, vp, vp, u64, u64, i32)
+    _sig(lib, "dampr_table_stats", vp, vp, pu64)
+    _sig(lib, "dampr_table_fetch", vp, vp, vp, vp, vp, u64, pu64)
+    _sig(lib, "dampr_table_to_kv", vp, vp, pvp)
+    _sig(lib, "dampr_kv_create", vp, u64, pvp)
+    _sig(lib, "dampr_kv_destroy", vp, vp)
+    _sig(lib, "dampr_kv_size", vp, vp, pu64)
+    _sig(lib, "dampr_kv_set_size", vp, vp, u64)
+    _sig(lib, "dampr_kv_devptr", vp, vp, pu64)
+    _sig(lib, "dampr_kv_upload", vp, vp, u64, vp, u64)
+    _sig(lib, "dampr_kv_download", vp, vp, u64, vp, u64)
+    _sig(lib, "dampr_kv_upload_columns", vp, vp, u64, vp, vp, u64)
+    _sig(lib, "dampr_kv_download_columns", vp, vp, u64, vp, vp, u64)
+    _sig(lib, "dampr_kv_sort", vp, vp, i32)
+    _sig(lib, "dampr_kv_reduce_by_key", vp, vp, i32, pvp)
+    _sig(lib, "dampr_kv_group_offsets", vp, vp, vp, u64, pu64)
+    _sig(lib, "dampr_kv_merge", vp, pvp, i32, i32, i32, pvp)
+    _sig(lib, "dampr_kv_sort_reduce", vp, vp, i32, i32, pvp)
+    _sig(lib, "dampr_kv_join_ranges", vp, vp, vp, i32, vp, u64, pu64)
+    _sig(lib, "dampr_kv_hash_probe", vp, vp, vp, pvp, vp)
+    _sig(lib, "dampr_kv_partition_by_owner", vp, vp, i32, pvp, pu64)
+    _sig(lib, "dampr_synth_text", vp, vp, u64, u64, vp, vp, u32, vp, pu64)
+    _sig(lib, "dampr_synth_kv", vp, vp, u64, u64, u64)
+    _lib = lib
+    return lib
+
+
+def device_count():
+    lib = load_library()
+    n = C.c_int32(0)
+    rc = lib.dampr_device_count(C.byref(n))
+    return n.value if rc == 0 else 0
+
+
+def set_option(name, value):
+    rc = load_library().dampr_set_option(name.encode(), int(value))
+    if rc:
+        raise DeviceError("unknown option %r" % name)
+
+
+def _ptr(a):
+    """Host pointer of a C-contiguous numpy array (or None)."""
+    if a is None:
+        return None
+    assert a.flags["C_CONTIGUOUS"]
+    return a.ctypes.data_as(C.c_void_p)
+
+
+class PinnedBuffer(object):
+    """Page-locked host memory exposed as a numpy uint8 array (ingest staging / spill ring)."""
+
+    def __init__(self, nbytes):
+        lib = load_library()
+        p = C.c_void_p()
+        rc = lib.dampr_host_alloc(int(nbytes), C.byref(p))
+        if rc:
+            raise DeviceError("pinned allocation of %d bytes failed" % nbytes)
+        self._p = p
+        self.nbytes = int(nbytes)
+        buf = (C.c_uint8 * max(1, self.nbytes)).from_address(p.value)
+        self.array = np.frombuffer(buf, dtype=np.uint8, count=self.nbytes)
+
+    def free(self):
+        if self._p is not None:
+            self.array = None
+            load_library().dampr_host_free(self._p)
+            self._p = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+class Ctx(object):
+    """One GPU: a compute stream, a copy stream and the kernels' event timings."""
+
+    def __init__(self, device=0):
+        self.lib = load_library()
+        h = C.c_void_p()
+        rc = self.lib.dampr_ctx_create(int(device), C.byref(h))
+        if rc:
+            raise DeviceError(
+                "cannot create a device context on cuda:%d (status %d): the B200 engine needs a "
+                "CUDA device and has no CPU fallback" % (device, rc))
+        self.h = h
+        self.device = device
+
+    # -- plumbing ---------------------------------------------------------------------------
+    def check(self, rc):
+        if rc:
+            msg = self.lib.dampr_last_error(self.h)
+            raise DeviceError("libdampr_b200 status %d: %s" % (rc, msg.decode() if msg else "?"))
+
+    def sync(self):
+        self.check(self.lib.dampr_ctx_sync(self.h))
+
+    def close(self):
+        if self.h is not None:
+            self.lib.dampr_ctx_destroy(self.h)
+            self.h = None
+
+    def launches(self):
+        n = C.c_uint64(0)
+        self.check(self.lib.dampr_ctx_launches(self.h, C.byref(n)))
+        return n.value
+
+    def stream(self):
+        s = C.c_uint64(0)
+        self.check(self.lib.dampr_ctx_stream(self.h, C.byref(s)))
+        return s.value
+
+    def timing_enable(self, on):
+        self.check(self.lib.dampr_ctx_timing_enable(self.h, 1 if on else 0))
+
+    def timings_reset(self):
+        self.check(self.lib.dampr_ctx_timings_reset(self.h))
+
+    def timings(self, cap=65536):
+        """[(kernel name, ms)] of every timed launch since the last reset (blocks)."""
+        ms = (C.c_double * cap)()
+        ids = (C.c_int32 * cap)()
+        n = C.c_int32(0)
+        self.check(self.lib.dampr_ctx_timings(self.h, ms, ids, cap, C.byref(n)))
+        return [(KERNEL_NAMES.get(ids[i], str(ids[i])), ms[i]) for i in range(n.value)]
+
+    # -- factories --------------------------------------------------------------------------
+    def textbuf(self, capacity):
+        return TextBuf(self, capacity)
+
+    def table(self, capacity_log2=22):
+        return Table(self, capacity_log2)
+
+    def kv(self, capacity):
+        return KV(self, capacity)
+
+    def kv_from_columns(self, keys, vals=None):
+        keys = np.ascontiguousarray(keys).view(np.uint64)
+        kv = KV(self, len(keys))
+        if vals is not None:
+            vals = np.ascontiguousarray(vals)
+            assert vals.dtype.itemsize == 8 and len(vals) == len(keys)
+            vals = vals.view(np.uint64)
+        self.check(self.lib.dampr_kv_upload_columns(self.h, kv.h, 0, _ptr(keys), _ptr(vals), len(keys)))
+        self.sync()  # the host arrays may be temporaries
+        return kv
+
+    def kv_from_records(self, recs):
+        """recs: numpy array of shape (n, 2) uint64 (or a structured 16-byte dtype)."""
+        recs = np.ascontiguousarray(recs)
+        assert recs.nbytes % 16 == 0
+        n = recs.nbytes // 16
+        kv = KV(self, n)
+        self.check(self.lib.dampr_kv_upload(self.h, kv.h, 0, _ptr(recs), n))
+        self.sync()
+        return kv
+
+
+class TextBuf(object):
+    def __init__(self, ctx, capacity):
+        self.ctx = ctx
+        h = C.c_void_p()
+        ctx.check(ctx.lib.dampr_textbuf_create(ctx.h, int(capacity), C.byref(h)))
+        self.h = h
+        self.capacity = int(capacity)
+        self.n = 0
+
+    def set_length(self, n):
+        self.ctx.check(self.ctx.lib.dampr_textbuf_set_length(self.ctx.h, self.h, int(n)))
+        self.n = int(n)
+
+    def upload(self, off, host_u8, length=None):
+        """Async copy of host bytes (numpy uint8 view; pinned for full speed) to text[off:]."""
+        length = len(host_u8) if length is None else length
+        self.ctx.check(self.ctx.lib.dampr_textbuf_upload(self.ctx.h, self.h, int(off), _ptr(host_u8), int(length)))
+
+    def upload_all(self, data):
+        """Convenience: whole text from bytes / numpy (blocking)."""
+        arr = np.frombuffer(data, dtype=np.uint8) if not isinstance(data, np.ndarray) else data
+        self.set_length(len(arr))
+        self.upload(0, arr)
+        self.ctx.sync()
+
+    def download(self, off, length):
+        out = np.empty(int(length), dtype=np.uint8)
+        self.ctx.check(self.ctx.lib.dampr_textbuf_download(self.ctx.h, self.h, int(off), _ptr(out), int(length)))
+        return out
+
+    def free(self):
+        if self.h is not None:
+            self.ctx.lib.dampr_textbuf_destroy(self.ctx.h, self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            if self.ctx.h is not None:
+                self.free()
+        except Exception:
+            pass
+
+
+class Table(object):
+    """Device combiner table: token key code -> count (ReducedWriter, dataset.py:84-117)."""
+
+    def __init__(self, ctx, capacity_log2=22):
+        self.ctx = ctx
+        h = C.c_void_p()
+        ctx.check(ctx.lib.dampr_table_create(ctx.h, int(capacity_log2), C.byref(h)))
+        self.h = h
+        self.capacity = 1 << capacity_log2
+
+    def clear(self):
+        self.ctx.check(self.ctx.lib.dampr_table_clear(self.ctx.h, self.h))
+
+    def count(self, tb, lo, hi, mode):
+        self.ctx.check(self.ctx.lib.dampr_text_count(self.ctx.h, self.h, tb.h, int(lo), int(hi), int(mode)))
+
+    def verify(self, tb, lo, hi, mode):
+        self.ctx.check(self.ctx.lib.dampr_text_verify(self.ctx.h, self.h, tb.h, int(lo), int(hi), int(mode)))
+
+    def stats(self):
+        st = (C.c_uint64 * 8)()
+        self.ctx.check(self.ctx.lib.dampr_table_stats(self.ctx.h, self.h, st))
+        return {"entries": st[0], "lines": st[1], "empty": st[2], "folded": st[3], "flags": st[4],
+                "hashed": st[5], "raw": st[6]}
+
+    def fetch(self):
+        """(codes, counts, reps) numpy uint64 arrays (unordered)."""
+        n = C.c_uint64(0)
+        self.ctx.check(self.ctx.lib.dampr_table_fetch(self.ctx.h, self.h, None, None, None, 0, C.byref(n)))
+        m = n.value
+        codes = np.empty(m, dtype=np.uint64)
+        counts = np.empty(m, dtype=np.uint64)
+        reps = np.empty(m, dtype=np.uint64)
+        if m:
+            self.ctx.check(self.ctx.lib.dampr_table_fetch(self.ctx.h, self.h, _ptr(codes), _ptr(counts), _ptr(reps),
+                                                          m, C.byref(n)))
+        return codes, counts, reps
+
+    def to_kv(self):
+        h = C.c_void_p()
+        self.ctx.check(self.ctx.lib.dampr_table_to_kv(self.ctx.h, self.h, C.byref(h)))
+        return KV(self.ctx, None, handle=h)
+
+    def free(self):
+        if self.h is not None:
+            self.ctx.lib.dampr_table_destroy(self.ctx.h, self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            if self.ctx.h is not None:
+                self.free()
+        except Exception:
+            pass
+
+
+class KV(object):
+    """Device array of 16-byte (u64 key, u64 value) records."""
+
+    def __init__(self, ctx, capacity, handle=None):
+        self.ctx = ctx
+        if handle is None:
+            handle = C.c_void_p()
+            ctx.check(ctx.lib.dampr_kv_create(ctx.h, int(capacity), C.byref(handle)))
+        self.h = handle
+
+    def __len__(self):
+        n = C.c_uint64(0)
+        self.ctx.check(self.ctx.lib.dampr_kv_size(self.ctx.h, self.h, C.byref(n)))
+        return n.value
+
+    def set_size(self, n):
+        self.ctx.check(self.ctx.lib.dampr_kv_set_size(self.ctx.h, self.h, int(n)))
+
+    def devptr(self):
+        p = C.c_uint64(0)
+        self.ctx.check(self.ctx.lib.dampr_kv_devptr(self.ctx.h, self.h, C.byref(p)))
+        return p.value
+
+    def upload(self, off, recs, count=None):
+        count = recs.nbytes // 16 if count is None else count
+        self.ctx.check(self.ctx.lib.dampr_kv_upload(self.ctx.h, self.h, int(off), _ptr(recs), int(count)))
+
+    def records(self):
+        """Download as an (n, 2) uint64 array."""
+        n = len(self)
+        out = np.empty((n, 2), dtype=np.uint64)
+        self.ctx.check(self.ctx.lib.dampr_kv_download(self.ctx.h, self.h, 0, _ptr(out), n))
+        return out
+
+    def columns(self):
+        n = len(self)
+        keys = np.empty(n, dtype=np.uint64)
+        vals = np.empty(n, dtype=np.uint64)
+        self.ctx.check(self.ctx.lib.dampr_kv_download_columns(self.ctx.h, self.h, 0, _ptr(keys), _ptr(vals), n))
+        return keys, vals
+
+    def sort(self, xform=KEY_MIX):
+        self.ctx.check(self.ctx.lib.dampr_kv_sort(self.ctx.h, self.h, int(xform)))
+        return self
+
+    def sort_reduce(self, op, xform=KEY_MIX):
+        h = C.c_void_p()
+        self.ctx.check(self.ctx.lib.dampr_kv_sort_reduce(self.ctx.h, self.h, int(xform), int(op), C.byref(h)))
+        return KV(self.ctx, None, handle=h)
+
+    def reduce_by_key(self, op):
+        h = C.c_void_p()
+        self.ctx.check(self.ctx.lib.dampr_kv_reduce_by_key(self.ctx.h, self.h, int(op), C.byref(h)))
+        return KV(self.ctx, None, handle=h)
+
+    def group_offsets(self):
+        g = C.c_uint64(0)
+        self.ctx.check(self.ctx.lib.dampr_kv_group_offsets(self.ctx.h, self.h, None, 0, C.byref(g)))
+        offs = np.empty(g.value + 1, dtype=np.uint64)
+        self.ctx.check(self.ctx.lib.dampr_kv_group_offsets(self.ctx.h, self.h, _ptr(offs), len(offs), C.byref(g)))
+        return offs
+
+    def join_ranges(self, right, xform):
+        g = C.c_uint64(0)
+        self.ctx.check(self.ctx.lib.dampr_kv_join_ranges(self.ctx.h, self.h, right.h, int(xform), None, 0, C.byref(g)))
+        rows = np.empty((g.value, 4), dtype=np.uint64)
+        if g.value:
+            self.ctx.check(self.ctx.lib.dampr_kv_join_ranges(self.ctx.h, self.h, right.h, int(xform), _ptr(rows),
+                                                             g.value, C.byref(g)))
+        return rows
+
+    def hash_probe(self, probe):
+        """self = build side (unique keys). Returns (values KV aligned with probe, hit uint8 array)."""
+        h = C.c_void_p()
+        hit = np.empty(len(probe), dtype=np.uint8)
+        self.ctx.check(self.ctx.lib.dampr_kv_hash_probe(self.ctx.h, self.h, probe.h, C.byref(h), _ptr(hit)))
+        return KV(self.ctx, None, handle=h), hit
+
+    def partition_by_owner(self, n_dest):
+        h = C.c_void_p()
+        counts = np.zeros(n_dest, dtype=np.uint64)
+        self.ctx.check(self.ctx.lib.dampr_kv_partition_by_owner(self.ctx.h, self.h, int(n_dest), C.byref(h), _ptr(counts)))
+        return KV(self.ctx, None, handle=h), counts
+
+    def free(self):
+        if self.h is not None:
+            self.ctx.lib.dampr_kv_destroy(self.ctx.h, self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            if self.ctx.h is not None:
+                self.free()
+        except Exception:
+            pass
+
+
+def kv_merge(ctx, runs, xform, op=-1):
+    arr = (C.c_void_p * len(runs))(*[r.h for r in runs])
+    h = C.c_void_p()
+    ctx.check(ctx.lib.dampr_kv_merge(ctx.h, arr, len(runs), int(xform), int(op), C.byref(h)))
+    return KV(ctx, None, handle=h)

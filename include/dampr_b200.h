@@ -1,0 +1,224 @@
+/*
+ * dampr_b200.h — C-ABI of libdampr_b200.so: the B200-native (sm_100a) replacement for the
+ * hot path of Refefer/Dampr: map -> partition-by-key -> spill -> external merge sort ->
+ * combiner/reduce.
+ *
+ * The reference has NO native interface (it is pure Python); the boundary it exposes is the
+ * Python DSL plus the runner slot `Dampr(graph, runner=MTRunner)` (reference dampr/dampr.py:835-843,
+ * call site dampr/dampr.py:73).  This header is what a ctypes stub on the reference side binds
+ * (see INTEGRATION.md).  Each entry point names the reference function(s) it replaces.
+ *
+ * Conventions
+ *   - plain C, extern "C"; every function returns int32 status, 0 = ok, <0 = error
+ *     (message: dampr_last_error(ctx), owned by the ctx, valid until the next call on it);
+ *   - handles are opaque; the library owns device memory, the caller owns host memory;
+ *   - variable-size outputs use a two-phase "count, then fetch into caller memory" protocol;
+ *   - one host thread drives one ctx; a ctx owns one compute stream and one copy stream on
+ *     one GPU; calls enqueue and return, dampr_ctx_sync / *_fetch / *_stats block;
+ *   - there is NO CPU fallback: without a CUDA device every compute entry point fails.
+ */
+#ifndef DAMPR_B200_H
+#define DAMPR_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct dampr_ctx dampr_ctx;         /* one GPU, streams, scratch arena            */
+typedef struct dampr_textbuf dampr_textbuf; /* device-resident byte range of a text file  */
+typedef struct dampr_table dampr_table;     /* map-side combiner table (key code -> acc)  */
+typedef struct dampr_kv dampr_kv;           /* device array of 16-byte (u64 key, u64 val) */
+
+/* ---- status codes ------------------------------------------------------------------- */
+#define DAMPR_OK 0
+#define DAMPR_ERR_CUDA (-1)     /* CUDA runtime error, see dampr_last_error            */
+#define DAMPR_ERR_ARG (-2)      /* bad argument                                         */
+#define DAMPR_ERR_NOMEM (-3)    /* device or pinned allocation failed                   */
+#define DAMPR_ERR_OVERFLOW (-4) /* table full / 64-bit accumulator overflow (B12)       */
+#define DAMPR_ERR_UNSUPPORTED (-5)
+
+/* ---- library ------------------------------------------------------------------------- */
+int32_t dampr_abi_version(void);
+int32_t dampr_device_count(int32_t *out_n);
+/* process-wide tuning switches: "scatter_tma" (1 = TMA bulk stores in the partition scatter,
+ * 0 = coalesced 16-byte stores) */
+int32_t dampr_set_option(const char *name, int64_t value);
+
+/* ---- context: replaces the process pool of StageRunner.run (stagerunner.py:15-43) ---- */
+int32_t dampr_ctx_create(int32_t device, dampr_ctx **out);
+int32_t dampr_ctx_destroy(dampr_ctx *ctx);
+int32_t dampr_ctx_sync(dampr_ctx *ctx);
+const char *dampr_last_error(dampr_ctx *ctx);
+/* CUDA-event timings of the kernels launched since the last reset:
+ * out[2*i] = kernel id (DAMPR_K_*), out[2*i+1] = milliseconds (as double bit pattern).
+ * Returns the number of entries through *n (at most cap). Blocks until they completed. */
+int32_t dampr_ctx_timings(dampr_ctx *ctx, double *out_ms, int32_t *out_ids, int32_t cap, int32_t *n);
+int32_t dampr_ctx_timings_reset(dampr_ctx *ctx);
+int32_t dampr_ctx_timing_enable(dampr_ctx *ctx, int32_t on);
+/* number of kernels this library launched on the ctx since creation */
+int32_t dampr_ctx_launches(dampr_ctx *ctx, uint64_t *out);
+/* raw handle of the compute stream (cudaStream_t) so torch.distributed collectives can be
+ * ordered against it */
+int32_t dampr_ctx_stream(dampr_ctx *ctx, uint64_t *out_stream);
+
+#define DAMPR_K_TEXT_COUNT 1
+#define DAMPR_K_TABLE_EXTRACT 2
+#define DAMPR_K_TEXT_VERIFY 3
+#define DAMPR_K_PART_HIST 4
+#define DAMPR_K_PART_SCATTER 5
+#define DAMPR_K_LEAF_SORT 6
+#define DAMPR_K_SEG_REDUCE 7
+#define DAMPR_K_MERGE 8
+#define DAMPR_K_JOIN 9
+#define DAMPR_K_PROBE 10
+#define DAMPR_K_SYNTH 11
+#define DAMPR_K_MISC 12
+
+/* ---- pinned host memory (spill ring / ingest staging) -------------------------------- */
+int32_t dampr_host_alloc(uint64_t nbytes, void **out);
+int32_t dampr_host_free(void *p);
+
+/* ---- text ingest: replaces TextInput.chunks (inputs.py:48-56) + TextLineDataset.read
+ *      (dataset.py:458-476): byte ranges of a file with the line-ownership rule ---------- */
+/* capacity = number of text bytes the buffer can hold (the library adds lead-in and padding) */
+int32_t dampr_textbuf_create(dampr_ctx *ctx, uint64_t capacity, dampr_textbuf **out);
+int32_t dampr_textbuf_destroy(dampr_ctx *ctx, dampr_textbuf *tb);
+/* declare the total length of the text that will be uploaded (pads the tail with '\n') */
+int32_t dampr_textbuf_set_length(dampr_ctx *ctx, dampr_textbuf *tb, uint64_t n);
+/* async host->device copy of text bytes [off, off+len) on the copy stream */
+int32_t dampr_textbuf_upload(dampr_ctx *ctx, dampr_textbuf *tb, uint64_t off, const void *host,
+                             uint64_t len);
+/* blocking device->host copy of text bytes [off, off+len) */
+int32_t dampr_textbuf_download(dampr_ctx *ctx, dampr_textbuf *tb, uint64_t off, void *host,
+                               uint64_t len);
+/* device pointer of text byte 0 (for tests / zero-copy producers such as the synthetic generator) */
+int32_t dampr_textbuf_devptr(dampr_ctx *ctx, dampr_textbuf *tb, uint64_t *out_ptr);
+
+/* ---- map-side combiner over text: replaces Map.stream of the tokenising lambdas
+ *      (base.py:30-33; examples/wc.py:12; benchmarks/tf-idf-dampr.py:12-14) fused with
+ *      ReducedWriter.add_record (dataset.py:100-105) --------------------------------------- */
+#define DAMPR_TOK_WS 0                /* str.split(): maximal runs of non-whitespace         */
+#define DAMPR_TOK_NONWORD_LOWER_SET 1 /* set(re.split(r'[^\w]+', line.lower())): per-line set */
+#define DAMPR_TOK_NONWORD_LOWER 2     /* re.split(r'[^\w]+', line.lower()) without set():
+                                         every token counts, '' tokens as re.split yields    */
+
+int32_t dampr_table_create(dampr_ctx *ctx, uint32_t capacity_log2, dampr_table **out);
+int32_t dampr_table_destroy(dampr_ctx *ctx, dampr_table *t);
+int32_t dampr_table_clear(dampr_ctx *ctx, dampr_table *t);
+
+/* tokenise the lines whose first byte lies in [own_lo, own_hi) and fold (token -> +1) into the
+ * table. Requires bytes [0, min(n, own_hi + halo)) to be uploaded. */
+int32_t dampr_text_count(dampr_ctx *ctx, dampr_table *t, dampr_textbuf *tb, uint64_t own_lo,
+                         uint64_t own_hi, int32_t mode);
+/* second pass over the same range that byte-compares every hashed (long) token with the
+ * representative of its table entry; sets DAMPR_TF_COLLISION if two different tokens share a code */
+int32_t dampr_text_verify(dampr_ctx *ctx, dampr_table *t, dampr_textbuf *tb, uint64_t own_lo,
+                          uint64_t own_hi, int32_t mode);
+
+/* stats[0]=entries stats[1]=lines stats[2]=count of the '' token stats[3]=tokens folded
+ * stats[4]=flags (DAMPR_TF_*) stats[5]=hashed(long) tokens stats[6]=raw tokens seen stats[7]=reserved */
+#define DAMPR_TF_NONASCII 1u
+#define DAMPR_TF_CR 2u
+#define DAMPR_TF_LONGLINE 4u
+#define DAMPR_TF_TABLEFULL 8u
+#define DAMPR_TF_LONGTOKEN 16u
+#define DAMPR_TF_COLLISION 32u
+int32_t dampr_table_stats(dampr_ctx *ctx, dampr_table *t, uint64_t stats[8]);
+/* compact the table into caller memory: codes[i], counts[i], reps[i] (rep = offset<<20 | len of the
+ * lowest-offset occurrence, hashed tokens only, else 0). cap = array capacity; *n = entries written.
+ * Pass all three arrays NULL to query *n only. Order is unspecified (dampr_table_to_kv +
+ * dampr_kv_sort give a sorted run). Replaces ReducedWriter.flush (dataset.py:107-117). */
+int32_t dampr_table_fetch(dampr_ctx *ctx, dampr_table *t, uint64_t *codes, uint64_t *counts,
+                          uint64_t *reps, uint64_t cap, uint64_t *n);
+/* same, but leaves the run on the device as a kv (key = code, val = count) */
+int32_t dampr_table_to_kv(dampr_ctx *ctx, dampr_table *t, dampr_kv **out);
+
+/* ---- kv records: 16-byte (u64 key, u64 value) pairs --------------------------------- */
+int32_t dampr_kv_create(dampr_ctx *ctx, uint64_t capacity, dampr_kv **out);
+int32_t dampr_kv_destroy(dampr_ctx *ctx, dampr_kv *kv);
+int32_t dampr_kv_size(dampr_ctx *ctx, dampr_kv *kv, uint64_t *n);
+int32_t dampr_kv_set_size(dampr_ctx *ctx, dampr_kv *kv, uint64_t n);
+int32_t dampr_kv_devptr(dampr_ctx *ctx, dampr_kv *kv, uint64_t *out_ptr);
+/* async copies of interleaved records [off, off+count) */
+int32_t dampr_kv_upload(dampr_ctx *ctx, dampr_kv *kv, uint64_t off, const void *host_records,
+                        uint64_t count);
+int32_t dampr_kv_download(dampr_ctx *ctx, dampr_kv *kv, uint64_t off, void *host_records,
+                          uint64_t count);
+/* columnar <-> interleaved: host keys[] and vals[] (8 bytes each) */
+int32_t dampr_kv_upload_columns(dampr_ctx *ctx, dampr_kv *kv, uint64_t off, const uint64_t *keys,
+                                const uint64_t *vals, uint64_t count);
+int32_t dampr_kv_download_columns(dampr_ctx *ctx, dampr_kv *kv, uint64_t off, uint64_t *keys,
+                                  uint64_t *vals, uint64_t count);
+
+/* key transforms applied on the fly by sort/partition (the stored key is never modified) */
+#define DAMPR_KEY_RAW 0   /* order by the unsigned 64-bit key                                   */
+#define DAMPR_KEY_MIX 1   /* order by a bijective 64-bit mix of the key: balanced partitions,
+                             grouping only (Splitter.partition, base.py:6-8)                      */
+#define DAMPR_KEY_I64 2   /* order as signed 64-bit                                              */
+#define DAMPR_KEY_F64 3   /* order as IEEE double                                                */
+
+/* partition-by-key + in-partition sort: replaces CSDatasetWriter.flush (dataset.py:236-253) +
+ * Splitter.partition (base.py:6-8) + SortedWriter sort (dataset.py:162-164). Stable.
+ * Result replaces the contents of `kv` (ping-pong buffer inside the library). */
+int32_t dampr_kv_sort(dampr_ctx *ctx, dampr_kv *kv, int32_t key_xform);
+
+/* reduce ops for the combiner / reducer (ARReduce.reduce binops, dampr.py:661-708) */
+#define DAMPR_OP_SUM_I64 0
+#define DAMPR_OP_SUM_F64 1
+#define DAMPR_OP_COUNT 2
+#define DAMPR_OP_MIN_I64 3
+#define DAMPR_OP_MAX_I64 4
+#define DAMPR_OP_MIN_F64 5
+#define DAMPR_OP_MAX_F64 6
+#define DAMPR_OP_FIRST 7
+#define DAMPR_OP_LAST 8
+
+/* segmented reduce of a key-sorted kv: one output record per key. Replaces
+ * Dataset.grouped_read + Reduce.reduce (dataset.py:429-433, base.py:204-207). out is created. */
+int32_t dampr_kv_reduce_by_key(dampr_ctx *ctx, dampr_kv *sorted, int32_t op, dampr_kv **out);
+/* group boundaries of a key-sorted kv: offsets[g] = first record of group g, offsets[G] = n.
+ * two-phase: pass offsets=NULL to get *n_groups. */
+int32_t dampr_kv_group_offsets(dampr_ctx *ctx, dampr_kv *sorted, uint64_t *offsets, uint64_t cap,
+                               uint64_t *n_groups);
+
+/* k-way merge of key-sorted runs + optional segmented reduce: replaces MergeDataset.read
+ * (dataset.py:571-579) + PartialReduceCombiner._combine (base.py:397-399). op < 0 = merge only. */
+int32_t dampr_kv_merge(dampr_ctx *ctx, dampr_kv **runs, int32_t n_runs, int32_t key_xform,
+                       int32_t op, dampr_kv **out);
+
+/* fused sort + reduce for associative ops (a_group_by(...).sum()/count()/...) */
+int32_t dampr_kv_sort_reduce(dampr_ctx *ctx, dampr_kv *kv, int32_t key_xform, int32_t op,
+                             dampr_kv **out);
+
+/* merge join of two key-sorted kvs: replaces InnerJoin.reduce / LeftJoin.reduce
+ * (base.py:264-283, 295-315). Both inputs must be sorted with `key_xform`. Emits one row per
+ * LEFT key group: rows[4*i+0..3] = left_begin, left_end, right_begin, right_end (record index
+ * ranges; right_begin == right_end when the key has no match, which is what the left join keeps
+ * and the inner join drops). Two-phase: rows == NULL returns *n_rows only. */
+int32_t dampr_kv_join_ranges(dampr_ctx *ctx, dampr_kv *left_sorted, dampr_kv *right_sorted,
+                             int32_t key_xform, uint64_t *rows, uint64_t cap, uint64_t *n_rows);
+
+/* broadcast hash-probe join: replaces MapAllJoin.map (base.py:165-178) for agg=dict/set with a
+ * membership/lookup crosser. build keys must be unique. out_vals[i] = build value of probe key i,
+ * out_hit[i] = 1/0. */
+int32_t dampr_kv_hash_probe(dampr_ctx *ctx, dampr_kv *build, dampr_kv *probe, dampr_kv **out_vals,
+                            uint8_t *out_hit_host);
+
+/* split a kv by destination rank: owner = mix(key) % n_dest; produces destination-contiguous
+ * records in `out` and counts[n_dest] on the host. The payload then moves with one all-to-all
+ * (torch.distributed/NCCL over NVLink) — replaces DefaultShuffler.shuffle (base.py:416-433). */
+int32_t dampr_kv_partition_by_owner(dampr_ctx *ctx, dampr_kv *kv, int32_t n_dest, dampr_kv **out,
+                                    uint64_t *counts_host);
+
+/* ---- synthetic inputs (bench/test tooling; deterministic, same algorithm as oracle/gen.py) */
+int32_t dampr_synth_text(dampr_ctx *ctx, dampr_textbuf *tb, uint64_t seed, uint64_t n_lines,
+                         const uint8_t *vocab_bytes, const uint32_t *vocab_off, uint32_t vocab_n,
+                         const uint64_t *cdf, uint64_t *out_nbytes);
+int32_t dampr_synth_kv(dampr_ctx *ctx, dampr_kv *kv, uint64_t seed, uint64_t n, uint64_t n_keys);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DAMPR_B200_H */

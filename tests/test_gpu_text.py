@@ -1,0 +1,151 @@
+"""GPU parity: text tokenise+combine kernels (csrc/text.cu) vs the oracle restatement.
+
+Bit-exact: counts, line counts, the '' token, key strings."""
+import numpy as np
+import pytest
+
+from dampr_b200 import device as dev
+from dampr_b200 import keycodes
+from oracle import gen, refsem
+
+pytestmark = pytest.mark.gpu
+
+
+def run_count(ctx, data, mode, chunk=None, verify=True):
+    tb = ctx.textbuf(len(data) + 64)
+    arr = np.frombuffer(data, dtype=np.uint8)
+    tb.upload_all(arr)
+    tab = ctx.table(20)
+    n = len(data)
+    if chunk is None:
+        tab.count(tb, 0, n, mode)
+    else:
+        lo = 0
+        while lo < n:
+            hi = min(n, lo + chunk)
+            tab.count(tb, lo, hi, mode)
+            lo = hi
+    st = tab.stats()
+    if verify and st["hashed"]:
+        tab.verify(tb, 0, n, mode)
+        st = tab.stats()
+    codes, counts, reps = tab.fetch()
+    words = keycodes.decode_table(codes, reps, mode, lambda off, ln: data[off:off + ln])
+    got = dict(zip(words, counts.tolist()))
+    assert len(got) == len(words), "two table entries decoded to the same word"
+    tb.free()
+    tab.free()
+    return got, st
+
+
+def check_wc(ctx, data, **kw):
+    got, st = run_count(ctx, data, dev.TOK_WS, **kw)
+    exp = refsem.wc_counts(data)
+    assert st["flags"] & ~dev.TF_CR == 0, st
+    assert got == dict(exp)
+    assert st["lines"] == len(refsem.text_lines(data))
+
+
+def check_df(ctx, data, **kw):
+    got, st = run_count(ctx, data, dev.TOK_NONWORD_LOWER_SET, **kw)
+    exp, n_lines = refsem.docfreq(data)
+    assert st["flags"] == 0, st
+    exp = dict(exp)
+    empty = exp.pop("", 0)
+    assert st["empty"] == empty
+    assert st["lines"] == n_lines
+    assert got == exp
+
+
+def check_tf(ctx, data, **kw):
+    got, st = run_count(ctx, data, dev.TOK_NONWORD_LOWER, **kw)
+    exp = dict(refsem.termfreq_nonset(data))
+    empty = exp.pop("", 0)
+    assert st["flags"] == 0, st
+    assert st["empty"] == empty
+    assert got == exp
+
+
+SMALL = [
+    b"", b"\n", b"a", b"a\n", b"a b", b"a\n\n", b"\n\n\n", b" a", b"a. b", b"...", b"...\n",
+    b"Hello hello HELLO\nhello world\n", b"x_1 X_1 x-1\n", b"one two  three\t\tfour\n\nfive",
+    b"a" * 12 + b" " + b"a" * 13 + b" " + b"A" * 13 + b"\n",
+    b"abcdefghi abcdefghij abcdefghij\n", b"tail without newline " * 3,
+]
+
+
+@pytest.mark.parametrize("data", SMALL)
+def test_small_cases(ctx, data):
+    check_wc(ctx, data)
+    check_df(ctx, data)
+    check_tf(ctx, data)
+
+
+def test_synthetic_zipf(ctx):
+    data = gen.text(1234, 30000, V=5000)
+    check_wc(ctx, data)
+    check_df(ctx, data)
+
+
+def test_synthetic_chunked_ownership(ctx):
+    """Ownership ranges split at arbitrary 16-byte multiples must count every line exactly once."""
+    data = gen.text(99, 8000, V=2000)
+    for chunk in (16, 4096 + 16, 6144, 100000):
+        check_df(ctx, data, chunk=chunk)
+        check_wc(ctx, data, chunk=chunk)
+
+
+def test_dirty_corpus(ctx):
+    data = gen.dirty_text()
+    check_wc(ctx, data)
+    check_df(ctx, data)
+    check_tf(ctx, data)
+
+
+def test_tile_boundaries(ctx):
+    """Tokens and lines straddling the 6 KB tile seams."""
+    rng = np.random.default_rng(5)
+    words = [b"w%d" % i for i in range(50)] + [b"LongerWord%d" % i for i in range(20)]
+    lines = []
+    for _ in range(4000):
+        k = int(rng.integers(1, 30))
+        lines.append(b" ".join(words[int(rng.integers(0, len(words)))] for _ in range(k)))
+    data = b"\n".join(lines) + b"\n"
+    check_wc(ctx, data)
+    check_df(ctx, data)
+
+
+def test_flags(ctx):
+    _, st = run_count(ctx, "café au lait\n".encode("utf-8"), dev.TOK_WS)
+    assert st["flags"] & dev.TF_NONASCII
+    _, st = run_count(ctx, b"a\r\nb\r\n", dev.TOK_NONWORD_LOWER_SET)
+    assert st["flags"] & dev.TF_CR
+    long_line = b"x " * 5000 + b"\n"
+    _, st = run_count(ctx, b"a\n" * 4000 + long_line + b"b\n" * 4000, dev.TOK_NONWORD_LOWER_SET)
+    assert st["flags"] & dev.TF_LONGLINE
+    # the whitespace tokeniser has no line dependence: long lines are fine there
+    check_wc(ctx, b"a\n" * 4000 + long_line + b"b\n" * 4000)
+
+
+def test_very_long_token(ctx):
+    data = b"short " + b"z" * 20000 + b" tail\n" + b"z" * 20000 + b"\n"
+    check_wc(ctx, data)
+
+
+def test_synth_text_matches_numpy_generator(ctx):
+    V = 3000
+    vocab = gen.make_vocab(V)
+    cdf = gen.make_cdf(V)
+    n_lines = 5000
+    ref = gen.text(77, n_lines, vocab=vocab, cdf=cdf)
+    tb = ctx.textbuf(len(ref) + 4096)
+    import ctypes as C
+    out = C.c_uint64(0)
+    vb, vo = vocab
+    ctx.check(ctx.lib.dampr_synth_text(ctx.h, tb.h, 77, n_lines, vb.ctypes.data_as(C.c_void_p),
+                                       vo.ctypes.data_as(C.c_void_p), V, cdf.ctypes.data_as(C.c_void_p),
+                                       C.byref(out)))
+    assert out.value == len(ref)
+    tb.n = out.value
+    got = tb.download(0, out.value).tobytes()
+    assert got == ref
