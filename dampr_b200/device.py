@@ -103,7 +103,7 @@ def load_library():
     _sig(lib, "dampr_kv_sort_reduce", vp, vp, i32, i32, pvp)
     _sig(lib, "dampr_kv_join_ranges", vp, vp, vp, i32, vp, u64, pu64)
     _sig(lib, "dampr_kv_hash_probe", vp, vp, vp, pvp, vp)
-    _sig(lib, "dampr_kv_partition_by_owner", vp, vp, i32, pvp, pu64)
+    _sig(lib, "dampr_kv_partition_by_owner", vp, vp, i32, pvp, vp)
     _sig(lib, "dampr_synth_text", vp, vp, u64, u64, vp, vp, u32, vp, pu64)
     _sig(lib, "dampr_synth_kv", vp, vp, u64, u64, u64)
     _lib = lib

@@ -1,0 +1,42 @@
+"""Engine tunables.  The names are the reference's (dampr/settings.py:5-37) so scripts that set
+``settings.max_processes`` or ``settings.partitions`` keep working; the meanings are re-mapped to
+the device engine (SURVEY §5 "Config / flags").
+"""
+import os
+
+# reference: number of worker processes. here: host threads used for file ingest and host-side
+# (non-lowered) map functions; the shuffle itself runs on the GPU(s).
+max_processes = os.cpu_count() or 1
+
+# reference: gzip level of spilled runs. here: unused (runs stay uncompressed in HBM / pinned host).
+compress_level = 1
+
+# reference: number of hash partitions (91). here: advisory; the device radix fan-out is chosen
+# from the record count (csrc/kv.cu: sort_range).
+partitions = 91
+
+# reference: max run files per partition before a compaction pass. here: merge fan-in of spilled runs.
+max_files_per_stage = 50
+
+# reference: tuples per pickle frame. here: unused.
+batch_size = 1000
+
+memory_checker_type = "interpolative"
+
+# reference: RSS growth (MB) that triggers a spill in a worker. here: device arena (MB) a single
+# stage may hold before sorted runs are spilled to pinned host memory.
+max_memory_per_worker = 512
+
+memory_check_base = 1.2
+memory_min_count = 10000
+memory_max_count_before_check = 100000
+
+# ---- additions of the device engine -------------------------------------------------------
+# GPU used by a single-process run (multi-GPU runs take LOCAL_RANK)
+device = int(os.environ.get("LOCAL_RANK", "0"))
+# bytes per host->device ingest chunk of text inputs
+ingest_chunk_bytes = 64 << 20
+# log2 of the combiner table capacity (entries) for text counting
+text_table_log2 = 24
+# device arena in bytes available to one sort before it spills runs (None = no cap)
+device_arena_bytes = None
