@@ -74,6 +74,12 @@ int32_t dampr_ctx_sync(dampr_ctx *ctx) {
     return DAMPR_OK;
 }
 
+int32_t dampr_ctx_sync_copy(dampr_ctx *ctx) {
+    if (!ctx) return DAMPR_ERR_ARG;
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->copy));
+    return DAMPR_OK;
+}
+
 const char *dampr_last_error(dampr_ctx *ctx) { return ctx ? ctx->err.c_str() : "no context"; }
 
 int32_t dampr_ctx_timings(dampr_ctx *ctx, double *out_ms, int32_t *out_ids, int32_t cap,

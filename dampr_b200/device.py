@@ -65,6 +65,7 @@ def load_library():
     _sig(lib, "dampr_ctx_create", i32, pvp)
     _sig(lib, "dampr_ctx_destroy", vp)
     _sig(lib, "dampr_ctx_sync", vp)
+    _sig(lib, "dampr_ctx_sync_copy", vp)
     _sig(lib, "dampr_last_error", vp, restype=C.c_char_p)
     _sig(lib, "dampr_ctx_timings", vp, C.POINTER(C.c_double), C.POINTER(i32), i32, C.POINTER(i32))
     _sig(lib, "dampr_ctx_timings_reset", vp)
@@ -180,6 +181,9 @@ class Ctx(object):
 
     def sync(self):
         self.check(self.lib.dampr_ctx_sync(self.h))
+
+    def sync_copy_stream(self):
+        self.check(self.lib.dampr_ctx_sync_copy(self.h))
 
     def close(self):
         if self.h is not None:

@@ -1,0 +1,736 @@
+"""Planner: recognises stages whose functions belong to the closed idiom set (lowering.py) and runs
+them as device pipelines over columnar data; returns None for everything else (host-map path).
+
+Lowered pipelines and the reference code they replace:
+  TextCount     Dampr.text(..).flat_map(tokenise).count()/fold_by(identity, +)  — MapStageRunner.medium_map
+                (stagerunner.py:79-129) with ReducedWriter (dataset.py:84-117): K0+K1+K2 in one kernel
+  KeyedFold     the KeyedReduce that completes an associative fold (dampr.py:678-691) over an
+                already fully combined frame: a relabelling, no work
+  LineCount     .len() over a text input (dampr.py:245-275): by-product of the tokenise kernel
+  KVFold        a_group_by(x[0], x[1]).sum()/min/max over binary kv records: K3+K4+K5
+  KVGroup       group_by(x[0], x[1]) + reduce(sum(it)/len/min/max): K3+K4 (+K5)
+  FrameSort     sort_by(+-x[i]) over a columnar frame: K3+K4 on (code, row) records
+  FrameCross    cross_left/right against a one-row collection with an analysable function,
+                evaluated once per distinct value of the fields it reads (exact Python results)
+  FrameSink     sink / sink_tsv of a frame: vectorised formatting
+"""
+import logging
+import math
+import os
+import threading
+
+import numpy as np
+
+from . import device as dev
+from . import keycodes, lowering, settings
+from . import operators as ops
+from .datasets import Dataset, RecordsDataset, TextLineDataset, CatDataset, EmptyDataset
+from .graph import GMap, GReduce, GSink
+from .inputs import PathInput, TextInput, KVInput, ArrayKVInput
+
+log = logging.getLogger("dampr_b200")
+
+
+class NotLowerable(Exception):
+    pass
+
+
+# ---- columnar stage output -----------------------------------------------------------------------
+class Frame(Dataset):
+    """Columnar collection. `keys` is the routing/sort key column (what read() yields as k), `cols`
+    are the value columns; the user-visible value is cols[0][i] when `scalar` else the tuple of the
+    columns. Columns are numpy arrays (numeric) or Python lists (strings / objects)."""
+
+    def __init__(self, keys, cols, scalar, combined=False):
+        self.keys = keys
+        self.cols = list(cols)
+        self.scalar = scalar
+        self.combined = combined  # every key appears once (map-side combine already complete)
+        self.n = len(cols[0]) if cols else 0
+        self.meta = {}
+
+    def __len__(self):
+        return self.n
+
+    @staticmethod
+    def _pylist(col):
+        return col.tolist() if isinstance(col, np.ndarray) else col
+
+    def values(self):
+        if self.scalar:
+            return self._pylist(self.cols[0])
+        return list(zip(*[self._pylist(c) for c in self.cols]))
+
+    def read(self):
+        keys = self._pylist(self.keys) if self.keys is not None else range(self.n)
+        return zip(keys, self.values())
+
+    def take(self, perm):
+        def tk(c):
+            if isinstance(c, np.ndarray):
+                return c[perm]
+            pl = perm.tolist()
+            return [c[i] for i in pl]
+        f = Frame(tk(self.keys) if self.keys is not None else None, [tk(c) for c in self.cols], self.scalar,
+                  self.combined)
+        return f
+
+    def delete(self):
+        self.keys, self.cols, self.n = None, [[]], 0
+
+
+# ---- text sources ----------------------------------------------------------------------------------
+class MemoryText(Dataset):
+    """Text held in host memory (a numpy uint8 array, ideally page-locked): the "file in pinned host
+    memory" starting point of the end-to-end metric. read() yields lines like
+    TextLineDataset."""
+
+    def __init__(self, array):
+        self.array = array
+
+    def read(self):
+        from .datasets import _iter_lines
+        return _iter_lines(self.array.tobytes(), 0)
+
+
+def _text_files(ds):
+    """[(kind, payload)] if the dataset is plain text the device can ingest, else None."""
+    if isinstance(ds, MemoryText):
+        return [("mem", ds.array)]
+    if isinstance(ds, PathInput):
+        files = ds.files()
+    elif isinstance(ds, TextInput):
+        files = [ds.path]
+    elif isinstance(ds, TextLineDataset) and ds.start == 0 and ds.end is None:
+        files = [ds.path]
+    elif isinstance(ds, CatDataset) and ds.datasets and all(
+            isinstance(d, TextLineDataset) and d.start == 0 and d.end is None for d in ds.datasets):
+        files = [d.path for d in ds.datasets]
+    else:
+        return None
+    if any(f.endswith(".gz") for f in files):
+        return None
+    return [("file", f) for f in files]
+
+
+_PIN_RING = {}
+
+
+def _pinned_ring(nslots, slot_bytes):
+    key = (nslots, slot_bytes)
+    ring = _PIN_RING.get(key)
+    if ring is None:
+        ring = [dev.PinnedBuffer(slot_bytes) for _ in range(nslots)]
+        _PIN_RING.clear()
+        _PIN_RING[key] = ring
+    return ring
+
+
+class TextScan(object):
+    """One pass of the tokenise+combine kernel over a set of files (or a memory text), with the
+    host->device copies pipelined against the kernel chunk by chunk."""
+
+    def __init__(self, runner, sources, mode):
+        self.runner = runner
+        self.sources = sources
+        self.mode = mode
+        self.words = None
+        self.counts = None
+        self.n_lines = 0
+        self.empty = 0
+        self.nbytes = 0
+
+    def run(self):
+        ctx = self.runner.ctx
+        sizes = []
+        for kind, p in self.sources:
+            sizes.append(len(p) if kind == "mem" else os.path.getsize(p))
+        total = sum(sizes) + len(sizes)
+        self.nbytes = sum(sizes)
+        tb = ctx.textbuf(total + 64)
+        tab = None
+        try:
+            offsets = self._upload_and_count(ctx, tb, sizes)
+            tab = self._tab
+            st = tab.stats()
+            flags = st["flags"]
+            if flags & dev.TF_TABLEFULL:
+                raise NotLowerable("combiner table overflow")
+            if flags & (dev.TF_NONASCII | dev.TF_LONGTOKEN):
+                raise NotLowerable("non-ASCII text or oversized token: device tokeniser is ASCII-only")
+            if self.mode != dev.TOK_WS and flags & (dev.TF_CR | dev.TF_LONGLINE):
+                raise NotLowerable("carriage returns or a line longer than the device window")
+            if st["hashed"]:
+                tab.verify(tb, 0, tb.n, self.mode)
+                if tab.stats()["flags"] & dev.TF_COLLISION:
+                    raise NotLowerable("64-bit key-code collision between two long tokens")
+            codes, counts, reps = tab.fetch()
+            self.words = keycodes.decode_table(codes, reps, self.mode,
+                                               lambda off, ln: tb.download(off, ln).tobytes())
+            self.counts = counts.view(np.int64)
+            self.n_lines = int(st["lines"])
+            self.empty = int(st["empty"])
+        finally:
+            if tab is not None:
+                tab.free()
+            elif getattr(self, "_tab", None) is not None:
+                self._tab.free()
+            tb.free()
+        return self
+
+    def _upload_and_count(self, ctx, tb, sizes):
+        chunk = int(settings.ingest_chunk_bytes)
+        chunk -= chunk % 4096
+        # layout: files back to back; a file that does not end in '\n' gets one (its last line is a
+        # line either way), so line and token semantics of the concatenation equal the per-file ones
+        self._tab = ctx.table(int(settings.text_table_log2))
+        tab = self._tab
+        # the total length must be known before the first kernel: files are stat'ed, the optional
+        # separator is reserved and patched if not needed (a spare '\n' after a terminated file would
+        # add an empty line, so the layout is decided by peeking at each file's last byte)
+        layout = []
+        pos = 0
+        for (kind, p), sz in zip(self.sources, sizes):
+            need_nl = False
+            if sz:
+                if kind == "mem":
+                    need_nl = p[sz - 1] != 10
+                else:
+                    with open(p, "rb") as f:
+                        f.seek(sz - 1)
+                        need_nl = f.read(1) != b"\n"
+            layout.append((pos, sz, need_nl))
+            pos += sz + (1 if need_nl else 0)
+        total = pos
+        tb.set_length(total)
+        nl = np.frombuffer(b"\n", dtype=np.uint8)
+        done = 0      # bytes uploaded
+        counted = 0   # bytes handed to the kernel
+        ring = None
+        for (kind, p), (base, sz, need_nl) in zip(self.sources, layout):
+            if kind == "mem":
+                off = 0
+                while off < sz:
+                    ln = min(chunk, sz - off)
+                    tb.upload(base + off, p[off:off + ln], ln)
+                    off += ln
+                    done = base + off
+                    counted = self._count_ready(tab, tb, counted, done, total, final=False)
+            else:
+                if ring is None:
+                    ring = _pinned_ring(4, chunk)
+                self._upload_file(ctx, tb, p, base, sz, ring, chunk, tab, counted, total)
+                done = base + sz
+                counted = self._counted
+            if need_nl:
+                tb.upload(base + sz, nl, 1)
+                done = base + sz + 1
+        self._count_ready(tab, tb, counted, total, total, final=True)
+        return layout
+
+    def _count_ready(self, tab, tb, counted, done, total, final):
+        """Launch the kernel over every 4 KB-aligned range whose halo has been uploaded."""
+        HALO = 16384
+        hi = total if final else max(counted, ((done - HALO) // 4096) * 4096 if done > HALO else 0)
+        if hi > counted:
+            tab.count(tb, counted, hi, self.mode)
+            counted = hi
+        self._counted = counted
+        return counted
+
+    def _upload_file(self, ctx, tb, path, base, sz, ring, chunk, tab, counted, total):
+        """page cache -> pinned ring (reader threads) -> device, kernel launches trailing the copies."""
+        self._counted = counted
+        nslots = len(ring)
+        nchunks = (sz + chunk - 1) // chunk
+        if nchunks == 0:
+            return
+        fd = os.open(path, os.O_RDONLY)
+        try:
+            results = [None] * nchunks
+            events = [threading.Event() for _ in range(nchunks)]
+            slot_free = [threading.Event() for _ in range(nslots)]
+            for e in slot_free:
+                e.set()
+
+            def reader(ci):
+                slot = ci % nslots
+                slot_free[slot].wait()
+                slot_free[slot].clear()
+                off = ci * chunk
+                ln = min(chunk, sz - off)
+                mv = memoryview(ring[slot].array)[:ln]
+                got = 0
+                while got < ln:
+                    r = os.preadv(fd, [mv[got:]], off + got)
+                    if r <= 0:
+                        break
+                    got += r
+                results[ci] = (slot, off, ln)
+                events[ci].set()
+
+            threads = []
+            nthreads = max(1, min(nslots, int(settings.max_processes)))
+            # simple pipeline: launch readers in order, at most nslots in flight
+            started = 0
+            for ci in range(nchunks):
+                while started < nchunks and started < ci + nslots:
+                    t = threading.Thread(target=reader, args=(started,))
+                    t.daemon = True
+                    t.start()
+                    threads.append(t)
+                    started += 1
+                events[ci].wait()
+                slot, off, ln = results[ci]
+                tb.upload(base + off, ring[slot].array[:ln], ln)
+                # the slot may be refilled only after the copy left it
+                ctx.sync_copy_stream()
+                slot_free[slot].set()
+                self._count_ready(tab, tb, self._counted, base + off + ln, total, final=False)
+            for t in threads:
+                t.join()
+        finally:
+            os.close(fd)
+
+
+def _source_key(sources):
+    out = []
+    for kind, p in sources:
+        if kind == "mem":
+            out.append(("mem", id(p), len(p)))
+        else:
+            st = os.stat(p)
+            out.append(("file", p, st.st_size, st.st_mtime_ns))
+    return tuple(out)
+
+
+# ---- stage matchers -----------------------------------------------------------------------------------
+def _parts(mapper):
+    if isinstance(mapper, ops.FusedMapper):
+        return mapper.parts()
+    return [mapper]
+
+
+def _opkinds(mapper):
+    """[(kind, Op)] for a mapper made only of DSL-generated Maps, else None."""
+    out = []
+    for p in _parts(mapper):
+        op = getattr(p, "op", None)
+        if not isinstance(p, (ops.Map, ops.StreamMapper)) or op is None:
+            return None
+        out.append((op.kind, op))
+    return out
+
+
+def _match_text_count(stage, inputs):
+    """flat_map(tokeniser) -> keyed(identity, const 1) + PartialReduceCombiner(add) over text."""
+    if not isinstance(stage, GMap) or len(inputs) != 1:
+        return None
+    src = _text_files(inputs[0])
+    if src is None:
+        return None
+    ks = _opkinds(stage.mapper)
+    if ks is None or [k for k, _ in ks] != ["flat_map", "keyed"]:
+        return None
+    mode = lowering.tokenizer_mode(ks[0][1].fn)
+    if mode is None:
+        return None
+    keyed = ks[1][1]
+    if not lowering.is_identity(keyed.fn):
+        return None
+    ok, v = lowering.constant_value(keyed.fn2)
+    if not ok or v != 1 or type(v) is not int:
+        return None
+    if not isinstance(stage.combiner, ops.PartialReduceCombiner):
+        return None
+    if lowering.binop_kind(stage.options.get("binop")) != lowering.ADD:
+        return None
+    return src, mode
+
+
+def _match_line_count(stage, inputs):
+    if not isinstance(stage, GMap) or len(inputs) != 1:
+        return None
+    ks = _opkinds(stage.mapper)
+    if ks is None or [k for k, _ in ks] != ["count_records"]:
+        return None
+    return True
+
+
+def text_scan(runner, src, mode):
+    # memoised per graph execution only: the same file is scanned once for len() and count()
+    cache = runner.__dict__.setdefault("_scan_cache", {})
+    key = (_source_key(src), mode)
+    hit = cache.get(key)
+    if hit is not None:
+        return hit
+    scan = TextScan(runner, src, mode).run()
+    cache[key] = scan
+    return scan
+
+
+def _future_text_count(runner, si, source):
+    """A later stage that tokenises the same text: its scan also yields the line count."""
+    for st in runner.graph.stages[si + 1:]:
+        if isinstance(st, GMap) and len(st.inputs) == 1 and st.inputs[0] == source:
+            inp = [runner.graph.inputs.get(st.inputs[0])]
+            if inp[0] is None:
+                continue
+            m = _match_text_count(st, inp)
+            if m is not None:
+                return m
+    return None
+
+
+def try_lower(runner, stage, inputs, si, data):
+    try:
+        if isinstance(stage, GMap):
+            return _lower_map(runner, stage, inputs, si)
+        if isinstance(stage, GReduce):
+            return _lower_reduce(runner, stage, inputs)
+        if isinstance(stage, GSink):
+            return _lower_sink(runner, stage, inputs)
+    except NotLowerable as e:
+        log.warning("stage %s not lowered (%s): running as host map + device shuffle", stage.output, e)
+    return None
+
+
+# ---- map stages ------------------------------------------------------------------------------------------
+def _lower_map(runner, stage, inputs, si):
+    m = _match_text_count(stage, inputs)
+    if m is not None:
+        src, mode = m
+        scan = text_scan(runner, src, mode)
+        words, counts = scan.words, scan.counts
+        if mode != dev.TOK_WS and scan.empty:
+            words = words + [""]
+            counts = np.concatenate((counts, np.array([scan.empty], dtype=np.int64)))
+        f = Frame(words, [counts], scalar=True, combined=True)
+        runner.stats.add(stage, "device text tokenise+combine",
+                         "bytes=%d terms=%d lines=%d" % (scan.nbytes, len(words), scan.n_lines))
+        return f
+    if _match_line_count(stage, inputs):
+        ds = inputs[0]
+        src = _text_files(ds)
+        if src is not None:
+            fut = _future_text_count(runner, si, stage.inputs[0])
+            mode = fut[1] if fut is not None else dev.TOK_WS
+            scan = text_scan(runner, src, mode)
+            runner.stats.add(stage, "device line count (tokenise kernel by-product)", "lines=%d" % scan.n_lines)
+            return RecordsDataset([1], [scan.n_lines])
+        if isinstance(ds, (Frame, RecordsDataset)):
+            runner.stats.add(stage, "frame length", "records=%d" % len(ds))
+            return RecordsDataset([1], [len(ds)])
+        return None
+    kv = _lower_kv_map(runner, stage, inputs)
+    if kv is not None:
+        return kv
+    if len(inputs) == 1 and isinstance(inputs[0], Frame):
+        return _lower_frame_map(runner, stage, inputs[0])
+    if isinstance(stage.mapper, ops.MapCrossJoin) and len(inputs) == 2 and isinstance(inputs[0], Frame):
+        return _lower_cross(runner, stage, inputs)
+    return None
+
+
+def _kv_columns(ds):
+    if isinstance(ds, (KVInput, ArrayKVInput)) or hasattr(ds, "columns"):
+        try:
+            return ds.columns()
+        except Exception:
+            return None
+    return None
+
+
+_FOLD_OPS = {lowering.ADD: dev.OP_SUM_I64, lowering.MIN: dev.OP_MIN_I64, lowering.MAX: dev.OP_MAX_I64,
+             lowering.FIRST: dev.OP_FIRST, lowering.LAST: dev.OP_LAST}
+
+
+def _key_xform_for(col):
+    return dev.KEY_I64 if col.dtype == np.int64 else dev.KEY_RAW
+
+
+def _lower_kv_map(runner, stage, inputs):
+    """keyed(x[0], x[1]) over binary (key, value) records."""
+    if len(inputs) != 1:
+        return None
+    cols = _kv_columns(inputs[0])
+    if cols is None:
+        return None
+    ks = _opkinds(stage.mapper)
+    if ks is None or [k for k, _ in ks] != ["keyed"]:
+        return None
+    kp = lowering.projection(ks[0][1].fn)
+    vp = lowering.projection(ks[0][1].fn2)
+    if kp is None or vp is None or kp[0] != "field" or kp[2] != 1 or kp[1] not in (0, 1):
+        return None
+    keys = cols[kp[1]]
+    count_only = False
+    if vp[0] == "field" and vp[2] == 1 and vp[1] in (0, 1):
+        vals = cols[vp[1]]
+    elif vp[0] == "const" and type(vp[1]) is int:
+        vals = np.full(len(keys), vp[1], dtype=np.int64)
+        count_only = vp[1] == 1
+    elif vp[0] == "ident":
+        return None
+    else:
+        return None
+    ctx = runner.ctx
+    binop = stage.options.get("binop")
+    n = len(keys)
+    if isinstance(stage.combiner, ops.PartialReduceCombiner) and callable(binop):
+        kind = lowering.binop_kind(binop)
+        if kind not in _FOLD_OPS or vals.dtype not in (np.int64, np.uint64):
+            return None
+        if kind == lowering.ADD and n and float(np.abs(vals.astype(np.float64)).sum()) >= float(1 << 62):
+            raise NotLowerable("64-bit sum could overflow (SURVEY B12)")
+        kv = ctx.kv_from_columns(keys, vals)
+        try:
+            red = kv.sort_reduce(dev.OP_COUNT if (count_only and kind == lowering.ADD) else _FOLD_OPS[kind], dev.KEY_MIX)
+            rk, rv = red.columns()
+            red.free()
+        finally:
+            kv.free()
+        f = Frame(rk.view(keys.dtype), [rv.view(np.int64)], scalar=True, combined=True)
+        runner.stats.add(stage, "device kv partition+sort+segmented-reduce", "records=%d groups=%d" % (n, len(rk)))
+        return f
+    if stage.combiner is None:
+        kv = ctx.kv_from_columns(keys, vals)
+        try:
+            kv.sort(_key_xform_for(keys))
+            rk, rv = kv.columns()
+        finally:
+            kv.free()
+        f = Frame(rk.view(keys.dtype), [rv.view(vals.dtype)], scalar=True)
+        f.meta["sorted_kv"] = True
+        runner.stats.add(stage, "device kv partition+sort", "records=%d" % n)
+        return f
+    return None
+
+
+def _numeric(col):
+    return isinstance(col, np.ndarray) and col.dtype.kind in "iuf" and col.dtype.itemsize == 8
+
+
+def _lower_frame_map(runner, stage, frame):
+    """sort_by(+-x[i]) / sort_by(+-x) over a frame."""
+    ks = _opkinds(stage.mapper)
+    if ks is None:
+        return None
+    kinds = [k for k, _ in ks]
+    if kinds == ["keyed"] and stage.combiner is None:
+        op = ks[0][1]
+        if not lowering.is_identity(op.fn2):
+            return None
+        kp = lowering.projection(op.fn)
+        if kp is None:
+            return None
+        if kp[0] == "field" and not frame.scalar and kp[1] < len(frame.cols):
+            col = frame.cols[kp[1]]
+        elif kp[0] == "ident" and frame.scalar:
+            col = frame.cols[0]
+        else:
+            return None
+        if not _numeric(col):
+            return None
+        sign = kp[2]
+        if col.dtype.kind == "f":
+            kcol = (col * sign) if sign < 0 else col
+            codes, xf = kcol.view(np.uint64), dev.KEY_F64
+        else:
+            kcol = (-col.astype(np.int64)) if sign < 0 else col.astype(np.int64)
+            codes, xf = kcol.view(np.uint64), dev.KEY_I64
+        n = frame.n
+        ctx = runner.ctx
+        kv = ctx.kv_from_columns(codes, np.arange(n, dtype=np.uint64))
+        try:
+            kv.sort(xf)
+            _k, perm = kv.columns()
+        finally:
+            kv.free()
+        perm = perm.view(np.int64)
+        out = frame.take(perm)
+        out.keys = kcol[perm]
+        out.combined = False
+        runner.stats.add(stage, "device sort of frame rows", "records=%d" % n)
+        return out
+    return None
+
+
+def _lower_cross(runner, stage, inputs):
+    """MapCrossJoin(outer=frame, inner=one row), cross analysable: evaluate the user's function once
+    per distinct value of the outer fields each output component reads."""
+    mapper = stage.mapper
+    cross = getattr(mapper, "user_cross", None)
+    if cross is None:
+        return None
+    outer = inputs[0]
+    inner_rows = [v for _k, v in ops.as_one_dataset(inputs[1]).read()]
+    if len(inner_rows) != 1 or outer.n == 0:
+        return None
+    inner = inner_rows[0]
+    e = _inline(cross)
+    if e is None:
+        return None
+    # cross(v_inner, v_outer): arg0 = inner value, arg1 = outer value
+    comps = e.a if e.op == "tuple" else (e,)
+    out_cols = []
+    values = None
+    for ci, comp in enumerate(comps):
+        f = lowering._field(_swap_to_arg0(comp, 1))
+        if f is not None and not outer.scalar and f < len(outer.cols):
+            out_cols.append(outer.cols[f])
+            continue
+        deps = lowering.depends_on(comp, 1)
+        if deps is None or outer.scalar or not deps or any(d >= len(outer.cols) for d in deps):
+            return None
+        dep = sorted(deps)
+        if len(dep) != 1 or not isinstance(outer.cols[dep[0]], np.ndarray):
+            return None
+        col = outer.cols[dep[0]]
+        uniq, first, inv = np.unique(col, return_index=True, return_inverse=True)
+        if values is None:
+            values = outer.values()
+        res = []
+        for i in first.tolist():
+            r = cross(inner, values[i])
+            res.append(r[ci] if e.op == "tuple" else r)
+        kinds = set(type(x) for x in res)
+        if kinds == {float}:
+            arr = np.array(res, dtype=np.float64)[inv]
+        elif kinds == {int}:
+            arr = np.array(res, dtype=np.int64)[inv]
+        else:
+            il = inv.tolist()
+            arr = [res[j] for j in il]
+        out_cols.append(arr)
+    f = Frame(outer.keys, out_cols, scalar=(e.op != "tuple"))
+    runner.stats.add(stage, "frame cross with a 1-row broadcast (memoised per distinct field value)",
+                     "records=%d" % outer.n)
+    return f
+
+
+def _swap_to_arg0(e, argi):
+    """Rewrite arg(argi) as arg(0) so that lowering._field can test `x[i]` patterns."""
+    E = lowering.E
+    if not isinstance(e, E):
+        return e
+    if e.op == "arg":
+        return E("arg", 0) if e.a == argi else E("arg", 99)
+    if e.op in ("const", "obj"):
+        return e
+
+    def sw(x):
+        if isinstance(x, tuple):
+            return tuple(sw(y) for y in x)
+        return _swap_to_arg0(x, argi) if isinstance(x, E) else x
+    return E(e.op, sw(e.a), sw(e.b), sw(e.c))
+
+
+def _inline(fn, depth=0):
+    """analyze(fn) with calls to analysable Python functions substituted (DSL wrappers such as
+    cross_right's `lambda xi, yi: cross(yi, xi)`)."""
+    E = lowering.E
+    e = lowering.analyze(fn)
+    if e is None or depth > 3:
+        return e
+
+    def subst(x, args):
+        if isinstance(x, tuple):
+            return tuple(subst(y, args) for y in x)
+        if not isinstance(x, E):
+            return x
+        if x.op == "arg":
+            return args[x.a]
+        if x.op in ("const", "obj"):
+            return x
+        return E(x.op, subst(x.a, args), subst(x.b, args), subst(x.c, args))
+
+    def walk(x):
+        if isinstance(x, tuple):
+            return tuple(walk(y) for y in x)
+        if not isinstance(x, E):
+            return x
+        if x.op in ("const", "obj", "arg"):
+            return x
+        y = E(x.op, walk(x.a), walk(x.b), walk(x.c))
+        if y.op == "call" and isinstance(y.a, E) and y.a.op == "obj":
+            import types
+            target = y.a.a
+            if isinstance(target, types.FunctionType) and target.__code__.co_argcount == len(y.b):
+                inner = _inline(target, depth + 1)
+                if inner is not None:
+                    return subst(inner, list(y.b))
+        return y
+
+    return walk(e)
+
+
+# ---- reduce stages ----------------------------------------------------------------------------------------
+def _lower_reduce(runner, stage, inputs):
+    red = stage.reducer
+    if len(inputs) == 1 and isinstance(inputs[0], Frame):
+        fr = inputs[0]
+        binop = getattr(red, "binop", None)
+        if isinstance(red, ops.KeyedReduce) and binop is not None and fr.combined and fr.scalar:
+            # fully combined on the map side: the fold of a one-element group is the element
+            out = Frame(fr.keys, [fr.keys, fr.cols[0]], scalar=False, combined=True)
+            runner.stats.add(stage, "keyed fold over a fully combined frame (relabel)", "records=%d" % fr.n)
+            return out
+        if isinstance(red, ops.KeyedReduce) and fr.meta.get("sorted_kv") and fr.scalar and _numeric(fr.cols[0]):
+            kind = lowering.group_reducer_kind(red.reducer)
+            opmap = {lowering.SUM: dev.OP_SUM_I64, lowering.COUNT: dev.OP_COUNT, lowering.MIN: dev.OP_MIN_I64,
+                     lowering.MAX: dev.OP_MAX_I64}
+            if kind in opmap and fr.cols[0].dtype.kind in "iu" and isinstance(fr.keys, np.ndarray):
+                vals = fr.cols[0]
+                if kind == lowering.SUM and fr.n and float(np.abs(vals.astype(np.float64)).sum()) >= float(1 << 62):
+                    return None
+                ctx = runner.ctx
+                kv = ctx.kv_from_columns(fr.keys, vals)
+                try:
+                    r = kv.sort_reduce(opmap[kind], _key_xform_for(fr.keys))
+                    rk, rv = r.columns()
+                    r.free()
+                finally:
+                    kv.free()
+                rk = rk.view(fr.keys.dtype)
+                out = Frame(rk, [rk, rv.view(np.int64)], scalar=False, combined=True)
+                runner.stats.add(stage, "device segmented reduce of sorted kv", "records=%d groups=%d" % (fr.n, len(rk)))
+                return out
+    return None
+
+
+# ---- sinks ---------------------------------------------------------------------------------------------------
+def _str_column(col):
+    """Python str() of every element, computed once per distinct value for numeric columns."""
+    if isinstance(col, np.ndarray):
+        uniq, inv = np.unique(col, return_inverse=True)
+        strs = [str(x) for x in uniq.tolist()]
+        il = inv.tolist()
+        return [strs[j] for j in il]
+    return [x if type(x) is str else str(x) for x in col]
+
+
+def _lower_sink(runner, stage, inputs):
+    if len(inputs) != 1 or not isinstance(inputs[0], Frame):
+        return None
+    fr = inputs[0]
+    parts = _parts(stage.mapper)
+    from .dsl import _tsv_line
+    lines = None
+    if len(parts) == 1 and getattr(parts[0], "op", None) is not None:
+        op = parts[0].op
+        if op.kind == "map" and op.fn is _tsv_line and not fr.scalar:
+            cols = [_str_column(c) for c in fr.cols]
+            lines = ["\t".join(t) for t in zip(*cols)]
+        elif op.kind == "identity" and fr.scalar:
+            lines = _str_column(fr.cols[0])
+    if lines is None:
+        return None
+    os.makedirs(stage.path, exist_ok=True)
+    fname = os.path.join(stage.path, "part-0")
+    with open(fname, "w", encoding="utf-8") as f:
+        if lines:
+            f.write("\n".join(lines))
+            f.write("\n")
+    runner.stats.add(stage, "vectorised frame sink", "records=%d" % len(lines))
+    return CatDataset([TextLineDataset(fname)])

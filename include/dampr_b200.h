@@ -50,6 +50,8 @@ int32_t dampr_set_option(const char *name, int64_t value);
 int32_t dampr_ctx_create(int32_t device, dampr_ctx **out);
 int32_t dampr_ctx_destroy(dampr_ctx *ctx);
 int32_t dampr_ctx_sync(dampr_ctx *ctx);
+/* wait for the copy stream only (host staging buffers may be reused afterwards) */
+int32_t dampr_ctx_sync_copy(dampr_ctx *ctx);
 const char *dampr_last_error(dampr_ctx *ctx);
 /* CUDA-event timings of the kernels launched since the last reset:
  * out[2*i] = kernel id (DAMPR_K_*), out[2*i+1] = milliseconds (as double bit pattern).

@@ -1,0 +1,169 @@
+"""GPU: the BASELINE workloads through the DSL vs the golden vectors of the real reference and vs
+the oracle at larger sizes. Bit-exact for counts / keys / sink lines."""
+import json
+import math
+import os
+import re
+
+import numpy as np
+import pytest
+
+import dampr_b200
+from dampr_b200 import Dampr, runner as runner_mod
+from dampr_b200.inputs import ArrayKVInput, KVInput
+from dampr_b200.plan import MemoryText
+from oracle import gen, refsem
+
+pytestmark = pytest.mark.gpu
+G = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+RX = re.compile(r"[^\w]+")
+
+
+def load(name):
+    with open(os.path.join(G, name)) as f:
+        return json.load(f)
+
+
+def run_wc(path):
+    """examples/wc.py:11-14"""
+    wc = Dampr.text(path) \
+        .flat_map(lambda x: x.split()) \
+        .fold_by(lambda x: x, value=lambda x: 1, binop=lambda x, y: x + y) \
+        .sort_by(lambda x: -x[1])
+    return wc.run("word-count").read()
+
+
+def run_tfidf(path, out_dir, chunk):
+    """benchmarks/tf-idf-dampr.py:9-21"""
+    docs = Dampr.text(path, chunk)
+    doc_freq = docs.flat_map(lambda x: set(RX.split(x.lower()))).count(reduce_buffer=float("inf"))
+    idf = doc_freq.cross_right(docs.len(),
+                               lambda df, total: (df[0], df[1], math.log(1 + (float(total) / df[1]))),
+                               memory=True)
+    idf.sink_tsv(out_dir).run()
+    lines = []
+    for fn in sorted(os.listdir(out_dir)):
+        with open(os.path.join(out_dir, fn)) as f:
+            lines.extend(l.rstrip("\n") for l in f)
+    return sorted(lines)
+
+
+def lowered(substr):
+    return any(substr in how for _s, how, _d in runner_mod.LAST_STATS.stages)
+
+
+@pytest.mark.parametrize("fixture,maker", [
+    ("text_zipf.json", lambda: gen.text(1234, 3000, vocab=gen.make_vocab(2000), cdf=gen.make_cdf(2000))),
+    ("text_dirty.json", lambda: gen.dirty_text(7, 1500, 2000)),
+])
+def test_text_workloads_match_reference_golden(ctx, tmp_path, fixture, maker):
+    fix = load(fixture)
+    data = maker()
+    p = tmp_path / "corpus.txt"
+    p.write_bytes(data)
+    rows = run_wc(str(p))
+    assert lowered("device text tokenise+combine")
+    assert sorted(rows) == [tuple(r) for r in fix["wc"]]
+    assert [c for _w, c in rows] == sorted((c for _w, c in rows), reverse=True)  # truly sorted
+    lines = run_tfidf(str(p), str(tmp_path / "idfs"), len(data) / 8 + 1)
+    assert lowered("device text tokenise+combine") and lowered("device line count")
+    assert lines == fix["tfidf_lines"]
+    assert Dampr.text(str(p)).len().read() == [fix["n_lines"]]
+
+
+def test_text_workloads_larger_vs_oracle(ctx, tmp_path):
+    data = gen.text(99, 120000, V=50000)
+    p = tmp_path / "big.txt"
+    p.write_bytes(data)
+    assert sorted(run_wc(str(p))) == sorted(refsem.wc_counts(data).items())
+    assert run_tfidf(str(p), str(tmp_path / "idfs"), 1 << 20) == refsem.tfidf_sink_lines(data)
+
+
+def test_text_from_pinned_memory_and_multiple_files(ctx, tmp_path):
+    from dampr_b200 import device as dev
+    data = gen.text(5, 20000, V=3000)
+    pin = dev.PinnedBuffer(len(data))
+    pin.array[:] = np.frombuffer(data, dtype=np.uint8)
+    got = Dampr.read_input(MemoryText(pin.array)).flat_map(lambda x: x.split()).count().read()
+    assert sorted(got) == sorted(refsem.wc_counts(data).items())
+    # several files, one without a final newline: the directory is one logical input
+    d = tmp_path / "dir"
+    d.mkdir()
+    parts = [gen.text(6, 3000, V=500), gen.dirty_text(8, 300, 500)[:-1], b"", gen.text(7, 10, V=50)]
+    for i, b in enumerate(parts):
+        (d / ("part%d.txt" % i)).write_bytes(b)
+    got = Dampr.text(str(d)).flat_map(lambda x: set(RX.split(x.lower()))).count().read()
+    exp = {}
+    n_lines = 0
+    for b in parts:
+        c, n = refsem.docfreq(b)
+        n_lines += n
+        for k, v in c.items():
+            exp[k] = exp.get(k, 0) + v
+    assert dict(got) == exp
+    assert Dampr.text(str(d)).len().read() == [n_lines]
+
+
+def test_non_lowerable_text_falls_back_to_host_map(ctx, tmp_path):
+    p = tmp_path / "u.txt"
+    data = "naïve café\nplain line\nÜber über\n".encode("utf-8")
+    p.write_bytes(data)
+    got = Dampr.text(str(p)).flat_map(lambda x: set(RX.split(x.lower()))).count().read()
+    assert dict(got) == dict(refsem.docfreq(data)[0])
+    assert not lowered("device text tokenise+combine")
+    got = Dampr.text(str(p)).flat_map(lambda x: x.upper().split()).count().read()  # not an idiom
+    assert dict(got) == {"NAÏVE": 1, "CAFÉ": 1, "PLAIN": 1, "LINE": 1, "ÜBER": 2}
+
+
+def test_kv_workloads_match_reference_golden(ctx, tmp_path):
+    fix = load("kv.json")
+    keys, vals = gen.kv(42, 20000, 700)
+    src = Dampr.read_input(ArrayKVInput(keys, vals, chunk_records=3000))
+    assert sorted(src.a_group_by(lambda x: x[0], lambda x: x[1]).sum().read()) == [tuple(r) for r in fix["sum"]]
+    assert lowered("device kv partition+sort+segmented-reduce")
+    assert sorted(src.count(lambda x: x[0]).read()) == [tuple(r) for r in fix["count"]]
+    assert sorted(src.group_by(lambda x: x[0], lambda x: x[1]).reduce(lambda k, it: sum(it)).read()) == \
+        [tuple(r) for r in fix["group_sum"]]
+    assert lowered("device segmented reduce of sorted kv")
+    assert sorted(src.a_group_by(lambda x: x[0], lambda x: x[1]).reduce(max).read()) == [tuple(r) for r in fix["max"]]
+    assert sorted(src.mean(lambda x: x[0], lambda x: x[1]).read()) == [tuple(r) for r in fix["mean"]]
+    srt = src.map(lambda x: x[1]).sort_by(lambda v: v).read()
+    import hashlib
+    assert srt == sorted(vals.tolist()) and srt[:50] == fix["sorted_vals_head"]
+    assert hashlib.sha256(json.dumps(srt).encode()).hexdigest() == fix["sorted_vals_sha256"]
+    lk, lv = gen.kv(1, 6000, 900)
+    rk, rv = gen.kv(2, 800, 1800)
+    L = Dampr.read_input(ArrayKVInput(lk, lv)).group_by(lambda x: x[0], lambda x: x[1])
+    R = Dampr.read_input(ArrayKVInput(rk, rv)).group_by(lambda x: x[0], lambda x: x[1])
+    inner = sorted((k, sorted(l), sorted(r)) for k, (l, r) in L.join(R).reduce(lambda l, r: (list(l), list(r))).read())
+    assert inner == [(k, l, r) for k, l, r in fix["inner"]]
+    left = L.join(R).left_reduce(lambda l, r: (list(l), list(r))).read()
+    assert len(left) == fix["left_len"] and sum(1 for _k, (_l, r) in left if not r) == fix["left_nomatch"]
+    small = Dampr.read_input(ArrayKVInput(rk, rv)).map(lambda x: x[0])
+    big = Dampr.read_input(ArrayKVInput(lk, lv))
+    probe = small.cross_set(big, lambda b, table: (b[0], b[0] in table), agg=set).read()
+    assert len(probe) == fix["probe_len"] and sum(1 for _k, h in probe if h) == fix["probe_true"]
+    # binary file input
+    recs = np.empty((len(keys), 2), dtype=np.uint64)
+    recs[:, 0], recs[:, 1] = keys, vals.view(np.uint64)
+    f = tmp_path / "kv.bin"
+    recs.tofile(str(f))
+    got = Dampr.read_input(KVInput(str(f), chunk_records=5000)).a_group_by(lambda x: x[0], lambda x: x[1]).sum().read()
+    assert sorted(got) == [tuple(r) for r in fix["sum"]]
+
+
+def test_kv_larger_vs_oracle(ctx):
+    keys, vals = gen.kv(3, 2_000_000, 150_000)
+    src = Dampr.read_input(ArrayKVInput(keys, vals))
+    got = dict(src.a_group_by(lambda x: x[0], lambda x: x[1]).sum().read())
+    assert got == refsem.group_sum(keys, vals)
+    got = dict(src.fold_by(lambda x: x[0], min, lambda x: x[1]).read())
+    assert got == refsem.group_fold(keys, vals, min)
+
+
+def test_shim_package_runs_reference_style_script(ctx, tmp_path):
+    """`from dampr import Dampr` resolves to the engine (drop-in for unmodified scripts)."""
+    import dampr
+    assert dampr.Dampr is dampr_b200.Dampr
+    from dampr import settings
+    assert settings.partitions == 91

@@ -1,0 +1,153 @@
+"""CPU: host-side logic of the engine (no device): key codec, lambda lowering, text chunk ownership,
+graph IR, token key-code decoding, C-ABI surface."""
+import ctypes
+import math
+import operator
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+from dampr_b200 import keycodec, keycodes, lowering
+from dampr_b200 import device as dev
+from dampr_b200.datasets import TextLineDataset
+from dampr_b200.inputs import TextInput, MemoryInput
+from oracle import gen, refsem
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_keycodec_ints_floats_order_and_roundtrip():
+    keys = [5, -3, 0, 2 ** 62, -2 ** 63, 7]
+    codes, codec = keycodec.encode(keys)
+    assert codec.kind == keycodec.INT and codec.exact
+    assert [keys[i] for i in np.argsort(codes, kind="stable")] == sorted(keys)
+    assert keycodec.decode_exact(codes, codec) == keys
+    fk = [1.5, -0.0, -2.25, 3e300, -1e-300, 2]
+    codes, codec = keycodec.encode(fk)
+    assert codec.kind == keycodec.FLOAT
+    assert [fk[i] for i in np.argsort(codes, kind="stable")] == sorted(fk)
+    assert keycodec.decode_exact(codes, codec) == [float(x) for x in fk]
+
+
+def test_keycodec_strings_prefix_order_and_refine():
+    keys = ["pear", "apple", "applesauce!", "applesauce", "fig", "apple"]
+    codes, codec = keycodec.encode(keys)
+    assert codec.kind == keycodec.STR and not codec.exact and codec.ordered
+    order = np.argsort(codes, kind="stable")
+    ks = [keys[i] for i in order]
+    vs = list(order)
+    ks, vs = keycodec.refine_runs(ks, vs, codes[order], codec)
+    assert ks == sorted(keys)
+    assert [keys[i] for i in vs] == ks
+
+
+def test_keycodec_hash_class_groups_equal_keys():
+    keys = [None, (1, "a"), (1, "a"), 2 ** 70, (1.0, "a"), None, "x"]
+    codes, codec = keycodec.encode(keys)
+    assert codec.kind == keycodec.HASH
+    assert codes[0] == codes[5] and codes[1] == codes[2] == codes[4]
+    assert len({int(c) for c in codes}) == 4
+    with pytest.raises(TypeError):
+        keycodec.encode([None, 1], need_order=True)
+    codes, codec = keycodec.encode([(2, "b"), (1, "z"), (1, "a")], need_order=True)
+    assert codec.kind == keycodec.TUPLE and codes[1] == codes[2] < codes[0]
+
+
+def test_lowering_idioms():
+    RX = re.compile(r"[^\w]+")
+    assert lowering.tokenizer_mode(lambda x: x.split()) == lowering.TOK_WS
+    assert lowering.tokenizer_mode(lambda x: set(RX.split(x.lower()))) == lowering.TOK_NONWORD_LOWER_SET
+    assert lowering.tokenizer_mode(lambda x: RX.split(x.lower())) == lowering.TOK_NONWORD_LOWER
+    assert lowering.tokenizer_mode(lambda x: re.split(r"\W+", x.lower())) == lowering.TOK_NONWORD_LOWER
+    assert lowering.tokenizer_mode(lambda x: x.split(",")) is None
+    assert lowering.tokenizer_mode(lambda x: set(RX.split(x))) is None  # no lower(): not the idiom
+    RXI = re.compile(r"[^\w]+", re.I)
+    assert lowering.tokenizer_mode(lambda x: set(RXI.split(x.lower()))) is None
+    assert lowering.is_identity(lambda x: x) and not lowering.is_identity(lambda x: x + 0)
+    assert lowering.constant_value(lambda x: 1) == (True, 1)
+    assert lowering.projection(lambda x: -x[1]) == ("field", 1, -1)
+    assert lowering.binop_kind(operator.add) == lowering.ADD
+    assert lowering.binop_kind(lambda x, y: y + x) == lowering.ADD
+    assert lowering.binop_kind(lambda x, y: x * y) is None
+    assert lowering.binop_kind(lambda x, _y: x) == lowering.FIRST
+    assert lowering.group_reducer_kind(lambda k, it: sum(it)) == lowering.SUM
+
+    def branchy(x):
+        if x:
+            return 1
+        return 2
+    assert lowering.analyze(branchy) is None
+    e = lowering.analyze(lambda df, total: (df[0], df[1], math.log(1 + (float(total) / df[1]))))
+    assert [lowering.depends_on(c, 0) for c in e.a] == [{0}, {1}, {1}]
+
+
+def test_text_chunk_ownership_every_line_once(tmp_path):
+    """every line belongs to exactly one chunk, for any chunk size (also float)."""
+    datas = [gen.dirty_text(3, 400, 700), b"a\nbb\n\nccc", b"\n\n", b"x" * 100 + b"\n" + b"y" * 5,
+             b"one\r\ntwo\rthree\n"]
+    for di, data in enumerate(datas):
+        p = tmp_path / ("f%d.txt" % di)
+        p.write_bytes(data)
+        want = [l for _o, l in refsem.text_lines(data)]
+        for cs in (1, 2, 3, 7, 64, 1000, 33.7, len(data) / 3.0 + 1, 10 ** 9):
+            got = []
+            for ch in TextInput(str(p), cs).chunks():
+                got.extend(ch.read())
+            assert [l for _o, l in got] == want, (di, cs)
+            assert [o for o, _l in got] == sorted(o for o, _l in got)
+
+
+def test_memory_input_chunks_cover_everything():
+    items = list(enumerate(range(103)))
+    got = [kv for ch in MemoryInput(items, 50).chunks() for kv in ch.read()]
+    assert got == items
+    assert [kv for ch in MemoryInput([], 50).chunks() for kv in ch.read()] == []
+
+
+def test_token_code_decoding():
+    def enc38(w):
+        sym = {c: i + 1 for i, c in enumerate("0123456789_abcdefghijklmnopqrstuvwxyz")}
+        code = 0
+        for ch in reversed(w):
+            code = code * 38 + sym[ch]
+        return code
+
+    words = ["a", "zz", "hello_world9", "0", "_"]
+    codes = np.array([enc38(w) for w in words], dtype=np.uint64)
+    assert keycodes.decode_exact(codes, dev.TOK_NONWORD_LOWER_SET) == words
+    ws = ["Hi!", "a", "x" * 9, "~"]
+    codes = np.array([sum(ord(c) << (7 * i) for i, c in enumerate(w)) for w in ws], dtype=np.uint64)
+    assert keycodes.decode_exact(codes, dev.TOK_WS) == ws
+
+
+def test_abi_exports_every_declared_symbol():
+    """The library loads on a CPU-only box and exports every function include/dampr_b200.h declares."""
+    hdr = open(os.path.join(ROOT, "include", "dampr_b200.h")).read()
+    declared = set(re.findall(r"\b(dampr_[a-z0-9_]+)\s*\(", hdr))
+    declared -= {"dampr_ctx", "dampr_textbuf", "dampr_table", "dampr_kv"}
+    assert len(declared) > 40
+    lib = ctypes.CDLL(dev.LIB_PATH)
+    missing = [n for n in sorted(declared) if not hasattr(lib, n)]
+    assert not missing, missing
+    assert lib.dampr_abi_version() == 1
+    dev.load_library()
+
+
+def test_no_gpu_fails_loudly():
+    if dev.device_count() > 0:
+        pytest.skip("GPU present")
+    from dampr_b200 import Dampr
+    with pytest.raises(dev.DeviceError):
+        Dampr.memory([1, 2, 3]).map(lambda x: x).read()
+
+
+def test_product_never_imports_oracle():
+    pkg = os.path.join(ROOT, "dampr_b200")
+    for dirpath, _d, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh")):
+                src = open(os.path.join(dirpath, f), errors="replace").read()
+                assert "import oracle" not in src and "from oracle" not in src, f
