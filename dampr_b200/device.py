@@ -235,6 +235,21 @@ class Ctx(object):
         self.sync()  # the host arrays may be temporaries
         return kv
 
+    def synth_text(self, seed, n_lines, vocab_bytes, vocab_off, cdf, capacity=None):
+        """Device-side synthetic corpus (bench/test tooling; same algorithm as oracle/gen.py)."""
+        cap = int(capacity) if capacity else int(n_lines) * 120 + (1 << 20)
+        tb = TextBuf(self, cap)
+        out = C.c_uint64(0)
+        self.check(self.lib.dampr_synth_text(self.h, tb.h, int(seed), int(n_lines), _ptr(vocab_bytes),
+                                             _ptr(vocab_off), len(vocab_off) - 1, _ptr(cdf), C.byref(out)))
+        tb.n = out.value
+        return tb
+
+    def synth_kv(self, seed, n, n_keys):
+        kv = KV(self, n)
+        self.check(self.lib.dampr_synth_kv(self.h, kv.h, int(seed), int(n), int(n_keys)))
+        return kv
+
     def kv_from_records(self, recs):
         """recs: numpy array of shape (n, 2) uint64 (or a structured 16-byte dtype)."""
         recs = np.ascontiguousarray(recs)

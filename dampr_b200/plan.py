@@ -22,7 +22,7 @@ import threading
 import numpy as np
 
 from . import device as dev
-from . import keycodes, lowering, settings
+from . import dist, keycodes, lowering, settings
 from . import operators as ops
 from .datasets import Dataset, RecordsDataset, TextLineDataset, CatDataset, EmptyDataset
 from .graph import GMap, GReduce, GSink
@@ -93,10 +93,24 @@ class MemoryText(Dataset):
         return _iter_lines(self.array.tobytes(), 0)
 
 
+class DeviceText(Dataset):
+    """Text already resident in HBM (a device.TextBuf): the starting point of the device-resident
+    throughput figure."""
+
+    def __init__(self, tb):
+        self.tb = tb
+
+    def read(self):
+        from .datasets import _iter_lines
+        return _iter_lines(self.tb.download(0, self.tb.n).tobytes(), 0)
+
+
 def _text_files(ds):
     """[(kind, payload)] if the dataset is plain text the device can ingest, else None."""
     if isinstance(ds, MemoryText):
         return [("mem", ds.array)]
+    if isinstance(ds, DeviceText):
+        return [("dev", ds.tb)]
     if isinstance(ds, PathInput):
         files = ds.files()
     elif isinstance(ds, TextInput):
@@ -142,18 +156,30 @@ class TextScan(object):
 
     def run(self):
         ctx = self.runner.ctx
-        sizes = []
-        for kind, p in self.sources:
-            sizes.append(len(p) if kind == "mem" else os.path.getsize(p))
-        total = sum(sizes) + len(sizes)
-        self.nbytes = sum(sizes)
-        tb = ctx.textbuf(total + 64)
+        resident = len(self.sources) == 1 and self.sources[0][0] == "dev"
         tab = None
+        self._tab = None
+        if resident:
+            tb = self.sources[0][1]
+            self.nbytes = tb.n
+        else:
+            sizes = []
+            for kind, p in self.sources:
+                sizes.append(len(p) if kind == "mem" else os.path.getsize(p))
+            total = sum(sizes) + len(sizes)
+            self.nbytes = sum(sizes)
+            tb = ctx.textbuf(total + 64)
         try:
-            offsets = self._upload_and_count(ctx, tb, sizes)
+            if resident:
+                self._tab = ctx.table(int(settings.text_table_log2))
+                self._tab.count(tb, 0, tb.n, self.mode)
+            else:
+                self._upload_and_count(ctx, tb, sizes)
             tab = self._tab
             st = tab.stats()
             flags = st["flags"]
+            if dist.active():
+                return self._finish_distributed(ctx, tb, tab, st)
             if flags & dev.TF_TABLEFULL:
                 raise NotLowerable("combiner table overflow")
             if flags & (dev.TF_NONASCII | dev.TF_LONGTOKEN):
@@ -175,7 +201,57 @@ class TextScan(object):
                 tab.free()
             elif getattr(self, "_tab", None) is not None:
                 self._tab.free()
-            tb.free()
+            if not resident:
+                tb.free()
+        return self
+
+    def _finish_distributed(self, ctx, tb, tab, st):
+        """world > 1: this rank scanned its shard; move every term to its owner with one all-to-all
+        (dist.shuffle_kv), finish the fold there (merge + segmented reduce), sum the line counts."""
+        rank, n = dist.world()
+        flags = int(st["flags"])
+        bad = flags & (dev.TF_TABLEFULL | dev.TF_NONASCII | dev.TF_LONGTOKEN)
+        if self.mode != dev.TOK_WS:
+            bad |= flags & (dev.TF_CR | dev.TF_LONGLINE)
+        hashed_words = {}
+        if st["hashed"] and not bad:
+            tab.verify(tb, 0, tb.n, self.mode)
+            if tab.stats()["flags"] & dev.TF_COLLISION:
+                bad |= dev.TF_COLLISION
+            else:
+                codes, _counts, reps = tab.fetch()
+                hs = np.flatnonzero((codes & keycodes.HASHED_BIT) != 0)
+                ws = keycodes.decode_table(codes[hs], reps[hs], self.mode,
+                                           lambda off, ln: tb.download(off, ln).tobytes())
+                hashed_words = dict(zip(codes[hs].tolist(), ws))
+        lines, empty, anybad = dist.all_reduce_sum_int([int(st["lines"]), int(st["empty"]), 1 if bad else 0])
+        if anybad:
+            raise RuntimeError("distributed text scan cannot be lowered on every rank (flags=%d); the "
+                               "host-map path is single-process only" % flags)
+        merged = {}
+        for d in dist.all_gather_objects(hashed_words):
+            for c, w in d.items():
+                if merged.setdefault(c, w) != w:
+                    raise RuntimeError("64-bit key-code collision between two long tokens across ranks")
+        local = tab.to_kv()
+        recv = dist.shuffle_kv(ctx, local)
+        local.free()
+        red = recv.sort_reduce(dev.OP_SUM_I64, dev.KEY_MIX)
+        recv.free()
+        codes, counts = red.columns()
+        red.free()
+        reps = np.zeros(len(codes), dtype=np.uint64)
+        hashed = (codes & keycodes.HASHED_BIT) != 0
+        words = [None] * len(codes)
+        ex = np.flatnonzero(~hashed)
+        for i, w in zip(ex.tolist(), keycodes.decode_exact(codes[ex], self.mode)):
+            words[i] = w
+        for i in np.flatnonzero(hashed).tolist():
+            words[i] = merged[int(codes[i])]
+        self.words = words
+        self.counts = counts.view(np.int64)
+        self.n_lines = int(lines)
+        self.empty = int(empty) if rank == 0 else 0
         return self
 
     def _upload_and_count(self, ctx, tb, sizes):
@@ -203,6 +279,15 @@ class TextScan(object):
             pos += sz + (1 if need_nl else 0)
         total = pos
         tb.set_length(total)
+        # files are a global input: under torch.distributed every rank owns one 4 KB-aligned byte range
+        # of the concatenation (line ownership at the seams is the kernel's rule); in-memory texts are
+        # rank-local shards already
+        self._own = (0, total)
+        if dist.active() and all(k == "file" for k, _p in self.sources):
+            r, n = dist.world()
+            lo = (total * r // n) // 4096 * 4096
+            hi = total if r == n - 1 else (total * (r + 1) // n) // 4096 * 4096
+            self._own = (lo, hi)
         nl = np.frombuffer(b"\n", dtype=np.uint8)
         done = 0      # bytes uploaded
         counted = 0   # bytes handed to the kernel
@@ -233,7 +318,9 @@ class TextScan(object):
         HALO = 16384
         hi = total if final else max(counted, ((done - HALO) // 4096) * 4096 if done > HALO else 0)
         if hi > counted:
-            tab.count(tb, counted, hi, self.mode)
+            a, b = max(counted, self._own[0]), min(hi, self._own[1])
+            if b > a:
+                tab.count(tb, a, b, self.mode)
             counted = hi
         self._counted = counted
         return counted
@@ -298,6 +385,8 @@ def _source_key(sources):
     for kind, p in sources:
         if kind == "mem":
             out.append(("mem", id(p), len(p)))
+        elif kind == "dev":
+            out.append(("dev", id(p), p.n))
         else:
             st = os.stat(p)
             out.append(("file", p, st.st_size, st.st_mtime_ns))
@@ -727,7 +816,7 @@ def _lower_sink(runner, stage, inputs):
     if lines is None:
         return None
     os.makedirs(stage.path, exist_ok=True)
-    fname = os.path.join(stage.path, "part-0")
+    fname = os.path.join(stage.path, "part-%d" % (dist.world()[0] if dist.active() else 0))
     with open(fname, "w", encoding="utf-8") as f:
         if lines:
             f.write("\n".join(lines))
