@@ -40,7 +40,7 @@ WORKER = textwrap.dedent("""
     gu, gc = np.unique(got[:, 0], return_counts=True)
     assert np.array_equal(u.astype(np.uint64), gu) and np.array_equal(c, gc)
     dist.destroy_process_group()
-    print("rank", rank, "ok")
+    open(os.path.join(os.environ["DAMPR_TEST_OUT"], "rank%d.ok" % rank), "w").write("ok")
 """)
 
 
@@ -53,6 +53,7 @@ def test_gloo_world2_exchange(tmp_path):
     s.close()
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
            "--master-addr", "127.0.0.1", "--master-port", str(port), str(script)]
-    r = subprocess.run(cmd, capture_output=True, text=True, timeout=300)
+    env = dict(os.environ, DAMPR_TEST_OUT=str(tmp_path))
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=300, env=env)
     assert r.returncode == 0, r.stdout + r.stderr
-    assert "rank 0 ok" in r.stdout and "rank 1 ok" in r.stdout
+    assert (tmp_path / "rank0.ok").exists() and (tmp_path / "rank1.ok").exists()
