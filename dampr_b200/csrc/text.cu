@@ -773,3 +773,144 @@ int32_t dampr_table_to_kv(dampr_ctx *ctx, dampr_table *t, dampr_kv **out) {
 }
 
 }  // extern "C"
+
+// ---- K9: key materialisation -------------------------------------------------------------------
+// Decodes every table entry into a fixed-width, NUL-padded ASCII string on the device so the host
+// never loops over keys in Python (strings travel inside pickles in the reference, dataset.py:129-137).
+namespace {
+
+__global__ void table_words_kernel(const u64 *__restrict__ keys, const u64 *__restrict__ counts,
+                                   const u64 *__restrict__ reps, u64 cap, const u8 *__restrict__ text, int mode,
+                                   u32 width, u8 *__restrict__ out_words, u64 *__restrict__ out_counts,
+                                   u64 *__restrict__ out_codes, u64 *__restrict__ out_reps, u64 out_cap,
+                                   u64 *cursor) {
+    u64 i = blockIdx.x * (u64)blockDim.x + threadIdx.x;
+    u64 stride = (u64)gridDim.x * blockDim.x;
+    for (; i < cap; i += stride) {
+        u64 k = keys[i];
+        bool have = k != 0;
+        u32 m = __ballot_sync(0xFFFFFFFFu, have);
+        u64 base = 0;
+        if (m) {
+            int leader = __ffs(m) - 1;
+            if ((int)(threadIdx.x & 31) == leader) base = atomicAdd(cursor, (u64)__popc(m));
+            base = __shfl_sync(0xFFFFFFFFu, base, leader);
+        }
+        if (!have) continue;
+        u64 idx = base + __popc(m & ((1u << (threadIdx.x & 31)) - 1u));
+        if (idx >= out_cap) continue;
+        u8 *w = out_words + idx * width;
+        u64 rep = reps[i];
+        u32 n = 0;
+        if (k >> 63) {
+            // hashed (long) token: bytes of its representative occurrence
+            u64 off = rep >> 20;
+            u32 len = (u32)(rep & 0xFFFFFu);
+            if (text && rep != ~0ULL) {
+                for (; n < len && n < width; ++n) {
+                    u32 c = text[off + n];
+                    if (mode != DAMPR_TOK_WS && c >= 'A' && c <= 'Z') c |= 0x20;
+                    w[n] = (u8)c;
+                }
+            }
+        } else if (mode == DAMPR_TOK_WS) {
+            u64 c = k;
+            for (; c && n < width; ++n) {
+                w[n] = (u8)(c & 127);
+                c >>= 7;
+            }
+        } else {
+            u64 c = k;
+            const char *sym = "\0" "0123456789_abcdefghijklmnopqrstuvwxyz";
+            for (; c && n < width; ++n) {
+                w[n] = (u8)sym[c % 38];
+                c /= 38;
+            }
+        }
+        for (; n < width; ++n) w[n] = 0;
+        out_counts[idx] = counts[i];
+        out_codes[idx] = k;
+        out_reps[idx] = (rep == ~0ULL) ? 0ULL : rep;
+    }
+}
+
+}  // namespace
+
+extern "C" int32_t dampr_table_fetch_words(dampr_ctx *ctx, dampr_table *t, dampr_textbuf *tb, int32_t mode,
+                                           uint32_t width, uint8_t *words, uint64_t *counts, uint64_t *codes,
+                                           uint64_t *reps, uint64_t cap, uint64_t *n) {
+    ARG_CHECK(ctx, ctx && t && n, "null");
+    ARG_CHECK(ctx, width >= 16 && width <= 256 && (width % 8) == 0, "width must be a multiple of 8 in [16, 256]");
+    uint64_t st[8];
+    int rc = dampr_table_stats(ctx, t, st);
+    if (rc) return rc;
+    *n = st[0];
+    if (!words) return DAMPR_OK;
+    ARG_CHECK(ctx, cap >= st[0] && counts && codes && reps, "fetch arrays too small");
+    u64 m = st[0];
+    if (m == 0) return DAMPR_OK;
+    u8 *d = nullptr;
+    u64 per = width + 24;
+    CUDA_TRY(ctx, cudaMalloc(&d, m * per + 8));
+    u8 *d_words = d;
+    u64 *d_counts = (u64 *)(d + m * width);
+    u64 *d_codes = d_counts + m;
+    u64 *d_reps = d_codes + m;
+    u64 *d_cur = d_reps + m;
+    CUDA_TRY(ctx, cudaMemsetAsync(d_cur, 0, 8, ctx->stream));
+    {
+        ScopedTimer tm(ctx, DAMPR_K_TABLE_EXTRACT);
+        table_words_kernel<<<ctx->num_sms * 4, 256, 0, ctx->stream>>>(t->keys, t->counts, t->reps, t->cap,
+                                                                     tb ? tb->text : nullptr, mode, width, d_words,
+                                                                     d_counts, d_codes, d_reps, m, d_cur);
+    }
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaMemcpyAsync(words, d_words, m * width, cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(counts, d_counts, m * 8, cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(codes, d_codes, m * 8, cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(reps, d_reps, m * 8, cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    cudaFree(d);
+    if (e != cudaSuccess) {
+        ctx->err = std::string("table fetch_words failed: ") + cudaGetErrorString(e);
+        return DAMPR_ERR_CUDA;
+    }
+    return DAMPR_OK;
+}
+
+// ---- host-side sink formatting (SinkWriter, dataset.py:264-282: one print(value) per record) --------
+// Joins k columns with '\t' and terminates rows with '\n'. Column kinds:
+//   0  fixed-width NUL-padded bytes  ptr = u8[n][width]
+//   1  dictionary                    ptr = u32 inv[n], aux = blob bytes, aux2 = u32 offsets[m+1]
+// out == NULL: only *out_len is computed.
+extern "C" int32_t dampr_host_join_tsv(uint64_t n, int32_t ncols, const int32_t *kinds, const void *const *ptrs,
+                                       const uint32_t *widths, const void *const *aux, const void *const *aux2,
+                                       uint8_t *out, uint64_t cap, uint64_t *out_len) {
+    if (!kinds || !ptrs || !out_len || ncols < 1 || ncols > 16) return DAMPR_ERR_ARG;
+    u64 pos = 0;
+    for (u64 i = 0; i < n; ++i) {
+        for (int c = 0; c < ncols; ++c) {
+            const u8 *src;
+            u32 len;
+            if (kinds[c] == 0) {
+                const u8 *w = (const u8 *)ptrs[c] + i * widths[c];
+                len = 0;
+                while (len < widths[c] && w[len]) ++len;
+                src = w;
+            } else {
+                u32 j = ((const u32 *)ptrs[c])[i];
+                const u32 *off = (const u32 *)aux2[c];
+                src = (const u8 *)aux[c] + off[j];
+                len = off[j + 1] - off[j];
+            }
+            if (out) {
+                if (pos + len + 1 > cap) return DAMPR_ERR_ARG;
+                memcpy(out + pos, src, len);
+                out[pos + len] = (c + 1 == ncols) ? '\n' : '\t';
+            }
+            pos += len + 1;
+        }
+    }
+    *out_len = pos;
+    return DAMPR_OK;
+}

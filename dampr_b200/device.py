@@ -88,6 +88,8 @@ def load_library():
     _sig(lib, "dampr_table_stats", vp, vp, pu64)
     _sig(lib, "dampr_table_fetch", vp, vp, vp, vp, vp, u64, pu64)
     _sig(lib, "dampr_table_to_kv", vp, vp, pvp)
+    _sig(lib, "dampr_table_fetch_words", vp, vp, vp, i32, u32, vp, vp, vp, vp, u64, pu64)
+    _sig(lib, "dampr_host_join_tsv", u64, i32, vp, vp, vp, vp, vp, vp, u64, pu64)
     _sig(lib, "dampr_kv_create", vp, u64, pvp)
     _sig(lib, "dampr_kv_destroy", vp, vp)
     _sig(lib, "dampr_kv_size", vp, vp, pu64)
@@ -342,6 +344,22 @@ class Table(object):
                                                           m, C.byref(n)))
         return codes, counts, reps
 
+    def fetch_words(self, tb, mode, width=32):
+        """(words 'S<width>' array decoded on the device, counts, codes, reps)."""
+        n = C.c_uint64(0)
+        self.ctx.check(self.ctx.lib.dampr_table_fetch_words(self.ctx.h, self.h, None, int(mode), int(width), None,
+                                                            None, None, None, 0, C.byref(n)))
+        m = n.value
+        words = np.zeros((m, width), dtype=np.uint8)
+        counts = np.empty(m, dtype=np.uint64)
+        codes = np.empty(m, dtype=np.uint64)
+        reps = np.empty(m, dtype=np.uint64)
+        if m:
+            self.ctx.check(self.ctx.lib.dampr_table_fetch_words(
+                self.ctx.h, self.h, tb.h if tb is not None else None, int(mode), int(width), _ptr(words),
+                _ptr(counts), _ptr(codes), _ptr(reps), m, C.byref(n)))
+        return words.view("S%d" % width).ravel(), counts, codes, reps
+
     def to_kv(self):
         h = C.c_void_p()
         self.ctx.check(self.ctx.lib.dampr_table_to_kv(self.ctx.h, self.h, C.byref(h)))
@@ -455,6 +473,50 @@ class KV(object):
                 self.free()
         except Exception:
             pass
+
+
+def host_join_tsv(columns):
+    """Rows of tab-separated text from columns (native host loop). Each column is either a numpy
+    'S<w>' array (NUL-padded fixed-width strings) or a pair (inv uint32 array, list of bytes)."""
+    lib = load_library()
+    k = len(columns)
+    n = None
+    kinds = (C.c_int32 * k)()
+    ptrs = (C.c_void_p * k)()
+    widths = (C.c_uint32 * k)()
+    aux = (C.c_void_p * k)()
+    aux2 = (C.c_void_p * k)()
+    keep = []
+    for c, col in enumerate(columns):
+        if isinstance(col, np.ndarray):
+            assert col.dtype.kind == "S"
+            arr = np.ascontiguousarray(col)
+            kinds[c], widths[c] = 0, arr.dtype.itemsize
+            ptrs[c] = arr.ctypes.data
+            keep.append(arr)
+            m = len(arr)
+        else:
+            inv, strs = col
+            inv = np.ascontiguousarray(inv, dtype=np.uint32)
+            blob = b"".join(strs)
+            off = np.zeros(len(strs) + 1, dtype=np.uint32)
+            np.cumsum([len(s) for s in strs], out=off[1:])
+            bl = np.frombuffer(blob, dtype=np.uint8) if blob else np.zeros(1, dtype=np.uint8)
+            kinds[c], widths[c] = 1, 0
+            ptrs[c], aux[c], aux2[c] = inv.ctypes.data, bl.ctypes.data, off.ctypes.data
+            keep.extend([inv, bl, off])
+            m = len(inv)
+        assert n is None or n == m
+        n = m
+    out_len = C.c_uint64(0)
+    rc = lib.dampr_host_join_tsv(n, k, kinds, ptrs, widths, aux, aux2, None, 0, C.byref(out_len))
+    if rc:
+        raise DeviceError("dampr_host_join_tsv failed (%d)" % rc)
+    out = np.empty(out_len.value, dtype=np.uint8)
+    rc = lib.dampr_host_join_tsv(n, k, kinds, ptrs, widths, aux, aux2, _ptr(out), len(out), C.byref(out_len))
+    if rc:
+        raise DeviceError("dampr_host_join_tsv failed (%d)" % rc)
+    return out
 
 
 def kv_merge(ctx, runs, xform, op=-1):

@@ -36,6 +36,51 @@ class NotLowerable(Exception):
 
 
 # ---- columnar stage output -----------------------------------------------------------------------
+class DictCol(object):
+    """Dictionary-encoded column: value[i] = uniq[inv[i]] (uniq: numpy array or list)."""
+
+    def __init__(self, inv, uniq):
+        self.inv = inv
+        self.uniq = uniq
+
+    def __len__(self):
+        return len(self.inv)
+
+    def materialize(self):
+        if isinstance(self.uniq, np.ndarray):
+            return self.uniq[self.inv]
+        il = self.inv.tolist()
+        u = self.uniq
+        return [u[j] for j in il]
+
+
+def unique_inverse(col):
+    """(sorted unique values, inverse index uint32) of an int64/float64 column. Small non-negative
+    ints (the bulk of count columns) go through a counting pass instead of a sort."""
+    n = len(col)
+    if n and col.dtype.kind in "iu":
+        T = 1 << 22
+        small = col < T
+        if col.min() >= 0 and small.mean() > 0.99:
+            cs = col[small].astype(np.int64)
+            present = np.zeros(T, dtype=bool)
+            present[cs] = True
+            us = np.flatnonzero(present)
+            rank = np.zeros(T, dtype=np.uint32)
+            rank[us] = np.arange(len(us), dtype=np.uint32)
+            inv = np.empty(n, dtype=np.uint32)
+            inv[small] = rank[cs]
+            if not small.all():
+                ul, il = np.unique(col[~small], return_inverse=True)
+                inv[~small] = il.astype(np.uint32) + np.uint32(len(us))
+                uniq = np.concatenate((us.astype(col.dtype), ul))
+            else:
+                uniq = us.astype(col.dtype)
+            return uniq, inv
+    uniq, inv = np.unique(col, return_inverse=True)
+    return uniq, inv.astype(np.uint32)
+
+
 class Frame(Dataset):
     """Columnar collection. `keys` is the routing/sort key column (what read() yields as k), `cols`
     are the value columns; the user-visible value is cols[0][i] when `scalar` else the tuple of the
@@ -54,7 +99,13 @@ class Frame(Dataset):
 
     @staticmethod
     def _pylist(col):
-        return col.tolist() if isinstance(col, np.ndarray) else col
+        if isinstance(col, DictCol):
+            col = col.materialize()
+        if isinstance(col, np.ndarray):
+            if col.dtype.kind == "S":  # device-decoded ASCII keys
+                return [b.decode("ascii") for b in col.tolist()]
+            return col.tolist()
+        return col
 
     def values(self):
         if self.scalar:
@@ -67,6 +118,8 @@ class Frame(Dataset):
 
     def take(self, perm):
         def tk(c):
+            if isinstance(c, DictCol):
+                return DictCol(c.inv[perm], c.uniq)
             if isinstance(c, np.ndarray):
                 return c[perm]
             pl = perm.tolist()
@@ -190,9 +243,19 @@ class TextScan(object):
                 tab.verify(tb, 0, tb.n, self.mode)
                 if tab.stats()["flags"] & dev.TF_COLLISION:
                     raise NotLowerable("64-bit key-code collision between two long tokens")
-            codes, counts, reps = tab.fetch()
-            self.words = keycodes.decode_table(codes, reps, self.mode,
-                                               lambda off, ln: tb.download(off, ln).tobytes())
+            # keys are materialised on the device (K9) as fixed-width ASCII; only tokens longer than the
+            # width (rare) are patched on the host from their representative occurrence
+            W = 32
+            words, counts, codes, reps = tab.fetch_words(tb, self.mode, W)
+            too_long = np.flatnonzero(((codes >> np.uint64(63)) != 0) & ((reps & np.uint64(0xFFFFF)) > W))
+            if len(too_long):
+                wl = [b.decode("ascii") for b in words.tolist()]
+                for i in too_long.tolist():
+                    rep = int(reps[i])
+                    s = tb.download(rep >> 20, rep & 0xFFFFF).tobytes().decode("ascii")
+                    wl[i] = s if self.mode == dev.TOK_WS else s.lower()
+                words = wl
+            self.words = words
             self.counts = counts.view(np.int64)
             self.n_lines = int(st["lines"])
             self.empty = int(st["empty"])
@@ -492,7 +555,10 @@ def _lower_map(runner, stage, inputs, si):
         scan = text_scan(runner, src, mode)
         words, counts = scan.words, scan.counts
         if mode != dev.TOK_WS and scan.empty:
-            words = words + [""]
+            if isinstance(words, np.ndarray):
+                words = np.concatenate((words, np.array([b""], dtype=words.dtype)))
+            else:
+                words = words + [""]
             counts = np.concatenate((counts, np.array([scan.empty], dtype=np.int64)))
         f = Frame(words, [counts], scalar=True, combined=True)
         runner.stats.add(stage, "device text tokenise+combine",
@@ -663,39 +729,59 @@ def _lower_cross(runner, stage, inputs):
     # cross(v_inner, v_outer): arg0 = inner value, arg1 = outer value
     comps = e.a if e.op == "tuple" else (e,)
     out_cols = []
-    values = None
+    dict_cache = {}
     for ci, comp in enumerate(comps):
         f = lowering._field(_swap_to_arg0(comp, 1))
         if f is not None and not outer.scalar and f < len(outer.cols):
-            out_cols.append(outer.cols[f])
+            src = outer.cols[f]
+            if _numeric(src) and src.dtype.kind in "iu":
+                # share the dictionary with the components computed from this field (and with the sink)
+                uq = dict_cache.get(f) or unique_inverse(src)
+                dict_cache[f] = uq
+                src = DictCol(uq[1], uq[0])
+            out_cols.append(src)
             continue
         deps = lowering.depends_on(comp, 1)
         if deps is None or outer.scalar or not deps or any(d >= len(outer.cols) for d in deps):
             return None
         dep = sorted(deps)
-        if len(dep) != 1 or not isinstance(outer.cols[dep[0]], np.ndarray):
+        if len(dep) != 1 or not (isinstance(outer.cols[dep[0]], DictCol) or _numeric(outer.cols[dep[0]])):
             return None
         col = outer.cols[dep[0]]
-        uniq, first, inv = np.unique(col, return_index=True, return_inverse=True)
-        if values is None:
-            values = outer.values()
+        if isinstance(col, DictCol):
+            uniq, inv = col.uniq, col.inv
+        else:
+            uniq, inv = dict_cache.get(dep[0]) or unique_inverse(col)
+            dict_cache[dep[0]] = (uniq, inv)
+        # one representative row per distinct value (any row holding it)
+        rep = np.empty(len(uniq), dtype=np.int64)
+        rep[inv] = np.arange(outer.n, dtype=np.int64)
         res = []
-        for i in first.tolist():
-            r = cross(inner, values[i])
+        for i in rep.tolist():
+            row = tuple(_cell(c, i) for c in outer.cols)
+            r = cross(inner, row)
             res.append(r[ci] if e.op == "tuple" else r)
         kinds = set(type(x) for x in res)
         if kinds == {float}:
-            arr = np.array(res, dtype=np.float64)[inv]
+            res = np.array(res, dtype=np.float64)
         elif kinds == {int}:
-            arr = np.array(res, dtype=np.int64)[inv]
-        else:
-            il = inv.tolist()
-            arr = [res[j] for j in il]
-        out_cols.append(arr)
+            res = np.array(res, dtype=np.int64)
+        out_cols.append(DictCol(inv, res))
     f = Frame(outer.keys, out_cols, scalar=(e.op != "tuple"))
     runner.stats.add(stage, "frame cross with a 1-row broadcast (memoised per distinct field value)",
                      "records=%d" % outer.n)
     return f
+
+
+def _cell(col, i):
+    """Python value of row i of a frame column."""
+    if isinstance(col, DictCol):
+        v = col.uniq[int(col.inv[i])]
+    else:
+        v = col[i]
+    if isinstance(v, bytes):
+        return v.decode("ascii")
+    return v.item() if isinstance(v, np.generic) else v
 
 
 def _swap_to_arg0(e, argi):
@@ -789,14 +875,25 @@ def _lower_reduce(runner, stage, inputs):
 
 
 # ---- sinks ---------------------------------------------------------------------------------------------------
-def _str_column(col):
-    """Python str() of every element, computed once per distinct value for numeric columns."""
+def _sink_column(col):
+    """A frame column in the form dampr_host_join_tsv takes: an 'S' array, or (inv, [bytes per distinct
+    value]) with Python's own str() of every distinct value (exact float repr); None if unsupported."""
+    if isinstance(col, DictCol):
+        u = col.uniq.tolist() if isinstance(col.uniq, np.ndarray) else col.uniq
+        return (col.inv, [str(x).encode("utf-8") for x in u])
     if isinstance(col, np.ndarray):
-        uniq, inv = np.unique(col, return_inverse=True)
-        strs = [str(x) for x in uniq.tolist()]
-        il = inv.tolist()
-        return [strs[j] for j in il]
-    return [x if type(x) is str else str(x) for x in col]
+        if col.dtype.kind == "S":
+            return col
+        if col.dtype.kind in "iuf":
+            uniq, inv = unique_inverse(col)
+            return (inv, [str(x).encode("utf-8") for x in uniq.tolist()])
+        return None
+    if isinstance(col, list) and all(type(x) is str for x in col):
+        uniq = sorted(set(col))
+        idx = {w: i for i, w in enumerate(uniq)}
+        inv = np.fromiter((idx[w] for w in col), dtype=np.uint32, count=len(col))
+        return (inv, [w.encode("utf-8") for w in uniq])
+    return None
 
 
 def _lower_sink(runner, stage, inputs):
@@ -805,21 +902,20 @@ def _lower_sink(runner, stage, inputs):
     fr = inputs[0]
     parts = _parts(stage.mapper)
     from .dsl import _tsv_line
-    lines = None
+    cols = None
     if len(parts) == 1 and getattr(parts[0], "op", None) is not None:
         op = parts[0].op
         if op.kind == "map" and op.fn is _tsv_line and not fr.scalar:
-            cols = [_str_column(c) for c in fr.cols]
-            lines = ["\t".join(t) for t in zip(*cols)]
+            cols = [_sink_column(c) for c in fr.cols]
         elif op.kind == "identity" and fr.scalar:
-            lines = _str_column(fr.cols[0])
-    if lines is None:
+            cols = [_sink_column(fr.cols[0])]
+    if cols is None or any(c is None for c in cols):
         return None
     os.makedirs(stage.path, exist_ok=True)
     fname = os.path.join(stage.path, "part-%d" % (dist.world()[0] if dist.active() else 0))
-    with open(fname, "w", encoding="utf-8") as f:
-        if lines:
-            f.write("\n".join(lines))
-            f.write("\n")
-    runner.stats.add(stage, "vectorised frame sink", "records=%d" % len(lines))
+    blob = dev.host_join_tsv(cols) if fr.n else np.zeros(0, dtype=np.uint8)
+    with open(fname, "wb") as f:
+        f.write(memoryview(blob))
+    lines = range(fr.n)
+    runner.stats.add(stage, "native frame sink (per-distinct-value formatting)", "records=%d" % len(lines))
     return CatDataset([TextLineDataset(fname)])

@@ -134,6 +134,20 @@ int32_t dampr_table_stats(dampr_ctx *ctx, dampr_table *t, uint64_t stats[8]);
  * dampr_kv_sort give a sorted run). Replaces ReducedWriter.flush (dataset.py:107-117). */
 int32_t dampr_table_fetch(dampr_ctx *ctx, dampr_table *t, uint64_t *codes, uint64_t *counts,
                           uint64_t *reps, uint64_t cap, uint64_t *n);
+/* key materialisation (K9): like dampr_table_fetch, plus every key decoded ON THE DEVICE into a
+ * fixed-width NUL-padded ASCII string words[i*width .. +width) (hashed tokens are read back from
+ * their representative occurrence in `tb`, truncated to `width`; their true length is in reps).
+ * width: multiple of 8 in [16, 256]. words == NULL queries *n only. */
+int32_t dampr_table_fetch_words(dampr_ctx *ctx, dampr_table *t, dampr_textbuf *tb, int32_t mode,
+                                uint32_t width, uint8_t *words, uint64_t *counts, uint64_t *codes,
+                                uint64_t *reps, uint64_t cap, uint64_t *n);
+/* host-side sink formatting (SinkWriter, dataset.py:264-282): joins ncols columns with '\t', rows end
+ * with '\n'. kinds[c] == 0: ptrs[c] = u8[n][widths[c]] NUL-padded strings; kinds[c] == 1: ptrs[c] =
+ * u32 inv[n] into a dictionary of strings aux[c] (bytes) / aux2[c] (u32 offsets[m+1]).
+ * out == NULL computes *out_len only. Pure host code, no device work. */
+int32_t dampr_host_join_tsv(uint64_t n, int32_t ncols, const int32_t *kinds, const void *const *ptrs,
+                            const uint32_t *widths, const void *const *aux, const void *const *aux2,
+                            uint8_t *out, uint64_t cap, uint64_t *out_len);
 /* same, but leaves the run on the device as a kv (key = code, val = count) */
 int32_t dampr_table_to_kv(dampr_ctx *ctx, dampr_table *t, dampr_kv **out);
 

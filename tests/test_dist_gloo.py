@@ -40,7 +40,7 @@ WORKER = textwrap.dedent("""
     gu, gc = np.unique(got[:, 0], return_counts=True)
     assert np.array_equal(u.astype(np.uint64), gu) and np.array_equal(c, gc)
     dist.destroy_process_group()
-    open(os.path.join(os.environ["DAMPR_TEST_OUT"], "rank%d.ok" % rank), "w").write("ok")
+    open(os.path.join(os.environ["DAMPR_TEST_OUT"], "rank%%d.ok" %% rank), "w").write("ok")
 """)
 
 
