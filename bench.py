@@ -299,7 +299,8 @@ def main():
             "vs_baseline": None, "dtype": "u8", "data": "synthetic",
             "config": {"workload": workload, "bytes_per_rank": nbytes, "lines_per_rank": n_lines,
                        "l2": "inputs (%.1f GB per rank) are larger than L2" % (nbytes / 1e9),
-                       "stages": [[s, h] for s, h, _d in stats]},
+                       "stages": [[s.split("`")[1][:40] if "`" in s else s, h] for s, h, _d in stats],
+                       "e2e_stage_ms": [round(ms, 2) for _s, ms in (runner_mod.LAST_STATS.ms if runner_mod.LAST_STATS else [])]},
             "e2e": {"value": e2e, "unit": "MB/s", "h2d_bytes_per_step": nbytes * world,
                     "d2h_bytes_per_step": int(n_terms) * 24 * 1, "ms_per_step": 1e3 * t_e2e / args.steps},
             "gpu_launches": int(launches), "clocks": sampler.summary(), "roofline": roof}

@@ -6,7 +6,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libdampr_b200.so")
-SOURCES = ["ctx.cu", "text.cu", "kv.cu", "ops.cu"]
+SOURCES = ["ctx.cu", "text.cu", "text2.cu", "kv.cu", "ops.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC",

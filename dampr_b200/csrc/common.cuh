@@ -64,6 +64,10 @@ struct dampr_kv {
     u64 n;
 };
 
+// tuning switches (dampr_set_option)
+extern int g_text_kernel;   // 2 = warp-autonomous kernel (text2.cu), 1 = first-generation kernel (text.cu)
+int launch_text_count_v2(dampr_ctx *ctx, dampr_table *t, dampr_textbuf *tb, u64 lo, u64 hi, int mode);
+
 #define TEXT_LEAD 64
 #define TEXT_TAIL_PAD (64 * 1024)
 

@@ -3,6 +3,8 @@
 // and the on-disk run files of dataset.py with device-resident buffers.
 #include "common.cuh"
 
+int g_text_kernel = 2;
+
 extern "C" {
 
 int32_t dampr_abi_version(void) { return 1; }

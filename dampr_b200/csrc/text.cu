@@ -683,6 +683,7 @@ int32_t dampr_text_count(dampr_ctx *ctx, dampr_table *t, dampr_textbuf *tb, uint
     ARG_CHECK(ctx, ctx && t && tb, "null");
     ARG_CHECK(ctx, own_lo <= own_hi && own_hi <= tb->n, "ownership range outside the text");
     ARG_CHECK(ctx, (own_lo % 16) == 0, "own_lo must be a multiple of 16");
+    if (g_text_kernel == 2) return launch_text_count_v2(ctx, t, tb, own_lo, own_hi, mode);
     switch (mode) {
         case DAMPR_TOK_WS: return launch_text<DAMPR_TOK_WS, false>(ctx, t, tb, own_lo, own_hi);
         case DAMPR_TOK_NONWORD_LOWER_SET:

@@ -237,6 +237,16 @@ class TextScan(object):
                 raise NotLowerable("combiner table overflow")
             if flags & (dev.TF_NONASCII | dev.TF_LONGTOKEN):
                 raise NotLowerable("non-ASCII text or oversized token: device tokeniser is ASCII-only")
+            if self.mode != dev.TOK_WS and flags & dev.TF_LONGLINE and not flags & dev.TF_CR \
+                    and not getattr(self, "_retry_v1", False):
+                # a line too long (or with too many distinct tokens) for the warp-autonomous kernel:
+                # the first-generation kernel has a 4 KB line window and no per-line token limit
+                self._retry_v1 = True
+                dev.set_option("text_kernel", 1)
+                try:
+                    return self.run()
+                finally:
+                    dev.set_option("text_kernel", 2)
             if self.mode != dev.TOK_WS and flags & (dev.TF_CR | dev.TF_LONGLINE):
                 raise NotLowerable("carriage returns or a line longer than the device window")
             if st["hashed"]:

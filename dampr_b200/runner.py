@@ -15,6 +15,7 @@ There is no CPU shuffle: without a CUDA device `run()` raises.
 """
 import logging
 import os
+import time
 
 import numpy as np
 
@@ -56,6 +57,7 @@ class StageStats(object):
 
     def __init__(self):
         self.stages = []
+        self.ms = []   # (stage output, wall milliseconds)
 
     def add(self, stage, how, detail=""):
         self.stages.append((str(stage.output), how, detail))
@@ -95,6 +97,7 @@ class B200Runner(object):
         for si, stage in enumerate(stages):
             log.info("Stage %s/%s: %s", si + 1, len(stages), stage)
             inputs = [data[s] for s in stage.inputs]
+            t_stage = time.perf_counter()
             lowered = plan.try_lower(self, stage, inputs, si, data)
             if lowered is not None:
                 out = lowered
@@ -107,6 +110,7 @@ class B200Runner(object):
             else:
                 raise TypeError("unknown stage type %r" % (stage,))
             data[stage.output] = out
+            self.stats.ms.append((str(stage.output), 1e3 * (time.perf_counter() - t_stage)))
             if not isinstance(stage, GSink):
                 produced.append(stage.output)
         ret = []

@@ -11,6 +11,14 @@ from oracle import gen, refsem
 pytestmark = pytest.mark.gpu
 
 
+@pytest.fixture(autouse=True, params=[2, 1], ids=["kernel-v2", "kernel-v1"])
+def text_kernel(request):
+    """Every case runs against both tokenise kernels (text2.cu is the default, text.cu the fallback)."""
+    dev.set_option("text_kernel", request.param)
+    yield request.param
+    dev.set_option("text_kernel", 2)
+
+
 def run_count(ctx, data, mode, chunk=None, verify=True):
     tb = ctx.textbuf(len(data) + 64)
     arr = np.frombuffer(data, dtype=np.uint8)
@@ -115,14 +123,26 @@ def test_tile_boundaries(ctx):
     check_df(ctx, data)
 
 
-def test_flags(ctx):
+def test_flags(ctx, text_kernel):
+    if text_kernel == 1:
+        pytest.skip("limits below are those of the v2 kernel")
     _, st = run_count(ctx, "café au lait\n".encode("utf-8"), dev.TOK_WS)
     assert st["flags"] & dev.TF_NONASCII
     _, st = run_count(ctx, b"a\r\nb\r\n", dev.TOK_NONWORD_LOWER_SET)
     assert st["flags"] & dev.TF_CR
-    long_line = b"x " * 5000 + b"\n"
+    long_line = b"x " * 20000 + b"\n"
     _, st = run_count(ctx, b"a\n" * 4000 + long_line + b"b\n" * 4000, dev.TOK_NONWORD_LOWER_SET)
     assert st["flags"] & dev.TF_LONGLINE
+    # more distinct tokens in one line than the de-duplication history holds
+    many = b" ".join(b"w%d" % i for i in range(400)) + b"\n"
+    _, st = run_count(ctx, b"a b\n" * 10 + many + b"c\n", dev.TOK_NONWORD_LOWER_SET)
+    assert st["flags"] & dev.TF_LONGLINE
+    # both are fine for the first-generation kernel when they fit its 4 KB window
+    dev.set_option("text_kernel", 1)
+    try:
+        check_df(ctx, b"a b\n" * 10 + many + b"c\n")
+    finally:
+        dev.set_option("text_kernel", 2)
     # the whitespace tokeniser has no line dependence: long lines are fine there
     check_wc(ctx, b"a\n" * 4000 + long_line + b"b\n" * 4000)
 
