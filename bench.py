@@ -262,8 +262,11 @@ def main():
     # ---- timed: host-resident input ("e2e") ----------------------------------------------------------------
     barrier()
     t0 = time.perf_counter()
+    e2e_steps = []
     for i in range(args.steps):
+        ts = time.perf_counter()
         d = step(False, i)
+        e2e_steps.append(round(1e3 * (time.perf_counter() - ts), 1))
     barrier()
     t_e2e = max_over_ranks(time.perf_counter() - t0)
     stats = runner_mod.LAST_STATS.stages if runner_mod.LAST_STATS else []
@@ -302,7 +305,8 @@ def main():
                        "stages": [[s.split("`")[1][:40] if "`" in s else s, h] for s, h, _d in stats],
                        "e2e_stage_ms": [round(ms, 2) for _s, ms in (runner_mod.LAST_STATS.ms if runner_mod.LAST_STATS else [])]},
             "e2e": {"value": e2e, "unit": "MB/s", "h2d_bytes_per_step": nbytes * world,
-                    "d2h_bytes_per_step": int(n_terms) * 24 * 1, "ms_per_step": 1e3 * t_e2e / args.steps},
+                    "d2h_bytes_per_step": int(n_terms) * 56, "ms_per_step": 1e3 * t_e2e / args.steps,
+                    "step_ms": e2e_steps},
             "gpu_launches": int(launches), "clocks": sampler.summary(), "roofline": roof}
 
     if rank == 0 and not args.no_cpu_baseline:

@@ -447,28 +447,42 @@ text_count2_kernel(const u8 *__restrict__ text, u64 n, u64 own_lo, u64 own_hi, u
                 }
                 const bool ins = live && !hashed;
                 const u32 imask = __ballot_sync(0xFFFFFFFFu, ins);
+                // every inserting lane looks its slot pair up (convergent loads); one lane per distinct
+                // key then updates the combiner
+                u32 h = (u32)key * 0x9E3779B1u ^ (u32)(key >> 32) * 0x85EBCA6Bu;
+                u32 slot = (h >> (32 - V_STAB_LOG)) & ~1u;
+                u64 k0 = 0, k1 = 0;
+                if (ins) {
+                    const ulonglong2 kk = *reinterpret_cast<const ulonglong2 *>(&s.tabk[slot]);
+                    k0 = kk.x;
+                    k1 = kk.y;
+                }
                 if (ins) {
                     u32 peers = __match_any_sync(imask, key);
                     if (((u32)__ffs(peers) - 1u) == lane) {
                         u32 cnt = (u32)__popc(peers);
-                        u32 h = (u32)key * 0x9E3779B1u ^ (u32)(key >> 32) * 0x85EBCA6Bu;
-                        u32 slot = h >> (32 - V_STAB_LOG);
-                        bool placed = false;
+                        if (k0 == key) {
+                            atomicAdd(&s.tabc[slot], cnt);
+                        } else if (k1 == key) {
+                            atomicAdd(&s.tabc[slot + 1], cnt);
+                        } else {
+                            bool placed = false;
 #pragma unroll 1
-                        for (int pr = 0; pr < 6; ++pr) {
-                            u64 k = s.tabk[slot];
-                            if (k == 0) {
-                                k = atomicCAS(&s.tabk[slot], 0ULL, key);
-                                if (k == 0) k = key;
+                            for (int pr = 0; pr < 6; ++pr) {
+                                u64 k = s.tabk[slot];
+                                if (k == 0) {
+                                    k = atomicCAS(&s.tabk[slot], 0ULL, key);
+                                    if (k == 0) k = key;
+                                }
+                                if (k == key) {
+                                    atomicAdd(&s.tabc[slot], cnt);
+                                    placed = true;
+                                    break;
+                                }
+                                slot = (slot + 1) & (V_STAB - 1);
                             }
-                            if (k == key) {
-                                atomicAdd(&s.tabc[slot], cnt);
-                                placed = true;
-                                break;
-                            }
-                            slot = (slot + 1) & (V_STAB - 1);
+                            if (!placed) gtab_add2(tab, key, (u64)cnt, ~0ULL);
                         }
-                        if (!placed) gtab_add2(tab, key, (u64)cnt, ~0ULL);
                     }
                 }
                 (void)lmask;

@@ -193,6 +193,53 @@ def _pinned_ring(nslots, slot_bytes):
     return ring
 
 
+_BUFFERS = {}
+
+
+def _cached_textbuf(ctx, capacity):
+    """Device text buffer reused across scans of one context (grow-only): a 10 GB cudaMalloc/cudaFree
+    per run costs tens of milliseconds."""
+    slot = _BUFFERS.setdefault(id(ctx), {})
+    tb = slot.get("tb")
+    if tb is None or tb.ctx.h is None or tb.capacity < capacity:
+        if tb is not None and tb.ctx.h is not None:
+            tb.free()
+        tb = ctx.textbuf(capacity)
+        slot["tb"] = tb
+    return tb
+
+
+def _cached_table(ctx):
+    slot = _BUFFERS.setdefault(id(ctx), {})
+    tab = slot.get("tab")
+    log2 = int(settings.text_table_log2)
+    if tab is None or tab.ctx.h is None or tab.capacity != (1 << log2):
+        if tab is not None and tab.ctx.h is not None:
+            tab.free()
+        tab = ctx.table(log2)
+        slot["tab"] = tab
+    else:
+        tab.clear()
+    return tab
+
+
+def release_buffers():
+    for slot in _BUFFERS.values():
+        for b in slot.values():
+            try:
+                if b.ctx.h is not None:
+                    b.free()
+            except Exception:
+                pass
+    _BUFFERS.clear()
+
+
+def resident_retry_block(scan):
+    """Bound the table-growth retries of one scan."""
+    scan._grow = getattr(scan, "_grow", 0) + 1
+    return scan._grow > 4
+
+
 class TextScan(object):
     """One pass of the tokenise+combine kernel over a set of files (or a memory text), with the
     host->device copies pipelined against the kernel chunk by chunk."""
@@ -221,10 +268,10 @@ class TextScan(object):
                 sizes.append(len(p) if kind == "mem" else os.path.getsize(p))
             total = sum(sizes) + len(sizes)
             self.nbytes = sum(sizes)
-            tb = ctx.textbuf(total + 64)
-        try:
+            tb = _cached_textbuf(ctx, total + 64)
+        if True:  # buffers are cached per context (see _cached_textbuf): nothing to release here
             if resident:
-                self._tab = ctx.table(int(settings.text_table_log2))
+                self._tab = _cached_table(ctx)
                 self._tab.count(tb, 0, tb.n, self.mode)
             else:
                 self._upload_and_count(ctx, tb, sizes)
@@ -233,6 +280,12 @@ class TextScan(object):
             flags = st["flags"]
             if dist.active():
                 return self._finish_distributed(ctx, tb, tab, st)
+            if (flags & dev.TF_TABLEFULL or st["entries"] * 2 > tab.capacity) and settings.text_table_log2 < 28 \
+                    and not resident_retry_block(self):
+                # ReducedWriter would flush a run here (dataset.py:107-113); with HBM to spare the table
+                # is simply made 4x larger and the scan repeated (later scans start at the new size)
+                settings.text_table_log2 = int(settings.text_table_log2) + 2
+                return self.run()
             if flags & dev.TF_TABLEFULL:
                 raise NotLowerable("combiner table overflow")
             if flags & (dev.TF_NONASCII | dev.TF_LONGTOKEN):
@@ -269,13 +322,6 @@ class TextScan(object):
             self.counts = counts.view(np.int64)
             self.n_lines = int(st["lines"])
             self.empty = int(st["empty"])
-        finally:
-            if tab is not None:
-                tab.free()
-            elif getattr(self, "_tab", None) is not None:
-                self._tab.free()
-            if not resident:
-                tb.free()
         return self
 
     def _finish_distributed(self, ctx, tb, tab, st):
@@ -332,7 +378,7 @@ class TextScan(object):
         chunk -= chunk % 4096
         # layout: files back to back; a file that does not end in '\n' gets one (its last line is a
         # line either way), so line and token semantics of the concatenation equal the per-file ones
-        self._tab = ctx.table(int(settings.text_table_log2))
+        self._tab = _cached_table(ctx)
         tab = self._tab
         # the total length must be known before the first kernel: files are stat'ed, the optional
         # separator is reserved and patched if not needed (a spare '\n' after a terminated file would

@@ -37,6 +37,6 @@ device = int(os.environ.get("LOCAL_RANK", "0"))
 # bytes per host->device ingest chunk of text inputs
 ingest_chunk_bytes = 64 << 20
 # log2 of the combiner table capacity (entries) for text counting
-text_table_log2 = 24
+text_table_log2 = 21  # grows (x4) and the scan re-runs when it overflows or fills beyond 50 %
 # device arena in bytes available to one sort before it spills runs (None = no cap)
 device_arena_bytes = None
