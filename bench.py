@@ -250,8 +250,12 @@ def main():
     runner_ctx.timings_reset()
     l0 = runner_ctx.launches()
     t0 = time.perf_counter()
+    dev_steps = []
     for i in range(args.steps):
+        ts = time.perf_counter()
         d = step(True, i)
+        dev_steps.append([round(1e3 * (time.perf_counter() - ts), 1)] +
+                         [round(ms, 1) for _s, ms in runner_mod.LAST_STATS.ms])
     barrier()
     t_dev = max_over_ranks(time.perf_counter() - t0)
     launches = runner_ctx.launches() - l0
@@ -266,7 +270,8 @@ def main():
     for i in range(args.steps):
         ts = time.perf_counter()
         d = step(False, i)
-        e2e_steps.append(round(1e3 * (time.perf_counter() - ts), 1))
+        e2e_steps.append([round(1e3 * (time.perf_counter() - ts), 1)] +
+                         [round(ms, 1) for _s, ms in runner_mod.LAST_STATS.ms])
     barrier()
     t_e2e = max_over_ranks(time.perf_counter() - t0)
     stats = runner_mod.LAST_STATS.stages if runner_mod.LAST_STATS else []
@@ -302,6 +307,7 @@ def main():
             "vs_baseline": None, "dtype": "u8", "data": "synthetic",
             "config": {"workload": workload, "bytes_per_rank": nbytes, "lines_per_rank": n_lines,
                        "l2": "inputs (%.1f GB per rank) are larger than L2" % (nbytes / 1e9),
+                       "resident_step_ms_total_then_stages": dev_steps,
                        "stages": [[s.split("`")[1][:40] if "`" in s else s, h] for s, h, _d in stats],
                        "e2e_stage_ms": [round(ms, 2) for _s, ms in (runner_mod.LAST_STATS.ms if runner_mod.LAST_STATS else [])]},
             "e2e": {"value": e2e, "unit": "MB/s", "h2d_bytes_per_step": nbytes * world,

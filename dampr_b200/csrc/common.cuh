@@ -65,6 +65,7 @@ struct dampr_kv {
 };
 
 // tuning switches (dampr_set_option)
+extern int g_text_ctas;     // resident CTAs per SM of the v2 tokenise kernel: 2 (double-buffered) or 3
 extern int g_text_kernel;   // 2 = warp-autonomous kernel (text2.cu), 1 = first-generation kernel (text.cu)
 int launch_text_count_v2(dampr_ctx *ctx, dampr_table *t, dampr_textbuf *tb, u64 lo, u64 hi, int mode);
 

@@ -4,6 +4,7 @@
 #include "common.cuh"
 
 int g_text_kernel = 2;
+int g_text_ctas = 3;
 
 extern "C" {
 

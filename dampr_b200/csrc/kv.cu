@@ -925,6 +925,11 @@ int32_t dampr_set_option(const char *name, int64_t value) {
         g_use_tma = value != 0;
         return DAMPR_OK;
     }
+    if (!strcmp(name, "text_ctas")) {
+        if (value != 2 && value != 3) return DAMPR_ERR_ARG;
+        g_text_ctas = (int)value;
+        return DAMPR_OK;
+    }
     if (!strcmp(name, "text_kernel")) {
         if (value != 1 && value != 2) return DAMPR_ERR_ARG;
         g_text_kernel = (int)value;

@@ -50,18 +50,23 @@ struct TableView2 {
 };
 enum { S_ENTRIES = 0, S_LINES = 1, S_EMPTY = 2, S_FOLDED = 3, S_FLAGS = 4, S_LONG = 5, S_RAW = 6 };
 
-struct WarpScratch {
-    alignas(8) u64 hist[V_HCAP];
+template <int HCAP>
+struct WarpScratchT {
+    alignas(8) u64 hist[HCAP];
     u16 tpos[V_TPOS];
 };
 
-struct Smem2 {
-    alignas(16) u8 text[2][V_WIN];
-    u32 w[2][V_WORDS + 3];
-    u32 nl[2][V_WORDS + 3];
+// NBUF = 2: double-buffered window, 2 CTAs/SM. NBUF = 1: single window, 3 CTAs/SM (more warps to
+// hide the smem / dependency latencies the ncu profile shows; the other CTAs cover the TMA wait).
+template <int NBUF>
+struct Smem2T {
+    static constexpr int HCAP = (NBUF == 2) ? V_HCAP : V_HCAP / 2;
+    alignas(16) u8 text[NBUF][V_WIN];
+    u32 w[NBUF][V_WORDS + 3];
+    u32 nl[NBUF][V_WORDS + 3];
     alignas(8) u64 tabk[V_STAB];
     u32 tabc[V_STAB];
-    WarpScratch ws[V_WARPS];
+    WarpScratchT<HCAP> ws[V_WARPS];
     alignas(8) u64 bar[2];
     u32 flags;
 };
@@ -228,15 +233,17 @@ __device__ __forceinline__ u64 token_code2(const u8 *text, u32 pos, u32 len, con
     return h | 0x8000000000000000ULL;
 }
 
-template <int MODE>
-__global__ void __launch_bounds__(V_THREADS, 2)
+template <int MODE, int NBUF>
+__global__ void __launch_bounds__(V_THREADS, (NBUF == 2) ? 2 : 3)
 text_count2_kernel(const u8 *__restrict__ text, u64 n, u64 own_lo, u64 own_hi, u64 base_offset, TableView2 tab) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
+    typedef Smem2T<NBUF> Smem2;
+    constexpr int HCAP = Smem2::HCAP;
     Smem2 &s = *reinterpret_cast<Smem2 *>(smem_raw);
     const u32 tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const u32 lt_mask = (1u << lane) - 1u;
     const u64 ntiles = (own_hi - own_lo + V_OWN - 1) / V_OWN;
-    WarpScratch &ws = s.ws[warp];
+    WarpScratchT<HCAP> &ws = s.ws[warp];
 
     if (tid == 0) {
         mbar_init(&s.bar[0], 1);
@@ -260,7 +267,7 @@ text_count2_kernel(const u8 *__restrict__ text, u64 n, u64 own_lo, u64 own_hi, u
         tma_load_1d(s.text[0], text + (own_lo + tile * (u64)V_OWN) - V_LEAD, V_WIN, &s.bar[0]);
     }
     u32 buf = 0;
-    for (; tile < ntiles; tile += gridDim.x, buf ^= 1) {
+    for (; tile < ntiles; tile += gridDim.x, buf ^= (NBUF - 1)) {
         const u64 sgl = own_lo + tile * (u64)V_OWN;
         const u32 own_len = (u32)min((u64)V_OWN, own_hi - sgl);
         const u8 *tx = s.text[buf];
@@ -289,7 +296,7 @@ text_count2_kernel(const u8 *__restrict__ text, u64 n, u64 own_lo, u64 own_hi, u
         if (bad) my_flags |= ((bad & 0x80808080u) ? DAMPR_TF_NONASCII : 0u) | ((bad & 0x40404040u) ? DAMPR_TF_CR : 0u);
         __syncthreads();
         // every warp is past tile-1: its buffer may be refilled while this tile is processed
-        if (tid == 0) {
+        if (NBUF == 2 && tid == 0) {
             u64 nxt = tile + gridDim.x;
             if (nxt < ntiles) {
                 fence_proxy_async();
@@ -298,9 +305,10 @@ text_count2_kernel(const u8 *__restrict__ text, u64 n, u64 own_lo, u64 own_hi, u
             }
         }
 
+        auto strip = [&]() {
         // ---- this warp's strip ----------------------------------------------------------------------
         const u32 st_lo = V_LEAD + warp * V_STRIP;  // window coords of the strip
-        if (st_lo >= V_LEAD + own_len) continue;    // (warp-uniform) strip beyond the owned bytes
+        if (st_lo >= V_LEAD + own_len) return;      // (warp-uniform) strip beyond the owned bytes
         const u32 st_hi = min(st_lo + (u32)V_STRIP, (u32)V_LEAD + own_len);
         const u8 *gwin = text + sgl - V_LEAD;
 
@@ -327,11 +335,11 @@ text_count2_kernel(const u8 *__restrict__ text, u64 n, u64 own_lo, u64 own_hi, u
             rhi = st_hi;
         } else {
             u32 q = warp_find_first(nm, st_lo - 1, (st_hi + 31) >> 5, lane);
-            if (q == 0xFFFFFFFFu || q + 1 >= st_hi) continue;  // no line starts inside the strip
+            if (q == 0xFFFFFFFFu || q + 1 >= st_hi) return;    // no line starts inside the strip
             u32 tl = warp_find_first(nm, st_hi - 1, V_WORDS, lane);
             if (tl == 0xFFFFFFFFu) {
                 my_flags |= DAMPR_TF_LONGLINE;
-                continue;
+                return;
             }
             rlo = q + 1;
             rhi = tl + 1;
@@ -421,7 +429,7 @@ text_count2_kernel(const u8 *__restrict__ text, u64 n, u64 own_lo, u64 own_hi, u
                     const bool add = valid && !dup && line == last_line;
                     const u32 am = __ballot_sync(0xFFFFFFFFu, add);
                     const u32 na = (u32)__popc(am);
-                    if (hist_n + na > (u32)V_HCAP) {
+                    if (hist_n + na > (u32)HCAP) {
                         my_flags |= DAMPR_TF_LONGLINE;
                     } else {
                         if (add) ws.hist[hist_n + __popc(am & lt_mask)] = key;
@@ -525,6 +533,20 @@ text_count2_kernel(const u8 *__restrict__ text, u64 n, u64 own_lo, u64 own_hi, u
             }
             __syncwarp();
         }
+        };
+        strip();
+        if (NBUF == 1) {
+            // single buffer: every warp must be done with the window before the next tile lands in it
+            __syncthreads();
+            if (tid == 0) {
+                u64 nxt = tile + gridDim.x;
+                if (nxt < ntiles) {
+                    fence_proxy_async();
+                    mbar_expect_tx(&s.bar[0], V_WIN);
+                    tma_load_1d(s.text[0], text + (own_lo + nxt * (u64)V_OWN) - V_LEAD, V_WIN, &s.bar[0]);
+                }
+            }
+        }
     }
 
     // ---- flush the shared-memory combiner, publish counters ----------------------------------------
@@ -553,14 +575,14 @@ text_count2_kernel(const u8 *__restrict__ text, u64 n, u64 own_lo, u64 own_hi, u
     if (tid == 0 && s.flags) atomicOr(&tab.stats[S_FLAGS], (u64)s.flags);
 }
 
-template <int MODE>
-int launch2(dampr_ctx *ctx, dampr_table *t, dampr_textbuf *tb, u64 lo, u64 hi) {
+template <int MODE, int NBUF>
+int launch2n(dampr_ctx *ctx, dampr_table *t, dampr_textbuf *tb, u64 lo, u64 hi) {
     if (hi <= lo) return DAMPR_OK;
-    size_t smem = sizeof(Smem2);
-    auto kern = text_count2_kernel<MODE>;
+    size_t smem = sizeof(Smem2T<NBUF>);
+    auto kern = text_count2_kernel<MODE, NBUF>;
     CUDA_TRY(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     u64 ntiles = (hi - lo + V_OWN - 1) / V_OWN;
-    u64 grid = (u64)ctx->num_sms * 2;
+    u64 grid = (u64)ctx->num_sms * ((NBUF == 2) ? 2 : 3);
     if (grid > ntiles) grid = ntiles;
     TableView2 tv{t->keys, t->counts, t->reps, t->stats, t->cap - 1, 0x243F6A8885A308D3ULL};
     wait_uploads(ctx);
@@ -570,6 +592,11 @@ int launch2(dampr_ctx *ctx, dampr_table *t, dampr_textbuf *tb, u64 lo, u64 hi) {
     }
     CUDA_TRY(ctx, cudaGetLastError());
     return DAMPR_OK;
+}
+
+template <int MODE>
+int launch2(dampr_ctx *ctx, dampr_table *t, dampr_textbuf *tb, u64 lo, u64 hi) {
+    return g_text_ctas == 3 ? launch2n<MODE, 1>(ctx, t, tb, lo, hi) : launch2n<MODE, 2>(ctx, t, tb, lo, hi);
 }
 
 }  // namespace
