@@ -71,6 +71,29 @@ class ClockSampler(threading.Thread):
         self.stop_flag = threading.Event()
 
     def run(self):
+        """In-process NVML sampling (spawning nvidia-smi every 200 ms stalls CUDA calls of this process
+        for tens of ms); nvidia-smi is the fallback when pynvml is missing."""
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            h = pynvml.nvmlDeviceGetHandleByIndex(self.gpu)
+            mx = pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM)
+            R = pynvml
+            bits = [("hw_slowdown", R.nvmlClocksThrottleReasonHwSlowdown),
+                    ("hw_thermal_slowdown", R.nvmlClocksThrottleReasonHwThermalSlowdown),
+                    ("sw_thermal_slowdown", R.nvmlClocksThrottleReasonSwThermalSlowdown),
+                    ("sw_power_cap", R.nvmlClocksThrottleReasonSwPowerCap)]
+            while not self.stop_flag.is_set():
+                sm = pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)
+                rs = pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                pw = pynvml.nvmlDeviceGetPowerUsage(h) / 1000.0
+                row = [str(self.gpu), str(sm), str(mx), str(pw), hex(rs)]
+                row += ["Active" if rs & b else "Not Active" for _n, b in bits]
+                self.samples.append(row)
+                self.stop_flag.wait(0.1)
+            return
+        except Exception:
+            pass
         while not self.stop_flag.is_set():
             try:
                 out = subprocess.run(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q,
@@ -232,17 +255,11 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
-    # ---- warm-up ------------------------------------------------------------------------------------------
-    last_dir = None
-    for i in range(args.warmup):
-        last_dir = step(True, -1 - i)
-        shutil.rmtree(last_dir, ignore_errors=True)
-        last_dir = step(False, -1 - i)
-        if i + 1 < args.warmup:
-            shutil.rmtree(last_dir, ignore_errors=True)
-
+    # ---- warm-up immediately before each timed loop (no host-side pause in between) -------------------
     sampler = ClockSampler(local)
     sampler.start()
+    for i in range(args.warmup):
+        shutil.rmtree(step(True, -1 - i), ignore_errors=True)
 
     # ---- timed: device-resident input ("value") ------------------------------------------------------------
     runner_ctx = runner_mod.get_ctx(local)
@@ -260,8 +277,8 @@ def main():
     t_dev = max_over_ranks(time.perf_counter() - t0)
     launches = runner_ctx.launches() - l0
     ktimes = runner_ctx.timings()
-    shutil.rmtree(out_root, ignore_errors=True)
-    os.makedirs(out_root, exist_ok=True)
+    for i in range(args.warmup):
+        shutil.rmtree(step(False, -1 - i), ignore_errors=True)
 
     # ---- timed: host-resident input ("e2e") ----------------------------------------------------------------
     barrier()

@@ -20,6 +20,10 @@
 //   * equal keys inside a warp are merged before touching the shared-memory combiner.
 #include "common.cuh"
 
+#ifndef DAMPR_TEXT_USE_MATCH
+#define DAMPR_TEXT_USE_MATCH 0
+#endif
+
 namespace {
 
 constexpr int V_THREADS = 256;
@@ -405,12 +409,35 @@ text_count2_kernel(const u8 *__restrict__ text, u64 n, u64 own_lo, u64 own_hi, u
                 }
                 bool dup = !valid;
                 if (MODE == DAMPR_TOK_NONWORD_LOWER_SET) {
+#if DAMPR_TEXT_USE_MATCH
                     u32 m1 = 0, m2 = 0;
                     if (valid) {
                         m1 = __match_any_sync(vmask, key);
                         m2 = __match_any_sync(vmask, line);
                     }
                     if (valid && (m1 & m2 & lt_mask)) dup = true;
+#else
+                    // tokens of one line sit in consecutive lanes: compare with the earlier lanes of the
+                    // same line by shuffles (MATCH.ANY iterates over the distinct values and is the slower
+                    // choice here). A 32-bit fold of the key is compared first; the 64-bit compare runs only
+                    // for the distances at which some lane saw a fold match.
+                    {
+                        const u32 lkey = valid ? line : (0xFFFFFF00u | lane);
+                        const u32 prev_line = __shfl_up_sync(0xFFFFFFFFu, lkey, 1);
+                        const u32 seg_start = __ballot_sync(0xFFFFFFFFu, lane == 0 || prev_line != lkey);
+                        const u32 dist = lane - (31u - (u32)__clz(seg_start & (lt_mask | (1u << lane))));
+                        const u32 maxd = __reduce_max_sync(0xFFFFFFFFu, valid ? dist : 0u);
+                        const u32 fold = (u32)key ^ (u32)(key >> 32);
+                        for (u32 d = 1; d <= maxd; ++d) {
+                            const u32 of = __shfl_up_sync(0xFFFFFFFFu, fold, d);
+                            const bool cand = valid && d <= dist && of == fold;
+                            if (__any_sync(0xFFFFFFFFu, cand)) {
+                                const u64 ok = __shfl_up_sync(0xFFFFFFFFu, key, d);
+                                if (cand && ok == key) dup = true;
+                            }
+                        }
+                    }
+#endif
                     // tokens of the line that started in an earlier round: compare with its history
                     const bool in_hist_line = valid && line == hist_line;
                     if (__ballot_sync(0xFFFFFFFFu, in_hist_line)) {
@@ -466,7 +493,11 @@ text_count2_kernel(const u8 *__restrict__ text, u64 n, u64 own_lo, u64 own_hi, u
                     k1 = kk.y;
                 }
                 if (ins) {
+#if DAMPR_TEXT_USE_MATCH
                     u32 peers = __match_any_sync(imask, key);
+#else
+                    u32 peers = 1u << lane;  // no in-warp merge: equal keys serialise in the smem atomic
+#endif
                     if (((u32)__ffs(peers) - 1u) == lane) {
                         u32 cnt = (u32)__popc(peers);
                         if (k0 == key) {

@@ -43,7 +43,8 @@ typedef struct dampr_kv dampr_kv;           /* device array of 16-byte (u64 key,
 int32_t dampr_abi_version(void);
 int32_t dampr_device_count(int32_t *out_n);
 /* process-wide tuning switches: "scatter_tma" (1 = TMA bulk stores in the partition scatter,
- * 0 = coalesced 16-byte stores); "text_kernel" (2 = warp-autonomous tokenise kernel, default;
+ * 0 = coalesced 16-byte stores); "text_ctas" (3 = single-window 3 CTAs/SM variant of the v2
+ * tokenise kernel, default; 2 = double-buffered 2 CTAs/SM); "text_kernel" (2 = warp-autonomous tokenise kernel, default;
  * 1 = first-generation kernel, also the fallback for lines longer than 2 KB) */
 int32_t dampr_set_option(const char *name, int64_t value);
 

@@ -11,12 +11,15 @@ from oracle import gen, refsem
 pytestmark = pytest.mark.gpu
 
 
-@pytest.fixture(autouse=True, params=[2, 1], ids=["kernel-v2", "kernel-v1"])
+@pytest.fixture(autouse=True, params=[(2, 3), (2, 2), (1, 2)], ids=["kernel-v2-3cta", "kernel-v2-2cta", "kernel-v1"])
 def text_kernel(request):
-    """Every case runs against both tokenise kernels (text2.cu is the default, text.cu the fallback)."""
-    dev.set_option("text_kernel", request.param)
-    yield request.param
+    """Every case runs against both tokenise kernels (text2.cu in both occupancy variants is the
+    default, text.cu the fallback)."""
+    dev.set_option("text_kernel", request.param[0])
+    dev.set_option("text_ctas", request.param[1])
+    yield request.param[0]
     dev.set_option("text_kernel", 2)
+    dev.set_option("text_ctas", 3)
 
 
 def run_count(ctx, data, mode, chunk=None, verify=True):

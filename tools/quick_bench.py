@@ -50,9 +50,11 @@ def main():
         ctx.sync()
         print("synth text: %d bytes, %d lines in %.2fs" % (tb.n, n_lines, time.time() - t0))
         ctx.timings_reset()
-        for mode, name in ((dev.TOK_NONWORD_LOWER_SET, "tfidf-set"), (dev.TOK_WS, "wc-split"), (dev.TOK_NONWORD_LOWER, "nonword")):
+        for mode, name, ctas in ((dev.TOK_NONWORD_LOWER_SET, "tfidf-set-3cta", 3), (dev.TOK_NONWORD_LOWER_SET, "tfidf-set-2cta", 2),
+                                 (dev.TOK_WS, "wc-split", 3), (dev.TOK_NONWORD_LOWER, "nonword", 3)):
+            dev.set_option("text_ctas", ctas)
             for rep in range(3):
-                tab = ctx.table(24)
+                tab = ctx.table(21)
                 ctx.sync()
                 ctx.timings_reset()
                 tab.count(tb, 0, tb.n, mode)
