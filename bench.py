@@ -257,9 +257,15 @@ def main():
 
     # ---- warm-up immediately before each timed loop (no host-side pause in between) -------------------
     sampler = ClockSampler(local)
-    sampler.start()
+    if not os.environ.get("DAMPR_BENCH_NOSAMPLER"):
+        sampler.start()
+    verbose = bool(os.environ.get("DAMPR_BENCH_VERBOSE"))
     for i in range(args.warmup):
+        ts = time.perf_counter()
         shutil.rmtree(step(True, -1 - i), ignore_errors=True)
+        if verbose:
+            print("warmup resident %d: %.1f ms %s" % (i, 1e3 * (time.perf_counter() - ts),
+                                                      [round(ms, 1) for _s, ms in runner_mod.LAST_STATS.ms]), file=sys.stderr)
 
     # ---- timed: device-resident input ("value") ------------------------------------------------------------
     runner_ctx = runner_mod.get_ctx(local)
@@ -278,7 +284,11 @@ def main():
     launches = runner_ctx.launches() - l0
     ktimes = runner_ctx.timings()
     for i in range(args.warmup):
+        ts = time.perf_counter()
         shutil.rmtree(step(False, -1 - i), ignore_errors=True)
+        if verbose:
+            print("warmup e2e %d: %.1f ms %s" % (i, 1e3 * (time.perf_counter() - ts),
+                                                 [round(ms, 1) for _s, ms in runner_mod.LAST_STATS.ms]), file=sys.stderr)
 
     # ---- timed: host-resident input ("e2e") ----------------------------------------------------------------
     barrier()
@@ -293,7 +303,8 @@ def main():
     t_e2e = max_over_ranks(time.perf_counter() - t0)
     stats = runner_mod.LAST_STATS.stages if runner_mod.LAST_STATS else []
     sampler.stop_flag.set()
-    sampler.join(timeout=5)
+    if sampler.is_alive():
+        sampler.join(timeout=5)
 
     # result size fetched from the device per step
     n_terms = 0

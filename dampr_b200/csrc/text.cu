@@ -14,6 +14,9 @@
 // per-line de-duplication (set() semantics) is a backward scan over the token array, and the
 // survivors are folded into a per-CTA shared-memory hash table that is flushed to the global
 // (L2-resident) table once per CTA. HBM traffic = the text, read once.
+#include <algorithm>
+#include <thread>
+
 #include "common.cuh"
 
 namespace {
@@ -884,34 +887,72 @@ extern "C" int32_t dampr_table_fetch_words(dampr_ctx *ctx, dampr_table *t, dampr
 //   0  fixed-width NUL-padded bytes  ptr = u8[n][width]
 //   1  dictionary                    ptr = u32 inv[n], aux = blob bytes, aux2 = u32 offsets[m+1]
 // out == NULL: only *out_len is computed.
-extern "C" int32_t dampr_host_join_tsv(uint64_t n, int32_t ncols, const int32_t *kinds, const void *const *ptrs,
-                                       const uint32_t *widths, const void *const *aux, const void *const *aux2,
-                                       uint8_t *out, uint64_t cap, uint64_t *out_len) {
-    if (!kinds || !ptrs || !out_len || ncols < 1 || ncols > 16) return DAMPR_ERR_ARG;
+namespace {
+struct JoinArgs {
+    u64 n;
+    int ncols;
+    const int32_t *kinds;
+    const void *const *ptrs;
+    const uint32_t *widths;
+    const void *const *aux;
+    const void *const *aux2;
+};
+
+// rows [lo, hi): returns the byte count; writes when out != nullptr
+static u64 join_rows(const JoinArgs &a, u64 lo, u64 hi, u8 *out) {
     u64 pos = 0;
-    for (u64 i = 0; i < n; ++i) {
-        for (int c = 0; c < ncols; ++c) {
+    for (u64 i = lo; i < hi; ++i) {
+        for (int c = 0; c < a.ncols; ++c) {
             const u8 *src;
             u32 len;
-            if (kinds[c] == 0) {
-                const u8 *w = (const u8 *)ptrs[c] + i * widths[c];
+            if (a.kinds[c] == 0) {
+                const u8 *w = (const u8 *)a.ptrs[c] + i * a.widths[c];
                 len = 0;
-                while (len < widths[c] && w[len]) ++len;
+                while (len < a.widths[c] && w[len]) ++len;
                 src = w;
             } else {
-                u32 j = ((const u32 *)ptrs[c])[i];
-                const u32 *off = (const u32 *)aux2[c];
-                src = (const u8 *)aux[c] + off[j];
+                u32 j = ((const u32 *)a.ptrs[c])[i];
+                const u32 *off = (const u32 *)a.aux2[c];
+                src = (const u8 *)a.aux[c] + off[j];
                 len = off[j + 1] - off[j];
             }
             if (out) {
-                if (pos + len + 1 > cap) return DAMPR_ERR_ARG;
                 memcpy(out + pos, src, len);
-                out[pos + len] = (c + 1 == ncols) ? '\n' : '\t';
+                out[pos + len] = (c + 1 == a.ncols) ? '\n' : '\t';
             }
             pos += len + 1;
         }
     }
-    *out_len = pos;
+    return pos;
+}
+}  // namespace
+
+extern "C" int32_t dampr_host_join_tsv(uint64_t n, int32_t ncols, const int32_t *kinds, const void *const *ptrs,
+                                       const uint32_t *widths, const void *const *aux, const void *const *aux2,
+                                       uint8_t *out, uint64_t cap, uint64_t *out_len) {
+    if (!kinds || !ptrs || !out_len || ncols < 1 || ncols > 16) return DAMPR_ERR_ARG;
+    JoinArgs a{n, ncols, kinds, ptrs, widths, aux, aux2};
+    unsigned hw = std::thread::hardware_concurrency();
+    int T = (int)std::min<u64>(std::max(1u, std::min(hw, 16u)), std::max<u64>(1, n / 65536));
+    std::vector<u64> lens(T, 0), offs(T + 1, 0);
+    auto span = [&](int t) { return std::make_pair(n * t / T, n * (t + 1) / T); };
+    {
+        std::vector<std::thread> th;
+        for (int t = 1; t < T; ++t) th.emplace_back([&, t] { auto r = span(t); lens[t] = join_rows(a, r.first, r.second, nullptr); });
+        auto r0 = span(0);
+        lens[0] = join_rows(a, r0.first, r0.second, nullptr);
+        for (auto &x : th) x.join();
+    }
+    for (int t = 0; t < T; ++t) offs[t + 1] = offs[t] + lens[t];
+    *out_len = offs[T];
+    if (!out) return DAMPR_OK;
+    if (offs[T] > cap) return DAMPR_ERR_ARG;
+    {
+        std::vector<std::thread> th;
+        for (int t = 1; t < T; ++t) th.emplace_back([&, t] { auto r = span(t); join_rows(a, r.first, r.second, out + offs[t]); });
+        auto r0 = span(0);
+        join_rows(a, r0.first, r0.second, out);
+        for (auto &x : th) x.join();
+    }
     return DAMPR_OK;
 }

@@ -812,9 +812,10 @@ def _lower_cross(runner, stage, inputs):
         # one representative row per distinct value (any row holding it)
         rep = np.empty(len(uniq), dtype=np.int64)
         rep[inv] = np.arange(outer.n, dtype=np.int64)
+        # representative rows, gathered column-wise (no per-cell Python dispatch)
+        rep_cols = [_gather(c, rep) for c in outer.cols]
         res = []
-        for i in rep.tolist():
-            row = tuple(_cell(c, i) for c in outer.cols)
+        for row in zip(*rep_cols):
             r = cross(inner, row)
             res.append(r[ci] if e.op == "tuple" else r)
         kinds = set(type(x) for x in res)
@@ -827,6 +828,21 @@ def _lower_cross(runner, stage, inputs):
     runner.stats.add(stage, "frame cross with a 1-row broadcast (memoised per distinct field value)",
                      "records=%d" % outer.n)
     return f
+
+
+def _gather(col, idx):
+    """Python values of rows idx (numpy int array) of a frame column, as a list."""
+    if isinstance(col, DictCol):
+        sub = col.inv[idx]
+        if isinstance(col.uniq, np.ndarray):
+            return _gather(col.uniq, sub)
+        return [col.uniq[j] for j in sub.tolist()]
+    if isinstance(col, np.ndarray):
+        v = col[idx]
+        if v.dtype.kind == "S":
+            return [b.decode("ascii") for b in v.tolist()]
+        return v.tolist()
+    return [col[i] for i in idx.tolist()]
 
 
 def _cell(col, i):

@@ -151,3 +151,49 @@ def test_product_never_imports_oracle():
             if f.endswith((".py", ".cu", ".cuh")):
                 src = open(os.path.join(dirpath, f), errors="replace").read()
                 assert "import oracle" not in src and "from oracle" not in src, f
+
+
+def test_host_join_tsv_native():
+    """Pure-host sink formatter of the library (no device needed)."""
+    words = np.array([b"alpha", b"b", b"", b"x" * 8], dtype="S8")
+    inv = np.array([2, 0, 1, 0], dtype=np.uint32)
+    strs = [b"1.5", b"", b"-3"]
+    out = dev.host_join_tsv([words, (inv, strs)]).tobytes()
+    assert out == b"alpha\t-3\nb\t1.5\n\t\nxxxxxxxx\t1.5\n"
+    n = 200000
+    w = np.array([b"w%d" % i for i in range(n)], dtype="S12")
+    iv = (np.arange(n) % 7).astype(np.uint32)
+    ss = [str(i * 0.5).encode() for i in range(7)]
+    out = dev.host_join_tsv([w, (iv, ss), (iv, ss)]).tobytes()
+    assert out == b"".join(b"w%d\t%s\t%s\n" % (i, ss[i % 7], ss[i % 7]) for i in range(n))
+
+
+def test_frame_cross_and_sink_lowering_exact_python_values(tmp_path):
+    """plan._lower_cross evaluates the user's own lambda once per distinct field value: the floats
+    are Python's (math.log), and the sink lines equal str() of the tuples."""
+    import math
+    from dampr_b200 import plan
+    from dampr_b200.datasets import RecordsDataset
+
+    class FakeRunner(object):
+        class stats(object):
+            @staticmethod
+            def add(*a, **k):
+                pass
+
+    words = np.array([b"a", b"bb", b"ccc", b"dd"], dtype="S32")
+    counts = np.array([3, 1, 3, 7], dtype=np.int64)
+    fr = plan.Frame(words, [words, counts], scalar=False, combined=True)
+    user = lambda df, total: (df[0], df[1], math.log(1 + (float(total) / df[1])))
+
+    class Stage(object):
+        pass
+    st = Stage()
+    st.mapper = Stage()
+    st.mapper.user_cross = lambda xi, yi: user(yi, xi)
+    out = plan._lower_cross(FakeRunner, st, [fr, RecordsDataset([0], [10])])
+    exp = [user((w.decode(), int(c)), 10) for w, c in zip(words.tolist(), counts.tolist())]
+    assert out.values() == exp
+    cols = [plan._sink_column(c) for c in out.cols]
+    blob = dev.host_join_tsv(cols).tobytes().decode()
+    assert blob == "".join(u"\t".join(str(p) for p in row) + "\n" for row in exp)
