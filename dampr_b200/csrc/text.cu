@@ -956,3 +956,53 @@ extern "C" int32_t dampr_host_join_tsv(uint64_t n, int32_t ncols, const int32_t 
     }
     return DAMPR_OK;
 }
+
+// ---- K9 for exchanged runs: decode the key codes of a kv (key = token code) into fixed-width ASCII ----
+namespace {
+__global__ void kv_words_kernel(const ulonglong2 *__restrict__ rec, u64 n, int mode, u32 width,
+                                u8 *__restrict__ out_words) {
+    for (u64 i = blockIdx.x * (u64)blockDim.x + threadIdx.x; i < n; i += (u64)gridDim.x * blockDim.x) {
+        u64 k = rec[i].x;
+        u8 *w = out_words + i * width;
+        u32 m = 0;
+        if (!(k >> 63)) {
+            if (mode == DAMPR_TOK_WS) {
+                for (; k && m < width; ++m) {
+                    w[m] = (u8)(k & 127);
+                    k >>= 7;
+                }
+            } else {
+                const char *sym = "\0" "0123456789_abcdefghijklmnopqrstuvwxyz";
+                for (; k && m < width; ++m) {
+                    w[m] = (u8)sym[k % 38];
+                    k /= 38;
+                }
+            }
+        }
+        for (; m < width; ++m) w[m] = 0;  // hashed codes stay empty: the caller patches them
+    }
+}
+}  // namespace
+
+extern "C" int32_t dampr_kv_decode_words(dampr_ctx *ctx, dampr_kv *kv, int32_t mode, uint32_t width,
+                                         uint8_t *words_host) {
+    ARG_CHECK(ctx, ctx && kv && (words_host || kv->n == 0), "null");
+    ARG_CHECK(ctx, width >= 16 && width <= 256 && (width % 8) == 0, "width must be a multiple of 8 in [16, 256]");
+    if (kv->n == 0) return DAMPR_OK;
+    wait_uploads(ctx);
+    u8 *d = nullptr;
+    CUDA_TRY(ctx, cudaMalloc(&d, kv->n * width));
+    {
+        ScopedTimer tm(ctx, DAMPR_K_TABLE_EXTRACT);
+        kv_words_kernel<<<ctx->num_sms * 4, 256, 0, ctx->stream>>>(kv->rec, kv->n, mode, width, d);
+    }
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaMemcpyAsync(words_host, d, kv->n * width, cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    cudaFree(d);
+    if (e != cudaSuccess) {
+        ctx->err = std::string("kv decode_words failed: ") + cudaGetErrorString(e);
+        return DAMPR_ERR_CUDA;
+    }
+    return DAMPR_OK;
+}

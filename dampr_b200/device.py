@@ -89,6 +89,7 @@ def load_library():
     _sig(lib, "dampr_table_fetch", vp, vp, vp, vp, vp, u64, pu64)
     _sig(lib, "dampr_table_to_kv", vp, vp, pvp)
     _sig(lib, "dampr_table_fetch_words", vp, vp, vp, i32, u32, vp, vp, vp, vp, u64, pu64)
+    _sig(lib, "dampr_kv_decode_words", vp, vp, i32, u32, vp)
     _sig(lib, "dampr_host_join_tsv", u64, i32, vp, vp, vp, vp, vp, vp, u64, pu64)
     _sig(lib, "dampr_kv_create", vp, u64, pvp)
     _sig(lib, "dampr_kv_destroy", vp, vp)
@@ -418,6 +419,13 @@ class KV(object):
         vals = np.empty(n, dtype=np.uint64)
         self.ctx.check(self.ctx.lib.dampr_kv_download_columns(self.ctx.h, self.h, 0, _ptr(keys), _ptr(vals), n))
         return keys, vals
+
+    def decode_words(self, mode, width=32):
+        """Keys are token codes: 'S<width>' array decoded on the device (hashed codes -> b'')."""
+        n = len(self)
+        words = np.zeros((n, width), dtype=np.uint8)
+        self.ctx.check(self.ctx.lib.dampr_kv_decode_words(self.ctx.h, self.h, int(mode), int(width), _ptr(words)))
+        return words.view("S%d" % width).ravel()
 
     def sort(self, xform=KEY_MIX):
         self.ctx.check(self.ctx.lib.dampr_kv_sort(self.ctx.h, self.h, int(xform)))

@@ -343,12 +343,13 @@ class TextScan(object):
                 ws = keycodes.decode_table(codes[hs], reps[hs], self.mode,
                                            lambda off, ln: tb.download(off, ln).tobytes())
                 hashed_words = dict(zip(codes[hs].tolist(), ws))
-        lines, empty, anybad = dist.all_reduce_sum_int([int(st["lines"]), int(st["empty"]), 1 if bad else 0])
+        lines, empty, anybad, any_hashed = dist.all_reduce_sum_int(
+            [int(st["lines"]), int(st["empty"]), 1 if bad else 0, len(hashed_words)])
         if anybad:
             raise RuntimeError("distributed text scan cannot be lowered on every rank (flags=%d); the "
                                "host-map path is single-process only" % flags)
         merged = {}
-        for d in dist.all_gather_objects(hashed_words):
+        for d in (dist.all_gather_objects(hashed_words) if any_hashed else ()):
             for c, w in d.items():
                 if merged.setdefault(c, w) != w:
                     raise RuntimeError("64-bit key-code collision between two long tokens across ranks")
@@ -358,15 +359,19 @@ class TextScan(object):
         red = recv.sort_reduce(dev.OP_SUM_I64, dev.KEY_MIX)
         recv.free()
         codes, counts = red.columns()
+        W = 32
+        words = red.decode_words(self.mode, W)   # exact codes decoded on the device
         red.free()
-        reps = np.zeros(len(codes), dtype=np.uint64)
-        hashed = (codes & keycodes.HASHED_BIT) != 0
-        words = [None] * len(codes)
-        ex = np.flatnonzero(~hashed)
-        for i, w in zip(ex.tolist(), keycodes.decode_exact(codes[ex], self.mode)):
-            words[i] = w
-        for i in np.flatnonzero(hashed).tolist():
-            words[i] = merged[int(codes[i])]
+        hs = np.flatnonzero((codes & keycodes.HASHED_BIT) != 0)
+        if len(hs):
+            strs = [merged[int(codes[i])] for i in hs.tolist()]
+            if max(len(x) for x in strs) <= W:
+                words[hs] = np.array([x.encode("ascii") for x in strs], dtype=words.dtype)
+            else:
+                wl = [b.decode("ascii") for b in words.tolist()]
+                for i, x in zip(hs.tolist(), strs):
+                    wl[i] = x
+                words = wl
         self.words = words
         self.counts = counts.view(np.int64)
         self.n_lines = int(lines)

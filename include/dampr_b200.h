@@ -143,6 +143,10 @@ int32_t dampr_table_fetch(dampr_ctx *ctx, dampr_table *t, uint64_t *codes, uint6
 int32_t dampr_table_fetch_words(dampr_ctx *ctx, dampr_table *t, dampr_textbuf *tb, int32_t mode,
                                 uint32_t width, uint8_t *words, uint64_t *counts, uint64_t *codes,
                                 uint64_t *reps, uint64_t cap, uint64_t *n);
+/* the same decoding for a kv whose keys are token codes (an exchanged / merged run): exact codes ->
+ * words_host[i*width ..], hashed codes -> all-NUL (the caller patches them from their strings) */
+int32_t dampr_kv_decode_words(dampr_ctx *ctx, dampr_kv *kv, int32_t mode, uint32_t width,
+                              uint8_t *words_host);
 /* host-side sink formatting (SinkWriter, dataset.py:264-282): joins ncols columns with '\t', rows end
  * with '\n'. kinds[c] == 0: ptrs[c] = u8[n][widths[c]] NUL-padded strings; kinds[c] == 1: ptrs[c] =
  * u32 inv[n] into a dictionary of strings aux[c] (bytes) / aux2[c] (u32 offsets[m+1]).
