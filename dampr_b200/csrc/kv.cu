@@ -281,6 +281,13 @@ leaf_sort_kernel(ulonglong2 *__restrict__ data, ulonglong2 *__restrict__ out, co
     for (u32 c = blockIdx.x; c < nchunks; c += gridDim.x) {
         const LeafChunk ch = chunks[c];
         const u32 n = ch.n;
+        if (c + gridDim.x < nchunks) {
+            // pull the chunk this CTA handles next into L2 (one 128-byte line per thread per pass)
+            const LeafChunk nx = chunks[c + gridDim.x];
+            const char *base = reinterpret_cast<const char *>(data + nx.start);
+            for (u32 off = tid * 128u; off < nx.n * 16u; off += L_THREADS * 128u)
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(base + off));
+        }
         for (u32 i = tid; i < L_BINS; i += L_THREADS) s.cnt[i] = 0;
         if (tid == 0) s.nbig = 0;
         __syncthreads();
@@ -338,58 +345,26 @@ leaf_sort_kernel(ulonglong2 *__restrict__ data, ulonglong2 *__restrict__ out, co
             s.ord[pos] = (u16)i;
         }
         __syncthreads();
-        // fix-up: order every bin by (key, input position)
-        for (u32 b = tid; b < L_BINS; b += L_THREADS) {
-            u32 st = s.cnt[b];
-            u32 en = (b + 1 < L_BINS) ? s.cnt[b + 1] : n;
-            u32 m = en - st;
-            if (m < 2) continue;
-            if (m <= L_SMALL) {
-                for (u32 i = st + 1; i < en; ++i) {
-                    u16 x = s.ord[i];
-                    u32 j = i;
-                    while (j > st && leaf_less(s, x, s.ord[j - 1])) {
-                        s.ord[j] = s.ord[j - 1];
-                        --j;
-                    }
-                    s.ord[j] = x;
-                }
-            } else {
-                u32 slot = atomicAdd(&s.nbig, 1u);
-                if (slot < 176) s.big[slot] = (u16)b;
+        // order inside every bin by (key, input position): each record counts the members of its own
+        // bin that precede it (thread per record: all lanes busy, loop length = bin population) and
+        // takes that rank. cur[] is free after the scatter and receives the final order.
+        for (u32 i = tid; i < n; i += L_THREADS) {
+            const u64 ki = s.sk[i];
+            u64 bin64 = (ki >> ch.bin_shift) - ch.bin_base;
+            u32 bin = (u32)min(bin64, (u64)(L_BINS - 1));
+            u32 st = s.cnt[bin];
+            u32 en = (bin + 1 < L_BINS) ? s.cnt[bin + 1] : n;
+            u32 r = 0;
+            for (u32 j = st; j < en; ++j) {
+                u32 o = s.ord[j];
+                u64 ko = s.sk[o];
+                r += (ko < ki || (ko == ki && o < i)) ? 1u : 0u;
             }
+            s.cur[st + r] = (u16)i;
         }
         __syncthreads();
-        // large bins: block-wide odd-even merge is overkill; use a block-parallel rank sort
-        // (each element counts how many precede it) — O(m^2/threads), m <= L_CAP
-        {
-            u32 nbig = min(s.nbig, 176u);
-            for (u32 q = 0; q < nbig; ++q) {
-                u32 b = s.big[q];
-                u32 st = s.cnt[b];
-                u32 en = (b + 1 < L_BINS) ? s.cnt[b + 1] : n;
-                u32 m = en - st;
-                // ranks are written into cur[] (free now) as scratch, then applied
-                for (u32 i = tid; i < m; i += L_THREADS) {
-                    u16 x = s.ord[st + i];
-                    u32 r = 0;
-                    for (u32 j = 0; j < m; ++j) r += leaf_less(s, s.ord[st + j], x) ? 1u : 0u;
-                    s.cur[i] = (u16)r;
-                }
-                __syncthreads();
-                u16 mine[L_CAP / L_THREADS];
-                u16 myr[L_CAP / L_THREADS];
-                u32 k = 0;
-                for (u32 i = tid; i < m; i += L_THREADS, ++k) {
-                    mine[k] = s.ord[st + i];
-                    myr[k] = s.cur[i];
-                }
-                __syncthreads();
-                k = 0;
-                for (u32 i = tid; i < m; i += L_THREADS, ++k) s.ord[st + myr[k]] = mine[k];
-                __syncthreads();
-            }
-        }
+        for (u32 i = tid; i < n; i += L_THREADS) s.ord[i] = s.cur[i];
+        __syncthreads();
         if (reduce_op < 0) {
             for (u32 i = tid; i < n; i += L_THREADS) out[ch.start + i] = s.rec[s.ord[i]];
             __syncthreads();
