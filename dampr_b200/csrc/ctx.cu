@@ -131,6 +131,16 @@ int32_t dampr_ctx_stream(dampr_ctx *ctx, uint64_t *out_stream) {
     return DAMPR_OK;
 }
 
+int32_t dampr_ctx_mem_info(dampr_ctx *ctx, uint64_t *free_bytes, uint64_t *total_bytes) {
+    if (!ctx || !free_bytes || !total_bytes) return DAMPR_ERR_ARG;
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    size_t f = 0, t = 0;
+    CUDA_TRY(ctx, cudaMemGetInfo(&f, &t));
+    *free_bytes = f;
+    *total_bytes = t;
+    return DAMPR_OK;
+}
+
 int32_t dampr_host_alloc(uint64_t nbytes, void **out) {
     if (!out) return DAMPR_ERR_ARG;
     *out = nullptr;

@@ -128,6 +128,8 @@ part_scatter_kernel(const ulonglong2 *__restrict__ in, ulonglong2 *__restrict__ 
     ScatterSmem &s = *reinterpret_cast<ScatterSmem *>(smem_raw);
     const u32 tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const u32 pb = cta_piece_begin[blockIdx.x], pe = cta_piece_begin[blockIdx.x + 1];
+    u32 dbits = 0;
+    while ((1u << dbits) < nb) ++dbits;
 
     for (u32 p = pb; p < pe; ++p) {
         const Piece pc = pieces[p];
@@ -152,7 +154,14 @@ part_scatter_kernel(const ulonglong2 *__restrict__ in, ulonglong2 *__restrict__ 
                     rec[r] = in[t0 + li];
                     u32 d = digit_of(rec[r].x, ds);
                     dig[r] = d;
-                    u32 peers = __match_any_sync(vmask, d);
+                    // lanes holding the same digit, from one ballot per digit bit (MATCH.ANY costs one
+                    // pass per distinct value, i.e. ~32 passes with 10-bit digits)
+                    u32 peers = vmask;
+                    for (u32 bit = 0; bit < dbits; ++bit) {
+                        const u32 mine = (d >> bit) & 1u;
+                        const u32 bal = __ballot_sync(vmask, mine);
+                        peers &= mine ? bal : ~bal;
+                    }
                     u32 leader = (u32)__ffs(peers) - 1u;
                     u32 old = 0;
                     if (lane == leader) {

@@ -71,6 +71,7 @@ def load_library():
     _sig(lib, "dampr_ctx_timings_reset", vp)
     _sig(lib, "dampr_ctx_timing_enable", vp, i32)
     _sig(lib, "dampr_ctx_launches", vp, pu64)
+    _sig(lib, "dampr_ctx_mem_info", vp, pu64, pu64)
     _sig(lib, "dampr_ctx_stream", vp, pu64)
     _sig(lib, "dampr_host_alloc", u64, pvp)
     _sig(lib, "dampr_host_free", vp)
@@ -192,6 +193,11 @@ class Ctx(object):
         if self.h is not None:
             self.lib.dampr_ctx_destroy(self.h)
             self.h = None
+
+    def mem_info(self):
+        f, t = C.c_uint64(0), C.c_uint64(0)
+        self.check(self.lib.dampr_ctx_mem_info(self.h, C.byref(f), C.byref(t)))
+        return f.value, t.value
 
     def launches(self):
         n = C.c_uint64(0)

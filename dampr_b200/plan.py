@@ -699,28 +699,49 @@ def _lower_kv_map(runner, stage, inputs):
             return None
         if kind == lowering.ADD and n and float(np.abs(vals.astype(np.float64)).sum()) >= float(1 << 62):
             raise NotLowerable("64-bit sum could overflow (SURVEY B12)")
-        kv = ctx.kv_from_columns(keys, vals)
-        try:
-            red = kv.sort_reduce(dev.OP_COUNT if (count_only and kind == lowering.ADD) else _FOLD_OPS[kind], dev.KEY_MIX)
-            rk, rv = red.columns()
-            red.free()
-        finally:
-            kv.free()
+        op = dev.OP_COUNT if (count_only and kind == lowering.ADD) else _FOLD_OPS[kind]
+        rk, rv, how = _device_group(runner, keys, vals, op, dev.KEY_MIX)
         f = Frame(rk.view(keys.dtype), [rv.view(np.int64)], scalar=True, combined=True)
-        runner.stats.add(stage, "device kv partition+sort+segmented-reduce", "records=%d groups=%d" % (n, len(rk)))
+        runner.stats.add(stage, "device kv partition+sort+segmented-reduce" + how, "records=%d groups=%d" % (n, len(rk)))
         return f
     if stage.combiner is None:
-        kv = ctx.kv_from_columns(keys, vals)
-        try:
-            kv.sort(_key_xform_for(keys))
-            rk, rv = kv.columns()
-        finally:
-            kv.free()
+        rk, rv, how = _device_group(runner, keys, vals, None, _key_xform_for(keys))
         f = Frame(rk.view(keys.dtype), [rv.view(vals.dtype)], scalar=True)
         f.meta["sorted_kv"] = True
-        runner.stats.add(stage, "device kv partition+sort", "records=%d" % n)
+        runner.stats.add(stage, "device kv partition+sort" + how, "records=%d" % n)
         return f
     return None
+
+
+def _device_group(runner, keys, vals, op, xform):
+    """Group (and fold, when op is given) kv columns on the device: in core when the records fit the
+    device arena, otherwise through the spill path (spill.py). Returns (keys, vals, how)."""
+    from . import spill
+    ctx = runner.ctx
+    n = len(keys)
+    if n and spill.needs_spill(ctx, n):
+        step = 1 << 22
+        chunks = ((keys[i:i + step], vals[i:i + step]) for i in range(0, n, step))
+        pieces, st = spill.external_group(ctx, chunks, n, op, xform if op is None else dev.KEY_MIX)
+        rk = np.concatenate([p[0] for p in pieces]) if pieces else np.zeros(0, dtype=np.uint64)
+        rv = np.concatenate([p[1] for p in pieces]) if pieces else np.zeros(0, dtype=np.uint64)
+        runner.stats.spill = st
+        return rk, rv, " [spilled: %d buckets, %d batches, arena %d MB]" % (
+            st["buckets"], st["batches"], st["arena_bytes"] >> 20)
+    kv = ctx.kv_from_columns(keys, vals)
+    try:
+        if op is None:
+            kv.sort(xform)
+            rk, rv = kv.columns()
+        else:
+            red = kv.sort_reduce(op, xform)
+            try:
+                rk, rv = red.columns()
+            finally:
+                red.free()
+    finally:
+        kv.free()
+    return rk, rv, ""
 
 
 def _numeric(col):
@@ -936,17 +957,10 @@ def _lower_reduce(runner, stage, inputs):
                 vals = fr.cols[0]
                 if kind == lowering.SUM and fr.n and float(np.abs(vals.astype(np.float64)).sum()) >= float(1 << 62):
                     return None
-                ctx = runner.ctx
-                kv = ctx.kv_from_columns(fr.keys, vals)
-                try:
-                    r = kv.sort_reduce(opmap[kind], _key_xform_for(fr.keys))
-                    rk, rv = r.columns()
-                    r.free()
-                finally:
-                    kv.free()
+                rk, rv, how = _device_group(runner, fr.keys, vals, opmap[kind], _key_xform_for(fr.keys))
                 rk = rk.view(fr.keys.dtype)
                 out = Frame(rk, [rk, rv.view(np.int64)], scalar=False, combined=True)
-                runner.stats.add(stage, "device segmented reduce of sorted kv", "records=%d groups=%d" % (fr.n, len(rk)))
+                runner.stats.add(stage, "device segmented reduce of sorted kv" + how, "records=%d groups=%d" % (fr.n, len(rk)))
                 return out
     return None
 

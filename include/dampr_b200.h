@@ -61,6 +61,9 @@ const char *dampr_last_error(dampr_ctx *ctx);
 int32_t dampr_ctx_timings(dampr_ctx *ctx, double *out_ms, int32_t *out_ids, int32_t cap, int32_t *n);
 int32_t dampr_ctx_timings_reset(dampr_ctx *ctx);
 int32_t dampr_ctx_timing_enable(dampr_ctx *ctx, int32_t on);
+/* free / total device memory: the arena the spill trigger compares against (replaces the RSS
+ * polling of InterpolativeMemoryChecker, memory.py:72-113) */
+int32_t dampr_ctx_mem_info(dampr_ctx *ctx, uint64_t *free_bytes, uint64_t *total_bytes);
 /* number of kernels this library launched on the ctx since creation */
 int32_t dampr_ctx_launches(dampr_ctx *ctx, uint64_t *out);
 /* raw handle of the compute stream (cudaStream_t) so torch.distributed collectives can be

@@ -167,3 +167,23 @@ def test_shim_package_runs_reference_style_script(ctx, tmp_path):
     assert dampr.Dampr is dampr_b200.Dampr
     from dampr import settings
     assert settings.partitions == 91
+
+
+def test_spill_path_with_capped_arena(ctx):
+    """BASELINE config 4 shape: the records do not fit the (capped) device arena, so batches are
+    partitioned on the device, spilled to host buckets and grouped bucket by bucket."""
+    from dampr_b200 import settings
+    keys, vals = gen.kv(17, 1_500_000, 200_000)
+    old = settings.device_arena_bytes
+    settings.device_arena_bytes = 8 << 20  # 8 MB arena: ~170 K records per batch
+    try:
+        src = Dampr.read_input(ArrayKVInput(keys, vals))
+        got = dict(src.a_group_by(lambda x: x[0], lambda x: x[1]).sum().read())
+        assert lowered("[spilled:")
+        assert got == refsem.group_sum(keys, vals)
+        got = dict(src.group_by(lambda x: x[0], lambda x: x[1]).reduce(lambda k, it: sum(it)).read())
+        assert got == refsem.group_sum(keys, vals)
+        got = dict(src.count(lambda x: x[0]).read())
+        assert got == refsem.group_count(keys)
+    finally:
+        settings.device_arena_bytes = old
