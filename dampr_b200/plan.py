@@ -719,6 +719,27 @@ def _device_group(runner, keys, vals, op, xform):
     from . import spill
     ctx = runner.ctx
     n = len(keys)
+    if op is not None and dist.active():
+        # kv inputs are global: every rank folds its record range, one all-to-all moves each key to its
+        # owner (dist.shuffle_kv), the owner finishes the fold. Runs arrive in rank order and the device
+        # sort is stable, so FIRST/LAST keep their input-order meaning.
+        r, w = dist.world()
+        lo, hi = n * r // w, n * (r + 1) // w
+        kv = ctx.kv_from_columns(keys[lo:hi], vals[lo:hi])
+        try:
+            part = kv.sort_reduce(op, dev.KEY_MIX)
+        finally:
+            kv.free()
+        recv = dist.shuffle_kv(ctx, part)
+        part.free()
+        op2 = dev.OP_SUM_I64 if op == dev.OP_COUNT else op
+        red = recv.sort_reduce(op2, dev.KEY_MIX)
+        recv.free()
+        try:
+            rk, rv = red.columns()
+        finally:
+            red.free()
+        return rk, rv, " [rank %d/%d: local fold, all-to-all, owner fold]" % (r, w)
     if n and spill.needs_spill(ctx, n):
         step = 1 << 22
         chunks = ((keys[i:i + step], vals[i:i + step]) for i in range(0, n, step))

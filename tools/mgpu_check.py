@@ -1,0 +1,77 @@
+"""Multi-GPU parity check (run under torchrun on a GPU box):
+   python -m torch.distributed.run --nproc-per-node 2 tools/mgpu_check.py
+Every rank runs the same DSL script; text files are sharded by byte range, kv inputs by record range,
+results live on their owner rank and are gathered here only to compare with the oracle."""
+import os
+import re
+import sys
+import tempfile
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from dampr_b200 import Dampr, settings
+from dampr_b200 import runner as runner_mod
+from dampr_b200.inputs import ArrayKVInput
+from oracle import gen, refsem
+
+RX = re.compile(r"[^\w]+")
+
+
+def main():
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    settings.device = local
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    rank, world = dist.get_rank(), dist.get_world_size()
+    data = gen.text(4321, 60000, V=20000) + gen.dirty_text(5, 2000, 1500)
+    path = os.path.join(tempfile.gettempdir(), "dampr_mgpu_corpus.txt")
+    if rank == 0:
+        with open(path, "wb") as f:
+            f.write(data)
+    dist.barrier()
+    # tf-idf document frequencies: every rank owns a slice of the terms
+    docs = Dampr.text(path)
+    mine = docs.flat_map(lambda x: set(RX.split(x.lower()))).count().read()
+    n_lines = docs.len().read()[0]
+    parts = [None] * world
+    dist.all_gather_object(parts, mine)
+    merged = {}
+    for p in parts:
+        for k, v in p:
+            assert k not in merged, "term %r owned by two ranks" % (k,)
+            merged[k] = v
+    exp, exp_lines = refsem.docfreq(data)
+    assert merged == dict(exp), "document frequencies differ from the oracle"
+    assert n_lines == exp_lines
+    assert any("device text tokenise+combine" in how for _s, how, _d in runner_mod.LAST_STATS.stages)
+    # word count (str.split, long tokens -> hashed codes + cross-rank string exchange)
+    mine = docs.flat_map(lambda x: x.split()).count().read()
+    dist.all_gather_object(parts, mine)
+    merged = {}
+    for p in parts:
+        for k, v in p:
+            assert k not in merged
+            merged[k] = v
+    assert merged == dict(refsem.wc_counts(data)), "word counts differ from the oracle"
+    # kv fold
+    keys, vals = gen.kv(77, 1_000_000, 90_000)
+    mine = Dampr.read_input(ArrayKVInput(keys, vals)).a_group_by(lambda x: x[0], lambda x: x[1]).sum().read()
+    dist.all_gather_object(parts, mine)
+    merged = {}
+    for p in parts:
+        for k, v in p:
+            assert k not in merged
+            merged[k] = v
+    assert merged == refsem.group_sum(keys, vals), "kv sums differ from the oracle"
+    dist.barrier()
+    if rank == 0:
+        print("mgpu_check ok: world=%d terms=%d lines=%d" % (world, len(exp), exp_lines))
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
