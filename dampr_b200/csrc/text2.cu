@@ -104,7 +104,8 @@ __device__ __forceinline__ void classify4(u32 x, u32 &wbits, u32 &nlbits, u32 &b
     nlbits = movemask4(nl);
 }
 
-__device__ __forceinline__ void gtab_add2(const TableView2 &t, u64 key, u64 cnt, u64 rep) {
+// returns the representative the entry held before this call (~0 if none / not a hashed token)
+__device__ __forceinline__ u64 gtab_add2(const TableView2 &t, u64 key, u64 cnt, u64 rep) {
     u64 slot = mix64(key) & t.mask;
     for (u32 probe = 0; probe < V_G_MAX_PROBES; ++probe) {
         u64 k = *((volatile u64 *)&t.keys[slot]);
@@ -117,12 +118,12 @@ __device__ __forceinline__ void gtab_add2(const TableView2 &t, u64 key, u64 cnt,
         }
         if (k == key) {
             atomicAdd(&t.counts[slot], cnt);
-            if (rep != ~0ULL) atomicMin(&t.reps[slot], rep);
-            return;
+            return (rep != ~0ULL) ? atomicMin(&t.reps[slot], rep) : ~0ULL;
         }
         slot = (slot + 1) & t.mask;
     }
     atomicOr(&t.stats[S_FLAGS], (u64)DAMPR_TF_TABLEFULL);
+    return ~0ULL;
 }
 
 // keep [lo, hi) of the 32 positions starting at base
@@ -475,8 +476,27 @@ text_count2_kernel(const u8 *__restrict__ text, u64 n, u64 own_lo, u64 own_hi, u
                             my_flags |= DAMPR_TF_LONGTOKEN;
                             l2 = (1u << 20) - 1;
                         }
-                        u64 goff = base_offset + (sgl - V_LEAD) + pos;
-                        gtab_add2(tab, key, 1ULL, (goff << 20) | l2);
+                        const u64 goff = base_offset + (sgl - V_LEAD) + pos;
+                        const u64 myrep = (goff << 20) | l2;
+                        const u64 old = gtab_add2(tab, key, 1ULL, myrep);
+                        // inline K9 verification: atomicMin hands back the representative some earlier
+                        // token of this code published; comparing every later token with it (bytes, case
+                        // folded) proves by induction that the entry holds ONE token, so a 64-bit code
+                        // collision cannot merge two words silently and no second pass is needed
+                        if (old != ~0ULL && old != myrep) {
+                            bool same = (u32)(old & 0xFFFFFu) == l2;
+                            const u8 *pa = gwin + pos;
+                            const u8 *pb = text + ((old >> 20) - base_offset);
+                            for (u32 i = 0; same && i < len; ++i) {
+                                u32 ca = pa[i], cb = pb[i];
+                                if (MODE != DAMPR_TOK_WS) {
+                                    if (ca >= 'A' && ca <= 'Z') ca |= 0x20;
+                                    if (cb >= 'A' && cb <= 'Z') cb |= 0x20;
+                                }
+                                same = ca == cb;
+                            }
+                            if (!same) my_flags |= DAMPR_TF_COLLISION;
+                        }
                         acc_long++;
                     }
                 }

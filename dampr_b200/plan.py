@@ -302,10 +302,13 @@ class TextScan(object):
                     dev.set_option("text_kernel", 2)
             if self.mode != dev.TOK_WS and flags & (dev.TF_CR | dev.TF_LONGLINE):
                 raise NotLowerable("carriage returns or a line longer than the device window")
-            if st["hashed"]:
+            if st["hashed"] and getattr(self, "_retry_v1", False):
+                # the first-generation kernel verifies long tokens in a second pass; the v2 kernel
+                # compares every long token with its entry's representative while counting
                 tab.verify(tb, 0, tb.n, self.mode)
-                if tab.stats()["flags"] & dev.TF_COLLISION:
-                    raise NotLowerable("64-bit key-code collision between two long tokens")
+                flags = tab.stats()["flags"]
+            if flags & dev.TF_COLLISION:
+                raise NotLowerable("64-bit key-code collision between two long tokens")
             # keys are materialised on the device (K9) as fixed-width ASCII; only tokens longer than the
             # width (rare) are patched on the host from their representative occurrence
             W = 32
@@ -333,11 +336,10 @@ class TextScan(object):
         if self.mode != dev.TOK_WS:
             bad |= flags & (dev.TF_CR | dev.TF_LONGLINE)
         hashed_words = {}
+        if flags & dev.TF_COLLISION:
+            bad |= dev.TF_COLLISION
         if st["hashed"] and not bad:
-            tab.verify(tb, 0, tb.n, self.mode)
-            if tab.stats()["flags"] & dev.TF_COLLISION:
-                bad |= dev.TF_COLLISION
-            else:
+            if True:
                 codes, _counts, reps = tab.fetch()
                 hs = np.flatnonzero((codes & keycodes.HASHED_BIT) != 0)
                 ws = keycodes.decode_table(codes[hs], reps[hs], self.mode,
