@@ -125,6 +125,10 @@ def analyze(fn):
                 r = stack.pop()
                 l = stack.pop()
                 stack.append(E("cmp", ins.argval, l, r))
+            elif name == "CONTAINS_OP":
+                r = stack.pop()
+                l = stack.pop()
+                stack.append(E("cmp", "not in" if ins.arg else "in", l, r))
             elif name == "RETURN_VALUE":
                 out = stack.pop()
                 return None if out is _NULL else out

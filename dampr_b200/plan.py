@@ -647,6 +647,8 @@ def _lower_map(runner, stage, inputs, si):
         return _lower_frame_map(runner, stage, inputs[0])
     if isinstance(stage.mapper, ops.MapCrossJoin) and len(inputs) == 2 and isinstance(inputs[0], Frame):
         return _lower_cross(runner, stage, inputs)
+    if isinstance(stage.mapper, ops.MapAllJoin) and len(inputs) == 2:
+        return _lower_probe(runner, stage, inputs)
     return None
 
 
@@ -892,6 +894,65 @@ def _gather(col, idx):
             return [b.decode("ascii") for b in v.tolist()]
         return v.tolist()
     return [col[i] for i in idx.tolist()]
+
+
+def _lower_probe(runner, stage, inputs):
+    """small.cross_set(big, lambda b, table: (..., b[i] in table, ...), agg=set): the broadcast join of
+    MapAllJoin.map (base.py:165-178) as a device hash build + probe (dampr_kv_hash_probe). Streams the
+    kv records of `big`; the table is the set of (integer) values of `small`."""
+    mapper = stage.mapper
+    cross, agg = getattr(mapper, "user_cross", None), getattr(mapper, "user_agg", None)
+    if cross is None or agg not in (set, frozenset):
+        return None
+    cols = _kv_columns(inputs[0])
+    if cols is None:
+        return None
+    e = lowering.analyze(cross)
+    if e is None or cross.__code__.co_argcount != 2:
+        return None
+    comps = e.a if e.op == "tuple" else (e,)
+    plan_ = []
+    for comp in comps:
+        f = lowering._field(comp)
+        if f is not None and f in (0, 1):
+            plan_.append(("col", f))
+            continue
+        if comp.op == "cmp" and comp.a in ("in", "not in") and lowering._is_arg(comp.c, 1):
+            f = lowering._field(comp.b)
+            if f in (0, 1):
+                plan_.append(("probe", f, comp.a == "not in"))
+                continue
+        return None
+    small_vals = [v for _k, v in ops.as_one_dataset(inputs[1]).read()]
+    if not all(type(v) is int and -(1 << 63) <= v < (1 << 64) for v in small_vals):
+        return None
+    ctx = runner.ctx
+    build_keys = np.unique(np.array([v & 0xFFFFFFFFFFFFFFFF for v in small_vals], dtype=np.uint64))
+    build = ctx.kv_from_columns(build_keys, np.ones(len(build_keys), dtype=np.uint64))
+    hits = {}
+    try:
+        for item in plan_:
+            if item[0] == "probe" and item[1] not in hits:
+                probe = ctx.kv_from_columns(cols[item[1]].view(np.uint64), np.zeros(len(cols[item[1]]), dtype=np.uint64))
+                try:
+                    vals, hit = build.hash_probe(probe)
+                    vals.free()
+                finally:
+                    probe.free()
+                hits[item[1]] = hit.astype(bool)
+    finally:
+        build.free()
+    out_cols = []
+    for item in plan_:
+        if item[0] == "col":
+            out_cols.append(cols[item[1]])
+        else:
+            h = hits[item[1]]
+            out_cols.append(~h if item[2] else h)
+    n = len(cols[0])
+    f = Frame(np.arange(n, dtype=np.int64), out_cols, scalar=(e.op != "tuple"))
+    runner.stats.add(stage, "device broadcast hash build+probe", "build=%d probe=%d" % (len(build_keys), n))
+    return f
 
 
 def _cell(col, i):

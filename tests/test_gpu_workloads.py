@@ -187,3 +187,17 @@ def test_spill_path_with_capped_arena(ctx):
         assert got == refsem.group_count(keys)
     finally:
         settings.device_arena_bytes = old
+
+
+def test_map_side_join_lowered_to_hash_probe(ctx):
+    """BASELINE config 5, map side: small.cross_set(big, probe, agg=set) -> device build + probe."""
+    lk, lv = gen.kv(1, 200000, 30000)
+    rk, _rv = gen.kv(2, 5000, 60000)
+    small = Dampr.read_input(ArrayKVInput(rk, _rv)).map(lambda x: x[0])
+    big = Dampr.read_input(ArrayKVInput(lk, lv))
+    got = small.cross_set(big, lambda b, table: (b[0], b[1], b[0] in table), agg=set).read()
+    assert lowered("device broadcast hash build+probe")
+    table = set(rk.tolist())
+    assert got == [(k, v, k in table) for k, v in zip(lk.tolist(), lv.tolist())]
+    got = small.cross_set(big, lambda b, table: b[0] not in table, agg=set).read()
+    assert got == [k not in table for k in lk.tolist()]
