@@ -36,6 +36,7 @@ def main():
     # tf-idf document frequencies: every rank owns a slice of the terms
     docs = Dampr.text(path)
     mine = docs.flat_map(lambda x: set(RX.split(x.lower()))).count().read()
+    assert any("device text tokenise+combine" in how for _s, how, _d in runner_mod.LAST_STATS.stages)
     n_lines = docs.len().read()[0]
     parts = [None] * world
     dist.all_gather_object(parts, mine)
@@ -47,7 +48,6 @@ def main():
     exp, exp_lines = refsem.docfreq(data)
     assert merged == dict(exp), "document frequencies differ from the oracle"
     assert n_lines == exp_lines
-    assert any("device text tokenise+combine" in how for _s, how, _d in runner_mod.LAST_STATS.stages)
     # word count (str.split, long tokens -> hashed codes + cross-rank string exchange)
     mine = docs.flat_map(lambda x: x.split()).count().read()
     dist.all_gather_object(parts, mine)
