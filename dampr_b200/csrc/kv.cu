@@ -143,6 +143,13 @@ part_scatter_kernel(const ulonglong2 *__restrict__ in, ulonglong2 *__restrict__ 
             ulonglong2 rec[P_ROUNDS];
             u32 dig[P_ROUNDS];
             u32 rnk[P_ROUNDS];
+            // all loads of the tile first (8 independent 16-byte loads in flight per thread) ...
+#pragma unroll
+            for (int r = 0; r < P_ROUNDS; ++r) {
+                u32 li = warp * P_PER_WARP + r * 32 + lane;
+                if (li < tn) rec[r] = in[t0 + li];
+            }
+            // ... then the stable ranking, round by round
 #pragma unroll
             for (int r = 0; r < P_ROUNDS; ++r) {
                 u32 li = warp * P_PER_WARP + r * 32 + lane;
@@ -151,7 +158,6 @@ part_scatter_kernel(const ulonglong2 *__restrict__ in, ulonglong2 *__restrict__ 
                 dig[r] = 0xFFFFFFFFu;
                 rnk[r] = 0;
                 if (valid) {
-                    rec[r] = in[t0 + li];
                     u32 d = digit_of(rec[r].x, ds);
                     dig[r] = d;
                     // lanes holding the same digit, from one ballot per digit bit (MATCH.ANY costs one
@@ -301,11 +307,22 @@ leaf_sort_kernel(ulonglong2 *__restrict__ data, ulonglong2 *__restrict__ out, co
         if (tid == 0) s.nbig = 0;
         __syncthreads();
         // load + histogram
-        for (u32 i = tid; i < n; i += L_THREADS) {
-            ulonglong2 r = data[ch.start + i];
-            s.rec[i] = r;
-            u64 k = key_xform(r.x, xf) - base;
-            s.sk[i] = k;
+        {
+            // L_CAP / L_THREADS independent loads in flight per thread
+            ulonglong2 rr[L_CAP / L_THREADS];
+#pragma unroll
+            for (int k = 0; k < L_CAP / L_THREADS; ++k) {
+                u32 i = tid + k * L_THREADS;
+                if (i < n) rr[k] = data[ch.start + i];
+            }
+#pragma unroll
+            for (int k = 0; k < L_CAP / L_THREADS; ++k) {
+                u32 i = tid + k * L_THREADS;
+                if (i < n) {
+                    s.rec[i] = rr[k];
+                    s.sk[i] = key_xform(rr[k].x, xf) - base;
+                }
+            }
         }
         __syncthreads();
         // counting with u16 counters packed two per u32 word: use 32-bit atomics on the pair

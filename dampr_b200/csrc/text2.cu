@@ -527,7 +527,7 @@ text_count2_kernel(const u8 *__restrict__ text, u64 n, u64 own_lo, u64 own_hi, u
                         } else {
                             bool placed = false;
 #pragma unroll 1
-                            for (int pr = 0; pr < 6; ++pr) {
+                            for (int pr = 0; pr < 2; ++pr) {  // 2-way bucket: a miss goes straight to the L2-resident global table
                                 u64 k = s.tabk[slot];
                                 if (k == 0) {
                                     k = atomicCAS(&s.tabk[slot], 0ULL, key);
