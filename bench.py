@@ -86,11 +86,12 @@ class ClockSampler(threading.Thread):
             while not self.stop_flag.is_set():
                 sm = pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)
                 rs = pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(h)
-                pw = pynvml.nvmlDeviceGetPowerUsage(h) / 1000.0
-                row = [str(self.gpu), str(sm), str(mx), str(pw), hex(rs)]
+                row = [str(self.gpu), str(sm), str(mx), "", hex(rs)]
                 row += ["Active" if rs & b else "Not Active" for _n, b in bits]
                 self.samples.append(row)
-                self.stop_flag.wait(0.1)
+                # NVML queries and CUDA calls share a driver lock: sample sparsely (2 Hz) so the
+                # sampler itself does not stall the allocation calls of the timed steps
+                self.stop_flag.wait(0.5)
             return
         except Exception:
             pass

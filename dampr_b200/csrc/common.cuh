@@ -5,6 +5,7 @@
 #include <stdio.h>
 #include <string.h>
 #include <string>
+#include <unordered_map>
 #include <vector>
 
 #include "../../include/dampr_b200.h"
@@ -21,7 +22,18 @@ struct TimedKernel {
     cudaEvent_t beg, end;
 };
 
+struct PoolBlock {
+    void *p;
+    size_t bytes;
+    cudaEvent_t ev_compute, ev_copy;  // work that may still touch the block when it was released
+};
+
 struct dampr_ctx {
+    // device-memory pool: cudaMalloc / cudaFree take the driver's global lock (and cudaFree
+    // synchronises the device); steady-state calls recycle blocks instead
+    std::vector<PoolBlock> pool_free_list;
+    std::unordered_map<void *, size_t> pool_live;
+    size_t pool_cached_bytes = 0;
     int device;
     int num_sms;
     cudaStream_t stream;  // compute
@@ -100,6 +112,36 @@ static inline int set_err(dampr_ctx *ctx, int code, const char *fmt, const char 
             return DAMPR_ERR_ARG;                               \
         }                                                       \
     } while (0)
+
+void *pool_alloc(dampr_ctx *ctx, size_t bytes);  // nullptr on failure
+void pool_free(dampr_ctx *ctx, void *p);
+void pool_trim(dampr_ctx *ctx, size_t keep_bytes);
+
+// scratch device buffer from the pool of the context the current API call runs on
+extern thread_local dampr_ctx *tl_ctx;
+struct CtxScope {
+    dampr_ctx *prev;
+    explicit CtxScope(dampr_ctx *c) : prev(tl_ctx) { tl_ctx = c; }
+    ~CtxScope() { tl_ctx = prev; }
+};
+struct DevBuf {
+    void *p = nullptr;
+    dampr_ctx *owner = nullptr;
+    ~DevBuf() {
+        if (p) {
+            if (owner) pool_free(owner, p);
+            else cudaFree(p);
+        }
+    }
+    cudaError_t alloc(size_t bytes) {
+        owner = tl_ctx;
+        if (owner) {
+            p = pool_alloc(owner, bytes ? bytes : 16);
+            return p ? cudaSuccess : cudaErrorMemoryAllocation;
+        }
+        return cudaMalloc(&p, bytes ? bytes : 16);
+    }
+};
 
 // ---- kernel timing helpers (CUDA events on the launching stream) ----------------------
 struct ScopedTimer {

@@ -4,6 +4,84 @@
 #include "common.cuh"
 
 int g_text_kernel = 2;
+thread_local dampr_ctx *tl_ctx = nullptr;
+
+static const size_t POOL_MAX_CACHED = 6ULL << 30;
+
+void *pool_alloc(dampr_ctx *ctx, size_t bytes) {
+    bytes = (bytes + 255) & ~(size_t)255;
+    int best = -1;
+    for (int i = 0; i < (int)ctx->pool_free_list.size(); ++i) {
+        const PoolBlock &b = ctx->pool_free_list[i];
+        if (b.bytes >= bytes && b.bytes <= 2 * bytes + (1 << 20) &&
+            (best < 0 || b.bytes < ctx->pool_free_list[best].bytes))
+            best = i;
+    }
+    if (best >= 0) {
+        PoolBlock b = ctx->pool_free_list[best];
+        ctx->pool_free_list.erase(ctx->pool_free_list.begin() + best);
+        ctx->pool_cached_bytes -= b.bytes;
+        // the previous user's work must be complete before anybody (either stream) touches it again
+        cudaEventSynchronize(b.ev_compute);
+        cudaEventSynchronize(b.ev_copy);
+        cudaEventDestroy(b.ev_compute);
+        cudaEventDestroy(b.ev_copy);
+        ctx->pool_live[b.p] = b.bytes;
+        return b.p;
+    }
+    void *p = nullptr;
+    cudaError_t e = cudaMalloc(&p, bytes);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        pool_trim(ctx, 0);
+        e = cudaMalloc(&p, bytes);
+        if (e != cudaSuccess) {
+            cudaGetLastError();
+            return nullptr;
+        }
+    }
+    ctx->pool_live[p] = bytes;
+    return p;
+}
+
+void pool_free(dampr_ctx *ctx, void *p) {
+    if (!p) return;
+    auto it = ctx->pool_live.find(p);
+    if (it == ctx->pool_live.end()) {
+        cudaFree(p);
+        return;
+    }
+    PoolBlock b;
+    b.p = p;
+    b.bytes = it->second;
+    ctx->pool_live.erase(it);
+    if (b.bytes > (2ULL << 30) ||
+        cudaEventCreateWithFlags(&b.ev_compute, cudaEventDisableTiming) != cudaSuccess) {
+        cudaFree(p);
+        return;
+    }
+    if (cudaEventCreateWithFlags(&b.ev_copy, cudaEventDisableTiming) != cudaSuccess) {
+        cudaEventDestroy(b.ev_compute);
+        cudaFree(p);
+        return;
+    }
+    cudaEventRecord(b.ev_compute, ctx->stream);
+    cudaEventRecord(b.ev_copy, ctx->copy);
+    ctx->pool_free_list.push_back(b);
+    ctx->pool_cached_bytes += b.bytes;
+    if (ctx->pool_cached_bytes > POOL_MAX_CACHED || ctx->pool_free_list.size() > 256) pool_trim(ctx, POOL_MAX_CACHED / 2);
+}
+
+void pool_trim(dampr_ctx *ctx, size_t keep_bytes) {
+    while (!ctx->pool_free_list.empty() && (ctx->pool_cached_bytes > keep_bytes || ctx->pool_free_list.size() > 128)) {
+        PoolBlock b = ctx->pool_free_list.front();
+        ctx->pool_free_list.erase(ctx->pool_free_list.begin());
+        ctx->pool_cached_bytes -= b.bytes;
+        cudaEventDestroy(b.ev_compute);
+        cudaEventDestroy(b.ev_copy);
+        cudaFree(b.p);  // synchronises: safe regardless of the events
+    }
+}
 int g_text_ctas = 3;
 
 extern "C" {
@@ -60,6 +138,9 @@ int32_t dampr_ctx_destroy(dampr_ctx *ctx) {
         cudaEventDestroy(t.beg);
         cudaEventDestroy(t.end);
     }
+    pool_trim(ctx, 0);
+    for (auto &kv : ctx->pool_live) cudaFree(kv.first);
+    ctx->pool_live.clear();
     cudaEventDestroy(ctx->upload_done);
     cudaFree(ctx->d_scratch);
     cudaFreeHost(ctx->h_scratch);
@@ -229,10 +310,10 @@ int32_t dampr_kv_create(dampr_ctx *ctx, uint64_t capacity, dampr_kv **out) {
     kv->alt = nullptr;
     kv->rec = nullptr;
     u64 bytes = (capacity ? capacity : 1) * sizeof(ulonglong2);
-    cudaError_t e = cudaMalloc(&kv->rec, bytes);
-    if (e != cudaSuccess) {
+    kv->rec = (ulonglong2 *)pool_alloc(ctx, bytes);
+    if (!kv->rec) {
         delete kv;
-        ctx->err = std::string("cudaMalloc(kv) failed: ") + cudaGetErrorString(e);
+        ctx->err = "device allocation (kv) failed";
         return DAMPR_ERR_NOMEM;
     }
     *out = kv;
@@ -243,11 +324,12 @@ int32_t dampr_kv_destroy(dampr_ctx *ctx, dampr_kv *kv) {
     if (!kv) return DAMPR_OK;
     if (ctx) {
         cudaSetDevice(ctx->device);
-        cudaStreamSynchronize(ctx->stream);
-        cudaStreamSynchronize(ctx->copy);
+        pool_free(ctx, kv->rec);  // recycled once the work recorded on both streams has finished
+        if (kv->alt) pool_free(ctx, kv->alt);
+    } else {
+        cudaFree(kv->rec);
+        if (kv->alt) cudaFree(kv->alt);
     }
-    cudaFree(kv->rec);
-    if (kv->alt) cudaFree(kv->alt);
     delete kv;
     return DAMPR_OK;
 }

@@ -600,14 +600,6 @@ __global__ void group_heads_kernel(const ulonglong2 *__restrict__ in, u64 n, u64
 }
 
 // ---- host-side orchestration ------------------------------------------------------------------
-struct DevBuf {
-    void *p = nullptr;
-    ~DevBuf() {
-        if (p) cudaFree(p);
-    }
-    cudaError_t alloc(size_t bytes) { return cudaMalloc(&p, bytes ? bytes : 16); }
-};
-
 static int bits_for(u64 n, u64 leaf_avg) {
     int b = 0;
     while (((n + leaf_avg - 1) / leaf_avg) > (1ULL << b)) ++b;
@@ -881,10 +873,9 @@ static int sort_range(dampr_ctx *ctx, ulonglong2 *cur, ulonglong2 *alt, u64 star
 
 static int ensure_alt(dampr_ctx *ctx, dampr_kv *kv) {
     if (!kv->alt) {
-        cudaError_t e = cudaMalloc(&kv->alt, (kv->capacity ? kv->capacity : 1) * sizeof(ulonglong2));
-        if (e != cudaSuccess) {
-            ctx->err = std::string("cudaMalloc(kv scratch) failed: ") + cudaGetErrorString(e);
-            cudaGetLastError();
+        kv->alt = (ulonglong2 *)pool_alloc(ctx, (kv->capacity ? kv->capacity : 1) * sizeof(ulonglong2));
+        if (!kv->alt) {
+            ctx->err = "device allocation (kv scratch) failed";
             return DAMPR_ERR_NOMEM;
         }
     }
@@ -941,6 +932,7 @@ int32_t dampr_set_option(const char *name, int64_t value) {
 
 int32_t dampr_kv_sort(dampr_ctx *ctx, dampr_kv *kv, int32_t key_xf) {
     ARG_CHECK(ctx, ctx && kv, "null");
+    CtxScope scope_(ctx);
     ARG_CHECK(ctx, key_xf >= 0 && key_xf <= DAMPR_KEY_F64, "unknown key transform");
     CUDA_TRY(ctx, cudaSetDevice(ctx->device));
     wait_uploads(ctx);
@@ -956,6 +948,7 @@ int32_t dampr_kv_sort(dampr_ctx *ctx, dampr_kv *kv, int32_t key_xf) {
 
 int32_t dampr_kv_sort_reduce(dampr_ctx *ctx, dampr_kv *kv, int32_t key_xf, int32_t op, dampr_kv **out) {
     ARG_CHECK(ctx, ctx && kv && out, "null");
+    CtxScope scope_(ctx);
     ARG_CHECK(ctx, key_xf >= 0 && key_xf <= DAMPR_KEY_F64, "unknown key transform");
     ARG_CHECK(ctx, op >= 0 && op <= DAMPR_OP_LAST, "unknown reduce op");
     CUDA_TRY(ctx, cudaSetDevice(ctx->device));
@@ -985,6 +978,7 @@ int32_t dampr_kv_reduce_by_key(dampr_ctx *ctx, dampr_kv *sorted, int32_t op, dam
 int32_t dampr_kv_group_offsets(dampr_ctx *ctx, dampr_kv *sorted, uint64_t *offsets, uint64_t cap,
                                uint64_t *n_groups) {
     ARG_CHECK(ctx, ctx && sorted && n_groups, "null");
+    CtxScope scope_(ctx);
     CUDA_TRY(ctx, cudaSetDevice(ctx->device));
     wait_uploads(ctx);
     const u64 n = sorted->n;
@@ -1033,6 +1027,7 @@ extern "C" {
 int32_t dampr_kv_partition_by_owner(dampr_ctx *ctx, dampr_kv *kv, int32_t n_dest, dampr_kv **out,
                                     uint64_t *counts_host) {
     ARG_CHECK(ctx, ctx && kv && out && counts_host, "null");
+    CtxScope scope_(ctx);
     ARG_CHECK(ctx, n_dest >= 1 && n_dest <= P_MAX_NB, "n_dest out of range");
     CUDA_TRY(ctx, cudaSetDevice(ctx->device));
     wait_uploads(ctx);

@@ -223,14 +223,6 @@ __global__ void synth_kv_kernel(u64 seed, u64 n, u64 n_keys, ulonglong2 *__restr
     }
 }
 
-struct DevBuf {
-    void *p = nullptr;
-    ~DevBuf() {
-        if (p) cudaFree(p);
-    }
-    cudaError_t alloc(size_t bytes) { return cudaMalloc(&p, bytes ? bytes : 16); }
-};
-
 // group offsets of a key-sorted kv into a device array (G+1 entries, last = n)
 static int device_group_offsets(dampr_ctx *ctx, dampr_kv *kv, DevBuf &offs, u64 *G) {
     const u64 n = kv->n;
@@ -276,14 +268,14 @@ int32_t dampr_kv_upload_columns(dampr_ctx *ctx, dampr_kv *kv, uint64_t off, cons
     ARG_CHECK(ctx, off + count <= kv->capacity, "upload exceeds kv capacity");
     CUDA_TRY(ctx, cudaSetDevice(ctx->device));
     if (count) {
-        u64 *tmp = nullptr;
-        CUDA_TRY(ctx, cudaMallocAsync(&tmp, count * 16, ctx->copy));
+        u64 *tmp = (u64 *)pool_alloc(ctx, count * 16);
+        ARG_CHECK(ctx, tmp != nullptr, "device allocation failed");
         CUDA_TRY(ctx, cudaMemcpyAsync(tmp, keys, count * 8, cudaMemcpyHostToDevice, ctx->copy));
         if (vals) CUDA_TRY(ctx, cudaMemcpyAsync(tmp + count, vals, count * 8, cudaMemcpyHostToDevice, ctx->copy));
         ctx->launches++;
         interleave_kernel<<<ctx->num_sms * 4, 256, 0, ctx->copy>>>(tmp, vals ? tmp + count : nullptr, kv->rec + off, count);
         CUDA_TRY(ctx, cudaGetLastError());
-        CUDA_TRY(ctx, cudaFreeAsync(tmp, ctx->copy));
+        pool_free(ctx, tmp);
     }
     if (off + count > kv->n) kv->n = off + count;
     CUDA_TRY(ctx, cudaEventRecord(ctx->upload_done, ctx->copy));
@@ -298,21 +290,22 @@ int32_t dampr_kv_download_columns(dampr_ctx *ctx, dampr_kv *kv, uint64_t off, ui
     CUDA_TRY(ctx, cudaSetDevice(ctx->device));
     wait_uploads(ctx);
     if (count == 0) return DAMPR_OK;
-    u64 *tmp = nullptr;
-    CUDA_TRY(ctx, cudaMallocAsync(&tmp, count * 16, ctx->stream));
+    u64 *tmp = (u64 *)pool_alloc(ctx, count * 16);
+    ARG_CHECK(ctx, tmp != nullptr, "device allocation failed");
     ctx->launches++;
     deinterleave_kernel<<<ctx->num_sms * 4, 256, 0, ctx->stream>>>(kv->rec + off, tmp, tmp + count, count);
     CUDA_TRY(ctx, cudaGetLastError());
     if (keys) CUDA_TRY(ctx, cudaMemcpyAsync(keys, tmp, count * 8, cudaMemcpyDeviceToHost, ctx->stream));
     if (vals) CUDA_TRY(ctx, cudaMemcpyAsync(vals, tmp + count, count * 8, cudaMemcpyDeviceToHost, ctx->stream));
-    CUDA_TRY(ctx, cudaFreeAsync(tmp, ctx->stream));
     CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    pool_free(ctx, tmp);
     return DAMPR_OK;
 }
 
 int32_t dampr_kv_join_ranges(dampr_ctx *ctx, dampr_kv *left_sorted, dampr_kv *right_sorted, int32_t key_xf,
                              uint64_t *rows, uint64_t cap, uint64_t *n_rows) {
     ARG_CHECK(ctx, ctx && left_sorted && right_sorted && n_rows, "null");
+    CtxScope scope_(ctx);
     CUDA_TRY(ctx, cudaSetDevice(ctx->device));
     wait_uploads(ctx);
     DevBuf lo, ro;
@@ -343,6 +336,7 @@ int32_t dampr_kv_join_ranges(dampr_ctx *ctx, dampr_kv *left_sorted, dampr_kv *ri
 int32_t dampr_kv_hash_probe(dampr_ctx *ctx, dampr_kv *build, dampr_kv *probe, dampr_kv **out_vals,
                             uint8_t *out_hit_host) {
     ARG_CHECK(ctx, ctx && build && probe && out_vals && out_hit_host, "null");
+    CtxScope scope_(ctx);
     CUDA_TRY(ctx, cudaSetDevice(ctx->device));
     wait_uploads(ctx);
     int rc = dampr_kv_create(ctx, probe->n, out_vals);
@@ -380,6 +374,7 @@ int32_t dampr_synth_text(dampr_ctx *ctx, dampr_textbuf *tb, uint64_t seed, uint6
                          const uint8_t *vocab_bytes, const uint32_t *vocab_off, uint32_t vocab_n,
                          const uint64_t *cdf, uint64_t *out_nbytes) {
     ARG_CHECK(ctx, ctx && tb && vocab_bytes && vocab_off && cdf && out_nbytes && vocab_n > 0, "null");
+    CtxScope scope_(ctx);
     CUDA_TRY(ctx, cudaSetDevice(ctx->device));
     DevBuf d_vb, d_vo, d_cdf, d_len, d_off;
     const u64 vbytes = vocab_off[vocab_n];

@@ -733,8 +733,8 @@ int32_t dampr_table_fetch(dampr_ctx *ctx, dampr_table *t, uint64_t *codes, uint6
     ARG_CHECK(ctx, cap >= st[0], "fetch arrays too small");
     u64 m = st[0];
     if (m == 0) return DAMPR_OK;
-    u64 *d = nullptr;
-    CUDA_TRY(ctx, cudaMalloc(&d, (3 * m + 1) * 8));
+    u64 *d = (u64 *)pool_alloc(ctx, (3 * m + 1) * 8);
+    ARG_CHECK(ctx, d != nullptr, "device allocation failed");
     CUDA_TRY(ctx, cudaMemsetAsync(d + 3 * m, 0, 8, ctx->stream));
     {
         ScopedTimer tm(ctx, DAMPR_K_TABLE_EXTRACT);
@@ -746,7 +746,7 @@ int32_t dampr_table_fetch(dampr_ctx *ctx, dampr_table *t, uint64_t *codes, uint6
     if (e == cudaSuccess && counts) e = cudaMemcpyAsync(counts, d + m, m * 8, cudaMemcpyDeviceToHost, ctx->stream);
     if (e == cudaSuccess && reps) e = cudaMemcpyAsync(reps, d + 2 * m, m * 8, cudaMemcpyDeviceToHost, ctx->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
-    cudaFree(d);
+    pool_free(ctx, d);
     if (e != cudaSuccess) {
         ctx->err = std::string("table fetch failed: ") + cudaGetErrorString(e);
         return DAMPR_ERR_CUDA;
@@ -853,9 +853,9 @@ extern "C" int32_t dampr_table_fetch_words(dampr_ctx *ctx, dampr_table *t, dampr
     ARG_CHECK(ctx, cap >= st[0] && counts && codes && reps, "fetch arrays too small");
     u64 m = st[0];
     if (m == 0) return DAMPR_OK;
-    u8 *d = nullptr;
     u64 per = width + 24;
-    CUDA_TRY(ctx, cudaMalloc(&d, m * per + 8));
+    u8 *d = (u8 *)pool_alloc(ctx, m * per + 8);
+    ARG_CHECK(ctx, d != nullptr, "device allocation failed");
     u8 *d_words = d;
     u64 *d_counts = (u64 *)(d + m * width);
     u64 *d_codes = d_counts + m;
@@ -874,7 +874,7 @@ extern "C" int32_t dampr_table_fetch_words(dampr_ctx *ctx, dampr_table *t, dampr
     if (e == cudaSuccess) e = cudaMemcpyAsync(codes, d_codes, m * 8, cudaMemcpyDeviceToHost, ctx->stream);
     if (e == cudaSuccess) e = cudaMemcpyAsync(reps, d_reps, m * 8, cudaMemcpyDeviceToHost, ctx->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
-    cudaFree(d);
+    pool_free(ctx, d);
     if (e != cudaSuccess) {
         ctx->err = std::string("table fetch_words failed: ") + cudaGetErrorString(e);
         return DAMPR_ERR_CUDA;
@@ -990,8 +990,8 @@ extern "C" int32_t dampr_kv_decode_words(dampr_ctx *ctx, dampr_kv *kv, int32_t m
     ARG_CHECK(ctx, width >= 16 && width <= 256 && (width % 8) == 0, "width must be a multiple of 8 in [16, 256]");
     if (kv->n == 0) return DAMPR_OK;
     wait_uploads(ctx);
-    u8 *d = nullptr;
-    CUDA_TRY(ctx, cudaMalloc(&d, kv->n * width));
+    u8 *d = (u8 *)pool_alloc(ctx, kv->n * width);
+    ARG_CHECK(ctx, d != nullptr, "device allocation failed");
     {
         ScopedTimer tm(ctx, DAMPR_K_TABLE_EXTRACT);
         kv_words_kernel<<<ctx->num_sms * 4, 256, 0, ctx->stream>>>(kv->rec, kv->n, mode, width, d);
@@ -999,7 +999,7 @@ extern "C" int32_t dampr_kv_decode_words(dampr_ctx *ctx, dampr_kv *kv, int32_t m
     cudaError_t e = cudaGetLastError();
     if (e == cudaSuccess) e = cudaMemcpyAsync(words_host, d, kv->n * width, cudaMemcpyDeviceToHost, ctx->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
-    cudaFree(d);
+    pool_free(ctx, d);
     if (e != cudaSuccess) {
         ctx->err = std::string("kv decode_words failed: ") + cudaGetErrorString(e);
         return DAMPR_ERR_CUDA;
