@@ -933,7 +933,7 @@ extern "C" int32_t dampr_host_join_tsv(uint64_t n, int32_t ncols, const int32_t 
     if (!kinds || !ptrs || !out_len || ncols < 1 || ncols > 16) return DAMPR_ERR_ARG;
     JoinArgs a{n, ncols, kinds, ptrs, widths, aux, aux2};
     unsigned hw = std::thread::hardware_concurrency();
-    int T = (int)std::min<u64>(std::max(1u, std::min(hw, 16u)), std::max<u64>(1, n / 65536));
+    int T = (int)std::min<u64>(std::max(1u, std::min(hw, 16u)), std::max<u64>(1, n / 16384));
     std::vector<u64> lens(T, 0), offs(T + 1, 0);
     auto span = [&](int t) { return std::make_pair(n * t / T, n * (t + 1) / T); };
     {
