@@ -325,8 +325,19 @@ def main():
         per_launch_ms = sum(tc) / len(tc)
         per_launch_bytes = nbytes * args.steps / len(tc)
         ach = per_launch_bytes / (per_launch_ms * 1e-3) / 1e9
+        traffic, traffic_src = None, None
+        try:
+            with open(os.path.join(ROOT, "profiles", "r01_text_traffic.json")) as f:
+                tj = json.load(f)
+            # dram__bytes_read+write of one ncu --set full capture of this kernel, scaled from the
+            # captured launch (250 MB of the same corpus) to this launch's bytes
+            traffic = tj["dram_bytes_per_input_byte"] * per_launch_bytes
+            traffic_src = "ncu capture scaled per input byte: " + tj["source"]
+        except Exception:
+            pass
         roof = {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-                "traffic": None, "kernel": "text_count_kernel<NONWORD_LOWER_SET>",
+                "traffic": traffic, "traffic_source": traffic_src,
+                "kernel": "text_count2_kernel<NONWORD_LOWER_SET> (csrc/text2.cu)",
                 "algorithmic_bytes_per_launch": per_launch_bytes, "ms_per_launch": per_launch_ms,
                 "peak_source": peak_kind + " (MEASURED_PEAKS.json hbm_gbs)"}
 

@@ -325,6 +325,69 @@ leaf_sort_kernel(ulonglong2 *__restrict__ data, ulonglong2 *__restrict__ out, co
             }
         }
         __syncthreads();
+        // ---- commutative integer folds under the MIX order (a_group_by(...).sum()/count()/min()/max()):
+        // no sort at all. Every record looks its key up in a shared-memory index (slot -> first record
+        // holding the key) and folds its value into that record with a shared-memory atomic: O(1) per
+        // record however many duplicates a key has (the sort path ranks inside bins: O(duplicates)).
+        if (xf == DAMPR_KEY_MIX && (reduce_op == DAMPR_OP_SUM_I64 || reduce_op == DAMPR_OP_COUNT ||
+                                    reduce_op == DAMPR_OP_MIN_I64 || reduce_op == DAMPR_OP_MAX_I64)) {
+            for (u32 i = tid; i < L_BINS; i += L_THREADS) s.cur[i] = 0;  // cnt[] is the index (zeroed above)
+            if (reduce_op == DAMPR_OP_COUNT)
+                for (u32 i = tid; i < n; i += L_THREADS) s.rec[i].y = 1ULL;
+            __syncthreads();
+            for (u32 i = tid; i < n; i += L_THREADS) {
+                const u64 ki = s.sk[i];
+                u32 slot = (u32)(ki >> 13) & (L_BINS - 1);  // the partition consumed the top bits
+                slot = (slot ^ (u32)(ki >> 37)) & (L_BINS - 1);
+                for (;;) {
+                    u32 cur = s.cnt[slot];
+                    if (cur == 0) {
+                        cur = atomicCAS(&s.cnt[slot], (unsigned short)0, (unsigned short)(i + 1));
+                        if (cur == 0) {
+                            s.cur[i] = 1;  // this record represents its key
+                            break;
+                        }
+                    }
+                    if (s.sk[cur - 1] == ki) {
+                        unsigned long long *acc = &s.rec[cur - 1].y;
+                        const u64 v = s.rec[i].y;
+                        if (reduce_op == DAMPR_OP_MIN_I64) atomicMin((long long *)acc, (long long)v);
+                        else if (reduce_op == DAMPR_OP_MAX_I64) atomicMax((long long *)acc, (long long)v);
+                        else atomicAdd(acc, v);
+                        break;
+                    }
+                    slot = (slot + 1) & (L_BINS - 1);
+                }
+            }
+            __syncthreads();
+            // compact the representatives (in record order)
+            constexpr int IPT = L_CAP / L_THREADS;
+            u32 flags = 0;
+#pragma unroll
+            for (int k = 0; k < IPT; ++k) {
+                u32 p = tid * IPT + k;
+                if (p < n && s.cur[p]) flags |= 1u << k;
+            }
+            u32 cntl = __popc(flags), v = cntl;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                u32 o = __shfl_up_sync(0xFFFFFFFFu, v, d);
+                if ((int)lane >= d) v += o;
+            }
+            if (lane == 31) s.wsum[warp] = v;
+            __syncthreads();
+            u32 woff = 0;
+            for (u32 w = 0; w < warp; ++w) woff += s.wsum[w];
+            u32 gidx = woff + v - cntl;
+            if (tid == L_THREADS - 1) s.total_groups = woff + v;
+#pragma unroll
+            for (int k = 0; k < IPT; ++k)
+                if (flags & (1u << k)) out[ch.start + gidx++] = s.rec[tid * IPT + k];
+            __syncthreads();
+            if (tid == 0) chunk_groups[c] = s.total_groups;
+            __syncthreads();
+            continue;
+        }
         // counting with u16 counters packed two per u32 word: use 32-bit atomics on the pair
         u32 *cnt32 = reinterpret_cast<u32 *>(s.cnt);
         for (u32 i = tid; i < n; i += L_THREADS) {

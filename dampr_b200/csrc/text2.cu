@@ -57,6 +57,7 @@ enum { S_ENTRIES = 0, S_LINES = 1, S_EMPTY = 2, S_FOLDED = 3, S_FLAGS = 4, S_LON
 template <int HCAP>
 struct WarpScratchT {
     alignas(8) u64 hist[HCAP];
+    alignas(8) u64 missq[64];  // keys that missed the shared-memory combiner, flushed 32 at a time
     u16 tpos[V_TPOS];
 };
 
@@ -354,6 +355,7 @@ text_count2_kernel(const u8 *__restrict__ text, u64 n, u64 own_lo, u64 own_hi, u
         u32 hist_n = 0;
         u32 hist_line = 0xFFFFFFFFu;
         u32 line_base = 0;
+        u32 nq = 0;  // queued combiner misses (warp-uniform)
         for (u32 wb = rlo >> 5; wb * 32 < rhi; wb += 32) {
             const u32 wi = wb + lane;
             u32 stm = 0, nlm = 0, wmk = 0;
@@ -502,6 +504,7 @@ text_count2_kernel(const u8 *__restrict__ text, u64 n, u64 own_lo, u64 own_hi, u
                 }
                 const bool ins = live && !hashed;
                 const u32 imask = __ballot_sync(0xFFFFFFFFu, ins);
+                bool miss = false;
                 // every inserting lane looks its slot pair up (convergent loads); one lane per distinct
                 // key then updates the combiner
                 u32 h = (u32)key * 0x9E3779B1u ^ (u32)(key >> 32) * 0x85EBCA6Bu;
@@ -540,11 +543,32 @@ text_count2_kernel(const u8 *__restrict__ text, u64 n, u64 own_lo, u64 own_hi, u
                                 }
                                 slot = (slot + 1) & (V_STAB - 1);
                             }
-                            if (!placed) gtab_add2(tab, key, (u64)cnt, ~0ULL);
+                            if (!placed) {
+#if DAMPR_TEXT_USE_MATCH
+                                gtab_add2(tab, key, (u64)cnt, ~0ULL);
+#else
+                                miss = true;
+#endif
+                            }
                         }
                     }
                 }
                 (void)lmask;
+                // misses go to the L2-resident global table in convergent batches of 32 (all lanes issue
+                // their load + atomic together) instead of a few lanes at a time inside every round
+                {
+                    const u32 mm = __ballot_sync(0xFFFFFFFFu, miss);
+                    if (mm) {
+                        if (miss) ws.missq[nq + __popc(mm & lt_mask)] = key;
+                        nq += (u32)__popc(mm);
+                        __syncwarp();
+                        if (nq >= 32) {
+                            const u64 qk = ws.missq[nq - 32 + lane];
+                            gtab_add2(tab, qk, 1ULL, ~0ULL);
+                            nq -= 32;
+                        }
+                    }
+                }
                 __syncwarp();
             }
             line_base += tot >> 16;
@@ -582,6 +606,10 @@ text_count2_kernel(const u8 *__restrict__ text, u64 n, u64 own_lo, u64 own_hi, u
                     else acc_empty += (A ? 1 : 0) + (B ? 1 : 0);
                 }
             }
+            __syncwarp();
+        }
+        if (nq) {  // leftover misses of this strip
+            if (lane < nq) gtab_add2(tab, ws.missq[lane], 1ULL, ~0ULL);
             __syncwarp();
         }
         };

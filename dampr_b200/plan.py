@@ -702,7 +702,7 @@ def _lower_kv_map(runner, stage, inputs):
         kind = lowering.binop_kind(binop)
         if kind not in _FOLD_OPS or vals.dtype not in (np.int64, np.uint64):
             return None
-        if kind == lowering.ADD and n and float(np.abs(vals.astype(np.float64)).sum()) >= float(1 << 62):
+        if kind == lowering.ADD and n and _may_overflow(vals):
             raise NotLowerable("64-bit sum could overflow (SURVEY B12)")
         op = dev.OP_COUNT if (count_only and kind == lowering.ADD) else _FOLD_OPS[kind]
         rk, rv, how = _device_group(runner, keys, vals, op, dev.KEY_MIX)
@@ -710,12 +710,64 @@ def _lower_kv_map(runner, stage, inputs):
         runner.stats.add(stage, "device kv partition+sort+segmented-reduce" + how, "records=%d groups=%d" % (n, len(rk)))
         return f
     if stage.combiner is None:
-        rk, rv, how = _device_group(runner, keys, vals, None, _key_xform_for(keys))
-        f = Frame(rk.view(keys.dtype), [rv.view(vals.dtype)], scalar=True)
+        # group_by: the partition + sort is deferred until somebody reads the grouped records; when the
+        # only consumer is a lowered reduce (sum(it), len, min, max) the sort and the fold run as ONE
+        # device pass (or one spill pipeline) over the original columns
+        f = LazyKVFrame(runner, keys, vals, _key_xform_for(keys))
         f.meta["sorted_kv"] = True
-        runner.stats.add(stage, "device kv partition+sort" + how, "records=%d" % n)
+        runner.stats.add(stage, "device kv partition+sort (deferred until read; fused into a lowered reduce)",
+                         "records=%d" % n)
         return f
     return None
+
+
+class LazyKVFrame(Frame):
+    """Grouped kv records whose device sort happens on first access."""
+
+    def __init__(self, runner, keys, vals, xform):
+        self._runner, self._rk, self._rv, self._xf = runner, keys, vals, xform
+        self._done = False
+        self.scalar, self.combined, self.meta = True, False, {}
+        self.n = len(keys)
+
+    def raw(self):
+        return self._rk, self._rv
+
+    def _materialise(self):
+        if not self._done:
+            rk, rv, how = _device_group(self._runner, self._rk, self._rv, None, self._xf)
+            self._keys = rk.view(self._rk.dtype)
+            self._cols = [rv.view(self._rv.dtype)]
+            self._done = True
+            self.meta["how"] = how
+
+    @property
+    def keys(self):
+        self._materialise()
+        return self._keys
+
+    @keys.setter
+    def keys(self, v):
+        self._keys = v
+
+    @property
+    def cols(self):
+        self._materialise()
+        return self._cols
+
+    @cols.setter
+    def cols(self, v):
+        self._cols = v
+
+    def delete(self):
+        self._rk = self._rv = None
+        self._keys, self._cols, self._done, self.n = None, [[]], True, 0
+
+
+def _may_overflow(vals):
+    """Cheap bound for Python-int semantics: n * max|v| must stay far below 2^63."""
+    lo, hi = int(vals.min()), int(vals.max())
+    return len(vals) * max(abs(lo), abs(hi)) >= (1 << 62)
 
 
 def _device_group(runner, keys, vals, op, xform):
@@ -1034,13 +1086,25 @@ def _lower_reduce(runner, stage, inputs):
             out = Frame(fr.keys, [fr.keys, fr.cols[0]], scalar=False, combined=True)
             runner.stats.add(stage, "keyed fold over a fully combined frame (relabel)", "records=%d" % fr.n)
             return out
+        if isinstance(red, ops.KeyedReduce) and isinstance(fr, LazyKVFrame) and not fr._done:
+            kind = lowering.group_reducer_kind(red.reducer)
+            opmap = {lowering.SUM: dev.OP_SUM_I64, lowering.COUNT: dev.OP_COUNT, lowering.MIN: dev.OP_MIN_I64,
+                     lowering.MAX: dev.OP_MAX_I64}
+            keys, vals = fr.raw()
+            if kind in opmap and vals.dtype.kind in "iu" and not (kind == lowering.SUM and len(vals) and _may_overflow(vals)):
+                rk, rv, how = _device_group(runner, keys, vals, opmap[kind], dev.KEY_MIX)
+                rk = rk.view(keys.dtype)
+                out = Frame(rk, [rk, rv.view(np.int64)], scalar=False, combined=True)
+                runner.stats.add(stage, "device kv partition+sort+segmented-reduce (fused group_by + reduce)" + how,
+                                 "records=%d groups=%d" % (len(keys), len(rk)))
+                return out
         if isinstance(red, ops.KeyedReduce) and fr.meta.get("sorted_kv") and fr.scalar and _numeric(fr.cols[0]):
             kind = lowering.group_reducer_kind(red.reducer)
             opmap = {lowering.SUM: dev.OP_SUM_I64, lowering.COUNT: dev.OP_COUNT, lowering.MIN: dev.OP_MIN_I64,
                      lowering.MAX: dev.OP_MAX_I64}
             if kind in opmap and fr.cols[0].dtype.kind in "iu" and isinstance(fr.keys, np.ndarray):
                 vals = fr.cols[0]
-                if kind == lowering.SUM and fr.n and float(np.abs(vals.astype(np.float64)).sum()) >= float(1 << 62):
+                if kind == lowering.SUM and fr.n and _may_overflow(vals):
                     return None
                 rk, rv, how = _device_group(runner, fr.keys, vals, opmap[kind], _key_xform_for(fr.keys))
                 rk = rk.view(fr.keys.dtype)

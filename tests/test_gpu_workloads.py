@@ -124,7 +124,7 @@ def test_kv_workloads_match_reference_golden(ctx, tmp_path):
     assert sorted(src.count(lambda x: x[0]).read()) == [tuple(r) for r in fix["count"]]
     assert sorted(src.group_by(lambda x: x[0], lambda x: x[1]).reduce(lambda k, it: sum(it)).read()) == \
         [tuple(r) for r in fix["group_sum"]]
-    assert lowered("device segmented reduce of sorted kv")
+    assert lowered("fused group_by + reduce")
     assert sorted(src.a_group_by(lambda x: x[0], lambda x: x[1]).reduce(max).read()) == [tuple(r) for r in fix["max"]]
     assert sorted(src.mean(lambda x: x[0], lambda x: x[1]).read()) == [tuple(r) for r in fix["mean"]]
     srt = src.map(lambda x: x[1]).sort_by(lambda v: v).read()
