@@ -356,7 +356,6 @@ text_count2_kernel(const u8 *__restrict__ text, u64 n, u64 own_lo, u64 own_hi, u
         u32 hist_line = 0xFFFFFFFFu;
         u32 line_base = 0;
         u32 nq = 0;  // queued combiner misses (warp-uniform)
-        u32 hist_blo = 0, hist_bhi = 0;  // Bloom word of the history keys
         for (u32 wb = rlo >> 5; wb * 32 < rhi; wb += 32) {
             const u32 wi = wb + lane;
             u32 stm = 0, nlm = 0, wmk = 0;
@@ -412,7 +411,6 @@ text_count2_kernel(const u8 *__restrict__ text, u64 n, u64 own_lo, u64 own_hi, u
                     line = nb_ + (u32)__popc(nlw & ((1u << (pos & 31)) - 1u));
                 }
                 bool dup = !valid;
-                u32 my_blo = 0, my_bhi = 0;
                 if (MODE == DAMPR_TOK_NONWORD_LOWER_SET) {
 #if DAMPR_TEXT_USE_MATCH
                     u32 m1 = 0, m2 = 0;
@@ -431,58 +429,35 @@ text_count2_kernel(const u8 *__restrict__ text, u64 n, u64 own_lo, u64 own_hi, u
                         const u32 prev_line = __shfl_up_sync(0xFFFFFFFFu, lkey, 1);
                         const u32 seg_start = __ballot_sync(0xFFFFFFFFu, lane == 0 || prev_line != lkey);
                         const u32 dist = lane - (31u - (u32)__clz(seg_start & (lt_mask | (1u << lane))));
+                        const u32 maxd = __reduce_max_sync(0xFFFFFFFFu, valid ? dist : 0u);
                         const u32 fold = (u32)key ^ (u32)(key >> 32);
-                        // 64-bit Bloom word per line: a segmented OR-scan over the earlier lanes of the same
-                        // line tells which tokens CAN have an earlier twin; only those enter the exact loop
-                        const u32 bidx = (fold * 0x9E3779B1u) >> 26;
-                        const u32 blo = bidx < 32 ? (1u << bidx) : 0u, bhi = bidx >= 32 ? (1u << (bidx - 32)) : 0u;
-                        u32 alo = valid ? blo : 0u, ahi = valid ? bhi : 0u;
-#pragma unroll
-                        for (int d = 1; d < 32; d <<= 1) {
-                            const u32 olo = __shfl_up_sync(0xFFFFFFFFu, alo, d);
-                            const u32 ohi = __shfl_up_sync(0xFFFFFFFFu, ahi, d);
-                            if ((u32)d <= dist) {
-                                alo |= olo;
-                                ahi |= ohi;
-                            }
-                        }
-                        const u32 plo = __shfl_up_sync(0xFFFFFFFFu, alo, 1), phi = __shfl_up_sync(0xFFFFFFFFu, ahi, 1);
-                        const bool maybe = valid && dist > 0 && ((plo & blo) | (phi & bhi));
-                        const u32 maxd = __reduce_max_sync(0xFFFFFFFFu, maybe ? dist : 0u);
                         for (u32 d = 1; d <= maxd; ++d) {
                             const u32 of = __shfl_up_sync(0xFFFFFFFFu, fold, d);
-                            const bool cand = maybe && d <= dist && of == fold;
+                            const bool cand = valid && d <= dist && of == fold;
                             if (__any_sync(0xFFFFFFFFu, cand)) {
                                 const u64 ok = __shfl_up_sync(0xFFFFFFFFu, key, d);
                                 if (cand && ok == key) dup = true;
                             }
                         }
-                        // tokens of the line that started in an earlier round: compare with its history, again
-                        // only when the history's Bloom word admits a match
-                        const bool in_hist_line = valid && line == hist_line;
-                        const bool hmaybe = in_hist_line && ((hist_blo & blo) | (hist_bhi & bhi));
-                        if (__ballot_sync(0xFFFFFFFFu, hmaybe)) {
-                            for (u32 j = 0; j < hist_n; ++j) {
-                                u64 hk = ws.hist[j];
-                                if (hmaybe && hk == key) dup = true;
-                            }
-                        }
-                        my_blo = blo;
-                        my_bhi = bhi;
                     }
 #endif
+                    // tokens of the line that started in an earlier round: compare with its history
+                    const bool in_hist_line = valid && line == hist_line;
+                    if (__ballot_sync(0xFFFFFFFFu, in_hist_line)) {
+                        for (u32 j = 0; j < hist_n; ++j) {
+                            u64 hk = ws.hist[j];
+                            if (in_hist_line && hk == key) dup = true;
+                        }
+                    }
                     // new history = distinct tokens of the line the last token of this round belongs to
                     const u32 last_lane = 31u - (u32)__clz(vmask);
                     const u32 last_line = __shfl_sync(0xFFFFFFFFu, line, last_lane);
                     if (last_line != hist_line) {
                         hist_line = last_line;
                         hist_n = 0;
-                        hist_blo = hist_bhi = 0;
                     }
                     const bool add = valid && !dup && line == last_line;
                     const u32 am = __ballot_sync(0xFFFFFFFFu, add);
-                    hist_blo |= __reduce_or_sync(0xFFFFFFFFu, add ? my_blo : 0u);
-                    hist_bhi |= __reduce_or_sync(0xFFFFFFFFu, add ? my_bhi : 0u);
                     const u32 na = (u32)__popc(am);
                     if (hist_n + na > (u32)HCAP) {
                         my_flags |= DAMPR_TF_LONGLINE;
