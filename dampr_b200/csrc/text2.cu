@@ -54,16 +54,19 @@ struct TableView2 {
 };
 enum { S_ENTRIES = 0, S_LINES = 1, S_EMPTY = 2, S_FOLDED = 3, S_FLAGS = 4, S_LONG = 5, S_RAW = 6 };
 
-template <int HCAP>
+// WS (str.split mode): no per-line history; the miss queue also carries the representative of a long token
+template <int HCAP, bool WS>
 struct WarpScratchT {
-    alignas(8) u64 hist[HCAP];
+    alignas(8) u64 hist[WS ? 1 : HCAP];
     alignas(8) u64 missq[64];  // keys that missed the shared-memory combiner, flushed 32 at a time
+    alignas(8) u64 missr[WS ? 64 : 1];
     u16 tpos[V_TPOS];
 };
+constexpr u32 V_REP_UNPUB = 0xFFFFFFFFu;
 
 // NBUF = 2: double-buffered window, 2 CTAs/SM. NBUF = 1: single window, 3 CTAs/SM (more warps to
 // hide the smem / dependency latencies the ncu profile shows; the other CTAs cover the TMA wait).
-template <int NBUF>
+template <int NBUF, bool WS>
 struct Smem2T {
     static constexpr int HCAP = (NBUF == 2) ? V_HCAP : V_HCAP / 2;
     alignas(16) u8 text[NBUF][V_WIN];
@@ -71,7 +74,9 @@ struct Smem2T {
     u32 nl[NBUF][V_WORDS + 3];
     alignas(8) u64 tabk[V_STAB];
     u32 tabc[V_STAB];
-    WarpScratchT<HCAP> ws[V_WARPS];
+    // str.split mode: last occurrence (byte offset from own_lo - V_LEAD) of the long token an entry holds
+    u32 tabr[WS ? V_STAB : 1];
+    WarpScratchT<HCAP, WS> ws[V_WARPS];
     alignas(8) u64 bar[2];
     u32 flags;
 };
@@ -239,17 +244,40 @@ __device__ __forceinline__ u64 token_code2(const u8 *text, u32 pos, u32 len, con
     return h | 0x8000000000000000ULL;
 }
 
+// str.split mode: is the token of `len` bytes at a equal to the token that STARTS at b? (b's token must
+// also end after len bytes.)  Aligned 4-byte loads + funnel shifts; reads up to 7 bytes past the tokens,
+// which the window halo / the text buffer's tail pad cover.
+__device__ __forceinline__ bool tok_equal_ws(const u8 *a, const u8 *b, u32 len) {
+    const u32 *aw = reinterpret_cast<const u32 *>(reinterpret_cast<uintptr_t>(a) & ~(uintptr_t)3);
+    const u32 *bw = reinterpret_cast<const u32 *>(reinterpret_cast<uintptr_t>(b) & ~(uintptr_t)3);
+    const u32 sa = (u32)(reinterpret_cast<uintptr_t>(a) & 3) * 8u, sb = (u32)(reinterpret_cast<uintptr_t>(b) & 3) * 8u;
+    u32 a0 = aw[0], b0 = bw[0], diff = 0, i = 0;
+    for (; i + 4 <= len; i += 4) {
+        const u32 a1 = aw[(i >> 2) + 1], b1 = bw[(i >> 2) + 1];
+        diff |= __funnelshift_r(a0, a1, sa) ^ __funnelshift_r(b0, b1, sb);
+        a0 = a1;
+        b0 = b1;
+    }
+    const u32 a1 = aw[(i >> 2) + 1], b1 = bw[(i >> 2) + 1];
+    const u32 xa = __funnelshift_r(a0, a1, sa), xb = __funnelshift_r(b0, b1, sb);
+    const u32 rem = len - i;  // 0..3
+    diff |= (xa ^ xb) & ((1u << (8u * rem)) - 1u);
+    const u32 term = (xb >> (8u * rem)) & 0xFFu;
+    return diff == 0 && !is_word_byte<DAMPR_TOK_WS>(term);
+}
+
 template <int MODE, int NBUF>
 __global__ void __launch_bounds__(V_THREADS, (NBUF == 2) ? 2 : 3)
 text_count2_kernel(const u8 *__restrict__ text, u64 n, u64 own_lo, u64 own_hi, u64 base_offset, TableView2 tab) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    typedef Smem2T<NBUF> Smem2;
+    constexpr bool WS = (MODE == DAMPR_TOK_WS);
+    typedef Smem2T<NBUF, WS> Smem2;
     constexpr int HCAP = Smem2::HCAP;
     Smem2 &s = *reinterpret_cast<Smem2 *>(smem_raw);
     const u32 tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const u32 lt_mask = (1u << lane) - 1u;
     const u64 ntiles = (own_hi - own_lo + V_OWN - 1) / V_OWN;
-    WarpScratchT<HCAP> &ws = s.ws[warp];
+    WarpScratchT<HCAP, WS> &ws = s.ws[warp];
 
     if (tid == 0) {
         mbar_init(&s.bar[0], 1);
@@ -260,12 +288,35 @@ text_count2_kernel(const u8 *__restrict__ text, u64 n, u64 own_lo, u64 own_hi, u
     for (int i = tid; i < V_STAB; i += V_THREADS) {
         s.tabk[i] = 0;
         s.tabc[i] = 0;
+        if (WS) s.tabr[i] = V_REP_UNPUB;
     }
     __syncthreads();
 
     u64 acc_lines = 0, acc_empty = 0, acc_folded = 0, acc_long = 0, acc_raw = 0;
     u32 my_flags = 0;
     u32 phase[2] = {0, 0};
+
+    // add cnt occurrences of a long token to the global table; false if the representative the entry
+    // already holds is a different string (a 64-bit code collision).  atomicMin hands back the
+    // representative an earlier token of this code published; comparing every later one with it proves by
+    // induction that the entry holds ONE token, so a collision cannot merge two words silently.
+    auto hashed_insert = [&](u64 k, u64 rep, u64 cnt) -> bool {
+        const u64 old = gtab_add2(tab, k, cnt, rep);
+        if (old == ~0ULL || old == rep) return true;
+        const u32 l2 = (u32)(rep & 0xFFFFFu);
+        if ((u32)(old & 0xFFFFFu) != l2) return false;
+        const u8 *pa = text + ((rep >> 20) - base_offset);
+        const u8 *pb = text + ((old >> 20) - base_offset);
+        if (WS) return tok_equal_ws(pa, pb, l2);
+        bool same = true;
+        for (u32 i = 0; same && i < l2; ++i) {
+            u32 ca = pa[i], cb = pb[i];
+            if (ca >= 'A' && ca <= 'Z') ca |= 0x20;
+            if (cb >= 'A' && cb <= 'Z') cb |= 0x20;
+            same = ca == cb;
+        }
+        return same;
+    };
 
     u64 tile = blockIdx.x;
     if (tile < ntiles && tid == 0) {
@@ -355,7 +406,7 @@ text_count2_kernel(const u8 *__restrict__ text, u64 n, u64 own_lo, u64 own_hi, u
         u32 hist_n = 0;
         u32 hist_line = 0xFFFFFFFFu;
         u32 line_base = 0;
-        u32 nq = 0;  // queued combiner misses (warp-uniform)
+        u32 nq = 0;   // queued combiner misses (warp-uniform)
         for (u32 wb = rlo >> 5; wb * 32 < rhi; wb += 32) {
             const u32 wi = wb + lane;
             u32 stm = 0, nlm = 0, wmk = 0;
@@ -471,38 +522,22 @@ text_count2_kernel(const u8 *__restrict__ text, u64 n, u64 own_lo, u64 own_hi, u
                 const bool live = valid && !dup;
                 const u32 lmask = __ballot_sync(0xFFFFFFFFu, live);
                 acc_folded += live ? 1 : 0;
-                if (live) {
-                    if (hashed) {
-                        u32 l2 = len;
-                        if (l2 >= (1u << 20)) {
-                            my_flags |= DAMPR_TF_LONGTOKEN;
-                            l2 = (1u << 20) - 1;
-                        }
-                        const u64 goff = base_offset + (sgl - V_LEAD) + pos;
-                        const u64 myrep = (goff << 20) | l2;
-                        const u64 old = gtab_add2(tab, key, 1ULL, myrep);
-                        // inline K9 verification: atomicMin hands back the representative some earlier
-                        // token of this code published; comparing every later token with it (bytes, case
-                        // folded) proves by induction that the entry holds ONE token, so a 64-bit code
-                        // collision cannot merge two words silently and no second pass is needed
-                        if (old != ~0ULL && old != myrep) {
-                            bool same = (u32)(old & 0xFFFFFu) == l2;
-                            const u8 *pa = gwin + pos;
-                            const u8 *pb = text + ((old >> 20) - base_offset);
-                            for (u32 i = 0; same && i < len; ++i) {
-                                u32 ca = pa[i], cb = pb[i];
-                                if (MODE != DAMPR_TOK_WS) {
-                                    if (ca >= 'A' && ca <= 'Z') ca |= 0x20;
-                                    if (cb >= 'A' && cb <= 'Z') cb |= 0x20;
-                                }
-                                same = ca == cb;
-                            }
-                            if (!same) my_flags |= DAMPR_TF_COLLISION;
-                        }
-                        acc_long++;
+                // long (hashed) tokens.  [^\\w]+ modes: rare, straight to the global table with inline K9
+                // verification.  str.split mode: 10+ byte tokens are common and Zipf-hot, so they go through
+                // the shared-memory combiner like the exact codes; an entry remembers the latest occurrence
+                // of its token and every hit is compared with it (bytes) before it is counted.
+                u64 myrep = ~0ULL;
+                if (live && hashed) {
+                    u32 l2 = len;
+                    if (l2 >= (1u << 20)) {
+                        my_flags |= DAMPR_TF_LONGTOKEN;
+                        l2 = (1u << 20) - 1;
                     }
+                    myrep = ((base_offset + (sgl - V_LEAD) + pos) << 20) | l2;
+                    acc_long++;
+                    if (!WS && !hashed_insert(key, myrep, 1ULL)) my_flags |= DAMPR_TF_COLLISION;
                 }
-                const bool ins = live && !hashed;
+                const bool ins = live && (WS || !hashed);
                 const u32 imask = __ballot_sync(0xFFFFFFFFu, ins);
                 bool miss = false;
                 // every inserting lane looks its slot pair up (convergent loads); one lane per distinct
@@ -522,34 +557,52 @@ text_count2_kernel(const u8 *__restrict__ text, u64 n, u64 own_lo, u64 own_hi, u
                     u32 peers = 1u << lane;  // no in-warp merge: equal keys serialise in the smem atomic
 #endif
                     if (((u32)__ffs(peers) - 1u) == lane) {
-                        u32 cnt = (u32)__popc(peers);
+                        const u32 cnt = (u32)__popc(peers);
+                        int hs = -1;       // combiner entry of this key
+                        bool fresh = false;  // this lane created it
                         if (k0 == key) {
-                            atomicAdd(&s.tabc[slot], cnt);
+                            hs = (int)slot;
                         } else if (k1 == key) {
-                            atomicAdd(&s.tabc[slot + 1], cnt);
+                            hs = (int)slot + 1;
                         } else {
-                            bool placed = false;
 #pragma unroll 1
                             for (int pr = 0; pr < 2; ++pr) {  // 2-way bucket: a miss goes straight to the L2-resident global table
                                 u64 k = s.tabk[slot];
                                 if (k == 0) {
                                     k = atomicCAS(&s.tabk[slot], 0ULL, key);
-                                    if (k == 0) k = key;
+                                    if (k == 0) {
+                                        k = key;
+                                        fresh = true;
+                                    }
                                 }
                                 if (k == key) {
-                                    atomicAdd(&s.tabc[slot], cnt);
-                                    placed = true;
+                                    hs = (int)slot;
                                     break;
                                 }
                                 slot = (slot + 1) & (V_STAB - 1);
                             }
-                            if (!placed) {
-#if DAMPR_TEXT_USE_MATCH
-                                gtab_add2(tab, key, (u64)cnt, ~0ULL);
-#else
-                                miss = true;
-#endif
+                        }
+                        if (WS && hashed && hs >= 0) {
+                            const u32 r32 = (u32)(sgl - own_lo) + pos;
+                            if (!fresh) {
+                                const u32 prev = *reinterpret_cast<volatile u32 *>(&s.tabr[hs]);
+                                if (prev == V_REP_UNPUB) {
+                                    hs = -1;  // creator has not published yet: count this one in the global table
+                                } else {
+                                    const u8 *mine = (pos + len + 8u <= (u32)V_WIN) ? tx + pos : gwin + pos;
+                                    if (!tok_equal_ws(mine, text + (own_lo + prev - V_LEAD), len)) my_flags |= DAMPR_TF_COLLISION;
+                                }
                             }
+                            if (hs >= 0) *reinterpret_cast<volatile u32 *>(&s.tabr[hs]) = r32;
+                        }
+                        if (hs >= 0) {
+                            atomicAdd(&s.tabc[hs], cnt);
+                        } else {
+#if DAMPR_TEXT_USE_MATCH
+                            if (!hashed_insert(key, myrep, (u64)cnt)) my_flags |= DAMPR_TF_COLLISION;
+#else
+                            miss = true;
+#endif
                         }
                     }
                 }
@@ -559,12 +612,16 @@ text_count2_kernel(const u8 *__restrict__ text, u64 n, u64 own_lo, u64 own_hi, u
                 {
                     const u32 mm = __ballot_sync(0xFFFFFFFFu, miss);
                     if (mm) {
-                        if (miss) ws.missq[nq + __popc(mm & lt_mask)] = key;
+                        if (miss) {
+                            const u32 qi = nq + __popc(mm & lt_mask);
+                            ws.missq[qi] = key;
+                            if (WS) ws.missr[qi] = myrep;
+                        }
                         nq += (u32)__popc(mm);
                         __syncwarp();
                         if (nq >= 32) {
-                            const u64 qk = ws.missq[nq - 32 + lane];
-                            gtab_add2(tab, qk, 1ULL, ~0ULL);
+                            const u32 qi = nq - 32 + lane;
+                            if (!hashed_insert(ws.missq[qi], WS ? ws.missr[qi] : ~0ULL, 1ULL)) my_flags |= DAMPR_TF_COLLISION;
                             nq -= 32;
                         }
                     }
@@ -609,7 +666,7 @@ text_count2_kernel(const u8 *__restrict__ text, u64 n, u64 own_lo, u64 own_hi, u
             __syncwarp();
         }
         if (nq) {  // leftover misses of this strip
-            if (lane < nq) gtab_add2(tab, ws.missq[lane], 1ULL, ~0ULL);
+            if (lane < nq && !hashed_insert(ws.missq[lane], WS ? ws.missr[lane] : ~0ULL, 1ULL)) my_flags |= DAMPR_TF_COLLISION;
             __syncwarp();
         }
         };
@@ -631,8 +688,17 @@ text_count2_kernel(const u8 *__restrict__ text, u64 n, u64 own_lo, u64 own_hi, u
     // ---- flush the shared-memory combiner, publish counters ----------------------------------------
     __syncthreads();
     for (int i = tid; i < V_STAB; i += V_THREADS) {
-        u64 k = s.tabk[i];
-        if (k) gtab_add2(tab, k, (u64)s.tabc[i], ~0ULL);
+        const u64 k = s.tabk[i];
+        if (!k) continue;
+        u64 rep = ~0ULL;
+        if (WS && (k >> 63)) {
+            // representative of a long token = its latest occurrence in this CTA; its length is re-read
+            const u64 goff = own_lo + s.tabr[i] - V_LEAD;
+            u32 len = 0;
+            while (len < (1u << 20) - 1u && is_word_byte<DAMPR_TOK_WS>(text[goff + len])) ++len;
+            rep = ((base_offset + goff) << 20) | len;
+        }
+        if (!hashed_insert(k, rep, (u64)s.tabc[i])) my_flags |= DAMPR_TF_COLLISION;
     }
     u64 vals[5] = {acc_lines, acc_empty, acc_folded, acc_long, acc_raw};
 #pragma unroll
@@ -657,7 +723,7 @@ text_count2_kernel(const u8 *__restrict__ text, u64 n, u64 own_lo, u64 own_hi, u
 template <int MODE, int NBUF>
 int launch2n(dampr_ctx *ctx, dampr_table *t, dampr_textbuf *tb, u64 lo, u64 hi) {
     if (hi <= lo) return DAMPR_OK;
-    size_t smem = sizeof(Smem2T<NBUF>);
+    size_t smem = sizeof(Smem2T<NBUF, MODE == DAMPR_TOK_WS>);
     auto kern = text_count2_kernel<MODE, NBUF>;
     CUDA_TRY(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     u64 ntiles = (hi - lo + V_OWN - 1) / V_OWN;
@@ -675,7 +741,15 @@ int launch2n(dampr_ctx *ctx, dampr_table *t, dampr_textbuf *tb, u64 lo, u64 hi) 
 
 template <int MODE>
 int launch2(dampr_ctx *ctx, dampr_table *t, dampr_textbuf *tb, u64 lo, u64 hi) {
-    return g_text_ctas == 3 ? launch2n<MODE, 1>(ctx, t, tb, lo, hi) : launch2n<MODE, 2>(ctx, t, tb, lo, hi);
+    // str.split mode keeps 32-bit offsets (from the launch's own_lo) in the shared-memory combiner
+    const u64 span = (MODE == DAMPR_TOK_WS) ? (1ULL << 31) : ~0ULL;
+    for (u64 a = lo; a < hi;) {
+        const u64 b = (hi - a > span) ? a + span : hi;
+        const int rc = g_text_ctas == 3 ? launch2n<MODE, 1>(ctx, t, tb, a, b) : launch2n<MODE, 2>(ctx, t, tb, a, b);
+        if (rc != DAMPR_OK) return rc;
+        a = b;
+    }
+    return DAMPR_OK;
 }
 
 }  // namespace

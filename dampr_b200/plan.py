@@ -270,62 +270,62 @@ class TextScan(object):
             total = sum(sizes) + len(sizes)
             self.nbytes = sum(sizes)
             tb = _cached_textbuf(ctx, total + 64)
-        if True:  # buffers are cached per context (see _cached_textbuf): nothing to release here
-            if resident:
-                self._tab = _cached_table(ctx)
-                self._tab.count(tb, 0, tb.n, self.mode)
-            else:
-                self._upload_and_count(ctx, tb, sizes)
-            tab = self._tab
-            st = tab.stats()
-            flags = st["flags"]
-            if dist.active():
-                return self._finish_distributed(ctx, tb, tab, st)
-            if (flags & dev.TF_TABLEFULL or st["entries"] * 2 > tab.capacity) and settings.text_table_log2 < 28 \
-                    and not resident_retry_block(self):
-                # ReducedWriter would flush a run here (dataset.py:107-113); with HBM to spare the table
-                # is simply made 4x larger and the scan repeated (later scans start at the new size)
-                settings.text_table_log2 = int(settings.text_table_log2) + 2
+        # buffers are cached per context (see _cached_textbuf): nothing to release here
+        if resident:
+            self._tab = _cached_table(ctx)
+            self._tab.count(tb, 0, tb.n, self.mode)
+        else:
+            self._upload_and_count(ctx, tb, sizes)
+        tab = self._tab
+        st = tab.stats()
+        flags = st["flags"]
+        if dist.active():
+            return self._finish_distributed(ctx, tb, tab, st)
+        if (flags & dev.TF_TABLEFULL or st["entries"] * 2 > tab.capacity) and settings.text_table_log2 < 28 \
+                and not resident_retry_block(self):
+            # ReducedWriter would flush a run here (dataset.py:107-113); with HBM to spare the table
+            # is simply made 4x larger and the scan repeated (later scans start at the new size)
+            settings.text_table_log2 = int(settings.text_table_log2) + 2
+            return self.run()
+        if flags & dev.TF_TABLEFULL:
+            raise NotLowerable("combiner table overflow")
+        if flags & (dev.TF_NONASCII | dev.TF_LONGTOKEN):
+            raise NotLowerable("non-ASCII text or oversized token: device tokeniser is ASCII-only")
+        if self.mode != dev.TOK_WS and flags & dev.TF_LONGLINE and not flags & dev.TF_CR \
+                and not getattr(self, "_retry_v1", False):
+            # a line too long (or with too many distinct tokens) for the warp-autonomous kernel:
+            # the first-generation kernel has a 4 KB line window and no per-line token limit
+            self._retry_v1 = True
+            dev.set_option("text_kernel", 1)
+            try:
                 return self.run()
-            if flags & dev.TF_TABLEFULL:
-                raise NotLowerable("combiner table overflow")
-            if flags & (dev.TF_NONASCII | dev.TF_LONGTOKEN):
-                raise NotLowerable("non-ASCII text or oversized token: device tokeniser is ASCII-only")
-            if self.mode != dev.TOK_WS and flags & dev.TF_LONGLINE and not flags & dev.TF_CR \
-                    and not getattr(self, "_retry_v1", False):
-                # a line too long (or with too many distinct tokens) for the warp-autonomous kernel:
-                # the first-generation kernel has a 4 KB line window and no per-line token limit
-                self._retry_v1 = True
-                dev.set_option("text_kernel", 1)
-                try:
-                    return self.run()
-                finally:
-                    dev.set_option("text_kernel", 2)
-            if self.mode != dev.TOK_WS and flags & (dev.TF_CR | dev.TF_LONGLINE):
-                raise NotLowerable("carriage returns or a line longer than the device window")
-            if st["hashed"] and getattr(self, "_retry_v1", False):
-                # the first-generation kernel verifies long tokens in a second pass; the v2 kernel
-                # compares every long token with its entry's representative while counting
-                tab.verify(tb, 0, tb.n, self.mode)
-                flags = tab.stats()["flags"]
-            if flags & dev.TF_COLLISION:
-                raise NotLowerable("64-bit key-code collision between two long tokens")
-            # keys are materialised on the device (K9) as fixed-width ASCII; only tokens longer than the
-            # width (rare) are patched on the host from their representative occurrence
-            W = 32
-            words, counts, codes, reps = tab.fetch_words(tb, self.mode, W)
-            too_long = np.flatnonzero(((codes >> np.uint64(63)) != 0) & ((reps & np.uint64(0xFFFFF)) > W))
-            if len(too_long):
-                wl = [b.decode("ascii") for b in words.tolist()]
-                for i in too_long.tolist():
-                    rep = int(reps[i])
-                    s = tb.download(rep >> 20, rep & 0xFFFFF).tobytes().decode("ascii")
-                    wl[i] = s if self.mode == dev.TOK_WS else s.lower()
-                words = wl
-            self.words = words
-            self.counts = counts.view(np.int64)
-            self.n_lines = int(st["lines"])
-            self.empty = int(st["empty"])
+            finally:
+                dev.set_option("text_kernel", 2)
+        if self.mode != dev.TOK_WS and flags & (dev.TF_CR | dev.TF_LONGLINE):
+            raise NotLowerable("carriage returns or a line longer than the device window")
+        if st["hashed"] and getattr(self, "_retry_v1", False):
+            # the first-generation kernel verifies long tokens in a second pass; the v2 kernel
+            # compares every long token with its entry's representative while counting
+            tab.verify(tb, 0, tb.n, self.mode)
+            flags = tab.stats()["flags"]
+        if flags & dev.TF_COLLISION:
+            raise NotLowerable("64-bit key-code collision between two long tokens")
+        # keys are materialised on the device (K9) as fixed-width ASCII; only tokens longer than the
+        # width (rare) are patched on the host from their representative occurrence
+        W = 32
+        words, counts, codes, reps = tab.fetch_words(tb, self.mode, W)
+        too_long = np.flatnonzero(((codes >> np.uint64(63)) != 0) & ((reps & np.uint64(0xFFFFF)) > W))
+        if len(too_long):
+            wl = [b.decode("ascii") for b in words.tolist()]
+            for i in too_long.tolist():
+                rep = int(reps[i])
+                s = tb.download(rep >> 20, rep & 0xFFFFF).tobytes().decode("ascii")
+                wl[i] = s if self.mode == dev.TOK_WS else s.lower()
+            words = wl
+        self.words = words
+        self.counts = counts.view(np.int64)
+        self.n_lines = int(st["lines"])
+        self.empty = int(st["empty"])
         return self
 
     def _finish_distributed(self, ctx, tb, tab, st):
@@ -340,12 +340,11 @@ class TextScan(object):
         if flags & dev.TF_COLLISION:
             bad |= dev.TF_COLLISION
         if st["hashed"] and not bad:
-            if True:
-                codes, _counts, reps = tab.fetch()
-                hs = np.flatnonzero((codes & keycodes.HASHED_BIT) != 0)
-                ws = keycodes.decode_table(codes[hs], reps[hs], self.mode,
-                                           lambda off, ln: tb.download(off, ln).tobytes())
-                hashed_words = dict(zip(codes[hs].tolist(), ws))
+            codes, _counts, reps = tab.fetch()
+            hs = np.flatnonzero((codes & keycodes.HASHED_BIT) != 0)
+            ws = keycodes.decode_table(codes[hs], reps[hs], self.mode,
+                                       lambda off, ln: tb.download(off, ln).tobytes())
+            hashed_words = dict(zip(codes[hs].tolist(), ws))
         lines, empty, anybad, any_hashed = dist.all_reduce_sum_int(
             [int(st["lines"]), int(st["empty"]), 1 if bad else 0, len(hashed_words)])
         if anybad:
@@ -1006,17 +1005,6 @@ def _lower_probe(runner, stage, inputs):
     f = Frame(np.arange(n, dtype=np.int64), out_cols, scalar=(e.op != "tuple"))
     runner.stats.add(stage, "device broadcast hash build+probe", "build=%d probe=%d" % (len(build_keys), n))
     return f
-
-
-def _cell(col, i):
-    """Python value of row i of a frame column."""
-    if isinstance(col, DictCol):
-        v = col.uniq[int(col.inv[i])]
-    else:
-        v = col[i]
-    if isinstance(v, bytes):
-        return v.decode("ascii")
-    return v.item() if isinstance(v, np.generic) else v
 
 
 def _swap_to_arg0(e, argi):

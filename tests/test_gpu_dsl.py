@@ -259,3 +259,39 @@ def test_mixed_and_big_keys(ctx):
 
 def test_unknown_kwargs_accepted(items):
     assert items.map(lambda x: x).read(n_partitions=1, n_maps=2, n_reducers=3, max_files_per_stage=7) == list(range(10, 20))
+
+
+def test_word_stats_example(ctx, tmp_path):
+    """The pipeline of the reference's examples/word-stats.py (one shared root, four outputs from one
+    Dampr.run, a join of two aggregates) against plain Python on the same file."""
+    import collections
+    import random
+    rng = random.Random(5)
+    vocab = ["w%d" % i for i in range(300)] + ["Supercalifragilistic", "naïve", "x", "antidisestablishment"]
+    lines = [" ".join(rng.choice(vocab) for _ in range(rng.randint(0, 12))) for _ in range(4000)]
+    path = tmp_path / "corpus.txt"
+    path.write_text("\n".join(lines) + "\n", encoding="utf-8")
+
+    words = Dampr.text(str(path), 1024 ** 2).flat_map(lambda line: line.split())
+    top_words = words.count(lambda x: x).sort_by(lambda wc: -wc[1])
+    total_count = top_words.fold_by(key=lambda word: 1, value=lambda x: x[1], binop=lambda x, y: x + y)
+    word_lengths = top_words \
+        .fold_by(lambda tc: len(tc[0]), value=lambda tc: tc[1], binop=lambda x, y: x + y) \
+        .sort_by(lambda cl: cl[0])
+    avg = word_lengths \
+        .map(lambda wl: wl[0] * wl[1]) \
+        .a_group_by(lambda x: 1).sum() \
+        .join(total_count) \
+        .reduce(lambda awl, tc: next(awl)[1] / float(next(tc)[1]))
+    tc, tw, wl, awl = Dampr.run(total_count, top_words, word_lengths, avg, name="word-stats")
+
+    exp = collections.Counter(w for line in lines for w in line.split())
+    n = sum(exp.values())
+    assert tc.read(1)[0][1] == n
+    got = list(tw)
+    assert dict(got) == dict(exp)
+    hist = collections.Counter()
+    for w, c in exp.items():
+        hist[len(w)] += c
+    assert sorted(wl) == sorted(hist.items())
+    assert awl.read(1)[0][1] == sum(k * v for k, v in hist.items()) / float(n)
