@@ -49,7 +49,21 @@ struct dampr_ctx {
     // last upload events (textbuf/kv uploads on `copy` that `stream` must wait for)
     cudaEvent_t upload_done;
     bool upload_pending;
+    // pinned staging ring for transfers from / to pageable host memory (see staged_h2d in ctx.cu)
+    static constexpr int STAGE_SLOTS = 4;
+    static constexpr size_t STAGE_BYTES = 32u << 20;
+    void *stage_slot[STAGE_SLOTS] = {nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t stage_ev[STAGE_SLOTS] = {nullptr, nullptr, nullptr, nullptr};
+    int host_threads = 4;
 };
+
+// Host <-> device copies that stay at PCIe speed for pageable host memory: the bytes go through the
+// context's page-locked ring, moved on the host side by several threads, instead of through the driver's
+// single-threaded staging copy.  Page-locked (cudaHostAlloc / dampr_host_alloc) memory is copied directly.
+// staged_h2d returns when `src` may be reused (pageable) or like cudaMemcpyAsync (page-locked);
+// staged_d2h returns when `dst` holds the data.
+int staged_h2d(dampr_ctx *ctx, void *dst, const void *src, size_t bytes, cudaStream_t st);
+int staged_d2h(dampr_ctx *ctx, void *dst, const void *src, size_t bytes, cudaStream_t st);
 
 struct dampr_textbuf {
     u8 *alloc;      // device allocation

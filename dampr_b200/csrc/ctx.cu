@@ -1,6 +1,9 @@
 // ctx.cu — context, streams, timings, pinned memory, text buffers and kv containers.
 // Replaces the process pool / Queue plumbing of StageRunner.run (reference stagerunner.py:15-43)
 // and the on-disk run files of dataset.py with device-resident buffers.
+#include <algorithm>
+#include <thread>
+
 #include "common.cuh"
 
 int g_text_kernel = 2;
@@ -84,6 +87,99 @@ void pool_trim(dampr_ctx *ctx, size_t keep_bytes) {
 }
 int g_text_ctas = 3;
 
+// ---- staged transfers ---------------------------------------------------------------------------
+namespace {
+
+void par_memcpy(void *dst, const void *src, size_t n, int threads) {
+    if (threads <= 1 || n < (4u << 20)) {
+        memcpy(dst, src, n);
+        return;
+    }
+    std::vector<std::thread> pool;
+    const size_t per = ((n + threads - 1) / threads + 4095) & ~(size_t)4095;
+    for (int t = 1; t < threads; ++t) {
+        const size_t lo = per * t;
+        if (lo >= n) break;
+        const size_t len = std::min(per, n - lo);
+        pool.emplace_back([=] { memcpy((char *)dst + lo, (const char *)src + lo, len); });
+    }
+    memcpy(dst, src, std::min(per, n));
+    for (auto &th : pool) th.join();
+}
+
+bool is_pinned(const void *p) {
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    return a.type == cudaMemoryTypeHost || a.type == cudaMemoryTypeManaged;
+}
+
+int stage_init(dampr_ctx *ctx) {
+    if (ctx->stage_slot[0]) return DAMPR_OK;
+    for (int i = 0; i < dampr_ctx::STAGE_SLOTS; ++i) {
+        CUDA_TRY(ctx, cudaHostAlloc(&ctx->stage_slot[i], dampr_ctx::STAGE_BYTES, cudaHostAllocDefault));
+        CUDA_TRY(ctx, cudaEventCreateWithFlags(&ctx->stage_ev[i], cudaEventDisableTiming));
+    }
+    unsigned hw = std::thread::hardware_concurrency();
+    ctx->host_threads = (int)std::max(2u, std::min(16u, hw / 4));
+    return DAMPR_OK;
+}
+
+}  // namespace
+
+int staged_h2d(dampr_ctx *ctx, void *dst, const void *src, size_t bytes, cudaStream_t st) {
+    if (bytes == 0) return DAMPR_OK;
+    if (bytes < (8u << 20) || is_pinned(src)) {
+        CUDA_TRY(ctx, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, st));
+        return DAMPR_OK;
+    }
+    int rc = stage_init(ctx);
+    if (rc) return rc;
+    const size_t B = dampr_ctx::STAGE_BYTES;
+    size_t i = 0;
+    for (size_t off = 0; off < bytes; off += B, ++i) {
+        const int slot = (int)(i % dampr_ctx::STAGE_SLOTS);
+        const size_t len = std::min(B, bytes - off);
+        CUDA_TRY(ctx, cudaEventSynchronize(ctx->stage_ev[slot]));  // the DMA that last read this slot
+        par_memcpy(ctx->stage_slot[slot], (const char *)src + off, len, ctx->host_threads);
+        CUDA_TRY(ctx, cudaMemcpyAsync((char *)dst + off, ctx->stage_slot[slot], len, cudaMemcpyHostToDevice, st));
+        CUDA_TRY(ctx, cudaEventRecord(ctx->stage_ev[slot], st));
+    }
+    return DAMPR_OK;
+}
+
+int staged_d2h(dampr_ctx *ctx, void *dst, const void *src, size_t bytes, cudaStream_t st) {
+    if (bytes == 0) return DAMPR_OK;
+    if (bytes < (8u << 20) || is_pinned(dst)) {
+        CUDA_TRY(ctx, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(ctx, cudaStreamSynchronize(st));
+        return DAMPR_OK;
+    }
+    int rc = stage_init(ctx);
+    if (rc) return rc;
+    const size_t B = dampr_ctx::STAGE_BYTES;
+    const size_t nchunks = (bytes + B - 1) / B;
+    const size_t S = dampr_ctx::STAGE_SLOTS;
+    // a slot may still be the source of an earlier upload's DMA
+    for (size_t s = 0; s < S; ++s) CUDA_TRY(ctx, cudaEventSynchronize(ctx->stage_ev[s]));
+    for (size_t i = 0; i < nchunks + S - 1; ++i) {
+        if (i >= S - 1) {  // drain chunk i-(S-1) before its slot is refilled by chunk i+1
+            const size_t j = i - (S - 1);
+            const size_t off = j * B, len = std::min(B, bytes - off);
+            CUDA_TRY(ctx, cudaEventSynchronize(ctx->stage_ev[j % S]));
+            par_memcpy((char *)dst + off, ctx->stage_slot[j % S], len, ctx->host_threads);
+        }
+        if (i < nchunks) {
+            const size_t off = i * B, len = std::min(B, bytes - off);
+            CUDA_TRY(ctx, cudaMemcpyAsync(ctx->stage_slot[i % S], (const char *)src + off, len, cudaMemcpyDeviceToHost, st));
+            CUDA_TRY(ctx, cudaEventRecord(ctx->stage_ev[i % S], st));
+        }
+    }
+    return DAMPR_OK;
+}
+
 extern "C" {
 
 int32_t dampr_abi_version(void) { return 1; }
@@ -144,6 +240,10 @@ int32_t dampr_ctx_destroy(dampr_ctx *ctx) {
     cudaEventDestroy(ctx->upload_done);
     cudaFree(ctx->d_scratch);
     cudaFreeHost(ctx->h_scratch);
+    for (int i = 0; i < dampr_ctx::STAGE_SLOTS; ++i) {
+        if (ctx->stage_slot[i]) cudaFreeHost(ctx->stage_slot[i]);
+        if (ctx->stage_ev[i]) cudaEventDestroy(ctx->stage_ev[i]);
+    }
     cudaStreamDestroy(ctx->stream);
     cudaStreamDestroy(ctx->copy);
     delete ctx;
@@ -286,7 +386,8 @@ int32_t dampr_textbuf_upload(dampr_ctx *ctx, dampr_textbuf *tb, uint64_t off, co
     ARG_CHECK(ctx, ctx && tb && (host || len == 0), "null");
     ARG_CHECK(ctx, off + len <= tb->capacity, "upload exceeds textbuf capacity");
     if (len) {
-        CUDA_TRY(ctx, cudaMemcpyAsync(tb->text + off, host, len, cudaMemcpyHostToDevice, ctx->copy));
+        int rc = staged_h2d(ctx, tb->text + off, host, len, ctx->copy);
+        if (rc) return rc;
         if (off + len > tb->uploaded_hi) tb->uploaded_hi = off + len;
     }
     CUDA_TRY(ctx, cudaEventRecord(ctx->upload_done, ctx->copy));
@@ -358,9 +459,10 @@ int32_t dampr_kv_upload(dampr_ctx *ctx, dampr_kv *kv, uint64_t off, const void *
     ARG_CHECK(ctx, ctx && kv && (host_records || count == 0), "null");
     ARG_CHECK(ctx, off + count <= kv->capacity, "upload exceeds kv capacity");
     // uploads must not overtake compute that still reads the buffer
-    if (count)
-        CUDA_TRY(ctx, cudaMemcpyAsync(kv->rec + off, host_records, count * sizeof(ulonglong2),
-                                      cudaMemcpyHostToDevice, ctx->copy));
+    if (count) {
+        int rc = staged_h2d(ctx, kv->rec + off, host_records, count * sizeof(ulonglong2), ctx->copy);
+        if (rc) return rc;
+    }
     if (off + count > kv->n) kv->n = off + count;
     CUDA_TRY(ctx, cudaEventRecord(ctx->upload_done, ctx->copy));
     ctx->upload_pending = true;
@@ -372,10 +474,7 @@ int32_t dampr_kv_download(dampr_ctx *ctx, dampr_kv *kv, uint64_t off, void *host
     ARG_CHECK(ctx, ctx && kv && (host_records || count == 0), "null");
     ARG_CHECK(ctx, off + count <= kv->n, "download exceeds kv size");
     wait_uploads(ctx);
-    if (count)
-        CUDA_TRY(ctx, cudaMemcpyAsync(host_records, kv->rec + off, count * sizeof(ulonglong2),
-                                      cudaMemcpyDeviceToHost, ctx->stream));
-    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    if (count) return staged_d2h(ctx, host_records, kv->rec + off, count * sizeof(ulonglong2), ctx->stream);
     return DAMPR_OK;
 }
 

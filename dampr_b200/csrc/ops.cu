@@ -270,8 +270,12 @@ int32_t dampr_kv_upload_columns(dampr_ctx *ctx, dampr_kv *kv, uint64_t off, cons
     if (count) {
         u64 *tmp = (u64 *)pool_alloc(ctx, count * 16);
         ARG_CHECK(ctx, tmp != nullptr, "device allocation failed");
-        CUDA_TRY(ctx, cudaMemcpyAsync(tmp, keys, count * 8, cudaMemcpyHostToDevice, ctx->copy));
-        if (vals) CUDA_TRY(ctx, cudaMemcpyAsync(tmp + count, vals, count * 8, cudaMemcpyHostToDevice, ctx->copy));
+        int rc = staged_h2d(ctx, tmp, keys, count * 8, ctx->copy);
+        if (rc == DAMPR_OK && vals) rc = staged_h2d(ctx, tmp + count, vals, count * 8, ctx->copy);
+        if (rc) {
+            pool_free(ctx, tmp);
+            return rc;
+        }
         ctx->launches++;
         interleave_kernel<<<ctx->num_sms * 4, 256, 0, ctx->copy>>>(tmp, vals ? tmp + count : nullptr, kv->rec + off, count);
         CUDA_TRY(ctx, cudaGetLastError());
@@ -295,10 +299,12 @@ int32_t dampr_kv_download_columns(dampr_ctx *ctx, dampr_kv *kv, uint64_t off, ui
     ctx->launches++;
     deinterleave_kernel<<<ctx->num_sms * 4, 256, 0, ctx->stream>>>(kv->rec + off, tmp, tmp + count, count);
     CUDA_TRY(ctx, cudaGetLastError());
-    if (keys) CUDA_TRY(ctx, cudaMemcpyAsync(keys, tmp, count * 8, cudaMemcpyDeviceToHost, ctx->stream));
-    if (vals) CUDA_TRY(ctx, cudaMemcpyAsync(vals, tmp + count, count * 8, cudaMemcpyDeviceToHost, ctx->stream));
-    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    int rc = DAMPR_OK;
+    if (keys) rc = staged_d2h(ctx, keys, tmp, count * 8, ctx->stream);
+    if (rc == DAMPR_OK && vals) rc = staged_d2h(ctx, vals, tmp + count, count * 8, ctx->stream);
+    if (rc == DAMPR_OK && !(keys || vals)) CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
     pool_free(ctx, tmp);
+    if (rc) return rc;
     return DAMPR_OK;
 }
 

@@ -681,7 +681,27 @@ def _lower_kv_map(runner, stage, inputs):
         return None
     kp = lowering.projection(ks[0][1].fn)
     vp = lowering.projection(ks[0][1].fn2)
-    if kp is None or vp is None or kp[0] != "field" or kp[2] != 1 or kp[1] not in (0, 1):
+    if kp is None or vp is None or kp[0] != "field" or kp[1] not in (0, 1):
+        return None
+    if vp[0] == "ident":
+        # sort_by(lambda x: +-x[i]) (or group_by with the whole record as value): one device sort of the
+        # records on that field; rows come back as a two-column frame in key order (stable)
+        if stage.combiner is not None:
+            return None
+        col, other = cols[kp[1]], cols[1 - kp[1]]
+        if kp[2] < 0:
+            if col.dtype != np.int64 or (len(col) and int(col.min()) == -(1 << 63)):
+                return None
+            kcol = -col
+        else:
+            kcol = col
+        rk, rv, how = _device_group(runner, kcol, other, None, _key_xform_for(kcol))
+        rk, rv = rk.view(kcol.dtype), rv.view(other.dtype)
+        orig = -rk if kp[2] < 0 else rk
+        f = Frame(rk, [orig, rv] if kp[1] == 0 else [rv, orig], scalar=False, combined=False)
+        runner.stats.add(stage, "device kv partition+sort of whole records" + how, "records=%d" % len(col))
+        return f
+    if kp[2] != 1:
         return None
     keys = cols[kp[1]]
     count_only = False
@@ -690,8 +710,6 @@ def _lower_kv_map(runner, stage, inputs):
     elif vp[0] == "const" and type(vp[1]) is int:
         vals = np.full(len(keys), vp[1], dtype=np.int64)
         count_only = vp[1] == 1
-    elif vp[0] == "ident":
-        return None
     else:
         return None
     ctx = runner.ctx
@@ -765,8 +783,17 @@ class LazyKVFrame(Frame):
 
 def _may_overflow(vals):
     """Cheap bound for Python-int semantics: n * max|v| must stay far below 2^63."""
-    lo, hi = int(vals.min()), int(vals.max())
-    return len(vals) * max(abs(lo), abs(hi)) >= (1 << 62)
+    n = len(vals)
+    if n > (1 << 24):
+        # numpy reductions release the GIL: a few threads keep this memory-bound scan off the critical path
+        from concurrent.futures import ThreadPoolExecutor
+        step = -(-n // 8)
+        with ThreadPoolExecutor(8) as ex:
+            parts = list(ex.map(lambda i: (int(vals[i:i + step].min()), int(vals[i:i + step].max())), range(0, n, step)))
+        lo, hi = min(p[0] for p in parts), max(p[1] for p in parts)
+    else:
+        lo, hi = int(vals.min()), int(vals.max())
+    return n * max(abs(lo), abs(hi)) >= (1 << 62)
 
 
 def _device_group(runner, keys, vals, op, xform):
@@ -799,7 +826,11 @@ def _device_group(runner, keys, vals, op, xform):
     if n and spill.needs_spill(ctx, n):
         step = 1 << 22
         chunks = ((keys[i:i + step], vals[i:i + step]) for i in range(0, n, step))
-        pieces, st = spill.external_group(ctx, chunks, n, op, xform if op is None else dev.KEY_MIX)
+        if op is None and xform != dev.KEY_MIX:
+            samp = keys[np.random.default_rng(0).integers(0, n, size=min(n, 1 << 16))]
+            pieces, st = spill.external_sort(ctx, chunks, n, xform, samp)
+        else:
+            pieces, st = spill.external_group(ctx, chunks, n, op, xform if op is None else dev.KEY_MIX)
         rk = np.concatenate([p[0] for p in pieces]) if pieces else np.zeros(0, dtype=np.uint64)
         rv = np.concatenate([p[1] for p in pieces]) if pieces else np.zeros(0, dtype=np.uint64)
         runner.stats.spill = st

@@ -201,3 +201,29 @@ def test_map_side_join_lowered_to_hash_probe(ctx):
     assert got == [(k, v, k in table) for k, v in zip(lk.tolist(), lv.tolist())]
     got = small.cross_set(big, lambda b, table: b[0] not in table, agg=set).read()
     assert got == [k not in table for k in lk.tolist()]
+
+
+def test_sort_by_over_binary_records(ctx):
+    """sort_by on a field of binary (key, value) records is one device partition+sort (stable); the
+    spill variant must give the same rows."""
+    from dampr_b200 import settings
+    keys, vals = gen.kv(23, 400_000, 50_000)
+    rows = list(zip(keys.tolist(), vals.tolist()))
+    src = Dampr.read_input(ArrayKVInput(keys, vals))
+    got = src.sort_by(lambda x: x[0]).read()
+    assert lowered("device kv partition+sort of whole records")
+    assert got == sorted(rows, key=lambda r: r[0])
+    got = src.sort_by(lambda x: x[1]).read()
+    assert got == sorted(rows, key=lambda r: r[1])
+    got = src.sort_by(lambda x: -x[1]).read()
+    assert got == sorted(rows, key=lambda r: -r[1])
+    old = settings.device_arena_bytes
+    settings.device_arena_bytes = 4 << 20
+    try:
+        got = src.sort_by(lambda x: x[1]).read()
+        assert lowered("[spilled:")
+        assert got == sorted(rows, key=lambda r: r[1])
+        got = src.sort_by(lambda x: x[0]).read()
+        assert got == sorted(rows, key=lambda r: r[0])
+    finally:
+        settings.device_arena_bytes = old
