@@ -2,6 +2,10 @@
 // Replaces the process pool / Queue plumbing of StageRunner.run (reference stagerunner.py:15-43)
 // and the on-disk run files of dataset.py with device-resident buffers.
 #include <algorithm>
+#include <atomic>
+#include <condition_variable>
+#include <memory>
+#include <mutex>
 #include <thread>
 
 #include "common.cuh"
@@ -90,22 +94,92 @@ int g_text_ctas = 3;
 // ---- staged transfers ---------------------------------------------------------------------------
 namespace {
 
-void par_memcpy(void *dst, const void *src, size_t n, int threads) {
-    if (threads <= 1 || n < (4u << 20)) {
-        memcpy(dst, src, n);
-        return;
+// Process-wide pool of copy threads (created on first use, parked on a condition variable).  One
+// memcpy job at a time; the caller takes part in it.  A job is its own heap object, so a worker that
+// wakes up late only ever sees a finished job (nothing left to claim), never a half-initialised one.
+class CopyPool {
+    static constexpr size_t PIECE = 1u << 20;
+    struct Job {
+        char *dst;
+        const char *src;
+        size_t n, pieces;
+        std::atomic<size_t> next{0}, left{0};
+    };
+
+  public:
+    static CopyPool &get() {
+        static CopyPool p;
+        return p;
     }
-    std::vector<std::thread> pool;
-    const size_t per = ((n + threads - 1) / threads + 4095) & ~(size_t)4095;
-    for (int t = 1; t < threads; ++t) {
-        const size_t lo = per * t;
-        if (lo >= n) break;
-        const size_t len = std::min(per, n - lo);
-        pool.emplace_back([=] { memcpy((char *)dst + lo, (const char *)src + lo, len); });
+    void run(void *dst, const void *src, size_t n, int threads) {
+        if (threads <= 1 || n < 4 * PIECE) {
+            memcpy(dst, src, n);
+            return;
+        }
+        std::lock_guard<std::mutex> job_lock(job_mu_);
+        auto job = std::make_shared<Job>();
+        job->dst = (char *)dst;
+        job->src = (const char *)src;
+        job->n = n;
+        job->pieces = (n + PIECE - 1) / PIECE;
+        job->left.store(job->pieces);
+        {
+            std::lock_guard<std::mutex> lk(mu_);
+            while ((int)workers_.size() < threads - 1) workers_.emplace_back([this] { loop(); });
+            cur_ = job;
+            ++gen_;
+        }
+        cv_.notify_all();
+        work(*job);
+        std::unique_lock<std::mutex> lk(mu_);
+        done_cv_.wait(lk, [&] { return job->left.load() == 0; });
     }
-    memcpy(dst, src, std::min(per, n));
-    for (auto &th : pool) th.join();
-}
+
+  private:
+    CopyPool() {}
+    ~CopyPool() {
+        {
+            std::lock_guard<std::mutex> lk(mu_);
+            stop_ = true;
+        }
+        cv_.notify_all();
+        for (auto &t : workers_) t.join();
+    }
+    void work(Job &j) {
+        for (;;) {
+            const size_t i = j.next.fetch_add(1);
+            if (i >= j.pieces) break;
+            const size_t lo = i * PIECE, len = std::min(PIECE, j.n - lo);
+            memcpy(j.dst + lo, j.src + lo, len);
+            if (j.left.fetch_sub(1) == 1) {
+                std::lock_guard<std::mutex> lk(mu_);
+                done_cv_.notify_all();
+            }
+        }
+    }
+    void loop() {
+        u64 seen = 0;
+        for (;;) {
+            std::shared_ptr<Job> job;
+            {
+                std::unique_lock<std::mutex> lk(mu_);
+                cv_.wait(lk, [&] { return stop_ || gen_ != seen; });
+                if (stop_) return;
+                seen = gen_;
+                job = cur_;
+            }
+            work(*job);
+        }
+    }
+    std::mutex job_mu_, mu_;
+    std::condition_variable cv_, done_cv_;
+    std::vector<std::thread> workers_;
+    std::shared_ptr<Job> cur_;
+    u64 gen_ = 0;
+    bool stop_ = false;
+};
+
+void par_memcpy(void *dst, const void *src, size_t n, int threads) { CopyPool::get().run(dst, src, n, threads); }
 
 bool is_pinned(const void *p) {
     cudaPointerAttributes a;
