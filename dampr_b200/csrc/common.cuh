@@ -211,6 +211,23 @@ __host__ __device__ __forceinline__ u64 key_xform(u64 k, int xf) {
     }
 }
 
+// inverse of key_xform (every transform is a bijection on u64)
+__host__ __device__ __forceinline__ u64 key_unxform(u64 t, int xf) {
+    switch (xf) {
+        case DAMPR_KEY_MIX: {
+            t ^= (t >> 31) ^ (t >> 62);
+            t *= 0x319642B2D24D8EC3ULL;  // inverse of 0x94D049BB133111EB mod 2^64
+            t ^= (t >> 27) ^ (t >> 54);
+            t *= 0x96DE1B173F119089ULL;  // inverse of 0xBF58476D1CE4E5B9 mod 2^64
+            t ^= (t >> 30) ^ (t >> 60);
+            return t;
+        }
+        case DAMPR_KEY_I64: return t ^ 0x8000000000000000ULL;
+        case DAMPR_KEY_F64: return t ^ ((t >> 63) ? 0x8000000000000000ULL : ~0ULL);
+        default: return t;
+    }
+}
+
 #ifdef __CUDACC__
 __device__ __forceinline__ u32 smem_u32(const void *p) {
     return (u32)__cvta_generic_to_shared(p);

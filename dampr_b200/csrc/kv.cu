@@ -34,7 +34,6 @@ constexpr int P_MAX_NB = 1 << P_MAX_BITS;
 constexpr int L_THREADS = 512;
 constexpr int L_CAP = 4096;    // records per leaf chunk
 constexpr int L_BINS = 8192;   // counting-sort bins
-constexpr int L_SMALL = 24;    // bins up to this size are fixed by one thread
 
 struct Piece {
     u64 start, end;
@@ -253,22 +252,17 @@ struct LeafChunk {
     u64 bin_base;
 };
 
+// 104 KB: two CTAs per SM.  Only the transformed key is kept (every transform is a bijection, the stored
+// key is rebuilt with key_unxform on the way out), which is what makes the second CTA fit.
 struct LeafSmem {
-    alignas(16) ulonglong2 rec[L_CAP];
-    u64 sk[L_CAP];
+    alignas(16) u64 sk[L_CAP];   // key_xform(key) - base
+    u64 val[L_CAP];
     u16 cnt[L_BINS];   // counts, then bin starts
     u16 cur[L_BINS];   // cursors
     u16 ord[L_CAP];    // sorted order -> record index
-    u16 big[176];      // bins too large for the one-thread fix-up (at most L_CAP/(L_SMALL+1))
-    u32 nbig;
     u32 wsum[32];
     u32 total_groups;
 };
-
-__device__ __forceinline__ bool leaf_less(const LeafSmem &s, u16 a, u16 b) {
-    u64 ka = s.sk[a], kb = s.sk[b];
-    return ka < kb || (ka == kb && a < b);
-}
 
 __device__ __forceinline__ u64 apply_op(int op, u64 acc, u64 v) {
     switch (op) {
@@ -304,7 +298,6 @@ leaf_sort_kernel(ulonglong2 *__restrict__ data, ulonglong2 *__restrict__ out, co
                 asm volatile("prefetch.global.L2 [%0];" ::"l"(base + off));
         }
         for (u32 i = tid; i < L_BINS; i += L_THREADS) s.cnt[i] = 0;
-        if (tid == 0) s.nbig = 0;
         __syncthreads();
         // load + histogram
         {
@@ -319,7 +312,7 @@ leaf_sort_kernel(ulonglong2 *__restrict__ data, ulonglong2 *__restrict__ out, co
             for (int k = 0; k < L_CAP / L_THREADS; ++k) {
                 u32 i = tid + k * L_THREADS;
                 if (i < n) {
-                    s.rec[i] = rr[k];
+                    s.val[i] = rr[k].y;
                     s.sk[i] = key_xform(rr[k].x, xf) - base;
                 }
             }
@@ -333,7 +326,7 @@ leaf_sort_kernel(ulonglong2 *__restrict__ data, ulonglong2 *__restrict__ out, co
                                     reduce_op == DAMPR_OP_MIN_I64 || reduce_op == DAMPR_OP_MAX_I64)) {
             for (u32 i = tid; i < L_BINS; i += L_THREADS) s.cur[i] = 0;  // cnt[] is the index (zeroed above)
             if (reduce_op == DAMPR_OP_COUNT)
-                for (u32 i = tid; i < n; i += L_THREADS) s.rec[i].y = 1ULL;
+                for (u32 i = tid; i < n; i += L_THREADS) s.val[i] = 1ULL;
             __syncthreads();
             for (u32 i = tid; i < n; i += L_THREADS) {
                 const u64 ki = s.sk[i];
@@ -349,8 +342,8 @@ leaf_sort_kernel(ulonglong2 *__restrict__ data, ulonglong2 *__restrict__ out, co
                         }
                     }
                     if (s.sk[cur - 1] == ki) {
-                        unsigned long long *acc = &s.rec[cur - 1].y;
-                        const u64 v = s.rec[i].y;
+                        unsigned long long *acc = &s.val[cur - 1];
+                        const u64 v = s.val[i];
                         if (reduce_op == DAMPR_OP_MIN_I64) atomicMin((long long *)acc, (long long)v);
                         else if (reduce_op == DAMPR_OP_MAX_I64) atomicMax((long long *)acc, (long long)v);
                         else atomicAdd(acc, v);
@@ -382,7 +375,10 @@ leaf_sort_kernel(ulonglong2 *__restrict__ data, ulonglong2 *__restrict__ out, co
             if (tid == L_THREADS - 1) s.total_groups = woff + v;
 #pragma unroll
             for (int k = 0; k < IPT; ++k)
-                if (flags & (1u << k)) out[ch.start + gidx++] = s.rec[tid * IPT + k];
+                if (flags & (1u << k)) {
+                    const u32 p = tid * IPT + k;
+                    out[ch.start + gidx++] = make_ulonglong2(key_unxform(s.sk[p] + base, xf), s.val[p]);
+                }
             __syncthreads();
             if (tid == 0) chunk_groups[c] = s.total_groups;
             __syncthreads();
@@ -455,7 +451,10 @@ leaf_sort_kernel(ulonglong2 *__restrict__ data, ulonglong2 *__restrict__ out, co
         for (u32 i = tid; i < n; i += L_THREADS) s.ord[i] = s.cur[i];
         __syncthreads();
         if (reduce_op < 0) {
-            for (u32 i = tid; i < n; i += L_THREADS) out[ch.start + i] = s.rec[s.ord[i]];
+            for (u32 i = tid; i < n; i += L_THREADS) {
+                const u32 o = s.ord[i];
+                out[ch.start + i] = make_ulonglong2(key_unxform(s.sk[o] + base, xf), s.val[o]);
+            }
             __syncthreads();
             continue;
         }
@@ -489,14 +488,13 @@ leaf_sort_kernel(ulonglong2 *__restrict__ data, ulonglong2 *__restrict__ out, co
             for (int k = 0; k < IPT; ++k) {
                 if (headbits & (1u << k)) {
                     u32 p = tid * IPT + k;
-                    u64 key = s.rec[s.ord[p]].x;
                     u64 ksk = s.sk[s.ord[p]];
-                    u64 acc = (reduce_op == DAMPR_OP_COUNT) ? 1ULL : s.rec[s.ord[p]].y;
+                    u64 acc = (reduce_op == DAMPR_OP_COUNT) ? 1ULL : s.val[s.ord[p]];
                     for (u32 q = p + 1; q < n && s.sk[s.ord[q]] == ksk; ++q) {
-                        u64 val = (reduce_op == DAMPR_OP_COUNT) ? 1ULL : s.rec[s.ord[q]].y;
+                        u64 val = (reduce_op == DAMPR_OP_COUNT) ? 1ULL : s.val[s.ord[q]];
                         acc = apply_op(reduce_op, acc, val);
                     }
-                    out[ch.start + gidx] = make_ulonglong2(key, acc);
+                    out[ch.start + gidx] = make_ulonglong2(key_unxform(ksk + base, xf), acc);
                     ++gidx;
                 }
             }
