@@ -148,35 +148,53 @@ part_scatter_kernel(const ulonglong2 *__restrict__ in, ulonglong2 *__restrict__ 
                 u32 li = warp * P_PER_WARP + r * 32 + lane;
                 if (li < tn) rec[r] = in[t0 + li];
             }
-            // ... then the stable ranking, round by round
+            // the tile after this one: pull it into L2 while this one is ranked and staged
+            if (t0 + P_TILE < pc.end) {
+                const char *nxt = reinterpret_cast<const char *>(in + t0 + P_TILE);
+                const u32 nbytes = (u32)min((u64)P_TILE, pc.end - t0 - P_TILE) * 16u;
+                if (tid * 128u < nbytes) asm volatile("prefetch.global.L2 [%0];" ::"l"(nxt + tid * 128u));
+            }
+            // ... then the stable ranking. Pass 1 (registers only): digit and same-digit lane set per round,
+            // from one ballot per digit bit (MATCH.ANY costs one pass per distinct value, i.e. ~32 passes
+            // with 10-bit digits).
+            // Per round one packed word: digit (10 bits) | leader lane << 10 | rank among the set's lanes << 15
+            // | (set size - 1) << 20 | valid << 25.
 #pragma unroll
             for (int r = 0; r < P_ROUNDS; ++r) {
-                u32 li = warp * P_PER_WARP + r * 32 + lane;
-                bool valid = li < tn;
-                u32 vmask = __ballot_sync(0xFFFFFFFFu, valid);
-                dig[r] = 0xFFFFFFFFu;
-                rnk[r] = 0;
-                if (valid) {
-                    u32 d = digit_of(rec[r].x, ds);
-                    dig[r] = d;
-                    // lanes holding the same digit, from one ballot per digit bit (MATCH.ANY costs one
-                    // pass per distinct value, i.e. ~32 passes with 10-bit digits)
-                    u32 peers = vmask;
-                    for (u32 bit = 0; bit < dbits; ++bit) {
-                        const u32 mine = (d >> bit) & 1u;
-                        const u32 bal = __ballot_sync(vmask, mine);
-                        peers &= mine ? bal : ~bal;
-                    }
-                    u32 leader = (u32)__ffs(peers) - 1u;
-                    u32 old = 0;
-                    if (lane == leader) {
-                        old = s.warp_hist[warp][d];
-                        s.warp_hist[warp][d] = (u16)(old + __popc(peers));
-                    }
-                    old = __shfl_sync(peers, old, leader);
-                    rnk[r] = old + __popc(peers & ((1u << lane) - 1u));
+                const u32 li = warp * P_PER_WARP + r * 32 + lane;
+                const bool valid = li < tn;
+                const u32 vmask = __ballot_sync(0xFFFFFFFFu, valid);
+                const u32 d = valid ? digit_of(rec[r].x, ds) : 0u;
+                u32 peers = vmask;
+                for (u32 bit = 0; bit < dbits; ++bit) {
+                    const u32 mine = (d >> bit) & 1u;
+                    const u32 bal = __ballot_sync(0xFFFFFFFFu, mine);
+                    peers &= mine ? bal : ~bal;
                 }
-                __syncwarp();
+                dig[r] = valid ? (d | (((u32)__ffs(peers) - 1u) << 10) | ((u32)__popc(peers & ((1u << lane) - 1u)) << 15) |
+                                  (((u32)__popc(peers) - 1u) << 20) | (1u << 25))
+                               : 0u;
+            }
+            // Pass 2: the leader of every lane set bumps the warp's digit counter. The eight shared-memory
+            // atomics of a thread do not depend on each other, so they pipeline (same-address ones complete
+            // in issue order); counters are u16 pairs updated through their 32-bit word.
+            u32 *wh32 = reinterpret_cast<u32 *>(s.warp_hist[warp]);
+#pragma unroll
+            for (int r = 0; r < P_ROUNDS; ++r) {
+                const u32 pk = dig[r];
+                rnk[r] = 0;
+                if ((pk >> 25) && ((pk >> 10) & 31u) == lane) {
+                    const u32 d = pk & 1023u, c = ((pk >> 20) & 31u) + 1u;
+                    const u32 w = atomicAdd(&wh32[d >> 1], (d & 1u) ? (c << 16) : c);
+                    rnk[r] = (d & 1u) ? (w >> 16) : (w & 0xFFFFu);
+                }
+            }
+#pragma unroll
+            for (int r = 0; r < P_ROUNDS; ++r) {
+                const u32 pk = dig[r];
+                const u32 old = __shfl_sync(0xFFFFFFFFu, rnk[r], (pk >> 25) ? ((pk >> 10) & 31u) : lane);
+                rnk[r] = old + ((pk >> 15) & 31u);
+                dig[r] = (pk >> 25) ? (pk & 1023u) : 0xFFFFFFFFu;
             }
             __syncthreads();
             // ---- per-bucket exclusive scan over warps, then over buckets ------------------------
