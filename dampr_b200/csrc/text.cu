@@ -14,7 +14,12 @@
 // per-line de-duplication (set() semantics) is a backward scan over the token array, and the
 // survivors are folded into a per-CTA shared-memory hash table that is flushed to the global
 // (L2-resident) table once per CTA. HBM traffic = the text, read once.
+#include <fcntl.h>
+#include <unistd.h>
+
 #include <algorithm>
+#include <atomic>
+#include <functional>
 #include <thread>
 
 #include "common.cuh"
@@ -954,6 +959,87 @@ extern "C" int32_t dampr_host_join_tsv(uint64_t n, int32_t ncols, const int32_t 
         join_rows(a, r0.first, r0.second, out);
         for (auto &x : th) x.join();
     }
+    return DAMPR_OK;
+}
+
+// The same rows straight into a file: every thread formats its row span into a private buffer and
+// pwrite()s it at its final offset (one length pass, no result array, the page-cache copies run in
+// parallel).  Replaces SinkWriter's print(value, file=...) loop (dataset.py:264-282).
+extern "C" int32_t dampr_host_sink_tsv(const char *path, uint64_t n, int32_t ncols, const int32_t *kinds,
+                                       const void *const *ptrs, const uint32_t *widths, const void *const *aux,
+                                       const void *const *aux2, uint64_t *out_len) {
+    if (!path || !kinds || !ptrs || !out_len || ncols < 1 || ncols > 16) return DAMPR_ERR_ARG;
+    JoinArgs a{n, ncols, kinds, ptrs, widths, aux, aux2};
+    unsigned hw = std::thread::hardware_concurrency();
+    int T = (int)std::min<u64>(std::max(1u, std::min(hw, 16u)), std::max<u64>(1, n / 16384));
+    std::vector<u64> lens(T, 0), offs(T + 1, 0);
+    auto span = [&](int t) { return std::make_pair(n * t / T, n * (t + 1) / T); };
+    auto fan = [&](const std::function<void(int)> &f) {
+        std::vector<std::thread> th;
+        for (int t = 1; t < T; ++t) th.emplace_back(f, t);
+        f(0);
+        for (auto &x : th) x.join();
+    };
+    fan([&](int t) { auto r = span(t); lens[t] = join_rows(a, r.first, r.second, nullptr); });
+    for (int t = 0; t < T; ++t) offs[t + 1] = offs[t] + lens[t];
+    *out_len = offs[T];
+    int fd = open(path, O_WRONLY | O_CREAT | O_TRUNC, 0644);
+    if (fd < 0) return DAMPR_ERR_ARG;
+    std::atomic<int> bad{0};
+    fan([&](int t) {
+        if (!lens[t]) return;
+        std::vector<u8> buf(lens[t]);
+        auto r = span(t);
+        join_rows(a, r.first, r.second, buf.data());
+        u64 done = 0;
+        while (done < lens[t]) {
+            ssize_t w = pwrite(fd, buf.data() + done, lens[t] - done, (off_t)(offs[t] + done));
+            if (w <= 0) {
+                bad.store(1);
+                return;
+            }
+            done += (u64)w;
+        }
+    });
+    if (close(fd) != 0) bad.store(1);
+    return bad.load() ? DAMPR_ERR_ARG : DAMPR_OK;
+}
+
+// Sorted distinct values + inverse index of a non-negative int64 column (the dictionary encoding of a
+// count column, plan.DictCol).  Values below `table` go through a presence table (two linear passes,
+// no sort); the others are returned as-is in big_vals/big_rows for the caller to sort (rare: the tail
+// of a Zipf count distribution).  uniq must hold min(n, table) values; *n_big <= big_cap or the call
+// fails.  inv[i] for big rows is left untouched.
+extern "C" int32_t dampr_host_unique_small(const int64_t *col, uint64_t n, uint64_t table, int64_t *uniq,
+                                           uint64_t *n_uniq, uint32_t *inv, int64_t *big_vals,
+                                           uint64_t *big_rows, uint64_t big_cap, uint64_t *n_big) {
+    if (!col || !uniq || !n_uniq || !inv || !n_big || table == 0 || table > (1ULL << 26)) return DAMPR_ERR_ARG;
+    std::vector<u32> rank(table, 0);
+    u64 nb = 0;
+    for (u64 i = 0; i < n; ++i) {
+        const int64_t v = col[i];
+        if (v >= 0 && (u64)v < table) {
+            rank[(u64)v] = 1;
+        } else {
+            if (nb >= big_cap) return DAMPR_ERR_ARG;
+            big_vals[nb] = v;
+            big_rows[nb] = i;
+            ++nb;
+        }
+    }
+    u64 m = 0;
+    for (u64 v = 0; v < table; ++v) {
+        if (rank[v]) {
+            uniq[m] = (int64_t)v;
+            rank[v] = (u32)m++;
+        }
+    }
+    for (u64 i = 0; i < n; ++i) {
+        const int64_t v = col[i];
+        if (v >= 0 && (u64)v < table) inv[i] = rank[(u64)v];
+    }
+    *n_uniq = m;
+    *n_big = nb;
     return DAMPR_OK;
 }
 

@@ -92,6 +92,8 @@ def load_library():
     _sig(lib, "dampr_table_fetch_words", vp, vp, vp, i32, u32, vp, vp, vp, vp, u64, pu64)
     _sig(lib, "dampr_kv_decode_words", vp, vp, i32, u32, vp)
     _sig(lib, "dampr_host_join_tsv", u64, i32, vp, vp, vp, vp, vp, vp, u64, pu64)
+    _sig(lib, "dampr_host_sink_tsv", C.c_char_p, u64, i32, vp, vp, vp, vp, vp, pu64)
+    _sig(lib, "dampr_host_unique_small", vp, u64, u64, vp, pu64, vp, vp, vp, u64, pu64)
     _sig(lib, "dampr_kv_create", vp, u64, pvp)
     _sig(lib, "dampr_kv_destroy", vp, vp)
     _sig(lib, "dampr_kv_size", vp, vp, pu64)
@@ -489,9 +491,10 @@ class KV(object):
             pass
 
 
-def host_join_tsv(columns):
+def host_join_tsv(columns, path=None):
     """Rows of tab-separated text from columns (native host loop). Each column is either a numpy
-    'S<w>' array (NUL-padded fixed-width strings) or a pair (inv uint32 array, list of bytes)."""
+    'S<w>' array (NUL-padded fixed-width strings) or a pair (inv uint32 array, list of bytes).
+    With `path` the rows are written to that file (returns the byte count) instead of returned."""
     lib = load_library()
     k = len(columns)
     n = None
@@ -523,6 +526,11 @@ def host_join_tsv(columns):
         assert n is None or n == m
         n = m
     out_len = C.c_uint64(0)
+    if path is not None:
+        rc = lib.dampr_host_sink_tsv(os.fsencode(path), n, k, kinds, ptrs, widths, aux, aux2, C.byref(out_len))
+        if rc:
+            raise DeviceError("dampr_host_sink_tsv(%r) failed (%d)" % (path, rc))
+        return out_len.value
     rc = lib.dampr_host_join_tsv(n, k, kinds, ptrs, widths, aux, aux2, None, 0, C.byref(out_len))
     if rc:
         raise DeviceError("dampr_host_join_tsv failed (%d)" % rc)
@@ -531,6 +539,34 @@ def host_join_tsv(columns):
     if rc:
         raise DeviceError("dampr_host_join_tsv failed (%d)" % rc)
     return out
+
+
+def host_unique_small(col, table=1 << 20):
+    """(uniq ascending, inv uint32) of an int64 column whose values are mostly in [0, table), or None
+    when too many values fall outside (the caller then uses a sort)."""
+    lib = load_library()
+    col = np.ascontiguousarray(col, dtype=np.int64)
+    n = len(col)
+    cap = n // 8 + 16
+    uniq = np.empty(min(n, table), dtype=np.int64)
+    inv = np.empty(n, dtype=np.uint32)
+    bv = np.empty(cap, dtype=np.int64)
+    br = np.empty(cap, dtype=np.uint64)
+    m, nb = C.c_uint64(0), C.c_uint64(0)
+    rc = lib.dampr_host_unique_small(_ptr(col), n, table, _ptr(uniq), C.byref(m), _ptr(inv), _ptr(bv), _ptr(br),
+                                     cap, C.byref(nb))
+    if rc:
+        return None
+    m, nb = m.value, nb.value
+    uniq = uniq[:m]
+    if nb:
+        bv, br = bv[:nb], br[:nb].astype(np.int64)
+        if int(bv.min()) < table:   # negative values: the two ranges would interleave
+            return None
+        ul, il = np.unique(bv, return_inverse=True)
+        inv[br] = il.astype(np.uint32) + np.uint32(m)
+        uniq = np.concatenate((uniq, ul))
+    return uniq, inv
 
 
 def kv_merge(ctx, runs, xform, op=-1):

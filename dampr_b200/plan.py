@@ -58,6 +58,10 @@ def unique_inverse(col):
     """(sorted unique values, inverse index uint32) of an int64/float64 column. Small non-negative
     ints (the bulk of count columns) go through a counting pass instead of a sort."""
     n = len(col)
+    if n >= 4096 and col.dtype == np.int64:
+        r = dev.host_unique_small(col)   # native presence-table pass; None if the values do not suit it
+        if r is not None:
+            return r
     if n and col.dtype.kind in "iu":
         # counting table sized by the bulk of the values (99.9th percentile, capped at 4 M entries)
         T = int(min(1 << 22, max(1024, int(np.partition(col, max(0, n - 1 - n // 1000))[max(0, n - 1 - n // 1000)]) + 1)))
@@ -1172,9 +1176,10 @@ def _lower_sink(runner, stage, inputs):
         return None
     os.makedirs(stage.path, exist_ok=True)
     fname = os.path.join(stage.path, "part-%d" % (dist.world()[0] if dist.active() else 0))
-    blob = dev.host_join_tsv(cols) if fr.n else np.zeros(0, dtype=np.uint8)
-    with open(fname, "wb") as f:
-        f.write(memoryview(blob))
+    if fr.n:
+        dev.host_join_tsv(cols, path=fname)   # formatted and written by native threads
+    else:
+        open(fname, "wb").close()
     lines = range(fr.n)
     runner.stats.add(stage, "native frame sink (per-distinct-value formatting)", "records=%d" % len(lines))
     return CatDataset([TextLineDataset(fname)])

@@ -157,6 +157,17 @@ int32_t dampr_kv_decode_words(dampr_ctx *ctx, dampr_kv *kv, int32_t mode, uint32
 int32_t dampr_host_join_tsv(uint64_t n, int32_t ncols, const int32_t *kinds, const void *const *ptrs,
                             const uint32_t *widths, const void *const *aux, const void *const *aux2,
                             uint8_t *out, uint64_t cap, uint64_t *out_len);
+/* the same rows written straight to `path` (created / truncated): the row spans are formatted and
+ * pwrite()n in parallel. Replaces SinkWriter's print-per-record loop (dataset.py:264-282). */
+int32_t dampr_host_sink_tsv(const char *path, uint64_t n, int32_t ncols, const int32_t *kinds,
+                            const void *const *ptrs, const uint32_t *widths, const void *const *aux,
+                            const void *const *aux2, uint64_t *out_len);
+/* dictionary encoding of an int64 column (host helper of the frame layer): values in [0, table) are
+ * ranked through a presence table -> uniq[0..*n_uniq) ascending and inv[i]; other values are handed
+ * back in big_vals / big_rows (at most big_cap, else the call fails) and their inv[] is untouched. */
+int32_t dampr_host_unique_small(const int64_t *col, uint64_t n, uint64_t table, int64_t *uniq,
+                                uint64_t *n_uniq, uint32_t *inv, int64_t *big_vals, uint64_t *big_rows,
+                                uint64_t big_cap, uint64_t *n_big);
 /* same, but leaves the run on the device as a kv (key = code, val = count) */
 int32_t dampr_table_to_kv(dampr_ctx *ctx, dampr_table *t, dampr_kv **out);
 
