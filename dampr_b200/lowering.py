@@ -279,6 +279,30 @@ def binop_kind(fn):
     return None
 
 
+def tuple_binop_kinds(fn):
+    """[kind per component] of a component-wise binary operator over tuples, e.g. mean()'s
+    `lambda x, y: (x[0] + y[0], x[1] + y[1])` (dampr.py:450-467) -> [ADD, ADD]; None otherwise."""
+    e = analyze(fn)
+    if e is None or getattr(fn, "__code__", None) is None or fn.__code__.co_argcount != 2 or e.op != "tuple":
+        return None
+    out = []
+    for i, comp in enumerate(e.a):
+        if not (isinstance(comp, E) and comp.op == "bin" and comp.a == "+"):
+            return None
+        sides = []
+        for side in (comp.b, comp.c):
+            if not (isinstance(side, E) and side.op == "sub" and isinstance(side.a, E) and side.a.op == "arg"):
+                return None
+            ok, j = _const(side.b)
+            if not ok or j != i:
+                return None
+            sides.append(side.a.a)
+        if sorted(sides) != [0, 1]:
+            return None
+        out.append(ADD)
+    return out or None
+
+
 SUM, COUNT = "sum", "count"
 
 

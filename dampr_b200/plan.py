@@ -22,7 +22,7 @@ import threading
 import numpy as np
 
 from . import device as dev
-from . import dist, keycodes, lowering, settings
+from . import dist, keycodes, lowering, settings, vexpr
 from . import operators as ops
 from .datasets import Dataset, RecordsDataset, TextLineDataset, CatDataset, EmptyDataset
 from .graph import GMap, GReduce, GSink
@@ -104,6 +104,8 @@ class Frame(Dataset):
 
     @staticmethod
     def _pylist(col):
+        if isinstance(col, vexpr.Tup):   # tuple-valued column (e.g. mean()'s (sum, count) pairs)
+            return list(zip(*[Frame._pylist(c) for c in col.items]))
         if isinstance(col, DictCol):
             col = col.materialize()
         if isinstance(col, np.ndarray):
@@ -123,6 +125,8 @@ class Frame(Dataset):
 
     def take(self, perm):
         def tk(c):
+            if isinstance(c, vexpr.Tup):
+                return vexpr.Tup([tk(x) for x in c.items])
             if isinstance(c, DictCol):
                 return DictCol(c.inv[perm], c.uniq)
             if isinstance(c, np.ndarray):
@@ -648,7 +652,10 @@ def _lower_map(runner, stage, inputs, si):
     if kv is not None:
         return kv
     if len(inputs) == 1 and isinstance(inputs[0], Frame):
-        return _lower_frame_map(runner, stage, inputs[0])
+        out = _lower_frame_map(runner, stage, inputs[0])
+        if out is None and not isinstance(inputs[0], LazyKVFrame):
+            out = _lower_frame_general(runner, stage, inputs[0])
+        return out
     if isinstance(stage.mapper, ops.MapCrossJoin) and len(inputs) == 2 and isinstance(inputs[0], Frame):
         return _lower_cross(runner, stage, inputs)
     if isinstance(stage.mapper, ops.MapAllJoin) and len(inputs) == 2:
@@ -902,6 +909,141 @@ def _lower_frame_map(runner, stage, frame):
         out.combined = False
         runner.stats.add(stage, "device sort of frame rows", "records=%d" % n)
         return out
+    return None
+
+
+_FOLD_OPS_F64 = {lowering.ADD: dev.OP_SUM_F64, lowering.MIN: dev.OP_MIN_F64, lowering.MAX: dev.OP_MAX_F64,
+                 lowering.FIRST: dev.OP_FIRST, lowering.LAST: dev.OP_LAST}
+
+
+def _fold_single_group(vals, kind):
+    """binop-fold of a whole column in record order (a constant key: one group)."""
+    if kind == lowering.ADD:
+        if vals.dtype == np.int64:
+            if _may_overflow(vals):
+                raise NotLowerable("64-bit sum could overflow (SURVEY B12)")
+            return int(vals.sum())
+        return float(np.cumsum(vals)[-1])   # the left fold binop(acc, v) in record order, exactly
+    if kind in (lowering.MIN, lowering.MAX):
+        if vals.dtype == np.float64 and np.isnan(vals).any():
+            raise NotLowerable("NaN under min/max")
+        r = vals.min() if kind == lowering.MIN else vals.max()
+        return r.item()
+    return (vals[0] if kind == lowering.FIRST else vals[-1]).item()
+
+
+def _fold_column(runner, kcodes, xf, vals, kind):
+    """Group `vals` by the 64-bit key codes on the device; returns (group key codes, folded values)."""
+    opmap = _FOLD_OPS if vals.dtype == np.int64 else _FOLD_OPS_F64
+    if kind not in opmap:
+        raise NotLowerable("fold %s" % kind)
+    if kind == lowering.ADD and vals.dtype == np.int64 and len(vals) and _may_overflow(vals):
+        raise NotLowerable("64-bit sum could overflow (SURVEY B12)")
+    rk, rv, how = _device_group(runner, kcodes, vals.view(np.uint64), opmap[kind], xf)
+    return rk, rv.view(vals.dtype), how
+
+
+def _lower_frame_general(runner, stage, frame):
+    """map / filter chains and keyed folds over a frame whose lambdas evaluate column-at-a-time
+    (vexpr): the stages after an aggregation in examples/word-stats.py:24-37, mean(), map_values() ..."""
+    ks = _opkinds(stage.mapper)
+    if not ks or frame.n == 0 or dist.active():   # frames are rank-local under torch.distributed
+        return None
+    body, last = ks, None
+    if ks[-1][0] == "keyed":
+        body, last = ks[:-1], ks[-1][1]
+    keys, cols, scalar, n = frame.keys, list(frame.cols), frame.scalar, frame.n
+    try:
+        for kind, op in body:
+            if kind == "identity":
+                continue
+            e = _inline(op.fn)
+            if e is None:
+                return None
+            v = vexpr.evaluate(e, cols, scalar, n)
+            if kind == "map":
+                if isinstance(v, vexpr.Tup):
+                    cols, scalar = [vexpr.broadcast(c, n) for c in v.items], False
+                else:
+                    cols, scalar = [vexpr.broadcast(v, n)], True
+            elif kind == "filter":
+                if not (isinstance(v, np.ndarray) and v.dtype == np.bool_):
+                    return None   # truthiness of a non-boolean: host path
+                idx = np.flatnonzero(v)
+                tmp = Frame(keys, cols, scalar).take(idx)
+                keys, cols, n = tmp.keys, tmp.cols, len(idx)
+                if n == 0:
+                    return None
+            else:
+                return None
+        if last is None:
+            out = Frame(keys, cols, scalar)
+            runner.stats.add(stage, "frame map/filter evaluated column-at-a-time", "records=%d" % n)
+            return out
+        ke, ve = _inline(last.fn), _inline(last.fn2)
+        if ke is None or ve is None:
+            return None
+        kv = vexpr.evaluate(ke, cols, scalar, n)
+        vv = vexpr.evaluate(ve, cols, scalar, n)
+        binop = stage.options.get("binop")
+        if isinstance(stage.combiner, ops.PartialReduceCombiner) and callable(binop):
+            comp_kinds = None
+            if isinstance(vv, vexpr.Tup):
+                comp_kinds = lowering.tuple_binop_kinds(binop)
+                if comp_kinds is None or len(comp_kinds) != len(vv.items):
+                    return None
+                vcols = [vexpr.broadcast(c, n) for c in vv.items]
+            else:
+                k1 = lowering.binop_kind(binop)
+                if k1 is None:
+                    return None
+                comp_kinds, vcols = [k1], [vexpr.broadcast(vv, n)]
+            if not all(isinstance(c, np.ndarray) and c.dtype in (np.int64, np.float64) for c in vcols):
+                return None
+            if isinstance(kv, vexpr.Const):
+                res = [_fold_single_group(c, k) for c, k in zip(vcols, comp_kinds)]
+                rcols = [np.array([r]) for r in res]
+                okeys, how = np.array([kv.v]), " [one group, folded on the host]"
+            else:
+                if not (isinstance(kv, np.ndarray) and kv.dtype == np.int64):
+                    return None   # float / string keys: equality is not bit equality
+                rk = None
+                rcols = []
+                for c, k in zip(vcols, comp_kinds):
+                    rk2, rv, how = _fold_column(runner, kv.view(np.uint64), dev.KEY_MIX, c, k)
+                    if rk is not None and not np.array_equal(rk, rk2):
+                        raise NotLowerable("component folds disagree on the group order")
+                    rk = rk2
+                    rcols.append(rv)
+                okeys = rk.view(np.int64)
+            val = vexpr.Tup(rcols) if isinstance(vv, vexpr.Tup) else rcols[0]
+            out = Frame(okeys, [val], scalar=True, combined=True)
+            runner.stats.add(stage, "frame keyed fold: columns evaluated on the host, groups folded on the device" + how,
+                             "records=%d groups=%d" % (n, len(okeys)))
+            return out
+        if stage.combiner is None and lowering.is_identity(last.fn2):
+            # sort_by(expr): device sort of (key code, row index)
+            kc = vexpr.broadcast(kv, n)
+            if not (isinstance(kc, np.ndarray) and kc.dtype in (np.int64, np.float64)):
+                return None
+            if kc.dtype == np.float64 and np.isnan(kc).any():
+                return None
+            if kc.dtype == np.float64:
+                kc = kc + 0.0   # -0.0 and 0.0 are one key for Python's sort
+            xf = dev.KEY_I64 if kc.dtype == np.int64 else dev.KEY_F64
+            kvh = runner.ctx.kv_from_columns(kc.view(np.uint64), np.arange(n, dtype=np.uint64))
+            try:
+                kvh.sort(xf)
+                _k, perm = kvh.columns()
+            finally:
+                kvh.free()
+            perm = perm.view(np.int64)
+            out = Frame(keys, cols, scalar).take(perm)
+            out.keys = kc[perm]
+            runner.stats.add(stage, "device sort of frame rows", "records=%d" % n)
+            return out
+    except vexpr.NotVec as why:
+        log.debug("stage %s not vectorised: %s", stage.output, why)
     return None
 
 

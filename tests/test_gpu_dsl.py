@@ -295,3 +295,60 @@ def test_word_stats_example(ctx, tmp_path):
         hist[len(w)] += c
     assert sorted(wl) == sorted(hist.items())
     assert awl.read(1)[0][1] == sum(k * v for k, v in hist.items()) / float(n)
+
+
+def test_frame_stages_evaluated_column_at_a_time(ctx):
+    """Stages that follow an aggregation (map / filter / map_values / fold_by / mean / sort_by on
+    computed keys) run over the aggregate's columns (dampr_b200/vexpr.py) with CPython's results."""
+    import numpy as np
+    from dampr_b200.inputs import ArrayKVInput
+    from dampr_b200 import runner as runner_mod
+
+    def how():
+        return [h for _s, h, _d in runner_mod.LAST_STATS.stages]
+
+    rng = np.random.default_rng(11)
+    keys = rng.integers(-500, 500, size=60000).astype(np.int64)
+    vals = rng.integers(-1000, 1000, size=60000).astype(np.int64)
+    agg = Dampr.read_input(ArrayKVInput(keys, vals)).a_group_by(lambda x: x[0], lambda x: x[1]).sum()
+    exp = {}
+    for k, v in zip(keys.tolist(), vals.tolist()):
+        exp[k] = exp.get(k, 0) + v
+    rows = sorted(exp.items())
+
+    got = agg.map(lambda kv: (kv[0], kv[1] * 3 - kv[0], kv[1] / 7)).read()
+    assert any("column-at-a-time" in h for h in how())
+    assert sorted(got) == [(k, v * 3 - k, v / 7) for k, v in rows]
+
+    got = agg.filter(lambda kv: kv[1] > 0).map_values(lambda v: v // 5).read()
+    assert any("column-at-a-time" in h for h in how())
+    assert sorted(got) == [(k, v // 5) for k, v in rows if v > 0]
+
+    got = agg.fold_by(lambda kv: kv[0] % 7, lambda x, y: x + y, value=lambda kv: kv[1]).read()
+    assert any("frame keyed fold" in h for h in how())
+    e2 = {}
+    for k, v in rows:
+        e2[k % 7] = e2.get(k % 7, 0) + v
+    assert sorted(got) == sorted(e2.items())
+
+    got = agg.mean(lambda kv: abs(kv[0]) % 5, lambda kv: kv[1]).read()
+    assert any("frame keyed fold" in h for h in how())
+    e3 = {}
+    for k, v in rows:
+        s, c = e3.get(abs(k) % 5, (0, 0))
+        e3[abs(k) % 5] = (s + v, c + 1)
+    assert sorted(got) == sorted((k, s / float(c)) for k, (s, c) in e3.items())
+
+    got = agg.mean(value=lambda kv: float(kv[1])).read()
+    tot = 0.0
+    # order of the float left fold is the frame's row order: compare with tolerance
+    assert len(got) == 1 and got[0][0] == 1
+    assert abs(got[0][1] - sum(v for _k, v in rows) / float(len(rows))) < 1e-9
+
+    got = agg.sort_by(lambda kv: kv[1] - 2 * kv[0]).read()
+    assert any("device sort of frame rows" in h for h in how())
+    assert [r[1] - 2 * r[0] for r in got] == sorted(v - 2 * k for k, v in rows) and sorted(got) == rows
+
+    # a guard trips (division by zero somewhere): the host path must give CPython's behaviour
+    with pytest.raises(ZeroDivisionError):
+        agg.map(lambda kv: kv[1] / (kv[0] - kv[0])).read()

@@ -197,3 +197,50 @@ def test_frame_cross_and_sink_lowering_exact_python_values(tmp_path):
     cols = [plan._sink_column(c) for c in out.cols]
     blob = dev.host_join_tsv(cols).tobytes().decode()
     assert blob == "".join(u"\t".join(str(p) for p in row) + "\n" for row in exp)
+
+
+def test_vexpr_matches_cpython_row_by_row():
+    """Column-at-a-time evaluation of lowered lambdas (dampr_b200/vexpr.py) gives exactly what CPython
+    gives per row, and refuses (NotVec) whenever that cannot be guaranteed."""
+    import math
+    import numpy as np
+    import pytest
+    from dampr_b200 import lowering, vexpr
+    rng = np.random.default_rng(3)
+    n = 5000
+    a = rng.integers(-10**6, 10**6, size=n).astype(np.int64)
+    b = rng.integers(1, 1000, size=n).astype(np.int64)
+    f = rng.normal(size=n) * 1e3
+    w = np.array([b"x" * int(k) for k in rng.integers(1, 20, size=n)], dtype="S32")
+    cols = [a, b, f, w]
+    rows = list(zip(a.tolist(), b.tolist(), f.tolist(), [x.decode() for x in w.tolist()]))
+    fns = [
+        lambda x: x[0] + x[1] * 3 - 7,
+        lambda x: (x[0], x[0] / x[1], x[0] // x[1], x[0] % x[1]),
+        lambda x: -x[0] * x[1],
+        lambda x: x[2] * x[0] + 0.5,
+        lambda x: float(x[0]) / x[2],
+        lambda x: len(x[3]) * x[1],
+        lambda x: abs(x[0]) - abs(x[2]),
+        lambda x: (x[0] < x[1], x[2] >= 0.0, x[0] == x[1], x[0] != 5),
+        lambda x: (x[1], (x[0], 1)),
+    ]
+    for fn in fns:
+        e = lowering.analyze(fn)
+        assert e is not None
+        v = vexpr.evaluate(e, cols, False, n)
+
+        def pyl(c):
+            if isinstance(c, vexpr.Tup):
+                return list(zip(*[pyl(x) for x in c.items]))
+            return vexpr.broadcast(c, n).tolist()
+        got = pyl(v)
+        exp = [fn(r) for r in rows]
+        assert got == exp, fn
+    big = np.full(n, 1 << 61, dtype=np.int64)
+    for fn, cs in [(lambda x: x[0] * x[1], [big, b]), (lambda x: x[0] + x[0], [big]), (lambda x: x[0] / x[1], [big, b]),
+                   (lambda x: x[0] / (x[1] - x[1]), [a, b]), (lambda x: math.sqrt(x[0]), [b]), (lambda x: x[0] + "s", [b])]:
+        with pytest.raises(vexpr.NotVec):
+            vexpr.evaluate(lowering.analyze(fn), cs, False, n)
+    assert lowering.tuple_binop_kinds(lambda x, y: (x[0] + y[0], x[1] + y[1])) == [lowering.ADD, lowering.ADD]
+    assert lowering.tuple_binop_kinds(lambda x, y: (x[0] + y[1], x[1] + y[0])) is None
