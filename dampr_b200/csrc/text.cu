@@ -855,7 +855,7 @@ extern "C" int32_t dampr_table_fetch_words(dampr_ctx *ctx, dampr_table *t, dampr
     if (rc) return rc;
     *n = st[0];
     if (!words) return DAMPR_OK;
-    ARG_CHECK(ctx, cap >= st[0] && counts && codes && reps, "fetch arrays too small");
+    ARG_CHECK(ctx, cap >= st[0] && counts, "fetch arrays too small");   // codes / reps are optional
     u64 m = st[0];
     if (m == 0) return DAMPR_OK;
     u64 per = width + 24;
@@ -874,17 +874,20 @@ extern "C" int32_t dampr_table_fetch_words(dampr_ctx *ctx, dampr_table *t, dampr
                                                                      d_counts, d_codes, d_reps, m, d_cur);
     }
     cudaError_t e = cudaGetLastError();
-    if (e == cudaSuccess) e = cudaMemcpyAsync(words, d_words, m * width, cudaMemcpyDeviceToHost, ctx->stream);
+    // the small columns first (asynchronous, pageable), then the words through the pinned staging ring,
+    // whose final synchronisation covers everything queued on the stream
     if (e == cudaSuccess) e = cudaMemcpyAsync(counts, d_counts, m * 8, cudaMemcpyDeviceToHost, ctx->stream);
-    if (e == cudaSuccess) e = cudaMemcpyAsync(codes, d_codes, m * 8, cudaMemcpyDeviceToHost, ctx->stream);
-    if (e == cudaSuccess) e = cudaMemcpyAsync(reps, d_reps, m * 8, cudaMemcpyDeviceToHost, ctx->stream);
-    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    if (e == cudaSuccess && codes) e = cudaMemcpyAsync(codes, d_codes, m * 8, cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess && reps) e = cudaMemcpyAsync(reps, d_reps, m * 8, cudaMemcpyDeviceToHost, ctx->stream);
+    int rc2 = DAMPR_OK;
+    if (e == cudaSuccess) rc2 = staged_d2h(ctx, words, d_words, m * width, ctx->stream);
+    if (e == cudaSuccess && rc2 == DAMPR_OK) e = cudaStreamSynchronize(ctx->stream);
     pool_free(ctx, d);
     if (e != cudaSuccess) {
         ctx->err = std::string("table fetch_words failed: ") + cudaGetErrorString(e);
         return DAMPR_ERR_CUDA;
     }
-    return DAMPR_OK;
+    return rc2;
 }
 
 // ---- host-side sink formatting (SinkWriter, dataset.py:264-282: one print(value) per record) --------

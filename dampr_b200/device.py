@@ -353,20 +353,22 @@ class Table(object):
                                                           m, C.byref(n)))
         return codes, counts, reps
 
-    def fetch_words(self, tb, mode, width=32):
-        """(words 'S<width>' array decoded on the device, counts, codes, reps)."""
+    def fetch_words(self, tb, mode, width=32, with_codes=True):
+        """(words 'S<width>' array decoded on the device, counts, codes, reps); codes and reps are None
+        when with_codes is false (tables without hashed tokens need neither)."""
         n = C.c_uint64(0)
         self.ctx.check(self.ctx.lib.dampr_table_fetch_words(self.ctx.h, self.h, None, int(mode), int(width), None,
                                                             None, None, None, 0, C.byref(n)))
         m = n.value
-        words = np.zeros((m, width), dtype=np.uint8)
+        words = np.empty((m, width), dtype=np.uint8)   # the kernel writes every byte (NUL padded)
         counts = np.empty(m, dtype=np.uint64)
-        codes = np.empty(m, dtype=np.uint64)
-        reps = np.empty(m, dtype=np.uint64)
+        codes = np.empty(m, dtype=np.uint64) if with_codes else None
+        reps = np.empty(m, dtype=np.uint64) if with_codes else None
         if m:
             self.ctx.check(self.ctx.lib.dampr_table_fetch_words(
                 self.ctx.h, self.h, tb.h if tb is not None else None, int(mode), int(width), _ptr(words),
-                _ptr(counts), _ptr(codes), _ptr(reps), m, C.byref(n)))
+                _ptr(counts), _ptr(codes) if with_codes else None, _ptr(reps) if with_codes else None, m,
+                C.byref(n)))
         return words.view("S%d" % width).ravel(), counts, codes, reps
 
     def to_kv(self):

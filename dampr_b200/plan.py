@@ -320,9 +320,12 @@ class TextScan(object):
             raise NotLowerable("64-bit key-code collision between two long tokens")
         # keys are materialised on the device (K9) as fixed-width ASCII; only tokens longer than the
         # width (rare) are patched on the host from their representative occurrence
-        W = 32
-        words, counts, codes, reps = tab.fetch_words(tb, self.mode, W)
-        too_long = np.flatnonzero(((codes >> np.uint64(63)) != 0) & ((reps & np.uint64(0xFFFFF)) > W))
+        # exact codes hold at most 12 characters: without hashed tokens 16 bytes per key are enough and
+        # neither codes nor representatives are needed on the host
+        hashed = bool(st["hashed"])
+        W = 32 if hashed else 16
+        words, counts, codes, reps = tab.fetch_words(tb, self.mode, W, with_codes=hashed)
+        too_long = np.flatnonzero(((codes >> np.uint64(63)) != 0) & ((reps & np.uint64(0xFFFFF)) > W)) if hashed else ()
         if len(too_long):
             wl = [b.decode("ascii") for b in words.tolist()]
             for i in too_long.tolist():
@@ -1011,8 +1014,18 @@ def _lower_frame_general(runner, stage, frame):
                 rcols = []
                 for c, k in zip(vcols, comp_kinds):
                     rk2, rv, how = _fold_column(runner, kv.view(np.uint64), dev.KEY_MIX, c, k)
+                    if len(vcols) > 1:
+                        # the group order of a hash-aggregated fold is not defined: bring every
+                        # component into key order (a device sort of the few group records)
+                        g = runner.ctx.kv_from_columns(rk2, rv.view(np.uint64))
+                        try:
+                            g.sort(dev.KEY_RAW)
+                            rk2, rv2 = g.columns()
+                        finally:
+                            g.free()
+                        rv = rv2.view(rv.dtype)
                     if rk is not None and not np.array_equal(rk, rk2):
-                        raise NotLowerable("component folds disagree on the group order")
+                        raise NotLowerable("component folds disagree on the groups")
                     rk = rk2
                     rcols.append(rv)
                 okeys = rk.view(np.int64)

@@ -41,6 +41,9 @@ class Tup(object):
     def __init__(self, items):
         self.items = list(items)
 
+    def __len__(self):
+        return len(self.items[0]) if self.items else 0
+
 
 def _is_num(c):
     return isinstance(c, np.ndarray) and c.dtype in (np.int64, np.float64)

@@ -142,7 +142,8 @@ int32_t dampr_table_fetch(dampr_ctx *ctx, dampr_table *t, uint64_t *codes, uint6
 /* key materialisation (K9): like dampr_table_fetch, plus every key decoded ON THE DEVICE into a
  * fixed-width NUL-padded ASCII string words[i*width .. +width) (hashed tokens are read back from
  * their representative occurrence in `tb`, truncated to `width`; their true length is in reps).
- * width: multiple of 8 in [16, 256]. words == NULL queries *n only. */
+ * width: multiple of 8 in [16, 256]. words == NULL queries *n only; codes / reps may be NULL when the
+ * caller does not need them (no hashed tokens in the table). */
 int32_t dampr_table_fetch_words(dampr_ctx *ctx, dampr_table *t, dampr_textbuf *tb, int32_t mode,
                                 uint32_t width, uint8_t *words, uint64_t *counts, uint64_t *codes,
                                 uint64_t *reps, uint64_t cap, uint64_t *n);
