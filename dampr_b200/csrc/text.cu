@@ -983,20 +983,54 @@ extern "C" int32_t dampr_host_sink_tsv(const char *path, uint64_t n, int32_t nco
         f(0);
         for (auto &x : th) x.join();
     };
-    fan([&](int t) { auto r = span(t); lens[t] = join_rows(a, r.first, r.second, nullptr); });
+    // longest possible row: fixed widths + the longest string of every dictionary + separators
+    u64 max_row = (u64)ncols;
+    for (int c = 0; c < ncols; ++c) {
+        if (kinds[c] == 0) {
+            max_row += widths[c];
+        } else {
+            // dictionary size = largest index in use + 1 is not known here: offsets are monotone, so the
+            // longest entry is found by walking them up to the blob end the caller encoded in aux2[c][m]
+            const u32 *off = (const u32 *)aux2[c];
+            const u32 *inv = (const u32 *)ptrs[c];
+            u32 m = 0;
+            for (u64 i = 0; i < n; ++i) m = std::max(m, inv[i]);
+            u32 longest = 0;
+            for (u32 j = 0; j <= m; ++j) longest = std::max(longest, off[j + 1] - off[j]);
+            max_row += longest;
+        }
+    }
+    // format every span into a private buffer sized for the longest possible rows (malloc: pages that are
+    // never written cost nothing), so one pass over the rows is enough ...
+    std::vector<u8 *> bufs(T, nullptr);
+    std::atomic<int> bad{0};
+    fan([&](int t) {
+        auto r = span(t);
+        const u64 rows = (u64)r.second - (u64)r.first;
+        if (!rows) return;
+        bufs[t] = (u8 *)malloc(rows * max_row);
+        if (!bufs[t]) {
+            bad.store(1);
+            return;
+        }
+        lens[t] = join_rows(a, r.first, r.second, bufs[t]);
+    });
+    if (bad.load()) {
+        for (auto p : bufs) free(p);
+        return DAMPR_ERR_ARG;
+    }
     for (int t = 0; t < T; ++t) offs[t + 1] = offs[t] + lens[t];
     *out_len = offs[T];
     int fd = open(path, O_WRONLY | O_CREAT | O_TRUNC, 0644);
-    if (fd < 0) return DAMPR_ERR_ARG;
-    std::atomic<int> bad{0};
+    if (fd < 0) {
+        for (auto p : bufs) free(p);
+        return DAMPR_ERR_ARG;
+    }
+    // ... then every thread writes its span at its final offset
     fan([&](int t) {
-        if (!lens[t]) return;
-        std::vector<u8> buf(lens[t]);
-        auto r = span(t);
-        join_rows(a, r.first, r.second, buf.data());
         u64 done = 0;
         while (done < lens[t]) {
-            ssize_t w = pwrite(fd, buf.data() + done, lens[t] - done, (off_t)(offs[t] + done));
+            ssize_t w = pwrite(fd, bufs[t] + done, lens[t] - done, (off_t)(offs[t] + done));
             if (w <= 0) {
                 bad.store(1);
                 return;
@@ -1005,6 +1039,7 @@ extern "C" int32_t dampr_host_sink_tsv(const char *path, uint64_t n, int32_t nco
         }
     });
     if (close(fd) != 0) bad.store(1);
+    for (auto p : bufs) free(p);
     return bad.load() ? DAMPR_ERR_ARG : DAMPR_OK;
 }
 
@@ -1012,16 +1047,21 @@ extern "C" int32_t dampr_host_sink_tsv(const char *path, uint64_t n, int32_t nco
 // count column, plan.DictCol).  Values below `table` go through a presence table (two linear passes,
 // no sort); the others are returned as-is in big_vals/big_rows for the caller to sort (rare: the tail
 // of a Zipf count distribution).  uniq must hold min(n, table) values; *n_big <= big_cap or the call
-// fails.  inv[i] for big rows is left untouched.
+// fails.  inv[i] for big rows is left untouched.  first_row (optional, min(n, table) entries) receives the
+// first row holding each distinct value.
 extern "C" int32_t dampr_host_unique_small(const int64_t *col, uint64_t n, uint64_t table, int64_t *uniq,
-                                           uint64_t *n_uniq, uint32_t *inv, int64_t *big_vals,
-                                           uint64_t *big_rows, uint64_t big_cap, uint64_t *n_big) {
-    if (!col || !uniq || !n_uniq || !inv || !n_big || table == 0 || table > (1ULL << 26)) return DAMPR_ERR_ARG;
+                                           uint64_t *n_uniq, uint32_t *inv, uint32_t *first_row,
+                                           int64_t *big_vals, uint64_t *big_rows, uint64_t big_cap,
+                                           uint64_t *n_big) {
+    if (!col || !uniq || !n_uniq || !inv || !n_big || table == 0 || table > (1ULL << 26) || n >= (1ULL << 32))
+        return DAMPR_ERR_ARG;
     std::vector<u32> rank(table, 0);
+    std::vector<u32> first(first_row ? table : 0);
     u64 nb = 0;
     for (u64 i = 0; i < n; ++i) {
         const int64_t v = col[i];
         if (v >= 0 && (u64)v < table) {
+            if (first_row && !rank[(u64)v]) first[(u64)v] = (u32)i;
             rank[(u64)v] = 1;
         } else {
             if (nb >= big_cap) return DAMPR_ERR_ARG;
@@ -1034,6 +1074,7 @@ extern "C" int32_t dampr_host_unique_small(const int64_t *col, uint64_t n, uint6
     for (u64 v = 0; v < table; ++v) {
         if (rank[v]) {
             uniq[m] = (int64_t)v;
+            if (first_row) first_row[m] = first[v];
             rank[v] = (u32)m++;
         }
     }

@@ -93,7 +93,7 @@ def load_library():
     _sig(lib, "dampr_kv_decode_words", vp, vp, i32, u32, vp)
     _sig(lib, "dampr_host_join_tsv", u64, i32, vp, vp, vp, vp, vp, vp, u64, pu64)
     _sig(lib, "dampr_host_sink_tsv", C.c_char_p, u64, i32, vp, vp, vp, vp, vp, pu64)
-    _sig(lib, "dampr_host_unique_small", vp, u64, u64, vp, pu64, vp, vp, vp, u64, pu64)
+    _sig(lib, "dampr_host_unique_small", vp, u64, u64, vp, pu64, vp, vp, vp, vp, u64, pu64)
     _sig(lib, "dampr_kv_create", vp, u64, pvp)
     _sig(lib, "dampr_kv_destroy", vp, vp)
     _sig(lib, "dampr_kv_size", vp, vp, pu64)
@@ -543,9 +543,9 @@ def host_join_tsv(columns, path=None):
     return out
 
 
-def host_unique_small(col, table=1 << 20):
-    """(uniq ascending, inv uint32) of an int64 column whose values are mostly in [0, table), or None
-    when too many values fall outside (the caller then uses a sort)."""
+def host_unique_small(col, table=1 << 20, with_rows=False):
+    """(uniq ascending, inv uint32[, first row of every distinct value]) of an int64 column whose values
+    are mostly in [0, table), or None when too many values fall outside (the caller then uses a sort)."""
     lib = load_library()
     col = np.ascontiguousarray(col, dtype=np.int64)
     n = len(col)
@@ -555,12 +555,14 @@ def host_unique_small(col, table=1 << 20):
     bv = np.empty(cap, dtype=np.int64)
     br = np.empty(cap, dtype=np.uint64)
     m, nb = C.c_uint64(0), C.c_uint64(0)
-    rc = lib.dampr_host_unique_small(_ptr(col), n, table, _ptr(uniq), C.byref(m), _ptr(inv), _ptr(bv), _ptr(br),
-                                     cap, C.byref(nb))
+    rows = np.empty(min(n, table), dtype=np.uint32) if with_rows else None
+    rc = lib.dampr_host_unique_small(_ptr(col), n, table, _ptr(uniq), C.byref(m), _ptr(inv), _ptr(rows), _ptr(bv),
+                                     _ptr(br), cap, C.byref(nb))
     if rc:
         return None
     m, nb = m.value, nb.value
     uniq = uniq[:m]
+    rows = rows[:m].astype(np.int64) if with_rows else None
     if nb:
         bv, br = bv[:nb], br[:nb].astype(np.int64)
         if int(bv.min()) < table:   # negative values: the two ranges would interleave
@@ -568,7 +570,11 @@ def host_unique_small(col, table=1 << 20):
         ul, il = np.unique(bv, return_inverse=True)
         inv[br] = il.astype(np.uint32) + np.uint32(m)
         uniq = np.concatenate((uniq, ul))
-    return uniq, inv
+        if with_rows:
+            rb = np.empty(len(ul), dtype=np.int64)
+            rb[il] = br
+            rows = np.concatenate((rows, rb))
+    return (uniq, inv, rows) if with_rows else (uniq, inv)
 
 
 def kv_merge(ctx, runs, xform, op=-1):

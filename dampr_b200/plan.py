@@ -54,6 +54,19 @@ class DictCol(object):
         return [u[j] for j in il]
 
 
+def unique_inverse_rows(col):
+    """unique_inverse plus one row index per distinct value (any row holding it)."""
+    n = len(col)
+    if n >= 4096 and col.dtype == np.int64:
+        r = dev.host_unique_small(col, with_rows=True)
+        if r is not None:
+            return r
+    uniq, inv = unique_inverse(col)
+    rep = np.empty(len(uniq), dtype=np.int64)
+    rep[inv] = np.arange(n, dtype=np.int64)
+    return uniq, inv, rep
+
+
 def unique_inverse(col):
     """(sorted unique values, inverse index uint32) of an int64/float64 column. Small non-negative
     ints (the bulk of count columns) go through a counting pass instead of a sort."""
@@ -1085,7 +1098,7 @@ def _lower_cross(runner, stage, inputs):
             src = outer.cols[f]
             if _numeric(src) and src.dtype.kind in "iu":
                 # share the dictionary with the components computed from this field (and with the sink)
-                uq = dict_cache.get(f) or unique_inverse(src)
+                uq = dict_cache.get(f) or unique_inverse_rows(src)
                 dict_cache[f] = uq
                 src = DictCol(uq[1], uq[0])
             out_cols.append(src)
@@ -1097,14 +1110,14 @@ def _lower_cross(runner, stage, inputs):
         if len(dep) != 1 or not (isinstance(outer.cols[dep[0]], DictCol) or _numeric(outer.cols[dep[0]])):
             return None
         col = outer.cols[dep[0]]
+        # one representative row per distinct value (any row holding it)
         if isinstance(col, DictCol):
             uniq, inv = col.uniq, col.inv
+            rep = np.empty(len(uniq), dtype=np.int64)
+            rep[inv] = np.arange(outer.n, dtype=np.int64)
         else:
-            uniq, inv = dict_cache.get(dep[0]) or unique_inverse(col)
-            dict_cache[dep[0]] = (uniq, inv)
-        # one representative row per distinct value (any row holding it)
-        rep = np.empty(len(uniq), dtype=np.int64)
-        rep[inv] = np.arange(outer.n, dtype=np.int64)
+            uniq, inv, rep = dict_cache.get(dep[0]) or unique_inverse_rows(col)
+            dict_cache[dep[0]] = (uniq, inv, rep)
         # representative rows, gathered column-wise (no per-cell Python dispatch)
         rep_cols = [_gather(c, rep) for c in outer.cols]
         res = []

@@ -165,10 +165,11 @@ int32_t dampr_host_sink_tsv(const char *path, uint64_t n, int32_t ncols, const i
                             const void *const *aux2, uint64_t *out_len);
 /* dictionary encoding of an int64 column (host helper of the frame layer): values in [0, table) are
  * ranked through a presence table -> uniq[0..*n_uniq) ascending and inv[i]; other values are handed
- * back in big_vals / big_rows (at most big_cap, else the call fails) and their inv[] is untouched. */
+ * back in big_vals / big_rows (at most big_cap, else the call fails) and their inv[] is untouched.
+ * first_row (optional) receives the first row holding each distinct value. n < 2^32. */
 int32_t dampr_host_unique_small(const int64_t *col, uint64_t n, uint64_t table, int64_t *uniq,
-                                uint64_t *n_uniq, uint32_t *inv, int64_t *big_vals, uint64_t *big_rows,
-                                uint64_t big_cap, uint64_t *n_big);
+                                uint64_t *n_uniq, uint32_t *inv, uint32_t *first_row, int64_t *big_vals,
+                                uint64_t *big_rows, uint64_t big_cap, uint64_t *n_big);
 /* same, but leaves the run on the device as a kv (key = code, val = count) */
 int32_t dampr_table_to_kv(dampr_ctx *ctx, dampr_table *t, dampr_kv **out);
 
