@@ -306,6 +306,23 @@ def main():
     sampler.stop_flag.set()
     if sampler.is_alive():
         sampler.join(timeout=5)
+    if os.environ.get("DAMPR_BENCH_PROFILE") and rank == 0:
+        # development aid: where the host time of a device-resident step goes (after the timed loops)
+        import cProfile
+        import io
+        import pstats
+        pr = cProfile.Profile()
+        pr.enable()
+        for i in range(5):
+            step(True, 100 + i)
+        pr.disable()
+        for key in ("cumulative", "tottime"):
+            sio = io.StringIO()
+            pstats.Stats(pr, stream=sio).sort_stats(key).print_stats(35)
+            print(sio.getvalue()[:7000], file=sys.stderr)
+    elif os.environ.get("DAMPR_BENCH_PROFILE"):
+        for i in range(5):
+            step(True, 100 + i)
 
     # result size fetched from the device per step
     n_terms = 0
