@@ -327,8 +327,9 @@ def main():
     # result size fetched from the device per step
     n_terms = 0
     try:
-        with open(os.path.join(d, "part-0")) as f:
-            n_terms = sum(1 for _ in f)
+        for fn in os.listdir(d):
+            with open(os.path.join(d, fn)) as f:
+                n_terms += sum(1 for _ in f)
     except Exception:
         pass
 

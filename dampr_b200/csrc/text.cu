@@ -965,32 +965,23 @@ extern "C" int32_t dampr_host_join_tsv(uint64_t n, int32_t ncols, const int32_t 
     return DAMPR_OK;
 }
 
-// The same rows straight into a file: every thread formats its row span into a private buffer and
-// pwrite()s it at its final offset (one length pass, no result array, the page-cache copies run in
-// parallel).  Replaces SinkWriter's print(value, file=...) loop (dataset.py:264-282).
-extern "C" int32_t dampr_host_sink_tsv(const char *path, uint64_t n, int32_t ncols, const int32_t *kinds,
-                                       const void *const *ptrs, const uint32_t *widths, const void *const *aux,
-                                       const void *const *aux2, uint64_t *out_len) {
-    if (!path || !kinds || !ptrs || !out_len || ncols < 1 || ncols > 16) return DAMPR_ERR_ARG;
+// The same rows straight into part files.  Buffered writes to ONE file serialise on its inode lock, so
+// large outputs are split by row range into up to max_files files `<prefix><first_index + j>`, each
+// formatted and written by its own thread (the reference writes one part file per sink job as well:
+// SinkStageRunner.sink stagerunner.py:165-189, SinkWriter dataset.py:264-282).
+extern "C" int32_t dampr_host_sink_tsv(const char *prefix, uint32_t first_index, uint32_t max_files, uint64_t n,
+                                       int32_t ncols, const int32_t *kinds, const void *const *ptrs,
+                                       const uint32_t *widths, const void *const *aux, const void *const *aux2,
+                                       uint64_t *out_len, uint32_t *n_files) {
+    if (!prefix || !kinds || !ptrs || !out_len || !n_files || ncols < 1 || ncols > 16 || max_files < 1)
+        return DAMPR_ERR_ARG;
     JoinArgs a{n, ncols, kinds, ptrs, widths, aux, aux2};
-    unsigned hw = std::thread::hardware_concurrency();
-    int T = (int)std::min<u64>(std::max(1u, std::min(hw, 16u)), std::max<u64>(1, n / 16384));
-    std::vector<u64> lens(T, 0), offs(T + 1, 0);
-    auto span = [&](int t) { return std::make_pair(n * t / T, n * (t + 1) / T); };
-    auto fan = [&](const std::function<void(int)> &f) {
-        std::vector<std::thread> th;
-        for (int t = 1; t < T; ++t) th.emplace_back(f, t);
-        f(0);
-        for (auto &x : th) x.join();
-    };
     // longest possible row: fixed widths + the longest string of every dictionary + separators
     u64 max_row = (u64)ncols;
     for (int c = 0; c < ncols; ++c) {
         if (kinds[c] == 0) {
             max_row += widths[c];
         } else {
-            // dictionary size = largest index in use + 1 is not known here: offsets are monotone, so the
-            // longest entry is found by walking them up to the blob end the caller encoded in aux2[c][m]
             const u32 *off = (const u32 *)aux2[c];
             const u32 *inv = (const u32 *)ptrs[c];
             u32 m = 0;
@@ -1000,46 +991,49 @@ extern "C" int32_t dampr_host_sink_tsv(const char *path, uint64_t n, int32_t nco
             max_row += longest;
         }
     }
-    // format every span into a private buffer sized for the longest possible rows (malloc: pages that are
-    // never written cost nothing), so one pass over the rows is enough ...
-    std::vector<u8 *> bufs(T, nullptr);
+    unsigned hw = std::thread::hardware_concurrency();
+    const int T = (int)std::min<u64>(std::min<u64>(std::max(1u, std::min(hw, 16u)), max_files), std::max<u64>(1, n / 98304));
+    std::vector<u64> lens(T, 0);
     std::atomic<int> bad{0};
-    fan([&](int t) {
-        auto r = span(t);
-        const u64 rows = (u64)r.second - (u64)r.first;
-        if (!rows) return;
-        bufs[t] = (u8 *)malloc(rows * max_row);
-        if (!bufs[t]) {
+    auto work = [&](int t) {
+        const u64 lo = n * t / T, hi = n * (t + 1) / T;
+        std::string path = std::string(prefix) + std::to_string(first_index + (u32)t);
+        int fd = open(path.c_str(), O_WRONLY | O_CREAT | O_TRUNC, 0644);
+        if (fd < 0) {
             bad.store(1);
             return;
         }
-        lens[t] = join_rows(a, r.first, r.second, bufs[t]);
-    });
-    if (bad.load()) {
-        for (auto p : bufs) free(p);
-        return DAMPR_ERR_ARG;
-    }
-    for (int t = 0; t < T; ++t) offs[t + 1] = offs[t] + lens[t];
-    *out_len = offs[T];
-    int fd = open(path, O_WRONLY | O_CREAT | O_TRUNC, 0644);
-    if (fd < 0) {
-        for (auto p : bufs) free(p);
-        return DAMPR_ERR_ARG;
-    }
-    // ... then every thread writes its span at its final offset
-    fan([&](int t) {
+        // malloc of the upper bound: pages that are never written cost nothing, one pass over the rows
+        u8 *buf = (hi > lo) ? (u8 *)malloc((hi - lo) * max_row) : nullptr;
+        if (hi > lo && !buf) {
+            bad.store(1);
+            close(fd);
+            return;
+        }
+        const u64 len = (hi > lo) ? join_rows(a, lo, hi, buf) : 0;
         u64 done = 0;
-        while (done < lens[t]) {
-            ssize_t w = pwrite(fd, bufs[t] + done, lens[t] - done, (off_t)(offs[t] + done));
+        while (done < len) {
+            ssize_t w = write(fd, buf + done, len - done);
             if (w <= 0) {
                 bad.store(1);
-                return;
+                break;
             }
             done += (u64)w;
         }
-    });
-    if (close(fd) != 0) bad.store(1);
-    for (auto p : bufs) free(p);
+        free(buf);
+        if (close(fd) != 0) bad.store(1);
+        lens[t] = len;
+    };
+    {
+        std::vector<std::thread> th;
+        for (int t = 1; t < T; ++t) th.emplace_back(work, t);
+        work(0);
+        for (auto &x : th) x.join();
+    }
+    u64 total = 0;
+    for (int t = 0; t < T; ++t) total += lens[t];
+    *out_len = total;
+    *n_files = (u32)T;
     return bad.load() ? DAMPR_ERR_ARG : DAMPR_OK;
 }
 

@@ -92,7 +92,8 @@ def load_library():
     _sig(lib, "dampr_table_fetch_words", vp, vp, vp, i32, u32, vp, vp, vp, vp, u64, pu64)
     _sig(lib, "dampr_kv_decode_words", vp, vp, i32, u32, vp)
     _sig(lib, "dampr_host_join_tsv", u64, i32, vp, vp, vp, vp, vp, vp, u64, pu64)
-    _sig(lib, "dampr_host_sink_tsv", C.c_char_p, u64, i32, vp, vp, vp, vp, vp, pu64)
+    _sig(lib, "dampr_host_sink_tsv", C.c_char_p, C.c_uint32, C.c_uint32, u64, i32, vp, vp, vp, vp, vp, pu64,
+         C.POINTER(C.c_uint32))
     _sig(lib, "dampr_host_unique_small", vp, u64, u64, vp, pu64, vp, vp, vp, vp, u64, pu64)
     _sig(lib, "dampr_kv_create", vp, u64, pvp)
     _sig(lib, "dampr_kv_destroy", vp, vp)
@@ -493,10 +494,11 @@ class KV(object):
             pass
 
 
-def host_join_tsv(columns, path=None):
+def host_join_tsv(columns, prefix=None, first=0, max_files=16):
     """Rows of tab-separated text from columns (native host loop). Each column is either a numpy
     'S<w>' array (NUL-padded fixed-width strings) or a pair (inv uint32 array, list of bytes).
-    With `path` the rows are written to that file (returns the byte count) instead of returned."""
+    With `prefix` the rows are written to part files prefix<first>, prefix<first+1>, ... (row ranges, one
+    writer thread per file; returns the file names) instead of returned."""
     lib = load_library()
     k = len(columns)
     n = None
@@ -528,11 +530,13 @@ def host_join_tsv(columns, path=None):
         assert n is None or n == m
         n = m
     out_len = C.c_uint64(0)
-    if path is not None:
-        rc = lib.dampr_host_sink_tsv(os.fsencode(path), n, k, kinds, ptrs, widths, aux, aux2, C.byref(out_len))
+    if prefix is not None:
+        nf = C.c_uint32(0)
+        rc = lib.dampr_host_sink_tsv(os.fsencode(prefix), int(first), int(max_files), n, k, kinds, ptrs, widths,
+                                     aux, aux2, C.byref(out_len), C.byref(nf))
         if rc:
-            raise DeviceError("dampr_host_sink_tsv(%r) failed (%d)" % (path, rc))
-        return out_len.value
+            raise DeviceError("dampr_host_sink_tsv(%r) failed (%d)" % (prefix, rc))
+        return ["%s%d" % (prefix, first + j) for j in range(nf.value)]
     rc = lib.dampr_host_join_tsv(n, k, kinds, ptrs, widths, aux, aux2, None, 0, C.byref(out_len))
     if rc:
         raise DeviceError("dampr_host_join_tsv failed (%d)" % rc)

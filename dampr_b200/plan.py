@@ -1343,11 +1343,14 @@ def _lower_sink(runner, stage, inputs):
     if cols is None or any(c is None for c in cols):
         return None
     os.makedirs(stage.path, exist_ok=True)
-    fname = os.path.join(stage.path, "part-%d" % (dist.world()[0] if dist.active() else 0))
+    # part files: up to 16 per process (row ranges written in parallel), numbered after the rank
+    first = 16 * dist.world()[0] if dist.active() else 0
+    prefix = os.path.join(stage.path, "part-")
     if fr.n:
-        dev.host_join_tsv(cols, path=fname)   # formatted and written by native threads
+        names = dev.host_join_tsv(cols, prefix=prefix, first=first)   # formatted and written by native threads
     else:
-        open(fname, "wb").close()
+        names = ["%s%d" % (prefix, first)]
+        open(names[0], "wb").close()
     lines = range(fr.n)
     runner.stats.add(stage, "native frame sink (per-distinct-value formatting)", "records=%d" % len(lines))
-    return CatDataset([TextLineDataset(fname)])
+    return CatDataset([TextLineDataset(fn) for fn in names])

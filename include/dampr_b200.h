@@ -158,11 +158,14 @@ int32_t dampr_kv_decode_words(dampr_ctx *ctx, dampr_kv *kv, int32_t mode, uint32
 int32_t dampr_host_join_tsv(uint64_t n, int32_t ncols, const int32_t *kinds, const void *const *ptrs,
                             const uint32_t *widths, const void *const *aux, const void *const *aux2,
                             uint8_t *out, uint64_t cap, uint64_t *out_len);
-/* the same rows written straight to `path` (created / truncated): the row spans are formatted and
- * pwrite()n in parallel. Replaces SinkWriter's print-per-record loop (dataset.py:264-282). */
-int32_t dampr_host_sink_tsv(const char *path, uint64_t n, int32_t ncols, const int32_t *kinds,
-                            const void *const *ptrs, const uint32_t *widths, const void *const *aux,
-                            const void *const *aux2, uint64_t *out_len);
+/* the same rows written straight to part files `<prefix><first_index + j>`, j < *n_files <= max_files:
+ * large outputs are split by row range, every file is formatted and written by its own thread (buffered
+ * writes to one file serialise on its inode lock). Replaces SinkStageRunner.sink (stagerunner.py:165-189)
+ * + SinkWriter's print-per-record loop (dataset.py:264-282). */
+int32_t dampr_host_sink_tsv(const char *prefix, uint32_t first_index, uint32_t max_files, uint64_t n,
+                            int32_t ncols, const int32_t *kinds, const void *const *ptrs,
+                            const uint32_t *widths, const void *const *aux, const void *const *aux2,
+                            uint64_t *out_len, uint32_t *n_files);
 /* dictionary encoding of an int64 column (host helper of the frame layer): values in [0, table) are
  * ranked through a presence table -> uniq[0..*n_uniq) ascending and inv[i]; other values are handed
  * back in big_vals / big_rows (at most big_cap, else the call fails) and their inv[] is untouched.
