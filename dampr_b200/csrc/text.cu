@@ -894,6 +894,7 @@ extern "C" int32_t dampr_table_fetch_words(dampr_ctx *ctx, dampr_table *t, dampr
 // Joins k columns with '\t' and terminates rows with '\n'. Column kinds:
 //   0  fixed-width NUL-padded bytes  ptr = u8[n][width]
 //   1  dictionary                    ptr = u32 inv[n], aux = blob bytes, aux2 = u32 offsets[m+1]
+//   2  dictionary of int64 values    ptr = u32 inv[n], aux = int64 values[m], widths = m (decimal text)
 // out == NULL: only *out_len is computed.
 namespace {
 struct JoinArgs {
@@ -905,6 +906,50 @@ struct JoinArgs {
     const void *const *aux;
     const void *const *aux2;
 };
+
+// kind 2 (dictionary of int64 values: ptr = u32 inv[n], aux = int64 values[m], widths = m) is turned into
+// kind 1 once per call: the m distinct values are formatted in decimal here instead of in Python
+struct IntDicts {
+    std::vector<std::vector<u8>> blobs;
+    std::vector<std::vector<u32>> offs;
+    std::vector<int32_t> kinds;
+    std::vector<const void *> aux, aux2;
+};
+static void lower_int_dicts(int ncols, const int32_t *kinds, const uint32_t *widths, const void *const *aux,
+                            const void *const *aux2, IntDicts &d) {
+    d.kinds.assign(kinds, kinds + ncols);
+    d.aux.assign(aux, aux + ncols);
+    d.aux2.assign(aux2, aux2 + ncols);
+    d.blobs.resize(ncols);
+    d.offs.resize(ncols);
+    for (int c = 0; c < ncols; ++c) {
+        if (kinds[c] != 2) continue;
+        const int64_t *vals = (const int64_t *)aux[c];
+        const u32 m = widths[c];
+        auto &blob = d.blobs[c];
+        auto &off = d.offs[c];
+        blob.reserve((size_t)m * 8);
+        off.resize((size_t)m + 1);
+        off[0] = 0;
+        for (u32 j = 0; j < m; ++j) {
+            char tmp[24];
+            int64_t v = vals[j];
+            u64 u = v < 0 ? (u64)0 - (u64)v : (u64)v;
+            int k = 24;
+            do {
+                tmp[--k] = (char)('0' + u % 10);
+                u /= 10;
+            } while (u);
+            if (v < 0) tmp[--k] = '-';
+            blob.insert(blob.end(), tmp + k, tmp + 24);
+            off[j + 1] = (u32)blob.size();
+        }
+        if (blob.empty()) blob.push_back(0);
+        d.kinds[c] = 1;
+        d.aux[c] = blob.data();
+        d.aux2[c] = off.data();
+    }
+}
 
 // rows [lo, hi): returns the byte count; writes when out != nullptr
 static u64 join_rows(const JoinArgs &a, u64 lo, u64 hi, u8 *out) {
@@ -939,7 +984,9 @@ extern "C" int32_t dampr_host_join_tsv(uint64_t n, int32_t ncols, const int32_t 
                                        const uint32_t *widths, const void *const *aux, const void *const *aux2,
                                        uint8_t *out, uint64_t cap, uint64_t *out_len) {
     if (!kinds || !ptrs || !out_len || ncols < 1 || ncols > 16) return DAMPR_ERR_ARG;
-    JoinArgs a{n, ncols, kinds, ptrs, widths, aux, aux2};
+    IntDicts idc;
+    lower_int_dicts(ncols, kinds, widths, aux, aux2, idc);
+    JoinArgs a{n, ncols, idc.kinds.data(), ptrs, widths, idc.aux.data(), idc.aux2.data()};
     unsigned hw = std::thread::hardware_concurrency();
     int T = (int)std::min<u64>(std::max(1u, std::min(hw, 16u)), std::max<u64>(1, n / 16384));
     std::vector<u64> lens(T, 0), offs(T + 1, 0);
@@ -975,6 +1022,11 @@ extern "C" int32_t dampr_host_sink_tsv(const char *prefix, uint32_t first_index,
                                        uint64_t *out_len, uint32_t *n_files) {
     if (!prefix || !kinds || !ptrs || !out_len || !n_files || ncols < 1 || ncols > 16 || max_files < 1)
         return DAMPR_ERR_ARG;
+    IntDicts idc;
+    lower_int_dicts(ncols, kinds, widths, aux, aux2, idc);
+    kinds = idc.kinds.data();
+    aux = idc.aux.data();
+    aux2 = idc.aux2.data();
     JoinArgs a{n, ncols, kinds, ptrs, widths, aux, aux2};
     // longest possible row: fixed widths + the longest string of every dictionary + separators
     u64 max_row = (u64)ncols;

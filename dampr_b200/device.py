@@ -496,8 +496,8 @@ class KV(object):
 
 def host_join_tsv(columns, prefix=None, first=0, max_files=16):
     """Rows of tab-separated text from columns (native host loop). Each column is either a numpy
-    'S<w>' array (NUL-padded fixed-width strings) or a pair (inv uint32 array, list of bytes).
-    With `prefix` the rows are written to part files prefix<first>, prefix<first+1>, ... (row ranges, one
+    'S<w>' array (NUL-padded fixed-width strings), a pair (inv uint32 array, list of bytes) or a pair
+    (inv uint32 array, int64 array of the distinct values). With `prefix` the rows are written to part files prefix<first>, prefix<first+1>, ... (row ranges, one
     writer thread per file; returns the file names) instead of returned."""
     lib = load_library()
     k = len(columns)
@@ -516,6 +516,14 @@ def host_join_tsv(columns, prefix=None, first=0, max_files=16):
             ptrs[c] = arr.ctypes.data
             keep.append(arr)
             m = len(arr)
+        elif isinstance(col[1], np.ndarray):   # (inv, int64 values): formatted natively
+            inv, vals = col
+            inv = np.ascontiguousarray(inv, dtype=np.uint32)
+            vals = np.ascontiguousarray(vals, dtype=np.int64)
+            kinds[c], widths[c] = 2, len(vals)
+            ptrs[c], aux[c] = inv.ctypes.data, vals.ctypes.data
+            keep.extend([inv, vals])
+            m = len(inv)
         else:
             inv, strs = col
             inv = np.ascontiguousarray(inv, dtype=np.uint32)

@@ -1310,6 +1310,8 @@ def _sink_column(col):
     """A frame column in the form dampr_host_join_tsv takes: an 'S' array, or (inv, [bytes per distinct
     value]) with Python's own str() of every distinct value (exact float repr); None if unsupported."""
     if isinstance(col, DictCol):
+        if isinstance(col.uniq, np.ndarray) and col.uniq.dtype == np.int64:
+            return (col.inv, col.uniq)   # decimal text of the distinct ints is produced natively
         u = col.uniq.tolist() if isinstance(col.uniq, np.ndarray) else col.uniq
         return (col.inv, [str(x).encode("utf-8") for x in u])
     if isinstance(col, np.ndarray):
@@ -1317,6 +1319,8 @@ def _sink_column(col):
             return col
         if col.dtype.kind in "iuf":
             uniq, inv = unique_inverse(col)
+            if uniq.dtype == np.int64:
+                return (inv, uniq)
             return (inv, [str(x).encode("utf-8") for x in uniq.tolist()])
         return None
     if isinstance(col, list) and all(type(x) is str for x in col):

@@ -153,7 +153,8 @@ int32_t dampr_kv_decode_words(dampr_ctx *ctx, dampr_kv *kv, int32_t mode, uint32
                               uint8_t *words_host);
 /* host-side sink formatting (SinkWriter, dataset.py:264-282): joins ncols columns with '\t', rows end
  * with '\n'. kinds[c] == 0: ptrs[c] = u8[n][widths[c]] NUL-padded strings; kinds[c] == 1: ptrs[c] =
- * u32 inv[n] into a dictionary of strings aux[c] (bytes) / aux2[c] (u32 offsets[m+1]).
+ * u32 inv[n] into a dictionary of strings aux[c] (bytes) / aux2[c] (u32 offsets[m+1]); kinds[c] == 2:
+ * the same with a dictionary of int64 values aux[c][widths[c]], written in decimal.
  * out == NULL computes *out_len only. Pure host code, no device work. */
 int32_t dampr_host_join_tsv(uint64_t n, int32_t ncols, const int32_t *kinds, const void *const *ptrs,
                             const uint32_t *widths, const void *const *aux, const void *const *aux2,
