@@ -370,8 +370,8 @@ def main():
                        "e2e_stage_ms": [round(ms, 2) for _s, ms in (runner_mod.LAST_STATS.ms if runner_mod.LAST_STATS else [])]},
             "e2e": {"value": e2e, "unit": "MB/s", "h2d_bytes_per_step": nbytes * world,
                     # result table per term: 16-byte key string + 8-byte count (single GPU; the synthetic
-                    # corpus has no hashed tokens), 32 + 8 + 8-byte code after the exchange (multi GPU)
-                    "d2h_bytes_per_step": int(n_terms) * (24 if world == 1 else 48),
+                    # corpus has no hashed tokens), plus the 8-byte code after the exchange (multi GPU)
+                    "d2h_bytes_per_step": int(n_terms) * (24 if world == 1 else 32),
                     "ms_per_step": 1e3 * t_e2e / args.steps,
                     "step_ms": e2e_steps},
             "gpu_launches": int(launches), "clocks": sampler.summary(), "roofline": roof}

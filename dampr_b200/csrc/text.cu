@@ -1173,12 +1173,12 @@ extern "C" int32_t dampr_kv_decode_words(dampr_ctx *ctx, dampr_kv *kv, int32_t m
         kv_words_kernel<<<ctx->num_sms * 4, 256, 0, ctx->stream>>>(kv->rec, kv->n, mode, width, d);
     }
     cudaError_t e = cudaGetLastError();
-    if (e == cudaSuccess) e = cudaMemcpyAsync(words_host, d, kv->n * width, cudaMemcpyDeviceToHost, ctx->stream);
-    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    int rc2 = DAMPR_OK;
+    if (e == cudaSuccess) rc2 = staged_d2h(ctx, words_host, d, kv->n * width, ctx->stream);
     pool_free(ctx, d);
     if (e != cudaSuccess) {
         ctx->err = std::string("kv decode_words failed: ") + cudaGetErrorString(e);
         return DAMPR_ERR_CUDA;
     }
-    return DAMPR_OK;
+    return rc2;
 }

@@ -434,7 +434,7 @@ class KV(object):
     def decode_words(self, mode, width=32):
         """Keys are token codes: 'S<width>' array decoded on the device (hashed codes -> b'')."""
         n = len(self)
-        words = np.zeros((n, width), dtype=np.uint8)
+        words = np.empty((n, width), dtype=np.uint8)
         self.ctx.check(self.ctx.lib.dampr_kv_decode_words(self.ctx.h, self.h, int(mode), int(width), _ptr(words)))
         return words.view("S%d" % width).ravel()
 

@@ -385,7 +385,7 @@ class TextScan(object):
         red = recv.sort_reduce(dev.OP_SUM_I64, dev.KEY_MIX)
         recv.free()
         codes, counts = red.columns()
-        W = 32
+        W = 32 if any_hashed else 16             # exact codes hold at most 12 characters
         words = red.decode_words(self.mode, W)   # exact codes decoded on the device
         red.free()
         hs = np.flatnonzero((codes & keycodes.HASHED_BIT) != 0)
