@@ -197,9 +197,23 @@ def _text_files(ds):
         files = [d.path for d in ds.datasets]
     else:
         return None
-    if any(f.endswith(".gz") for f in files):
-        return None
-    return [("file", f) for f in files]
+    # .gz inputs (TextInput on a gzip file: one unsplittable chunk, inputs.py:43-46 / dataset.py:484-499 in
+    # the reference) are inflated on the host and ingested like in-memory text
+    return [("gz" if f.endswith(".gz") else "file", f) for f in files]
+
+
+def _inflate(paths):
+    """Decompressed bytes of gzip files as uint8 arrays (zlib releases the GIL: one thread per file)."""
+    import gzip
+    from concurrent.futures import ThreadPoolExecutor
+
+    def one(p):
+        with gzip.open(p, "rb") as f:
+            return np.frombuffer(f.read(), dtype=np.uint8)
+    if len(paths) == 1:
+        return [one(paths[0])]
+    with ThreadPoolExecutor(min(len(paths), max(1, int(settings.max_processes)))) as ex:
+        return list(ex.map(one, paths))
 
 
 _PIN_RING = {}
@@ -285,6 +299,12 @@ class TextScan(object):
             tb = self.sources[0][1]
             self.nbytes = tb.n
         else:
+            gz = [p for kind, p in self.sources if kind == "gz"]
+            if gz:
+                if dist.active():
+                    raise NotLowerable("gzip inputs are not sharded across ranks")
+                texts = iter(_inflate(gz))
+                self.sources = [("mem", next(texts)) if kind == "gz" else (kind, p) for kind, p in self.sources]
             sizes = []
             for kind, p in self.sources:
                 sizes.append(len(p) if kind == "mem" else os.path.getsize(p))

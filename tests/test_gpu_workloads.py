@@ -227,3 +227,26 @@ def test_sort_by_over_binary_records(ctx):
         assert got == sorted(rows, key=lambda r: r[0])
     finally:
         settings.device_arena_bytes = old
+
+
+def test_gzip_text_inputs_are_lowered(ctx, tmp_path):
+    """A .gz text file (one unsplittable chunk in the reference, inputs.py:43-46) is inflated on the host
+    and goes through the same device tokenise+combine pass as plain text."""
+    import gzip
+    text = gen.text(77, 4000, vocab=gen.make_vocab(500), cdf=gen.make_cdf(500))
+    plain = tmp_path / "c.txt"
+    plain.write_bytes(text)
+    with gzip.open(str(tmp_path / "c.txt.gz"), "wb") as f:
+        f.write(text)
+    exp = run_wc(str(plain))
+    got = run_wc(str(tmp_path / "c.txt.gz"))
+    assert lowered("device text tokenise+combine")
+    assert sorted(got) == sorted(exp)
+    d = tmp_path / "both"
+    d.mkdir()
+    (d / "a.txt").write_bytes(text)
+    with gzip.open(str(d / "b.txt.gz"), "wb") as f:
+        f.write(text)
+    got2 = dict(run_wc(str(d)))
+    assert lowered("device text tokenise+combine")
+    assert got2 == {w: 2 * c for w, c in exp}
