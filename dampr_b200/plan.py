@@ -137,7 +137,14 @@ class Frame(Dataset):
         return zip(keys, self.values())
 
     def take(self, perm):
+        done = {}   # a column object that appears twice (keys == cols[0] after a relabel) is gathered once
+
         def tk(c):
+            if id(c) not in done:
+                done[id(c)] = tk1(c)
+            return done[id(c)]
+
+        def tk1(c):
             if isinstance(c, vexpr.Tup):
                 return vexpr.Tup([tk(x) for x in c.items])
             if isinstance(c, DictCol):
