@@ -89,7 +89,7 @@ void pool_trim(dampr_ctx *ctx, size_t keep_bytes) {
         cudaFree(b.p);  // synchronises: safe regardless of the events
     }
 }
-int g_text_ctas = 3;
+int g_text_ctas = 4;
 
 // ---- staged transfers ---------------------------------------------------------------------------
 namespace {

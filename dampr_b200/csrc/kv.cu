@@ -997,7 +997,7 @@ int32_t dampr_set_option(const char *name, int64_t value) {
         return DAMPR_OK;
     }
     if (!strcmp(name, "text_ctas")) {
-        if (value != 2 && value != 3) return DAMPR_ERR_ARG;
+        if (value < 2 || value > 4) return DAMPR_ERR_ARG;
         g_text_ctas = (int)value;
         return DAMPR_OK;
     }

@@ -64,18 +64,24 @@ struct WarpScratchT {
 };
 constexpr u32 V_REP_UNPUB = 0xFFFFFFFFu;
 
-// NBUF = 2: double-buffered window, 2 CTAs/SM. NBUF = 1: single window, 3 CTAs/SM (more warps to
-// hide the smem / dependency latencies the ncu profile shows; the other CTAs cover the TMA wait).
-template <int NBUF, bool WS>
+// Three builds of the kernel, named by the CTAs per SM they are sized for (VAR):
+//   2  double-buffered window (the next tile is in flight while this one is processed), 2048-entry combiner
+//   3  single window, 2048-entry combiner: more warps to hide the smem / dependency latencies the ncu
+//      profile shows; the other CTAs cover the TMA wait
+//   4  single window, 1024-entry combiner, shorter per-line history (<= 64 registers per thread)
+template <int VAR, bool WS>
 struct Smem2T {
-    static constexpr int HCAP = (NBUF == 2) ? V_HCAP : V_HCAP / 2;
+    static constexpr int NBUF = (VAR == 2) ? 2 : 1;
+    static constexpr int HCAP = (VAR == 2) ? V_HCAP : (VAR == 3 ? V_HCAP / 2 : V_HCAP / 4);
+    static constexpr int STAB_LOG = (VAR == 4) ? V_STAB_LOG - 1 : V_STAB_LOG;
+    static constexpr int STAB = 1 << STAB_LOG;
     alignas(16) u8 text[NBUF][V_WIN];
     u32 w[NBUF][V_WORDS + 3];
     u32 nl[NBUF][V_WORDS + 3];
-    alignas(8) u64 tabk[V_STAB];
-    u32 tabc[V_STAB];
+    alignas(8) u64 tabk[STAB];
+    u32 tabc[STAB];
     // str.split mode: last occurrence (byte offset from own_lo - V_LEAD) of the long token an entry holds
-    u32 tabr[WS ? V_STAB : 1];
+    u32 tabr[WS ? STAB : 1];
     WarpScratchT<HCAP, WS> ws[V_WARPS];
     alignas(8) u64 bar[2];
     u32 flags;
@@ -266,13 +272,16 @@ __device__ __forceinline__ bool tok_equal_ws(const u8 *a, const u8 *b, u32 len) 
     return diff == 0 && !is_word_byte<DAMPR_TOK_WS>(term);
 }
 
-template <int MODE, int NBUF>
-__global__ void __launch_bounds__(V_THREADS, (NBUF == 2) ? 2 : 3)
+template <int MODE, int VAR>
+__global__ void __launch_bounds__(V_THREADS, VAR)
 text_count2_kernel(const u8 *__restrict__ text, u64 n, u64 own_lo, u64 own_hi, u64 base_offset, TableView2 tab) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     constexpr bool WS = (MODE == DAMPR_TOK_WS);
-    typedef Smem2T<NBUF, WS> Smem2;
+    typedef Smem2T<VAR, WS> Smem2;
+    constexpr int NBUF = Smem2::NBUF;
     constexpr int HCAP = Smem2::HCAP;
+    constexpr int V_STAB = Smem2::STAB;          // shadows the namespace-level defaults inside the kernel
+    constexpr int V_STAB_LOG = Smem2::STAB_LOG;
     Smem2 &s = *reinterpret_cast<Smem2 *>(smem_raw);
     const u32 tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const u32 lt_mask = (1u << lane) - 1u;
@@ -720,14 +729,14 @@ text_count2_kernel(const u8 *__restrict__ text, u64 n, u64 own_lo, u64 own_hi, u
     if (tid == 0 && s.flags) atomicOr(&tab.stats[S_FLAGS], (u64)s.flags);
 }
 
-template <int MODE, int NBUF>
+template <int MODE, int VAR>
 int launch2n(dampr_ctx *ctx, dampr_table *t, dampr_textbuf *tb, u64 lo, u64 hi) {
     if (hi <= lo) return DAMPR_OK;
-    size_t smem = sizeof(Smem2T<NBUF, MODE == DAMPR_TOK_WS>);
-    auto kern = text_count2_kernel<MODE, NBUF>;
+    size_t smem = sizeof(Smem2T<VAR, MODE == DAMPR_TOK_WS>);
+    auto kern = text_count2_kernel<MODE, VAR>;
     CUDA_TRY(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     u64 ntiles = (hi - lo + V_OWN - 1) / V_OWN;
-    u64 grid = (u64)ctx->num_sms * ((NBUF == 2) ? 2 : 3);
+    u64 grid = (u64)ctx->num_sms * VAR;
     if (grid > ntiles) grid = ntiles;
     TableView2 tv{t->keys, t->counts, t->reps, t->stats, t->cap - 1, 0x243F6A8885A308D3ULL};
     wait_uploads(ctx);
@@ -745,7 +754,9 @@ int launch2(dampr_ctx *ctx, dampr_table *t, dampr_textbuf *tb, u64 lo, u64 hi) {
     const u64 span = (MODE == DAMPR_TOK_WS) ? (1ULL << 31) : ~0ULL;
     for (u64 a = lo; a < hi;) {
         const u64 b = (hi - a > span) ? a + span : hi;
-        const int rc = g_text_ctas == 3 ? launch2n<MODE, 1>(ctx, t, tb, a, b) : launch2n<MODE, 2>(ctx, t, tb, a, b);
+        const int rc = g_text_ctas == 4   ? launch2n<MODE, 4>(ctx, t, tb, a, b)
+                       : g_text_ctas == 3 ? launch2n<MODE, 3>(ctx, t, tb, a, b)
+                                          : launch2n<MODE, 2>(ctx, t, tb, a, b);
         if (rc != DAMPR_OK) return rc;
         a = b;
     }

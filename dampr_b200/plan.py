@@ -341,8 +341,17 @@ class TextScan(object):
             raise NotLowerable("non-ASCII text or oversized token: device tokeniser is ASCII-only")
         if self.mode != dev.TOK_WS and flags & dev.TF_LONGLINE and not flags & dev.TF_CR \
                 and not getattr(self, "_retry_v1", False):
-            # a line too long (or with too many distinct tokens) for the warp-autonomous kernel:
-            # the first-generation kernel has a 4 KB line window and no per-line token limit
+            # a line with too many distinct tokens for the default build of the kernel (64 remembered per
+            # straddling line at 4 CTAs/SM): the 2-CTA build remembers 256 ...
+            if not getattr(self, "_retry_2cta", False):
+                self._retry_2cta = True
+                dev.set_option("text_ctas", 2)
+                try:
+                    return self.run()
+                finally:
+                    dev.set_option("text_ctas", int(settings.text_kernel_ctas))
+            # ... and a line too long for the warp-autonomous kernel altogether goes to the first-generation
+            # kernel (4 KB line window, no per-line token limit)
             self._retry_v1 = True
             dev.set_option("text_kernel", 1)
             try:

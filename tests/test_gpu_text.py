@@ -11,15 +11,16 @@ from oracle import gen, refsem
 pytestmark = pytest.mark.gpu
 
 
-@pytest.fixture(autouse=True, params=[(2, 3), (2, 2), (1, 2)], ids=["kernel-v2-3cta", "kernel-v2-2cta", "kernel-v1"])
+@pytest.fixture(autouse=True, params=[(2, 3), (2, 4), (2, 2), (1, 2)],
+                ids=["kernel-v2-3cta", "kernel-v2-4cta", "kernel-v2-2cta", "kernel-v1"])
 def text_kernel(request):
-    """Every case runs against both tokenise kernels (text2.cu in both occupancy variants is the
+    """Every case runs against both tokenise kernels (text2.cu in its three occupancy variants is the
     default, text.cu the fallback)."""
     dev.set_option("text_kernel", request.param[0])
     dev.set_option("text_ctas", request.param[1])
     yield request.param[0]
     dev.set_option("text_kernel", 2)
-    dev.set_option("text_ctas", 3)
+    dev.set_option("text_ctas", 4)
 
 
 def run_count(ctx, data, mode, chunk=None, verify=True):

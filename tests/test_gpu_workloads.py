@@ -115,6 +115,24 @@ def test_non_lowerable_text_falls_back_to_host_map(ctx, tmp_path):
     assert dict(got) == {"NAÏVE": 1, "CAFÉ": 1, "PLAIN": 1, "LINE": 1, "ÜBER": 2}
 
 
+def test_lines_with_many_distinct_tokens_stay_on_the_device(ctx, tmp_path):
+    """Lines with more distinct tokens than the default kernel build remembers (64) are retried on the
+    build with the longer history; lines beyond that go to the first-generation kernel."""
+    import random
+    rng = random.Random(9)
+    vocab = ["t%d" % i for i in range(3000)]
+    for per_line in (150, 400):
+        lines = [" ".join(rng.sample(vocab, rng.randint(1, 12))) for _ in range(300)]
+        lines[100] = " ".join(rng.sample(vocab, per_line))
+        lines[200] = " ".join(rng.sample(vocab, per_line) + rng.sample(vocab, 20))
+        data = ("\n".join(lines) + "\n").encode("ascii")
+        p = tmp_path / ("many%d.txt" % per_line)
+        p.write_bytes(data)
+        got = Dampr.text(str(p)).flat_map(lambda x: set(RX.split(x.lower()))).count().read()
+        assert lowered("device text tokenise+combine")
+        assert dict(got) == dict(refsem.docfreq(data)[0])
+
+
 def test_kv_workloads_match_reference_golden(ctx, tmp_path):
     fix = load("kv.json")
     keys, vals = gen.kv(42, 20000, 700)

@@ -50,8 +50,10 @@ def main():
         ctx.sync()
         print("synth text: %d bytes, %d lines in %.2fs" % (tb.n, n_lines, time.time() - t0))
         ctx.timings_reset()
-        for mode, name, ctas in ((dev.TOK_NONWORD_LOWER_SET, "tfidf-set-3cta", 3), (dev.TOK_NONWORD_LOWER_SET, "tfidf-set-2cta", 2),
-                                 (dev.TOK_WS, "wc-split", 3), (dev.TOK_NONWORD_LOWER, "nonword", 3)):
+        for mode, name, ctas in ((dev.TOK_NONWORD_LOWER_SET, "tfidf-set-3cta", 3), (dev.TOK_NONWORD_LOWER_SET, "tfidf-set-4cta", 4),
+                                 (dev.TOK_NONWORD_LOWER_SET, "tfidf-set-2cta", 2),
+                                 (dev.TOK_WS, "wc-split-3cta", 3), (dev.TOK_WS, "wc-split-4cta", 4),
+                                 (dev.TOK_NONWORD_LOWER, "nonword-3cta", 3), (dev.TOK_NONWORD_LOWER, "nonword-4cta", 4)):
             dev.set_option("text_ctas", ctas)
             for rep in range(3):
                 tab = ctx.table(21)
