@@ -54,6 +54,8 @@ def main():
                                  (dev.TOK_NONWORD_LOWER_SET, "tfidf-set-2cta", 2),
                                  (dev.TOK_WS, "wc-split-3cta", 3), (dev.TOK_WS, "wc-split-4cta", 4),
                                  (dev.TOK_NONWORD_LOWER, "nonword-3cta", 3), (dev.TOK_NONWORD_LOWER, "nonword-4cta", 4)):
+            if os.environ.get("QB_ONLY") and os.environ["QB_ONLY"] != name:
+                continue
             dev.set_option("text_ctas", ctas)
             for rep in range(3):
                 tab = ctx.table(21)
