@@ -11,12 +11,13 @@
 // Design (B200): MSD radix partition on the top bits of the (transformed) key, at most 10 bits
 // per level, two levels for up to ~3e9 records; every level is histogram -> scan -> scatter with
 // per-CTA contiguous record ranges ("pieces") so ranks are stable and no atomics touch HBM. The
-// scatter ranks records with warp match_any, stages a tile in shared memory bucket-major and
-// writes each bucket's run with one TMA bulk store (cp.async.bulk.global.shared::cta) or
-// coalesced 16-byte stores. Leaves (whole segments, <= 4096 records) are sorted in shared memory
-// by a counting sort on the next key bits plus a per-bin fix-up ordered by (key, input position),
-// which makes the whole sort stable and deterministic; the same kernel optionally folds each key
-// group (segmented reduce) before anything is written back.
+// scatter ranks records inside a warp with one ballot per digit bit, stages a tile in shared memory
+// bucket-major and writes each bucket's run with one TMA bulk store (cp.async.bulk.global.shared::cta)
+// or coalesced 16-byte stores. Leaves (whole segments, <= 4096 records) are sorted in shared memory
+// by a counting sort on the next key bits, after which every record ranks itself inside its bin by
+// (key, input position), which makes the whole sort stable and deterministic; the same kernel
+// optionally folds each key group (segmented reduce, or a shared-memory hash aggregate for commutative
+// integer folds) before anything is written back.
 #include <algorithm>
 
 #include "common.cuh"

@@ -7,17 +7,19 @@
 //
 // What changed, driven by the ncu profile of v1 (profiles/r01_text_v1_*.txt: 7.2 warp-instructions per
 // byte, 9 of 32 lanes active, 34 % of samples at block barriers):
-//   * one block barrier per 16 KB tile: the tile arrives by TMA (cp.async.bulk, double buffered, the
-//     next tile is in flight while this one is processed), all threads classify it 4 bytes per SWAR
-//     step into bit masks, then every warp owns one 2 KB strip and needs no further block sync;
+//   * one block barrier per 16 KB tile: the tile arrives by TMA (cp.async.bulk + mbarrier; single window
+//     at 3-4 CTAs/SM, double buffered at 2), all threads classify it 4 bytes per SWAR step into bit masks,
+//     then every warp owns one 2 KB strip and needs no further block sync;
 //   * one token per lane: token starts of 32 mask words are ranked with a warp scan and scattered to a
 //     per-warp position buffer, so all lanes do the same work on different tokens;
 //   * key codes without a per-character loop: the token's 12 bytes are fetched with three funnel
 //     shifts, mapped to symbols with SWAR arithmetic and packed base-38 (or 7 bits per char for
 //     str.split) in a fixed number of instructions;
-//   * set() de-duplication with two warp match_any (key, line) plus a short per-warp history of the
-//     line that straddles a round, instead of a per-token backward scan;
-//   * equal keys inside a warp are merged before touching the shared-memory combiner.
+//   * set() de-duplication by shuffle compares with the earlier lanes of the same line (the MATCH.ANY
+//     variant, kept behind DAMPR_TEXT_USE_MATCH, measured slower) plus a short per-warp history of the
+//     line that straddles a round;
+//   * a 2-way bucketed shared-memory combiner absorbs the Zipf head; misses are queued per warp and
+//     flushed 32 at a time to the L2-resident global table.
 #include "common.cuh"
 
 #ifndef DAMPR_TEXT_USE_MATCH
