@@ -561,6 +561,8 @@ def host_unique_small(col, table=1 << 20, with_rows=False):
     lib = load_library()
     col = np.ascontiguousarray(col, dtype=np.int64)
     n = len(col)
+    # the presence table is cleared and scanned once: keep it proportional to the column
+    table = int(min(table, max(4096, 1 << int(2 * n - 1).bit_length())))
     cap = n // 8 + 16
     uniq = np.empty(min(n, table), dtype=np.int64)
     inv = np.empty(n, dtype=np.uint32)
