@@ -1046,13 +1046,28 @@ int32_t dampr_kv_sort_reduce(dampr_ctx *ctx, dampr_kv *kv, int32_t key_xf, int32
     rc = sort_range(ctx, kv->rec, kv->alt, 0, kv->n, key_xf, base, top, op, (*out)->rec, &g, 0);
     if (rc) return rc;
     (*out)->n = g;
+    // the partition levels ping-pong between the two buffers of `kv` and the leaves stage their group
+    // records in whichever is free: the input is consumed
+    kv->n = 0;
     return DAMPR_OK;
 }
 
 int32_t dampr_kv_reduce_by_key(dampr_ctx *ctx, dampr_kv *sorted, int32_t op, dampr_kv **out) {
-    // a key-sorted run is reduced by the same machinery (grouping order = mixed key order is not
-    // what the caller has, so keep RAW order: the input is already sorted, levels are cheap)
-    return dampr_kv_sort_reduce(ctx, sorted, DAMPR_KEY_RAW, op, out);
+    ARG_CHECK(ctx, ctx && sorted && out, "null");
+    // a key-sorted run is reduced by the same machinery in RAW key order (the levels only re-discover
+    // the order the input already has), on a copy: the caller keeps its sorted run
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    wait_uploads(ctx);
+    dampr_kv *tmp = nullptr;
+    int rc = dampr_kv_create(ctx, sorted->n, &tmp);
+    if (rc) return rc;
+    if (sorted->n)
+        CUDA_TRY(ctx, cudaMemcpyAsync(tmp->rec, sorted->rec, sorted->n * sizeof(ulonglong2), cudaMemcpyDeviceToDevice,
+                                      ctx->stream));
+    tmp->n = sorted->n;
+    rc = dampr_kv_sort_reduce(ctx, tmp, DAMPR_KEY_RAW, op, out);
+    dampr_kv_destroy(ctx, tmp);
+    return rc;
 }
 
 int32_t dampr_kv_group_offsets(dampr_ctx *ctx, dampr_kv *sorted, uint64_t *offsets, uint64_t cap,

@@ -218,7 +218,8 @@ int32_t dampr_kv_sort(dampr_ctx *ctx, dampr_kv *kv, int32_t key_xform);
 #define DAMPR_OP_LAST 8
 
 /* segmented reduce of a key-sorted kv: one output record per key. Replaces
- * Dataset.grouped_read + Reduce.reduce (dataset.py:429-433, base.py:204-207). out is created. */
+ * Dataset.grouped_read + Reduce.reduce (dataset.py:429-433, base.py:204-207). out is created; `sorted`
+ * is left untouched (the reduction runs on a device copy). */
 int32_t dampr_kv_reduce_by_key(dampr_ctx *ctx, dampr_kv *sorted, int32_t op, dampr_kv **out);
 /* group boundaries of a key-sorted kv: offsets[g] = first record of group g, offsets[G] = n.
  * two-phase: pass offsets=NULL to get *n_groups. */
@@ -230,7 +231,9 @@ int32_t dampr_kv_group_offsets(dampr_ctx *ctx, dampr_kv *sorted, uint64_t *offse
 int32_t dampr_kv_merge(dampr_ctx *ctx, dampr_kv **runs, int32_t n_runs, int32_t key_xform,
                        int32_t op, dampr_kv **out);
 
-/* fused sort + reduce for associative ops (a_group_by(...).sum()/count()/...) */
+/* fused sort + reduce for associative ops (a_group_by(...).sum()/count()/...). CONSUMES `kv`: the
+ * partition levels and the leaves use both of its buffers as scratch, so its contents are undefined
+ * afterwards and its size is reset to 0 (destroy it, or upload new records). out is created. */
 int32_t dampr_kv_sort_reduce(dampr_ctx *ctx, dampr_kv *kv, int32_t key_xform, int32_t op,
                              dampr_kv **out);
 

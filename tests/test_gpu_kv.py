@@ -126,6 +126,25 @@ def test_reduce_float_sum_tolerance(ctx):
         assert abs(got[k] - exact) <= tol
 
 
+def test_reduce_consumes_or_keeps_its_input_as_documented(ctx):
+    """dampr_kv_sort_reduce consumes its input; dampr_kv_reduce_by_key leaves the sorted run alone, also
+    when segments are larger than a leaf (heavy keys) and the sizes force one or two partition levels."""
+    for n, nk in ((300_000, 40), (3_000_000, 1500)):
+        keys, vals = gen.kv(31, n, nk)
+        kv = ctx.kv_from_columns(keys, vals)
+        out = kv.sort_reduce(dev.OP_SUM_I64, dev.KEY_RAW)
+        assert len(kv) == 0
+        k1, v1 = out.columns()
+        assert dict(zip(k1.tolist(), v1.view(np.int64).tolist())) == refsem.group_sum(keys, vals)
+        kv = ctx.kv_from_columns(keys, vals).sort(dev.KEY_RAW)
+        before = kv.records().copy()
+        for op, exp in ((dev.OP_SUM_I64, refsem.group_sum(keys, vals)), (dev.OP_COUNT, refsem.group_count(keys))):
+            red = kv.reduce_by_key(op)
+            rk, rv = red.columns()
+            assert dict(zip(rk.tolist(), rv.view(np.int64).tolist())) == exp
+            assert len(kv) == n and np.array_equal(kv.records(), before)
+
+
 def test_heavy_single_key_reduce(ctx):
     n = 1_000_000
     keys = np.full(n, 12345, dtype=np.uint64)
