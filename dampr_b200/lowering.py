@@ -44,6 +44,20 @@ class E(object):
 _NULL = object()
 
 
+_INSTR_CACHE = {}
+
+
+def _instructions(code):
+    """Decoded bytecode of a code object (cached: graphs are rebuilt with fresh lambdas on every run, but
+    their code objects are the same, and decoding is the expensive part of the analysis)."""
+    ins = _INSTR_CACHE.get(code)
+    if ins is None:
+        if len(_INSTR_CACHE) > 4096:
+            _INSTR_CACHE.clear()
+        ins = _INSTR_CACHE[code] = list(dis.get_instructions(code))
+    return ins
+
+
 def analyze(fn):
     """Expression tree of a plain Python function / lambda, or None if it is not a straight-line
     expression over whitelisted opcodes."""
@@ -58,7 +72,7 @@ def analyze(fn):
     argnames = code.co_varnames[:nargs]
     stack = []
     try:
-        for ins in dis.get_instructions(fn):
+        for ins in _instructions(code):
             name = ins.opname
             if name in ("RESUME", "NOP", "COPY_FREE_VARS", "MAKE_CELL", "PRECALL", "CACHE"):
                 continue
