@@ -343,13 +343,6 @@ text_count2_kernel(const u8 *__restrict__ text, u64 n, u64 own_lo, u64 own_hi, u
         u32 *nm = s.nl[buf];
         mbar_wait(&s.bar[buf], phase[buf]);
         phase[buf] ^= 1;
-        if (NBUF == 1) {
-            // single window: the next tile's TMA can only be issued when this one is done, so pull its lines
-            // into L2 now and the copy that follows the end-of-tile barrier is an L2 -> smem transfer
-            const u64 nxt = tile + gridDim.x;
-            if (nxt < ntiles && tid * 128u < (u32)V_WIN)
-                asm volatile("prefetch.global.L2 [%0];" ::"l"(text + (own_lo + nxt * (u64)V_OWN) - V_LEAD + tid * 128u));
-        }
 
         // ---- classify the whole window (all threads) ------------------------------------------------
         u32 bad = 0;
