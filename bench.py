@@ -343,7 +343,7 @@ def main():
         per_launch_ms = sum(tc) / len(tc)
         per_launch_bytes = nbytes * args.steps / len(tc)
         ach = per_launch_bytes / (per_launch_ms * 1e-3) / 1e9
-        traffic, traffic_src = None, None
+        traffic, traffic_src, issue = None, None, None
         try:
             with open(os.path.join(ROOT, "profiles", "r01_text_traffic.json")) as f:
                 tj = json.load(f)
@@ -351,13 +351,21 @@ def main():
             # captured launch (250 MB of the same corpus) to this launch's bytes
             traffic = tj["dram_bytes_per_input_byte"] * per_launch_bytes
             traffic_src = "ncu capture scaled per input byte: " + tj["source"]
+            # what actually bounds this kernel: instruction issue. smsp__inst_executed of the same capture
+            # per input byte against 4 schedulers x SMs x SM clock (one warp instruction per cycle each)
+            wipb = tj.get("warp_instructions_per_input_byte")
+            clk = (sampler.summary().get("sm_mhz") or 0) * 1e6
+            if wipb and clk:
+                issue_peak = 4 * ctx.num_sms() * clk / wipb / 1e9
+                issue = {"bound": "issue", "warp_instructions_per_byte": wipb, "peak": issue_peak, "unit": "GB/s",
+                         "frac": ach / issue_peak}
         except Exception:
             pass
         roof = {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
                 "traffic": traffic, "traffic_source": traffic_src,
                 "kernel": "text_count2_kernel<NONWORD_LOWER_SET> (csrc/text2.cu)",
                 "algorithmic_bytes_per_launch": per_launch_bytes, "ms_per_launch": per_launch_ms,
-                "peak_source": peak_kind + " (MEASURED_PEAKS.json hbm_gbs)"}
+                "peak_source": peak_kind + " (MEASURED_PEAKS.json hbm_gbs)", "issue_roofline": issue}
 
     line = {"metric": "MB/s ingested end-to-end, TF-IDF synthetic text", "value": value, "unit": "MB/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup,

@@ -396,6 +396,12 @@ int32_t dampr_ctx_mem_info(dampr_ctx *ctx, uint64_t *free_bytes, uint64_t *total
     return DAMPR_OK;
 }
 
+int32_t dampr_ctx_num_sms(dampr_ctx *ctx, int32_t *out) {
+    if (!ctx || !out) return DAMPR_ERR_ARG;
+    *out = ctx->num_sms;
+    return DAMPR_OK;
+}
+
 int32_t dampr_host_alloc(uint64_t nbytes, void **out) {
     if (!out) return DAMPR_ERR_ARG;
     *out = nullptr;

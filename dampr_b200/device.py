@@ -72,6 +72,7 @@ def load_library():
     _sig(lib, "dampr_ctx_timing_enable", vp, i32)
     _sig(lib, "dampr_ctx_launches", vp, pu64)
     _sig(lib, "dampr_ctx_mem_info", vp, pu64, pu64)
+    _sig(lib, "dampr_ctx_num_sms", vp, C.POINTER(i32))
     _sig(lib, "dampr_ctx_stream", vp, pu64)
     _sig(lib, "dampr_host_alloc", u64, pvp)
     _sig(lib, "dampr_host_free", vp)
@@ -196,6 +197,11 @@ class Ctx(object):
         if self.h is not None:
             self.lib.dampr_ctx_destroy(self.h)
             self.h = None
+
+    def num_sms(self):
+        n = C.c_int32(0)
+        self.check(self.lib.dampr_ctx_num_sms(self.h, C.byref(n)))
+        return n.value
 
     def mem_info(self):
         f, t = C.c_uint64(0), C.c_uint64(0)

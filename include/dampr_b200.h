@@ -64,6 +64,8 @@ int32_t dampr_ctx_timing_enable(dampr_ctx *ctx, int32_t on);
 /* free / total device memory: the arena the spill trigger compares against (replaces the RSS
  * polling of InterpolativeMemoryChecker, memory.py:72-113) */
 int32_t dampr_ctx_mem_info(dampr_ctx *ctx, uint64_t *free_bytes, uint64_t *total_bytes);
+/* multiprocessor count of the context's device (grid sizing, roofline bookkeeping) */
+int32_t dampr_ctx_num_sms(dampr_ctx *ctx, int32_t *out);
 /* number of kernels this library launched on the ctx since creation */
 int32_t dampr_ctx_launches(dampr_ctx *ctx, uint64_t *out);
 /* raw handle of the compute stream (cudaStream_t) so torch.distributed collectives can be
