@@ -62,6 +62,7 @@ struct WarpScratchT {
     alignas(8) u64 hist[WS ? 1 : HCAP];
     alignas(8) u64 missq[64];  // keys that missed the shared-memory combiner, flushed 32 at a time
     alignas(8) u64 missr[WS ? 64 : 1];
+    u32 dtab[WS ? 1 : 64];  // set() de-duplication of a round: lanes per hash slot
     u16 tpos[V_TPOS];
 };
 constexpr u32 V_REP_UNPUB = 0xFFFFFFFFu;
@@ -482,33 +483,59 @@ text_count2_kernel(const u8 *__restrict__ text, u64 n, u64 own_lo, u64 own_hi, u
                     }
                     if (valid && (m1 & m2 & lt_mask)) dup = true;
 #else
-                    // tokens of one line sit in consecutive lanes: compare with the earlier lanes of the
-                    // same line by shuffles (MATCH.ANY iterates over the distinct values and is the slower
-                    // choice here). A 32-bit fold of the key is compared first; the 64-bit compare runs only
-                    // for the distances at which some lane saw a fold match.
+                    // tokens of one line sit in consecutive lanes. Every lane drops its bit into the slot its
+                    // key hashes to; the earlier lanes of the same line found in that slot are the only ones
+                    // that can hold the same token, and they are compared exactly (64-bit key via shuffle).
+                    // No false negatives: an equal key always lands in the same slot. (A compare with every
+                    // earlier lane of the line by shuffles costs ~5 instructions per lane distance; MATCH.ANY
+                    // iterates over the distinct values and is slower still.)
                     {
                         const u32 lkey = valid ? line : (0xFFFFFF00u | lane);
                         const u32 prev_line = __shfl_up_sync(0xFFFFFFFFu, lkey, 1);
                         const u32 seg_start = __ballot_sync(0xFFFFFFFFu, lane == 0 || prev_line != lkey);
-                        const u32 dist = lane - (31u - (u32)__clz(seg_start & (lt_mask | (1u << lane))));
-                        const u32 maxd = __reduce_max_sync(0xFFFFFFFFu, valid ? dist : 0u);
-                        const u32 fold = (u32)key ^ (u32)(key >> 32);
-                        for (u32 d = 1; d <= maxd; ++d) {
-                            const u32 of = __shfl_up_sync(0xFFFFFFFFu, fold, d);
-                            const bool cand = valid && d <= dist && of == fold;
-                            if (__any_sync(0xFFFFFFFFu, cand)) {
-                                const u64 ok = __shfl_up_sync(0xFFFFFFFFu, key, d);
-                                if (cand && ok == key) dup = true;
+                        const u32 first = 31u - (u32)__clz(seg_start & (lt_mask | (1u << lane)));  // first lane of my line
+                        const u32 slot = (((u32)key ^ (u32)(key >> 32)) * 0x9E3779B1u) >> 26;
+                        ws.dtab[lane] = 0;
+                        ws.dtab[lane + 32] = 0;
+                        __syncwarp();
+                        if (valid) atomicOr(&ws.dtab[slot], 1u << lane);
+                        __syncwarp();
+                        u32 cand = valid ? (ws.dtab[slot] & lt_mask & ~((1u << first) - 1u)) : 0u;
+                        while (__any_sync(0xFFFFFFFFu, cand != 0)) {
+                            const u32 src = cand ? (31u - (u32)__clz(cand)) : lane;
+                            const u64 ok = __shfl_sync(0xFFFFFFFFu, key, src);
+                            if (cand) {
+                                if (ok == key) dup = true;
+                                cand &= ~(1u << src);
                             }
                         }
                     }
 #endif
                     // tokens of the line that started in an earlier round: compare with its history
                     const bool in_hist_line = valid && line == hist_line;
-                    if (__ballot_sync(0xFFFFFFFFu, in_hist_line)) {
-                        for (u32 j = 0; j < hist_n; ++j) {
-                            u64 hk = ws.hist[j];
-                            if (in_hist_line && hk == key) dup = true;
+                    if (__ballot_sync(0xFFFFFFFFu, in_hist_line) && hist_n) {
+                        // the same slot scheme: lane j holds history entry j (the first 32 of them), tokens of
+                        // the line look their slot up and compare with the entries found there
+                        const u32 hslot = (((u32)key ^ (u32)(key >> 32)) * 0x9E3779B1u) >> 26;
+                        const u64 hk = (lane < hist_n) ? ws.hist[lane] : 0ULL;
+                        ws.dtab[lane] = 0;
+                        ws.dtab[lane + 32] = 0;
+                        __syncwarp();
+                        if (lane < hist_n) atomicOr(&ws.dtab[(((u32)hk ^ (u32)(hk >> 32)) * 0x9E3779B1u) >> 26], 1u << lane);
+                        __syncwarp();
+                        u32 cand = in_hist_line ? ws.dtab[hslot] : 0u;
+                        while (__any_sync(0xFFFFFFFFu, cand != 0)) {
+                            const u32 src = cand ? (31u - (u32)__clz(cand)) : lane;
+                            const u64 ok = __shfl_sync(0xFFFFFFFFu, hk, src);
+                            if (cand) {
+                                if (ok == key) dup = true;
+                                cand &= ~(1u << src);
+                            }
+                        }
+                        __syncwarp();
+                        for (u32 j = 32; j < hist_n; ++j) {  // long lines: the rest of the history, entry by entry
+                            const u64 hj = ws.hist[j];
+                            if (in_hist_line && hj == key) dup = true;
                         }
                     }
                     // new history = distinct tokens of the line the last token of this round belongs to
