@@ -977,8 +977,8 @@ def _fold_single_group(vals, kind):
             return int(vals.sum())
         return float(np.cumsum(vals)[-1])   # the left fold binop(acc, v) in record order, exactly
     if kind in (lowering.MIN, lowering.MAX):
-        if vals.dtype == np.float64 and np.isnan(vals).any():
-            raise NotLowerable("NaN under min/max")
+        if vals.dtype == np.float64 and (np.isnan(vals).any() or (vals == 0).any()):
+            raise NotLowerable("NaN or signed zeros under min/max")   # which of -0.0 / 0.0 wins depends on the order
         r = vals.min() if kind == lowering.MIN else vals.max()
         return r.item()
     return (vals[0] if kind == lowering.FIRST else vals[-1]).item()
