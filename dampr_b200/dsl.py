@@ -266,7 +266,10 @@ class PMap(PBase):
     def cross_right(self, other, cross, memory=False):
         """For every item of self (outer) and every item of other (inner): cross(x, y)."""
         assert isinstance(other, PMap)
-        return other.cross_left(self, lambda xi, yi: cross(yi, xi), memory)
+        def swapped(xi, yi):
+            return cross(yi, xi)
+        swapped.swapped_of = cross   # lets the frame lowering call the user's function without the hop
+        return other.cross_left(self, swapped, memory)
 
     def cross_left(self, other, cross, memory=False, **options):
         """Outer loop over `other`, inner over self (cached when `memory`); emits cross(self_item,

@@ -1157,9 +1157,16 @@ def _lower_cross(runner, stage, inputs):
         # representative rows, gathered column-wise (no per-cell Python dispatch)
         rep_cols = [_gather(c, rep) for c in outer.cols]
         res = []
-        for row in zip(*rep_cols):
-            r = cross(inner, row)
-            res.append(r[ci] if e.op == "tuple" else r)
+        direct = getattr(cross, "swapped_of", None)
+        pick = ci if e.op == "tuple" else None
+        if direct is not None:   # cross_right's argument swap, without the extra call per value
+            for row in zip(*rep_cols):
+                r = direct(row, inner)
+                res.append(r if pick is None else r[pick])
+        else:
+            for row in zip(*rep_cols):
+                r = cross(inner, row)
+                res.append(r if pick is None else r[pick])
         kinds = set(type(x) for x in res)
         if kinds == {float}:
             res = np.array(res, dtype=np.float64)
