@@ -316,7 +316,10 @@ leaf_sort_kernel(ulonglong2 *__restrict__ data, ulonglong2 *__restrict__ out, co
             for (u32 off = tid * 128u; off < nx.n * 16u; off += L_THREADS * 128u)
                 asm volatile("prefetch.global.L2 [%0];" ::"l"(base + off));
         }
-        for (u32 i = tid; i < L_BINS; i += L_THREADS) s.cnt[i] = 0;
+        {
+            uint4 *z = reinterpret_cast<uint4 *>(s.cnt);  // 8 counters per 16-byte store
+            for (u32 i = tid; i < L_BINS / 8; i += L_THREADS) z[i] = make_uint4(0, 0, 0, 0);
+        }
         __syncthreads();
         // load + histogram
         {
@@ -415,10 +418,16 @@ leaf_sort_kernel(ulonglong2 *__restrict__ data, ulonglong2 *__restrict__ out, co
         {
             u32 loc[16];
             u32 sum = 0;
+            {
+                const uint4 *c4 = reinterpret_cast<const uint4 *>(s.cnt) + tid * 2;
+                const uint4 a = c4[0], b = c4[1];
+                const u32 w[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
 #pragma unroll
-            for (int k = 0; k < 16; ++k) {
-                loc[k] = s.cnt[tid * 16 + k];
-                sum += loc[k];
+                for (int k = 0; k < 8; ++k) {
+                    loc[2 * k] = w[k] & 0xFFFFu;
+                    loc[2 * k + 1] = w[k] >> 16;
+                    sum += loc[2 * k] + loc[2 * k + 1];
+                }
             }
             u32 v = sum;
 #pragma unroll
@@ -431,11 +440,22 @@ leaf_sort_kernel(ulonglong2 *__restrict__ data, ulonglong2 *__restrict__ out, co
             u32 woff = 0;
             for (u32 w = 0; w < warp; ++w) woff += s.wsum[w];
             u32 run = woff + v - sum;
+            {
+                u32 w[8];
 #pragma unroll
-            for (int k = 0; k < 16; ++k) {
-                s.cnt[tid * 16 + k] = (u16)run;  // bin start
-                s.cur[tid * 16 + k] = (u16)run;  // cursor
-                run += loc[k];
+                for (int k = 0; k < 8; ++k) {
+                    const u32 lo = run;
+                    run += loc[2 * k];
+                    w[k] = lo | (run << 16);
+                    run += loc[2 * k + 1];
+                }
+                const uint4 a = make_uint4(w[0], w[1], w[2], w[3]), b = make_uint4(w[4], w[5], w[6], w[7]);
+                uint4 *c4 = reinterpret_cast<uint4 *>(s.cnt) + tid * 2;  // bin starts
+                uint4 *u4 = reinterpret_cast<uint4 *>(s.cur) + tid * 2;  // cursors
+                c4[0] = a;
+                c4[1] = b;
+                u4[0] = a;
+                u4[1] = b;
             }
         }
         __syncthreads();
@@ -467,11 +487,10 @@ leaf_sort_kernel(ulonglong2 *__restrict__ data, ulonglong2 *__restrict__ out, co
             s.cur[st + r] = (u16)i;
         }
         __syncthreads();
-        for (u32 i = tid; i < n; i += L_THREADS) s.ord[i] = s.cur[i];
-        __syncthreads();
+        const u16 *fin = s.cur;   // final order: position -> record index
         if (reduce_op < 0) {
             for (u32 i = tid; i < n; i += L_THREADS) {
-                const u32 o = s.ord[i];
+                const u32 o = fin[i];
                 out[ch.start + i] = make_ulonglong2(key_unxform(s.sk[o] + base, xf), s.val[o]);
             }
             __syncthreads();
@@ -486,7 +505,7 @@ leaf_sort_kernel(ulonglong2 *__restrict__ data, ulonglong2 *__restrict__ out, co
             for (int k = 0; k < IPT; ++k) {
                 u32 p = tid * IPT + k;
                 if (p < n) {
-                    bool head = (p == 0) || (s.sk[s.ord[p]] != s.sk[s.ord[p - 1]]);
+                    bool head = (p == 0) || (s.sk[fin[p]] != s.sk[fin[p - 1]]);
                     headbits |= head ? (1u << k) : 0u;
                 }
             }
@@ -507,10 +526,10 @@ leaf_sort_kernel(ulonglong2 *__restrict__ data, ulonglong2 *__restrict__ out, co
             for (int k = 0; k < IPT; ++k) {
                 if (headbits & (1u << k)) {
                     u32 p = tid * IPT + k;
-                    u64 ksk = s.sk[s.ord[p]];
-                    u64 acc = (reduce_op == DAMPR_OP_COUNT) ? 1ULL : s.val[s.ord[p]];
-                    for (u32 q = p + 1; q < n && s.sk[s.ord[q]] == ksk; ++q) {
-                        u64 val = (reduce_op == DAMPR_OP_COUNT) ? 1ULL : s.val[s.ord[q]];
+                    u64 ksk = s.sk[fin[p]];
+                    u64 acc = (reduce_op == DAMPR_OP_COUNT) ? 1ULL : s.val[fin[p]];
+                    for (u32 q = p + 1; q < n && s.sk[fin[q]] == ksk; ++q) {
+                        u64 val = (reduce_op == DAMPR_OP_COUNT) ? 1ULL : s.val[fin[q]];
                         acc = apply_op(reduce_op, acc, val);
                     }
                     out[ch.start + gidx] = make_ulonglong2(key_unxform(ksk + base, xf), acc);
