@@ -48,6 +48,23 @@ def main():
     exp, exp_lines = refsem.docfreq(data)
     assert merged == dict(exp), "document frequencies differ from the oracle"
     assert n_lines == exp_lines
+    # the whole tf-idf job: every rank sinks the terms it owns into its own part files
+    import math
+    import shutil
+    out_dir = os.path.join(tempfile.gettempdir(), "dampr_mgpu_idf")
+    if rank == 0:
+        shutil.rmtree(out_dir, ignore_errors=True)
+    dist.barrier()
+    doc_freq = docs.flat_map(lambda x: set(RX.split(x.lower()))).count(reduce_buffer=float("inf"))
+    doc_freq.cross_right(docs.len(), lambda df, total: (df[0], df[1], math.log(1 + (float(total) / df[1]))),
+                         memory=True).sink_tsv(out_dir).run()
+    dist.barrier()
+    if rank == 0:
+        lines = []
+        for fn in sorted(os.listdir(out_dir)):
+            with open(os.path.join(out_dir, fn)) as f:
+                lines.extend(l.rstrip("\n") for l in f)
+        assert sorted(lines) == sorted(refsem.tfidf_sink_lines(data)), "tf-idf sink lines differ from the oracle"
     # word count (str.split, long tokens -> hashed codes + cross-rank string exchange)
     mine = docs.flat_map(lambda x: x.split()).count().read()
     dist.all_gather_object(parts, mine)
