@@ -1080,9 +1080,15 @@ int32_t dampr_kv_reduce_by_key(dampr_ctx *ctx, dampr_kv *sorted, int32_t op, dam
     dampr_kv *tmp = nullptr;
     int rc = dampr_kv_create(ctx, sorted->n, &tmp);
     if (rc) return rc;
-    if (sorted->n)
-        CUDA_TRY(ctx, cudaMemcpyAsync(tmp->rec, sorted->rec, sorted->n * sizeof(ulonglong2), cudaMemcpyDeviceToDevice,
-                                      ctx->stream));
+    if (sorted->n) {
+        cudaError_t e = cudaMemcpyAsync(tmp->rec, sorted->rec, sorted->n * sizeof(ulonglong2), cudaMemcpyDeviceToDevice,
+                                        ctx->stream);
+        if (e != cudaSuccess) {
+            dampr_kv_destroy(ctx, tmp);
+            ctx->err = std::string("reduce_by_key copy failed: ") + cudaGetErrorString(e);
+            return DAMPR_ERR_CUDA;
+        }
+    }
     tmp->n = sorted->n;
     rc = dampr_kv_sort_reduce(ctx, tmp, DAMPR_KEY_RAW, op, out);
     dampr_kv_destroy(ctx, tmp);
