@@ -51,6 +51,10 @@ def config2(out):
     tgen = time.time() - t0
     total = int(vals.sum())
     ctx = runner_mod.get_ctx()
+    t0 = time.time()
+    res = Dampr.read_input(ArrayKVInput(keys, vals)).a_group_by(lambda x: x[0], lambda x: x[1]).sum().run()
+    cold = time.time() - t0    # first run: device pool and staging ring are allocated here
+    del res
     ctx.timings_reset()
     t0 = time.time()
     res = Dampr.read_input(ArrayKVInput(keys, vals)).a_group_by(lambda x: x[0], lambda x: x[1]).sum().run()
@@ -63,7 +67,8 @@ def config2(out):
     for name, ms in ctx.timings():
         kt[name] = kt.get(name, 0.0) + ms
     dev_ms = sum(v for k, v in kt.items() if k in ("part_hist", "part_scatter", "leaf_sort", "seg_reduce", "misc"))
-    out["config2"] = {"records": n, "groups": int(len(rk)), "wall_s": round(wall, 3), "gen_s": round(tgen, 1),
+    out["config2"] = {"records": n, "groups": int(len(rk)), "wall_s": round(wall, 3), "cold_wall_s": round(cold, 3),
+                      "gen_s": round(tgen, 1),
                       "MB_per_s_end_to_end": round(16 * n / wall / 1e6, 1), "kernel_ms": {k: round(v, 2) for k, v in kt.items()},
                       "device_partition_sort_reduce_ms": round(dev_ms, 2),
                       "roofline_16N_plus_16G_GBps": round((16 * n + 16 * len(rk)) / dev_ms / 1e6, 1),
