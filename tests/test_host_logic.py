@@ -244,3 +244,37 @@ def test_vexpr_matches_cpython_row_by_row():
             vexpr.evaluate(lowering.analyze(fn), cs, False, n)
     assert lowering.tuple_binop_kinds(lambda x, y: (x[0] + y[0], x[1] + y[1])) == [lowering.ADD, lowering.ADD]
     assert lowering.tuple_binop_kinds(lambda x, y: (x[0] + y[1], x[1] + y[0])) is None
+
+
+def test_native_host_helpers(tmp_path):
+    """Host-side entry points of the library (no device work): sink formatting into part files, decimal
+    formatting of int dictionaries, dictionary encoding of count columns."""
+    import numpy as np
+    from dampr_b200 import device as dev
+    from dampr_b200 import plan
+    rng = np.random.default_rng(4)
+    for n, W in ((0, 16), (7, 16), (70000, 24), (150000, 32)):
+        vals = np.array([0, -1, 5, 123456789, -42, 10, 100, -9223372036854775808, 9223372036854775807], dtype=np.int64)
+        inv = rng.integers(0, len(vals), size=n).astype(np.uint32)
+        words = np.array([b"x" * int(l) for l in rng.integers(0, W + 1, size=n)], dtype="S%d" % W)
+        fl = [repr(float(i) / 7).encode() for i in range(40)]
+        inv2 = rng.integers(0, 40, size=n).astype(np.uint32)
+        exp = b"".join(b"%s\t%d\t%s\n" % (words[i], vals[inv[i]], fl[inv2[i]]) for i in range(n))
+        cols = [words, (inv, vals), (inv2, fl)]
+        if n:
+            assert dev.host_join_tsv(cols).tobytes() == exp
+            d = tmp_path / ("s%d" % n)
+            d.mkdir()
+            names = dev.host_join_tsv(cols, prefix=str(d / "part-"), first=16)
+            assert names[0].endswith("part-16") and len(names) == max(1, min(16, n // 32768))
+            assert b"".join(open(f, "rb").read() for f in names) == exp
+    for trial in range(4):
+        x = rng.integers(0, 3000, size=60000).astype(np.int64)
+        if trial >= 1:
+            x[rng.integers(0, len(x), size=200)] = rng.integers(1 << 30, 1 << 40, size=200)
+        if trial == 3:
+            x[11] = -5   # negative value: the presence table does not apply, numpy path
+        u, inv, rows = plan.unique_inverse_rows(x)
+        assert np.array_equal(u, np.unique(x)) and np.array_equal(u[inv], x) and np.array_equal(x[rows], u)
+        u2, inv2 = plan.unique_inverse(x)
+        assert np.array_equal(u2, u) and np.array_equal(u2[inv2], x)
