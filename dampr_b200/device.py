@@ -419,6 +419,14 @@ class KV(object):
         self.ctx.check(self.ctx.lib.dampr_kv_devptr(self.ctx.h, self.h, C.byref(p)))
         return p.value
 
+    def upload_columns(self, off, keys, vals):
+        """Column chunks -> records [off, off + len(keys)) (interleaved on the device)."""
+        keys = np.ascontiguousarray(keys).view(np.uint64)
+        vals = np.ascontiguousarray(vals)
+        assert vals.dtype.itemsize == 8 and len(vals) == len(keys)
+        self.ctx.check(self.ctx.lib.dampr_kv_upload_columns(self.ctx.h, self.h, int(off), _ptr(keys),
+                                                            _ptr(vals.view(np.uint64)), len(keys)))
+
     def upload(self, off, recs, count=None):
         count = recs.nbytes // 16 if count is None else count
         self.ctx.check(self.ctx.lib.dampr_kv_upload(self.ctx.h, self.h, int(off), _ptr(recs), int(count)))

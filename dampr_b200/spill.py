@@ -46,6 +46,28 @@ def needs_spill(ctx, n_records):
     return n_records * RECORD_FOOTPRINT > arena_bytes(ctx)
 
 
+def _upload_chunks(ctx, kchunks, vchunks):
+    """One device kv from column chunks, uploaded back to back (no host-side concatenation)."""
+    kv = ctx.kv(max(1, sum(len(k) for k in kchunks)))
+    off = 0
+    for k, v in zip(kchunks, vchunks):
+        kv.upload_columns(off, k, v)
+        off += len(k)
+    ctx.sync()
+    return kv
+
+
+def _upload_runs(ctx, runs):
+    """One device kv from (n_i, 2) uint64 record runs, uploaded back to back in run order."""
+    kv = ctx.kv(max(1, sum(len(r) for r in runs)))
+    off = 0
+    for r in runs:
+        kv.upload(off, r, len(r))
+        off += len(r)
+    ctx.sync()
+    return kv
+
+
 def external_group(ctx, chunk_iter, n_records, op=None, xform=dev.KEY_MIX):
     """chunk_iter yields (keys uint64[], vals 8-byte[]) column chunks. Returns a list of
     (keys, vals) numpy result pieces: key-sorted (under `xform`) inside each piece; with `op` one
@@ -56,8 +78,8 @@ def external_group(ctx, chunk_iter, n_records, op=None, xform=dev.KEY_MIX):
     buckets = [[] for _ in range(n_buckets)]
     stats = {"buckets": n_buckets, "batches": 0, "spilled_bytes": 0, "arena_bytes": arena}
 
-    def flush_batch(keys, vals):
-        kv = ctx.kv_from_columns(keys, vals)
+    def flush_batch(kchunks, vchunks):
+        kv = _upload_chunks(ctx, kchunks, vchunks)
         try:
             parts, counts = kv.partition_by_owner(n_buckets)
         finally:
@@ -84,18 +106,17 @@ def external_group(ctx, chunk_iter, n_records, op=None, xform=dev.KEY_MIX):
             pend_n += take
             pos += take
             if pend_n >= per_batch:
-                flush_batch(np.concatenate(pend_k), np.concatenate(pend_v))
+                flush_batch(pend_k, pend_v)
                 pend_k, pend_v, pend_n = [], [], 0
     if pend_n:
-        flush_batch(np.concatenate(pend_k), np.concatenate(pend_v))
+        flush_batch(pend_k, pend_v)
 
     out = []
     for b in range(n_buckets):
         if not buckets[b]:
             continue
-        recs = np.concatenate(buckets[b]) if len(buckets[b]) > 1 else buckets[b][0]
+        kv = _upload_runs(ctx, buckets[b])
         buckets[b] = None
-        kv = ctx.kv_from_records(recs)
         try:
             if op is None:
                 kv.sort(xform)
@@ -140,8 +161,8 @@ def external_sort(ctx, chunk_iter, n_records, xform, sample_keys, _depth=0):
     sizes = [0] * nb
     stats = {"buckets": nb, "batches": 0, "spilled_bytes": 0, "arena_bytes": arena}
 
-    def flush_batch(keys, vals):
-        kv = ctx.kv_from_columns(keys, vals)
+    def flush_batch(kchunks, vchunks):
+        kv = _upload_chunks(ctx, kchunks, vchunks)
         try:
             kv.sort(xform)
             recs = kv.records()
@@ -166,10 +187,10 @@ def external_sort(ctx, chunk_iter, n_records, xform, sample_keys, _depth=0):
             pend_n += take
             pos += take
             if pend_n >= per_batch:
-                flush_batch(np.concatenate(pend_k), np.concatenate(pend_v))
+                flush_batch(pend_k, pend_v)
                 pend_k, pend_v, pend_n = [], [], 0
     if pend_n:
-        flush_batch(np.concatenate(pend_k), np.concatenate(pend_v))
+        flush_batch(pend_k, pend_v)
 
     out = []
     for b in range(nb):
@@ -196,7 +217,7 @@ def external_sort(ctx, chunk_iter, n_records, xform, sample_keys, _depth=0):
                 stats["batches"] += st["batches"]
                 stats["spilled_bytes"] += st["spilled_bytes"]
                 continue
-        kv = ctx.kv_from_records(np.concatenate(runs))
+        kv = _upload_runs(ctx, runs)
         try:
             kv.sort(xform)
             k, v = kv.columns()
