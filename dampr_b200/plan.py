@@ -150,6 +150,10 @@ class Frame(Dataset):
             if isinstance(c, DictCol):
                 return DictCol(c.inv[perm], c.uniq)
             if isinstance(c, np.ndarray):
+                if c.dtype.kind == "S" and c.dtype.itemsize % 8 == 0 and c.flags["C_CONTIGUOUS"] and c.ndim == 1:
+                    # fixed-width strings gather faster as rows of 8-byte words than as 'S' elements
+                    w = c.dtype.itemsize // 8
+                    return np.take(c.view(np.uint64).reshape(len(c), w), perm, axis=0).view(c.dtype).ravel()
                 return c[perm]
             pl = perm.tolist()
             return [c[i] for i in pl]

@@ -278,3 +278,21 @@ def test_native_host_helpers(tmp_path):
         assert np.array_equal(u, np.unique(x)) and np.array_equal(u[inv], x) and np.array_equal(x[rows], u)
         u2, inv2 = plan.unique_inverse(x)
         assert np.array_equal(u2, u) and np.array_equal(u2[inv2], x)
+
+
+def test_frame_take_and_tuple_columns():
+    import numpy as np
+    from dampr_b200 import plan, vexpr
+    n = 1000
+    rng = np.random.default_rng(2)
+    words = np.array([b"w%d" % i for i in range(n)], dtype="S16")
+    counts = rng.integers(0, 50, size=n).astype(np.int64)
+    uq, inv = np.unique(counts, return_inverse=True)
+    fr = plan.Frame(words, [words, plan.DictCol(inv.astype(np.uint32), uq), vexpr.Tup([counts, counts * 2])], scalar=False)
+    perm = rng.permutation(n)[:300]
+    out = fr.take(perm)
+    assert out.cols[0] is out.keys                      # the shared column object is gathered once
+    exp = [(words[i].decode(), int(counts[i]), (int(counts[i]), int(2 * counts[i]))) for i in perm]
+    assert out.values() == exp and list(k for k, _v in out.read()) == [words[i].decode() for i in perm]
+    empty = fr.take(np.zeros(0, dtype=np.int64))
+    assert empty.values() == [] and len(empty) == 0
