@@ -20,7 +20,7 @@ import time
 import numpy as np
 
 from . import device as dev
-from . import keycodec, lowering, settings
+from . import dist, hostmap, keycodec, lowering, settings
 from . import operators as ops
 from .datasets import (Chunker, Dataset, RecordsDataset, ColumnDataset, TextLineDataset, EmptyDataset)
 from .graph import GMap, GReduce, GSink
@@ -44,6 +44,20 @@ def close_all():
     for c in list(_CTX.values()):
         c.close()
     _CTX.clear()
+
+
+def _chunk_bytes(chunks):
+    """Input bytes behind a list of chunks when every chunk is a byte range of a text file, else 0."""
+    total = 0
+    for ch in chunks:
+        if not isinstance(ch, TextLineDataset):
+            return 0
+        try:
+            end = os.path.getsize(ch.path) if ch.end is None else ch.end
+        except OSError:
+            return 0
+        total += max(0, end - ch.start)
+    return total
 
 
 def _chunks_of(ds):
@@ -160,14 +174,17 @@ class B200Runner(object):
 
     # ---- generic stages -----------------------------------------------------------------------
     def _collect_map(self, stage, inputs):
+        """Run the stage's mapper over the input chunks on the host. Large text inputs are mapped by forked
+        workers (hostmap.parallel: the reference's process pool, stagerunner.py:54-129), folding equal keys
+        inside the workers when the stage has a combiner; everything else runs in this process."""
         main, supp = inputs[0], inputs[1:]
-        keys, vals = [], []
-        ka, va = keys.append, vals.append
-        for ch in _chunks_of(main):
-            for k, v in stage.mapper.map(ch, *supp):
-                ka(k)
-                va(v)
-        return keys, vals
+        chunks = _chunks_of(main)
+        nproc = int(settings.max_processes)
+        if nproc > 1 and len(chunks) > 1 and not dist.active() and _chunk_bytes(chunks) >= settings.host_map_parallel_bytes:
+            binop = stage.options.get("binop")
+            fold = binop if isinstance(stage.combiner, ops.PartialReduceCombiner) and callable(binop) else None
+            return hostmap.parallel(stage.mapper, chunks, supp, fold, nproc)
+        return hostmap.sequential(stage.mapper, chunks, supp)
 
     def _map_generic(self, stage, inputs):
         keys, vals = self._collect_map(stage, inputs)

@@ -43,3 +43,6 @@ device_arena_bytes = None
 # build of the tokenise kernel the scans start with: CTAs per SM it is sized for (4, 3 or 2; lines with more
 # distinct tokens than a build remembers are retried on the 2-CTA build, see plan.TextScan.run)
 text_kernel_ctas = 4
+# host maps (stages whose lambdas are not lowered) over text files of at least this many bytes run in
+# forked worker processes (settings.max_processes of them), like the reference's process pool
+host_map_parallel_bytes = 16 << 20

@@ -268,3 +268,25 @@ def test_gzip_text_inputs_are_lowered(ctx, tmp_path):
     got2 = dict(run_wc(str(d)))
     assert lowered("device text tokenise+combine")
     assert got2 == {w: 2 * c for w, c in exp}
+
+
+def test_non_lowerable_map_runs_in_forked_workers(ctx, tmp_path):
+    """A map the device cannot take (here .upper()) over a text file is mapped by forked workers with
+    the in-worker fold, then shuffled / combined on the device; the result equals plain Python."""
+    import collections
+    from dampr_b200 import settings
+    lines = ["row %d alpha beta %s gamma" % (i, "delta" * (i % 3)) for i in range(30000)]
+    p = tmp_path / "t.txt"
+    p.write_text("\n".join(lines) + "\n")
+    old = settings.host_map_parallel_bytes, settings.max_processes
+    settings.host_map_parallel_bytes, settings.max_processes = 64 << 10, 4
+    try:
+        got = Dampr.text(str(p), 128 * 1024).flat_map(lambda x: x.upper().split()).count().read()
+        assert lowered("host-map + device shuffle/combine")
+        assert dict(got) == dict(collections.Counter(w for l in lines for w in l.upper().split()))
+        got = Dampr.text(str(p), 128 * 1024).map(lambda x: x.upper()).filter(lambda x: x.endswith("GAMMA")) \
+            .group_by(lambda x: len(x)).reduce(lambda k, it: sum(1 for _ in it)).read()
+        exp = collections.Counter(len(l) for l in lines if l.upper().endswith("GAMMA"))
+        assert dict(got) == dict(exp)
+    finally:
+        settings.host_map_parallel_bytes, settings.max_processes = old

@@ -296,3 +296,40 @@ def test_frame_take_and_tuple_columns():
     assert out.values() == exp and list(k for k, _v in out.read()) == [words[i].decode() for i in perm]
     empty = fr.take(np.zeros(0, dtype=np.int64))
     assert empty.values() == [] and len(empty) == 0
+
+
+def test_parallel_host_map_matches_sequential(tmp_path):
+    """hostmap.parallel (forked workers over contiguous chunk ranges, optional in-worker fold) gives the
+    sequential record order / the same folds, and re-raises the user's exception."""
+    import pytest
+    from dampr_b200 import hostmap
+    from dampr_b200 import operators as ops
+    from dampr_b200.inputs import TextInput
+    lines = ["Line %d has the words alpha beta %s gamma" % (i, "delta" * (i % 3)) for i in range(20000)]
+    p = tmp_path / "t.txt"
+    p.write_text("\n".join(lines) + "\n")
+    chunks = list(TextInput(str(p), 64 * 1024).chunks())
+    assert len(chunks) > 8
+
+    def fm(k, v):
+        for w in v.upper().split():     # .upper(): not a lowered idiom
+            yield w, 1
+    mapper = ops.Map(fm)
+    k1, v1 = hostmap.sequential(mapper, chunks, ())
+    k2, v2 = hostmap.parallel(mapper, chunks, (), None, 4)
+    assert (k1, v1) == (k2, v2)
+    k3, v3 = hostmap.parallel(mapper, chunks, (), lambda a, b: a + b, 3)
+    exp = {}
+    for k in k1:
+        exp[k] = exp.get(k, 0) + 1
+    got = {}
+    for k, v in zip(k3, v3):
+        got[k] = got.get(k, 0) + v
+    assert got == exp and len(k3) <= 3 * len(exp)
+
+    def bad(k, v):
+        if "Line 777 " in v:
+            raise ZeroDivisionError("boom")
+        yield k, v
+    with pytest.raises(ZeroDivisionError):
+        hostmap.parallel(ops.Map(bad), chunks, (), None, 4)
