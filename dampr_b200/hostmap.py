@@ -15,6 +15,7 @@ import multiprocessing
 import os
 import pickle
 import traceback
+import warnings
 
 
 def sequential(mapper, chunks, supp):
@@ -71,7 +72,11 @@ def parallel(mapper, chunks, supp, binop=None, processes=None):
         recv, send = ctx.Pipe(duplex=False)
         p = ctx.Process(target=_worker, args=(send, mapper, chunks[bounds[i]:bounds[i + 1]], supp, binop))
         p.daemon = True
-        p.start()
+        with warnings.catch_warnings():
+            # CPython 3.12 warns about fork() in a process that has threads (the copy pool, CUDA's own):
+            # the children only run the user's map functions and leave through os._exit
+            warnings.simplefilter("ignore", DeprecationWarning)
+            p.start()
         send.close()
         procs.append((p, recv))
     keys, vals, err = [], [], None
