@@ -220,7 +220,7 @@ def main():
             if i >= args.warmup:
                 times.append(sec)
         val = len(sample) * len(times) / sum(times) / MB
-        line = {"impl": "reference", "metric": "MB/s ingested end-to-end, TF-IDF synthetic text", "value": val,
+        line = {"impl": "reference", "metric": "MB/s ingested end-to-end, TF-IDF 10 GB synthetic text, 1/2/4/8 GPU", "value": val,
                 "unit": "MB/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": 1e3 * sum(times) / len(times), "higher_is_better": True, "scaling": "strong",
                 "vs_baseline": None, "dtype": "u8", "data": "synthetic",
@@ -367,7 +367,7 @@ def main():
                 "algorithmic_bytes_per_launch": per_launch_bytes, "ms_per_launch": per_launch_ms,
                 "peak_source": peak_kind + " (MEASURED_PEAKS.json hbm_gbs)", "issue_roofline": issue}
 
-    line = {"metric": "MB/s ingested end-to-end, TF-IDF synthetic text", "value": value, "unit": "MB/s",
+    line = {"metric": "MB/s ingested end-to-end, TF-IDF 10 GB synthetic text, 1/2/4/8 GPU", "value": value, "unit": "MB/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": 1e3 * t_dev / args.steps, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "u8", "data": "synthetic",
