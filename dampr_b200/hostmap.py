@@ -97,3 +97,38 @@ def parallel(mapper, chunks, supp, binop=None, processes=None):
             raise err[0] from RuntimeError("raised in a host map worker:\n%s" % err[1])
         raise RuntimeError("host map worker failed: %s" % err)
     return keys, vals
+
+
+def parallel_reduce(reducer, ds, processes=None):
+    """reducer.reduce over a grouped RecordsDataset (equal keys adjacent), the groups split over forked
+    workers at group boundaries — the reference's ReduceStageRunner runs one reduce job per partition in
+    its process pool (stagerunner.py:269-282); any split between two groups is such a partitioning.
+    Results come back in group order."""
+    from .datasets import RecordsDataset
+    keys, values = ds.keys, ds.values
+    n = len(keys)
+    nproc = max(1, min(int(processes or os.cpu_count() or 1), n))
+    cuts = [0]
+    for i in range(1, nproc):
+        t = max(cuts[-1], n * i // nproc)
+        while 0 < t < n and keys[t] == keys[t - 1]:
+            t += 1
+        if t > cuts[-1] and t < n:
+            cuts.append(t)
+    cuts.append(n)
+    if len(cuts) <= 2:
+        ks, vs = [], []
+        for k, v in reducer.reduce(ds):
+            ks.append(k)
+            vs.append(v)
+        return ks, vs
+
+    class _Sub(object):   # Mapper-like adapter so that _worker / sequential can drive the reducer
+        def map(self, part):
+            return reducer.reduce(part)
+
+    def sub(a, b):
+        codes = ds.codes[a:b] if ds.codes is not None else None
+        return RecordsDataset(keys[a:b], values[a:b], codes, ds.codec)
+    parts = [sub(a, b) for a, b in zip(cuts[:-1], cuts[1:])]
+    return parallel(_Sub(), parts, (), None, len(parts))

@@ -244,6 +244,14 @@ class B200Runner(object):
             out = self._join(stage, inputs)
             self.stats.add(stage, "device join ranges + host aggregate", "rows=%d" % len(out))
             return out
+        nproc = int(settings.max_processes)
+        if len(inputs) == 1 and isinstance(inputs[0], RecordsDataset) and nproc > 1 and not dist.active() \
+                and len(inputs[0]) >= settings.host_reduce_parallel_records:
+            # many groups and a reducer the device cannot take: forked workers, one contiguous range of
+            # groups each (hostmap.parallel_reduce)
+            keys, vals = hostmap.parallel_reduce(red, inputs[0], nproc)
+            self.stats.add(stage, "host reduce over device-grouped records (forked workers)", "records=%d" % len(keys))
+            return RecordsDataset(keys, vals)
         keys, vals = [], []
         for k, v in red.reduce(*inputs):
             keys.append(k)

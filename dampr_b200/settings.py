@@ -46,3 +46,6 @@ text_kernel_ctas = 4
 # host maps (stages whose lambdas are not lowered) over text files of at least this many bytes run in
 # forked worker processes (settings.max_processes of them), like the reference's process pool
 host_map_parallel_bytes = 16 << 20
+# host reduces (reducers that are not lowered) over at least this many grouped records are split over forked
+# workers at group boundaries
+host_reduce_parallel_records = 500000

@@ -290,3 +290,23 @@ def test_non_lowerable_map_runs_in_forked_workers(ctx, tmp_path):
         assert dict(got) == dict(exp)
     finally:
         settings.host_map_parallel_bytes, settings.max_processes = old
+
+
+def test_non_lowerable_reduce_runs_in_forked_workers(ctx):
+    """A reducer the device cannot take, over many device-grouped records, is split over forked workers at
+    group boundaries; results equal plain Python."""
+    import collections
+    from dampr_b200 import settings
+    items = [(i * 7919) % 5003 for i in range(60000)]
+    old = settings.host_reduce_parallel_records, settings.max_processes
+    settings.host_reduce_parallel_records, settings.max_processes = 1000, 4
+    try:
+        got = Dampr.memory(items, partitions=3).group_by(lambda x: x % 997) \
+            .reduce(lambda k, it: sorted(it)[-1] * 2 + k).read()
+        assert lowered("forked workers")
+        groups = collections.defaultdict(list)
+        for x in items:
+            groups[x % 997].append(x)
+        assert sorted(got) == sorted((k, max(v) * 2 + k) for k, v in groups.items())
+    finally:
+        settings.host_reduce_parallel_records, settings.max_processes = old

@@ -333,3 +333,21 @@ def test_parallel_host_map_matches_sequential(tmp_path):
         yield k, v
     with pytest.raises(ZeroDivisionError):
         hostmap.parallel(ops.Map(bad), chunks, (), None, 4)
+
+
+def test_parallel_host_reduce_matches_sequential():
+    from dampr_b200 import hostmap
+    from dampr_b200 import operators as ops
+    from dampr_b200.datasets import RecordsDataset
+    keys, vals = [], []
+    for k in range(3000):
+        for j in range(1 + (k * 7) % 23):
+            keys.append("k%05d" % k)
+            vals.append(k * 1000 + j)
+    red = ops.KeyedReduce(lambda k, it: sum(it) - len(k))
+    seq = list(red.reduce(RecordsDataset(keys, vals)))
+    for nproc in (1, 2, 5, 16):
+        ks, vs = hostmap.parallel_reduce(red, RecordsDataset(keys, vals), nproc)
+        assert list(zip(ks, vs)) == seq
+    one = RecordsDataset(["a"] * 50, list(range(50)))       # a single group cannot be split
+    assert hostmap.parallel_reduce(red, one, 4) == (["a"], [("a", sum(range(50)) - 1)])
