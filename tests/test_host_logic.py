@@ -351,3 +351,56 @@ def test_parallel_host_reduce_matches_sequential():
         assert list(zip(ks, vs)) == seq
     one = RecordsDataset(["a"] * 50, list(range(50)))       # a single group cannot be split
     assert hostmap.parallel_reduce(red, one, 4) == (["a"], [("a", sum(range(50)) - 1)])
+
+
+def test_vexpr_random_expressions_agree_with_cpython():
+    """Seeded random arithmetic over the whitelisted forms: column-at-a-time evaluation either raises
+    NotVec or gives, row for row, exactly what CPython gives (value and type)."""
+    import random
+    import numpy as np
+    from dampr_b200 import lowering, vexpr
+    rng = random.Random(12345)
+    nrng = np.random.default_rng(99)
+    n = 400
+    a = nrng.integers(-50, 50, size=n).astype(np.int64)
+    b = nrng.integers(-3, 4, size=n).astype(np.int64)          # has zeros: division guards must trip
+    c = (nrng.normal(size=n) * 10).astype(np.float64)
+    cols = [a, b, c]
+    rows = list(zip(a.tolist(), b.tolist(), c.tolist()))
+
+    def gen(depth):
+        if depth == 0 or rng.random() < 0.25:
+            return rng.choice(["x[0]", "x[1]", "x[2]", str(rng.randint(-5, 5)), repr(round(rng.uniform(-3, 3), 2))])
+        k = rng.random()
+        if k < 0.6:
+            return "(%s %s %s)" % (gen(depth - 1), rng.choice(["+", "-", "*", "/", "//", "%"]), gen(depth - 1))
+        if k < 0.7:
+            return "(-%s)" % gen(depth - 1)
+        if k < 0.8:
+            return "abs(%s)" % gen(depth - 1)
+        if k < 0.9:
+            return "float(%s)" % gen(depth - 1)
+        return "(%s %s %s)" % (gen(depth - 1), rng.choice(["<", "<=", "==", "!=", ">", ">="]), gen(depth - 1))
+
+    checked = refused = 0
+    for _ in range(400):
+        src = "lambda x: " + gen(3)
+        fn = eval(src)
+        e = lowering.analyze(fn)
+        if e is None:
+            continue
+        try:
+            exp = [fn(r) for r in rows]
+        except (ZeroDivisionError, OverflowError):
+            exp = None
+        try:
+            v = vexpr.evaluate(e, cols, False, n)
+        except vexpr.NotVec:
+            refused += 1
+            continue
+        assert exp is not None, src     # CPython raised for some row: the evaluation must have refused
+        got = vexpr.broadcast(v, n).tolist()
+        for g, x in zip(got, exp):
+            assert type(g) is type(x) and (g == x or (g != g and x != x)), (src, g, x)
+        checked += 1
+    assert checked > 50 and refused > 20
