@@ -44,7 +44,10 @@ def _worker(conn, mapper, chunks, supp, binop):
     try:
         try:
             out = _fold(mapper, chunks, supp, binop) if binop is not None else sequential(mapper, chunks, supp)
-            payload = pickle.dumps(("ok", out), protocol=pickle.HIGHEST_PROTOCOL)
+            try:
+                payload = pickle.dumps(("ok", out), protocol=pickle.HIGHEST_PROTOCOL)
+            except Exception as pe:   # records that cannot cross a process boundary: the parent maps in-process
+                payload = pickle.dumps(("unpicklable", "%s: %s" % (type(pe).__name__, pe)))
         except BaseException as e:   # the parent re-raises: a failing lambda must not hang the run
             text = "%s: %s\n%s" % (type(e).__name__, e, traceback.format_exc())
             try:
@@ -79,7 +82,7 @@ def parallel(mapper, chunks, supp, binop=None, processes=None):
             p.start()
         send.close()
         procs.append((p, recv))
-    keys, vals, err = [], [], None
+    keys, vals, err, local = [], [], None, False
     for p, recv in procs:
         try:
             tag, out = pickle.loads(recv.recv_bytes())
@@ -90,12 +93,16 @@ def parallel(mapper, chunks, supp, binop=None, processes=None):
         if tag == "ok" and err is None:
             keys.extend(out[0])
             vals.extend(out[1])
+        elif tag == "unpicklable":
+            local = True
         elif tag != "ok" and err is None:
             err = out
     if err is not None:
         if isinstance(err, tuple):   # the user's own exception, with the worker's traceback as its cause
             raise err[0] from RuntimeError("raised in a host map worker:\n%s" % err[1])
         raise RuntimeError("host map worker failed: %s" % err)
+    if local:   # some records (lambdas, generators, open files ...) only live in one process: map here instead
+        return _fold(mapper, chunks, supp, binop) if binop is not None else sequential(mapper, chunks, supp)
     return keys, vals
 
 

@@ -334,6 +334,11 @@ def test_parallel_host_map_matches_sequential(tmp_path):
     with pytest.raises(ZeroDivisionError):
         hostmap.parallel(ops.Map(bad), chunks, (), None, 4)
 
+    def unpicklable(k, v):
+        yield k, (lambda: v)            # a record that cannot cross a process boundary
+    k4, v4 = hostmap.parallel(ops.Map(unpicklable), chunks, (), None, 4)
+    assert len(k4) == len(lines) and [f() for f in v4] == lines
+
 
 def test_parallel_host_reduce_matches_sequential():
     from dampr_b200 import hostmap
