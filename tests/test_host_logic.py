@@ -409,3 +409,135 @@ def test_vexpr_random_expressions_agree_with_cpython():
             assert type(g) is type(x) and (g == x or (g != g and x != x)), (src, g, x)
         checked += 1
     assert checked > 50 and refused > 20
+
+
+class _FakeKV(object):
+    """numpy stand-in for device.KV: enough of the interface for the host logic of spill.py."""
+
+    def __init__(self, ctx, capacity):
+        self.ctx = ctx
+        self.rec = np.zeros((capacity, 2), dtype=np.uint64)
+        self.n = 0
+
+    def __len__(self):
+        return self.n
+
+    def upload_columns(self, off, keys, vals):
+        k = np.asarray(keys).view(np.uint64)
+        self.rec[off:off + len(k), 0] = k
+        self.rec[off:off + len(k), 1] = np.asarray(vals).view(np.uint64)
+        self.n = max(self.n, off + len(k))
+
+    def upload(self, off, recs, count=None):
+        c = len(recs) if count is None else count
+        self.rec[off:off + c] = recs[:c]
+        self.n = max(self.n, off + c)
+
+    @staticmethod
+    def _order(keys, xform):
+        from dampr_b200 import spill
+        from dampr_b200 import device as dev
+        if xform == dev.KEY_MIX:
+            x = keys.copy()
+            with np.errstate(over="ignore"):
+                x ^= x >> np.uint64(30); x *= np.uint64(0xBF58476D1CE4E5B9)
+                x ^= x >> np.uint64(27); x *= np.uint64(0x94D049BB133111EB)
+                x ^= x >> np.uint64(31)
+            return x
+        return spill._order_domain(keys, xform)
+
+    def sort(self, xform):
+        o = np.argsort(self._order(self.rec[:self.n, 0], xform), kind="stable")
+        self.rec[:self.n] = self.rec[:self.n][o]
+        return self
+
+    def records(self):
+        return self.rec[:self.n].copy()
+
+    def columns(self):
+        return self.rec[:self.n, 0].copy(), self.rec[:self.n, 1].copy()
+
+    def partition_by_owner(self, nb):
+        own = self._order(self.rec[:self.n, 0], 1) % np.uint64(nb)
+        o = np.argsort(own, kind="stable")
+        out = _FakeKV(self.ctx, max(1, self.n))
+        out.rec[:self.n] = self.rec[:self.n][o]
+        out.n = self.n
+        return out, np.bincount(own.astype(np.int64), minlength=nb).astype(np.uint64)
+
+    def sort_reduce(self, op, xform):
+        from dampr_b200 import device as dev
+        self.sort(xform)
+        k, v = self.columns()
+        heads = np.flatnonzero(np.concatenate(([True], k[1:] != k[:-1]))) if len(k) else np.zeros(0, dtype=np.int64)
+        out = _FakeKV(self.ctx, max(1, len(heads)))
+        vi = v.view(np.int64)
+        if op == dev.OP_SUM_I64:
+            r = np.add.reduceat(vi, heads) if len(heads) else vi[:0]
+        elif op == dev.OP_COUNT:
+            r = np.diff(np.concatenate((heads, [len(k)])))
+        else:
+            r = vi[heads]                     # FIRST (stable sort keeps input order)
+        out.rec[:len(heads), 0] = k[heads]
+        out.rec[:len(heads), 1] = np.asarray(r, dtype=np.int64).view(np.uint64)
+        out.n = len(heads)
+        self.n = 0
+        return out
+
+    def free(self):
+        pass
+
+
+class _FakeCtx(object):
+    def kv(self, capacity):
+        return _FakeKV(self, capacity)
+
+    def sync(self):
+        pass
+
+    def mem_info(self):
+        return (1 << 30, 1 << 30)
+
+
+def test_spill_host_logic_with_a_numpy_device(monkeypatch):
+    """external_group / external_sort (dampr_b200/spill.py) against numpy, with an arena so small that
+    batches, buckets, splitter ties, heavy single keys and the recursive re-split all occur."""
+    from dampr_b200 import settings, spill
+    from dampr_b200 import device as dev
+    ctx = _FakeCtx()
+    monkeypatch.setattr(settings, "device_arena_bytes", 48 * 70000)     # 70 000 records per batch
+    rng = np.random.default_rng(8)
+    n = 400000
+
+    def chunks(k, v, step=30000):
+        return ((k[i:i + step], v[i:i + step]) for i in range(0, len(k), step))
+
+    # grouping (hash buckets): sums and first-by-input-order
+    keys = rng.integers(0, 5000, size=n).astype(np.uint64) * np.uint64(0x9E3779B97F4A7C15)
+    vals = rng.integers(-1000, 1000, size=n).astype(np.int64)
+    for op in (dev.OP_SUM_I64, dev.OP_FIRST):
+        pieces, st = spill.external_group(ctx, chunks(keys, vals), n, op, dev.KEY_MIX)
+        assert st["buckets"] > 2 and st["batches"] > 2
+        gk = np.concatenate([p[0] for p in pieces])
+        gv = np.concatenate([p[1] for p in pieces]).view(np.int64)
+        assert len(np.unique(gk)) == len(gk)
+        u, first_idx, inv = np.unique(keys, return_index=True, return_inverse=True)
+        exp = np.zeros(len(u), dtype=np.int64)
+        if op == dev.OP_SUM_I64:
+            np.add.at(exp, inv, vals)
+        else:
+            exp = vals[first_idx]
+        o = np.argsort(gk)
+        assert np.array_equal(gk[o], u) and np.array_equal(gv[o], exp)
+
+    # sorting (range buckets): stable global order, for uniform keys, heavy ties and one dominant key
+    for name, k in (("uniform", rng.integers(-10**9, 10**9, size=n).astype(np.int64)),
+                    ("ties", rng.integers(-20, 20, size=n).astype(np.int64)),
+                    ("dominant", np.where(rng.random(n) < 0.7, 5, rng.integers(-1000, 1000, size=n)).astype(np.int64))):
+        v = np.arange(n, dtype=np.int64)
+        samp = k[rng.integers(0, n, size=4096)]
+        pieces, st = spill.external_sort(ctx, chunks(k.view(np.uint64), v), n, dev.KEY_I64, samp)
+        sk = np.concatenate([p[0] for p in pieces]).view(np.int64)
+        sv = np.concatenate([p[1] for p in pieces]).view(np.int64)
+        o = np.argsort(k, kind="stable")
+        assert np.array_equal(sk, k[o]) and np.array_equal(sv, v[o]), name
