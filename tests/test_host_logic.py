@@ -541,3 +541,75 @@ def test_spill_host_logic_with_a_numpy_device(monkeypatch):
         sv = np.concatenate([p[1] for p in pieces]).view(np.int64)
         o = np.argsort(k, kind="stable")
         assert np.array_equal(sk, k[o]) and np.array_equal(sv, v[o]), name
+
+
+def test_frame_general_lowering_with_a_numpy_device():
+    """plan._lower_frame_general (map / filter chains, keyed folds incl. mean's pair fold, single-group
+    folds, sort_by on a computed key) against plain Python, on the numpy stand-in for the device."""
+    from dampr_b200 import operators as ops
+    from dampr_b200 import plan
+    from dampr_b200.operators import Op
+
+    class Ctx(_FakeCtx):
+        def kv_from_columns(self, keys, vals=None):
+            kv = _FakeKV(self, max(1, len(keys)))
+            kv.upload_columns(0, keys, vals if vals is not None else np.zeros(len(keys), dtype=np.int64))
+            return kv
+
+    class Runner(object):
+        ctx = Ctx()
+
+        class stats(object):
+            @staticmethod
+            def add(*a, **k):
+                pass
+
+    def stage(opsl, binop=None):
+        class S(object):
+            pass
+        st = S()
+        maps = [ops.Map(lambda k, v: [(k, v)], op=o) for o in opsl]
+        st.mapper = maps[0] if len(maps) == 1 else ops.FusedMapper(maps[0], maps[1:])
+        st.combiner = ops.PartialReduceCombiner(None) if binop is not None else None
+        st.options = {"binop": binop} if binop is not None else {}
+        st.output = "test"
+        return st
+
+    rng = np.random.default_rng(6)
+    n = 5000
+    words = np.array([b"w" * int(l) for l in rng.integers(1, 12, size=n)], dtype="S16")
+    counts = rng.integers(1, 500, size=n).astype(np.int64)
+    fr = plan.Frame(words, [words, counts], scalar=False, combined=True)
+    rows = list(zip([w.decode() for w in words.tolist()], counts.tolist()))
+
+    # fold_by(len(word), count, +)  (examples/word-stats.py:24-28)
+    out = plan._lower_frame_general(Runner, stage([Op("keyed", lambda tc: len(tc[0]), lambda tc: tc[1])], lambda x, y: x + y), fr)
+    exp = {}
+    for w, c in rows:
+        exp[len(w)] = exp.get(len(w), 0) + c
+    assert out is not None and out.combined and dict(zip(out.keys.tolist(), out.values())) == exp
+
+    # fold with a constant key: one group, folded on the host
+    out = plan._lower_frame_general(Runner, stage([Op("keyed", lambda x: 1, lambda x: x[1])], lambda x, y: x + y), fr)
+    assert out.values() == [sum(c for _w, c in rows)] and out.keys.tolist() == [1]
+
+    # mean(): (value, 1) pairs under a component-wise add
+    out = plan._lower_frame_general(
+        Runner, stage([Op("keyed", lambda tc: tc[1] % 7, lambda tc: (tc[1] * 2, 1))], lambda x, y: (x[0] + y[0], x[1] + y[1])), fr)
+    e2 = {}
+    for _w, c in rows:
+        s0, s1 = e2.get(c % 7, (0, 0))
+        e2[c % 7] = (s0 + 2 * c, s1 + 1)
+    assert dict(zip(out.keys.tolist(), out.values())) == e2
+
+    # map + filter chain, then sort_by on a computed key (stable)
+    st = stage([Op("map", lambda tc: (tc[0], tc[1] * 3, tc[1] / 4)), Op("filter", lambda r: r[1] > 300),
+                Op("keyed", lambda r: -r[1] + len(r[0]), lambda r: r)])
+    out = plan._lower_frame_general(Runner, st, fr)
+    exp_rows = [(w, c * 3, c / 4) for w, c in rows if c * 3 > 300]
+    exp_rows.sort(key=lambda r: -r[1] + len(r[0]))
+    assert out.values() == exp_rows
+
+    # a guard trips (possible int64 overflow): not lowered
+    big = plan.Frame(words, [words, np.full(n, 1 << 61, dtype=np.int64)], scalar=False)
+    assert plan._lower_frame_general(Runner, stage([Op("map", lambda tc: tc[1] * 4)]), big) is None
