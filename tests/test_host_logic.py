@@ -411,92 +411,7 @@ def test_vexpr_random_expressions_agree_with_cpython():
     assert checked > 50 and refused > 20
 
 
-class _FakeKV(object):
-    """numpy stand-in for device.KV: enough of the interface for the host logic of spill.py."""
-
-    def __init__(self, ctx, capacity):
-        self.ctx = ctx
-        self.rec = np.zeros((capacity, 2), dtype=np.uint64)
-        self.n = 0
-
-    def __len__(self):
-        return self.n
-
-    def upload_columns(self, off, keys, vals):
-        k = np.asarray(keys).view(np.uint64)
-        self.rec[off:off + len(k), 0] = k
-        self.rec[off:off + len(k), 1] = np.asarray(vals).view(np.uint64)
-        self.n = max(self.n, off + len(k))
-
-    def upload(self, off, recs, count=None):
-        c = len(recs) if count is None else count
-        self.rec[off:off + c] = recs[:c]
-        self.n = max(self.n, off + c)
-
-    @staticmethod
-    def _order(keys, xform):
-        from dampr_b200 import spill
-        from dampr_b200 import device as dev
-        if xform == dev.KEY_MIX:
-            x = keys.copy()
-            with np.errstate(over="ignore"):
-                x ^= x >> np.uint64(30); x *= np.uint64(0xBF58476D1CE4E5B9)
-                x ^= x >> np.uint64(27); x *= np.uint64(0x94D049BB133111EB)
-                x ^= x >> np.uint64(31)
-            return x
-        return spill._order_domain(keys, xform)
-
-    def sort(self, xform):
-        o = np.argsort(self._order(self.rec[:self.n, 0], xform), kind="stable")
-        self.rec[:self.n] = self.rec[:self.n][o]
-        return self
-
-    def records(self):
-        return self.rec[:self.n].copy()
-
-    def columns(self):
-        return self.rec[:self.n, 0].copy(), self.rec[:self.n, 1].copy()
-
-    def partition_by_owner(self, nb):
-        own = self._order(self.rec[:self.n, 0], 1) % np.uint64(nb)
-        o = np.argsort(own, kind="stable")
-        out = _FakeKV(self.ctx, max(1, self.n))
-        out.rec[:self.n] = self.rec[:self.n][o]
-        out.n = self.n
-        return out, np.bincount(own.astype(np.int64), minlength=nb).astype(np.uint64)
-
-    def sort_reduce(self, op, xform):
-        from dampr_b200 import device as dev
-        self.sort(xform)
-        k, v = self.columns()
-        heads = np.flatnonzero(np.concatenate(([True], k[1:] != k[:-1]))) if len(k) else np.zeros(0, dtype=np.int64)
-        out = _FakeKV(self.ctx, max(1, len(heads)))
-        vi = v.view(np.int64)
-        if op == dev.OP_SUM_I64:
-            r = np.add.reduceat(vi, heads) if len(heads) else vi[:0]
-        elif op == dev.OP_COUNT:
-            r = np.diff(np.concatenate((heads, [len(k)])))
-        else:
-            r = vi[heads]                     # FIRST (stable sort keeps input order)
-        out.rec[:len(heads), 0] = k[heads]
-        out.rec[:len(heads), 1] = np.asarray(r, dtype=np.int64).view(np.uint64)
-        out.n = len(heads)
-        self.n = 0
-        return out
-
-    def free(self):
-        pass
-
-
-class _FakeCtx(object):
-    def kv(self, capacity):
-        return _FakeKV(self, capacity)
-
-    def sync(self):
-        pass
-
-    def mem_info(self):
-        return (1 << 30, 1 << 30)
+from fake_device import FakeCtx as _FakeCtx, FakeKV as _FakeKV  # noqa: E402
 
 
 def test_spill_host_logic_with_a_numpy_device(monkeypatch):
