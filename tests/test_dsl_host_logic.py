@@ -34,3 +34,42 @@ def test_dsl_case_on_the_numpy_device(name, monkeypatch, tmp_path):
         else:
             pytest.skip("fixture %s is not available on CPU" % arg)
     fn(**kwargs)
+
+
+import test_gpu_workloads as W
+
+WORKLOADS = ["test_kv_larger_vs_oracle", "test_kv_workloads_match_reference_golden", "test_map_side_join_lowered_to_hash_probe",
+             "test_non_lowerable_map_runs_in_forked_workers", "test_non_lowerable_reduce_runs_in_forked_workers",
+             "test_non_lowerable_text_falls_back_to_host_map", "test_shim_package_runs_reference_style_script",
+             "test_sort_by_over_binary_records", "test_spill_path_with_capped_arena", "test_text_workloads_larger_vs_oracle"]
+
+
+@pytest.mark.parametrize("name", WORKLOADS)
+def test_workload_on_the_numpy_device(name, monkeypatch, tmp_path):
+    """The BASELINE-shaped workloads that do not need the device tokeniser: kv folds / sorts / joins / spill on
+    the stand-in, text workloads through the host-map path (compared with the oracle like on the GPU)."""
+    fake = FakeCtx()
+    monkeypatch.setattr(runner_mod, "_CTX", {settings.device: fake})
+    monkeypatch.setattr(plan, "_BUFFERS", {})
+    fn = getattr(W, name)
+    kwargs = {a: (fake if a == "ctx" else tmp_path) for a in inspect.signature(fn).parameters}
+    fn(**kwargs)
+
+
+@pytest.mark.parametrize("fixture,maker", W.test_text_workloads_match_reference_golden.pytestmark[0].args[1],
+                         ids=["text_zipf", "text_dirty"])
+def test_reference_golden_text_workloads_through_the_host_map_path(fixture, maker, monkeypatch, tmp_path):
+    """wc.py / tf-idf-dampr.py on the golden corpora give the REAL reference's recorded outputs also when
+    every text stage runs as a host map (the path non-lowerable pipelines take)."""
+    fake = FakeCtx()
+    monkeypatch.setattr(runner_mod, "_CTX", {settings.device: fake})
+    monkeypatch.setattr(plan, "_BUFFERS", {})
+    fix = W.load(fixture)
+    data = maker()
+    p = tmp_path / "corpus.txt"
+    p.write_bytes(data)
+    rows = W.run_wc(str(p))
+    assert sorted(rows) == [tuple(r) for r in fix["wc"]]
+    assert [c for _w, c in rows] == sorted((c for _w, c in rows), reverse=True)
+    assert W.run_tfidf(str(p), str(tmp_path / "idfs"), len(data) / 8 + 1) == fix["tfidf_lines"]
+    assert Dampr.text(str(p)).len().read() == [fix["n_lines"]]
