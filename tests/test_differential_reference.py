@@ -89,3 +89,69 @@ def test_random_pipelines_agree_with_the_reference(monkeypatch):
             assert len(g) == len(e) and all(a[0] == b[0] and abs(a[1] - b[1]) <= 1e-9 * max(1.0, abs(b[1])) for a, b in zip(g, e)), src
         else:
             assert got == exp, src
+
+
+TEXT_DRIVER = r"""
+import sys, json, re, math
+sys.path.insert(0, sys.argv[1])
+from dampr import Dampr
+RX = re.compile(r'[^\w]+')
+path = sys.argv[2]
+res = []
+for src in json.loads(sys.argv[3]):
+    r = list(eval(src).run())
+    res.append(sorted(repr(x) for x in r))
+print(json.dumps(res))
+"""
+
+
+def text_pipelines(seed, n_cases, longest):
+    """chunk sizes start above the longest line: below that the reference yields the line that follows an
+    over-long line once per chunk the long line spans, which the parity contract excludes."""
+    rng = random.Random(seed)
+    out = []
+    for _ in range(n_cases):
+        chunk = rng.choice([longest + 1, 2 * longest + 3, max(4096, longest + 7), 1 << 20])
+        base = "Dampr.text(path, %d)" % chunk
+        out.append(base + rng.choice([
+            ".flat_map(lambda x: x.split()).count()",
+            ".flat_map(lambda x: set(RX.split(x.lower()))).count()",
+            ".flat_map(lambda x: RX.split(x.lower())).count()",
+            ".len()",
+            ".map(lambda x: len(x)).a_group_by(lambda x: x % 5).sum()",
+            ".filter(lambda x: len(x) % 2 == 0).map(lambda x: x[:3]).count()",
+            ".flat_map(lambda x: x.upper().split()).fold_by(lambda w: w[:1], lambda a, b: a + b, lambda w: 1)",
+            ".flat_map(lambda x: x.split()).count().sort_by(lambda wc: (-wc[1], wc[0]))",
+            ".flat_map(lambda x: set(RX.split(x.lower()))).count().cross_right(" + base +
+            ".len(), lambda df, total: (df[0], df[1], math.log(1 + (float(total) / df[1]))))",
+        ]))
+    return out
+
+
+def test_random_text_pipelines_agree_with_the_reference(monkeypatch, tmp_path):
+    """Text inputs with assorted chunk sizes (line ownership at chunk seams, the '' token of re.split,
+    str.split) through the reference and through this engine's host-map path."""
+    import math
+    import re
+    from fake_device import FakeCtx
+    from oracle import gen
+    from dampr_b200 import Dampr, settings, plan
+    from dampr_b200 import runner as runner_mod
+    RX = re.compile(r"[^\w]+")
+    for ci, data in enumerate((gen.text(5, 400, V=300), gen.dirty_text(11, 300, 200), b"", b"one line without newline")):
+        path = str(tmp_path / ("c%d.txt" % ci))
+        with open(path, "wb") as f:
+            f.write(data)
+        longest = max([len(l) + 1 for l in data.split(b"\n")] + [1])
+        srcs = text_pipelines(100 + ci, 14, longest)
+        env = dict(os.environ)
+        env.pop("PYTHONPATH", None)
+        p = subprocess.run([sys.executable, "-c", TEXT_DRIVER, REF, path, json.dumps(srcs)], capture_output=True,
+                           text=True, env=env, cwd="/tmp", timeout=600)
+        assert p.returncode == 0, p.stderr[-2000:]
+        ref = json.loads(p.stdout.strip().split("\n")[-1])
+        monkeypatch.setattr(runner_mod, "_CTX", {settings.device: FakeCtx()})
+        monkeypatch.setattr(plan, "_BUFFERS", {})
+        for src, exp in zip(srcs, ref):
+            got = sorted(repr(x) for x in eval(src, {"Dampr": Dampr, "path": path, "RX": RX, "math": math}).run())
+            assert got == exp, (ci, src)
