@@ -203,3 +203,52 @@ def test_more_random_pipelines_agree_with_the_reference(monkeypatch):
         for src, exp in zip(srcs, ref):
             got = sorted(repr(x) for x in eval(src, {"Dampr": Dampr, "items": items}).run())
             assert got == exp, (n_items, src)
+
+
+SINK_DRIVER = r"""
+import sys, json, os
+sys.path.insert(0, sys.argv[1])
+from dampr import Dampr
+items = json.loads(sys.argv[2])
+res = []
+for i, src in enumerate(json.loads(sys.argv[3])):
+    out = os.path.join(sys.argv[4], "ref%d" % i)
+    eval(src).run()
+    lines = []
+    for fn in sorted(os.listdir(out)):
+        with open(os.path.join(out, fn)) as f:
+            lines.extend(l.rstrip("\n") for l in f)
+    res.append(sorted(lines))
+print(json.dumps(res))
+"""
+
+
+def test_sinks_write_the_lines_the_reference_writes(monkeypatch, tmp_path):
+    from fake_device import FakeCtx
+    from dampr_b200 import Dampr, settings, plan
+    from dampr_b200 import runner as runner_mod
+    rng = random.Random(21)
+    items = [rng.randint(-50, 200) for _ in range(150)]
+    templates = [
+        "Dampr.memory(items, partitions=3).count(lambda x: x % 7).sink_tsv(out)",
+        "Dampr.memory(items, partitions=2).map(lambda x: (str(x), x / 7.0, x * 10 ** 18)).sink_tsv(out)",
+        "Dampr.memory(items, partitions=2).map(lambda x: ('k%d' % x, [x, x / 3.0], {'a': x})).sink_json(out)",
+        "Dampr.memory(items, partitions=4).map(lambda x: 'line %d' % x).sink(out)",
+        "Dampr.memory(items, partitions=1).mean(lambda x: x % 3, lambda x: x).sink_tsv(out)",
+    ]
+    env = dict(os.environ)
+    env.pop("PYTHONPATH", None)
+    p = subprocess.run([sys.executable, "-c", SINK_DRIVER, REF, json.dumps(items), json.dumps(templates), str(tmp_path)],
+                       capture_output=True, text=True, env=env, cwd="/tmp", timeout=240)
+    assert p.returncode == 0, p.stderr[-2000:]
+    ref = json.loads(p.stdout.strip().split("\n")[-1])
+    monkeypatch.setattr(runner_mod, "_CTX", {settings.device: FakeCtx()})
+    monkeypatch.setattr(plan, "_BUFFERS", {})
+    for i, (src, exp) in enumerate(zip(templates, ref)):
+        out = str(tmp_path / ("ours%d" % i))
+        eval(src, {"Dampr": Dampr, "items": items, "out": out}).run()
+        lines = []
+        for fn in sorted(os.listdir(out)):
+            with open(os.path.join(out, fn)) as f:
+                lines.extend(l.rstrip("\n") for l in f)
+        assert sorted(lines) == exp, src
