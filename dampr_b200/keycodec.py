@@ -28,12 +28,16 @@ _BIAS = 1 << 63
 
 
 class Codec(object):
-    __slots__ = ("kind", "exact", "ordered")
+    __slots__ = ("kind", "exact", "ordered", "decodable")
 
-    def __init__(self, kind):
+    def __init__(self, kind, decodable=False):
         self.kind = kind
-        self.exact = kind in (INT, FLOAT)
+        self.exact = kind in (INT, FLOAT)      # equal codes <=> equal keys
         self.ordered = kind != HASH
+        # the key OBJECTS can be rebuilt from the codes: only when every key has exactly the type the
+        # decoder produces (True == 1 == 1.0 and -0.0 == 0.0 are equal keys with one code, but a rebuilt key
+        # must be the object the reference would show, so such inputs keep their original key objects)
+        self.decodable = self.exact and decodable
 
     def __repr__(self):
         return "Codec(%s)" % self.kind
@@ -112,10 +116,13 @@ def encode(keys, need_order=False, force=None):
         kind = _tuple_kind(keys)
     if kind == INT:
         arr = np.fromiter((int(k) for k in keys), dtype=np.int64, count=len(keys))
-        return (arr.view(np.uint64) ^ np.uint64(_BIAS)), Codec(INT)
+        return (arr.view(np.uint64) ^ np.uint64(_BIAS)), Codec(INT, all(type(k) is int for k in keys))
     if kind == FLOAT:
         arr = np.fromiter((float(k) for k in keys), dtype=np.float64, count=len(keys))
-        return _float_codes(arr), Codec(FLOAT)
+        zeros = arr == 0
+        faithful = all(type(k) is float for k in keys) and not bool(np.signbit(arr[zeros]).any())
+        arr = arr + 0.0   # -0.0 == 0.0: one key, one code
+        return _float_codes(arr), Codec(FLOAT, faithful)
     if kind == STR:
         return _prefix_codes([k.encode("utf-8") for k in keys]), Codec(STR)
     if kind == BYTES:

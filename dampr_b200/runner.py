@@ -205,7 +205,7 @@ class B200Runner(object):
         kind = lowering.binop_kind(binop)
         codes, codec = keycodec.encode(keys)
         n = len(keys)
-        if n and codec.exact and kind in (lowering.ADD, lowering.MIN, lowering.MAX, lowering.FIRST, lowering.LAST):
+        if n and codec.decodable and kind in (lowering.ADD, lowering.MIN, lowering.MAX, lowering.FIRST, lowering.LAST):
             col, op = _numeric_column(vals, kind)
             if col is not None:
                 kv = self.ctx.kv_from_columns(codes, col)

@@ -252,3 +252,38 @@ def test_sinks_write_the_lines_the_reference_writes(monkeypatch, tmp_path):
             with open(os.path.join(out, fn)) as f:
                 lines.extend(l.rstrip("\n") for l in f)
         assert sorted(lines) == exp, src
+
+
+def key_type_pipelines():
+    """Grouping / folding / sorting / joining on keys of assorted types: strings sharing an 8-byte prefix, ints
+    beyond 2^63, floats, -0.0, tuples, bools (True == 1), mixed int / float, bytes, the empty string."""
+    keyfs = ["lambda x: 'prefix-shared-%03d' % (x % 40)", "lambda x: 'abcdefgh' + str(x % 9) * (x % 4)", "lambda x: x * 10 ** 18", "lambda x: -(x % 5) * 2 ** 62",
+             "lambda x: float(x % 6) / 3", "lambda x: (x % 2) * -0.0", "lambda x: (x % 3, str(x % 4))", "lambda x: (x % 3 == 0)", "lambda x: x % 3 if x % 2 else (x % 3 == 1)",
+             "lambda x: ''", "lambda x: 2 ** 63 + (x % 3)", "lambda x: -2 ** 63 + (x % 3)", "lambda x: float(x % 3) if x % 2 else x % 3", "lambda x: (str(x % 3),)", "lambda x: b'k%d' % (x % 5)"]
+    tails = [".group_by(%s).reduce(lambda k, it: sum(it))", ".a_group_by(%s).sum()", ".count(%s)", ".fold_by(%s, min)", ".sort_by(%s)",
+             ".group_by(%s).reduce(lambda k, it: len(list(it))).join(Dampr.memory(items[::3], partitions=2).group_by(%s).reduce(lambda k, it: sum(it))).reduce(lambda l, r: (list(l), list(r)))"]
+    srcs=[]
+    for kf in keyfs:
+        for t in tails:
+            srcs.append("Dampr.memory(items, partitions=3)" + (t % ((kf,) * t.count("%s"))))
+    return srcs
+
+
+def test_key_types_agree_with_the_reference(monkeypatch):
+    from fake_device import FakeCtx
+    from dampr_b200 import Dampr, settings, plan
+    from dampr_b200 import runner as runner_mod
+    rng = random.Random(5)
+    items = [rng.randint(-50, 200) for _ in range(90)]
+    srcs = key_type_pipelines()
+    env = dict(os.environ)
+    env.pop("PYTHONPATH", None)
+    p = subprocess.run([sys.executable, "-c", DRIVER, REF, json.dumps(items), json.dumps(srcs)], capture_output=True,
+                       text=True, env=env, cwd="/tmp", timeout=400)
+    assert p.returncode == 0, p.stderr[-2000:]
+    ref = json.loads(p.stdout.strip().split("\n")[-1])
+    monkeypatch.setattr(runner_mod, "_CTX", {settings.device: FakeCtx()})
+    monkeypatch.setattr(plan, "_BUFFERS", {})
+    for src, exp in zip(srcs, ref):
+        got = sorted(repr(x) for x in eval(src, {"Dampr": Dampr, "items": items}).run())
+        assert got == exp, src
