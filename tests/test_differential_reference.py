@@ -287,3 +287,60 @@ def test_key_types_agree_with_the_reference(monkeypatch):
     for src, exp in zip(srcs, ref):
         got = sorted(repr(x) for x in eval(src, {"Dampr": Dampr, "items": items}).run())
         assert got == exp, src
+
+
+EXPR_DRIVER = r"""
+import sys, json
+sys.path.insert(0, sys.argv[1])
+from dampr import Dampr
+items = json.loads(sys.argv[2]); jpath = sys.argv[4]
+print(json.dumps([repr(eval(src)) for src in json.loads(sys.argv[3])]))
+"""
+
+
+def test_inputs_outputs_and_empty_cases_agree_with_the_reference(monkeypatch, tmp_path):
+    """Dampr.json inputs, multi-output Dampr.run, read(k), empty inputs through every stage kind, topk, sample(0/1),
+    first(), empty sides of inner / left joins."""
+    from fake_device import FakeCtx
+    from dampr_b200 import Dampr, settings, plan
+    from dampr_b200 import runner as runner_mod
+    rng = random.Random(9)
+    jpath = str(tmp_path / "j.json")
+    with open(jpath, "w") as f:
+        for i in range(200):
+            f.write(json.dumps({"id": i, "tag": "t%d" % (i % 7), "v": rng.randint(-5, 50), "w": [i, i % 3]}) + "\n")
+    items = [rng.randint(-20, 60) for _ in range(80)]
+    srcs = [
+     "sorted(Dampr.json(jpath).map(lambda d: (d['tag'], d['v'])).a_group_by(lambda kv: kv[0], lambda kv: kv[1]).sum().run())",
+     "sorted(Dampr.json(jpath, 512).filter(lambda d: d['v'] > 10).map(lambda d: d['id']).run())",
+     "sorted(Dampr.json(jpath).group_by(lambda d: d['w'][1], lambda d: d['v']).reduce(lambda k, it: max(it)).run())",
+     "[sorted(x) for x in Dampr.run(Dampr.memory(items).count(lambda x: x % 3), Dampr.memory(items).map(lambda x: x + 1).a_group_by(lambda x: x % 2).sum())]",
+     "sorted(Dampr.memory(items, partitions=4).count(lambda x: x % 5).read(2))[:0]",
+     "len(Dampr.memory(items, partitions=4).count(lambda x: x % 5).read(2))",
+     "sorted(Dampr.memory(items).map(lambda x: x % 4).sort_by(lambda x: x).read())",
+     "sorted(Dampr.memory(items).group_by(lambda x: x % 3).reduce(lambda k, it: sum(it)).run().read(1)) [:0]",
+     "list(Dampr.memory([]).len().run())",
+     "list(Dampr.memory([]).count().run())",
+     "list(Dampr.memory([5]).mean().run())",
+     "sorted(Dampr.memory(items).a_group_by(lambda x: x % 3).first().run())[:0]",
+     "sorted(k for k, v in Dampr.memory(items).a_group_by(lambda x: x % 3).first().run())",
+     "sorted(Dampr.memory(items).topk(3, lambda x: -x).run())",
+     "sorted(Dampr.memory(items).topk(300).run()) == sorted(items)",
+     "sorted(Dampr.memory(items).sample(1.0).run()) == sorted(items)",
+     "list(Dampr.memory(items).sample(0.0).run())",
+     "sorted(Dampr.memory(items).flat_map(lambda x: []).count().run())",
+     "sorted(Dampr.memory(items).filter(lambda x: False).group_by(lambda x: x).reduce(lambda k, it: 1).run())",
+     "sorted(Dampr.memory(items).filter(lambda x: False).sort_by(lambda x: x).run())",
+     "sorted(Dampr.memory(items).filter(lambda x: False).a_group_by(lambda x: 1).sum().join(Dampr.memory(items).a_group_by(lambda x: 1).sum()).reduce(lambda l, r: 1).run())",
+     "sorted(Dampr.memory(items).a_group_by(lambda x: 1).sum().join(Dampr.memory(items).filter(lambda x: False).a_group_by(lambda x: 1).sum()).left_reduce(lambda l, r: (list(l), list(r))).run())",
+    ]
+    env = dict(os.environ)
+    env.pop("PYTHONPATH", None)
+    p = subprocess.run([sys.executable, "-c", EXPR_DRIVER, REF, json.dumps(items), json.dumps(srcs), jpath],
+                       capture_output=True, text=True, env=env, cwd="/tmp", timeout=400)
+    assert p.returncode == 0, p.stderr[-2000:]
+    ref = json.loads(p.stdout.strip().split("\n")[-1])
+    monkeypatch.setattr(runner_mod, "_CTX", {settings.device: FakeCtx()})
+    monkeypatch.setattr(plan, "_BUFFERS", {})
+    for src, exp in zip(srcs, ref):
+        assert repr(eval(src, {"Dampr": Dampr, "items": items, "jpath": jpath})) == exp, src
