@@ -350,3 +350,56 @@ def test_inputs_outputs_and_empty_cases_agree_with_the_reference(monkeypatch, tm
     monkeypatch.setattr(plan, "_BUFFERS", {})
     for src, exp in zip(srcs, ref):
         assert repr(eval(src, {"Dampr": Dampr, "items": items, "jpath": jpath})) == exp, src
+
+
+RECS_DRIVER = r"""
+import sys, json
+sys.path.insert(0, sys.argv[1])
+from dampr import Dampr
+recs = [tuple(r) for r in json.loads(sys.argv[2])]
+print(json.dumps([sorted(repr(x) for x in eval(src).run()) for src in json.loads(sys.argv[3])]))
+"""
+
+
+def test_lowered_kv_and_frame_stages_agree_with_the_reference(monkeypatch):
+    """Binary (key, value) records through the LOWERED path of this engine — device folds / sorts of the
+    columns, then the column-at-a-time frame stages (vexpr) — against the reference running the same lambdas
+    record by record over the same tuples."""
+    import numpy as np
+    from fake_device import FakeCtx
+    from dampr_b200 import Dampr, settings, plan
+    from dampr_b200 import runner as runner_mod
+    from dampr_b200.inputs import ArrayKVInput
+    rng = random.Random(13)
+    keys = [rng.randint(-40, 40) for _ in range(4000)]
+    vals = [rng.randint(-1000, 1000) for _ in range(4000)]
+    heads = [".a_group_by(lambda x: x[0], lambda x: x[1]).sum()", ".count(lambda x: x[0])", ".fold_by(lambda x: x[0], min, lambda x: x[1])", ".fold_by(lambda x: x[1] % 50, max, lambda x: x[0])",
+             ".group_by(lambda x: x[0], lambda x: x[1]).reduce(lambda k, it: sum(it))", ".group_by(lambda x: x[0], lambda x: x[1]).reduce(lambda k, it: len(list(it)))"]
+    tails = ["", ".map(lambda kv: (kv[0], kv[1] * 3 - kv[0], kv[1] / 7))", ".filter(lambda kv: kv[1] > 0).map_values(lambda v: v // 5)", ".fold_by(lambda kv: kv[0] % 7, lambda x, y: x + y, value=lambda kv: kv[1])",
+             ".mean(lambda kv: abs(kv[0]) % 5, lambda kv: kv[1])", ".mean(value=lambda kv: float(kv[1]))", ".sort_by(lambda kv: kv[1] - 2 * kv[0])", ".map(lambda kv: kv[0] * kv[1]).a_group_by(lambda x: 1).sum()",
+             ".filter(lambda kv: kv[0] != 0).map(lambda kv: (kv[0], kv[1] % kv[0], kv[1] // kv[0], float(kv[1]) / kv[0]))", ".map(lambda kv: -kv[1]).sort_by(lambda x: x)", ".len()",
+             ".fold_by(lambda kv: kv[1] % 3, lambda a, b: a if a < b else b, lambda kv: kv[0])", ".map(lambda kv: (kv[0] < kv[1], kv[0] == 0, abs(kv[1]) >= 10))"]
+    srcs_ref=[]; srcs_ours=[]
+    for h in heads:
+        for t in tails:
+            srcs_ref.append("Dampr.memory(recs, partitions=3)"+h+t); srcs_ours.append("Dampr.read_input(ArrayKVInput(K, V))"+h+t)
+    env = dict(os.environ)
+    env.pop("PYTHONPATH", None)
+    p = subprocess.run([sys.executable, "-c", RECS_DRIVER, REF, json.dumps(list(zip(keys, vals))), json.dumps(srcs_ref)],
+                       capture_output=True, text=True, env=env, cwd="/tmp", timeout=600)
+    assert p.returncode == 0, p.stderr[-2000:]
+    ref = json.loads(p.stdout.strip().split("\n")[-1])
+    K, V = np.array(keys, dtype=np.int64), np.array(vals, dtype=np.int64)
+    lowered = 0
+    for so, exp in zip(srcs_ours, ref):
+        monkeypatch.setattr(runner_mod, "_CTX", {settings.device: FakeCtx()})
+        monkeypatch.setattr(plan, "_BUFFERS", {})
+        got = sorted(repr(x) for x in eval(so, {"Dampr": Dampr, "ArrayKVInput": ArrayKVInput, "K": K, "V": V}).run())
+        hows = [h for _s, h, _d in runner_mod.LAST_STATS.stages]
+        lowered += any("column-at-a-time" in h or "frame keyed fold" in h or "device sort of frame rows" in h for h in hows)
+        if ".mean(" in so:
+            g, e = [eval(x) for x in got], [eval(x) for x in exp]
+            assert len(g) == len(e) and all(a[0] == b[0] and abs(a[1] - b[1]) <= 1e-9 * max(1.0, abs(b[1])) for a, b in zip(g, e)), so
+        else:
+            assert got == exp, so
+    assert lowered >= 40     # the frame stages really took the lowered path
