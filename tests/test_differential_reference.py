@@ -403,3 +403,52 @@ def test_lowered_kv_and_frame_stages_agree_with_the_reference(monkeypatch):
         else:
             assert got == exp, so
     assert lowered >= 40     # the frame stages really took the lowered path
+
+
+def test_lowered_cross_and_sink_agree_with_the_reference(monkeypatch, tmp_path):
+    """The tf-idf tail — cross_right with the 1-row total (memoised per distinct value) and the native
+    sink_tsv — over a lowered count frame, against the reference's files for the same records."""
+    import math
+    import numpy as np
+    from fake_device import FakeCtx
+    from dampr_b200 import Dampr, settings, plan
+    from dampr_b200 import runner as runner_mod
+    from dampr_b200.inputs import ArrayKVInput
+    rng = random.Random(17)
+    keys = [int(rng.paretovariate(1.2)) % 500 for _ in range(6000)]
+    vals = [rng.randint(0, 9) for _ in range(6000)]
+    tail = ".count(lambda x: x[0]).cross_right(%s.len(), lambda df, total: (df[0], df[1], math.log(1 + (float(total) / df[1]))), " \
+           "memory=True).sink_tsv(out)"
+    ref_src = "Dampr.memory(recs, partitions=3)" + tail % "Dampr.memory(recs, partitions=3)"
+    driver = r"""
+import sys, json, os, math
+sys.path.insert(0, sys.argv[1])
+from dampr import Dampr
+recs = [tuple(r) for r in json.loads(sys.argv[2])]
+out = sys.argv[4]
+eval(sys.argv[3]).run()
+lines = []
+for fn in sorted(os.listdir(out)):
+    with open(os.path.join(out, fn)) as f:
+        lines.extend(l.rstrip("\n") for l in f)
+print(json.dumps(sorted(lines)))
+"""
+    env = dict(os.environ)
+    env.pop("PYTHONPATH", None)
+    p = subprocess.run([sys.executable, "-c", driver, REF, json.dumps(list(zip(keys, vals))), ref_src, str(tmp_path / "ref")],
+                       capture_output=True, text=True, env=env, cwd="/tmp", timeout=300)
+    assert p.returncode == 0, p.stderr[-2000:]
+    exp = json.loads(p.stdout.strip().split("\n")[-1])
+    monkeypatch.setattr(runner_mod, "_CTX", {settings.device: FakeCtx()})
+    monkeypatch.setattr(plan, "_BUFFERS", {})
+    K, V = np.array(keys, dtype=np.int64), np.array(vals, dtype=np.int64)
+    out = str(tmp_path / "ours")
+    src = "Dampr.read_input(ArrayKVInput(K, V))" + tail % "Dampr.read_input(ArrayKVInput(K, V))"
+    eval(src, {"Dampr": Dampr, "ArrayKVInput": ArrayKVInput, "K": K, "V": V, "math": math, "out": out}).run()
+    hows = [h for _s, h, _d in runner_mod.LAST_STATS.stages]
+    assert any("memoised per distinct" in h for h in hows) and any("native frame sink" in h for h in hows), hows
+    lines = []
+    for fn in sorted(os.listdir(out)):
+        with open(os.path.join(out, fn)) as f:
+            lines.extend(l.rstrip("\n") for l in f)
+    assert sorted(lines) == exp
