@@ -167,3 +167,129 @@ class FakeCtx(object):
 
     table = textbuf
 
+
+
+# ---- text side: a stand-in tokeniser, so that plan.TextScan's plumbing (layout of several files in one
+# buffer, chunked uploads, owner ranges, flag handling, table growth, result fetch) runs on CPU too. The
+# token rules restate the reference's lambdas (examples/wc.py:12, benchmarks/tf-idf-dampr.py:12-14) the way
+# oracle/refsem.py does; the device kernels are checked against the oracle by the -m gpu suites, not here.
+import re as _re
+
+_RX = _re.compile(r"[^\w]+")
+
+
+class FakeTextBuf(object):
+    def __init__(self, ctx, capacity):
+        self.ctx = ctx
+        self.capacity = int(capacity)
+        self.buf = np.full(self.capacity + 64, 10, dtype=np.uint8)   # '\n' padding
+        self.n = 0
+
+    def set_length(self, n):
+        assert n <= self.capacity
+        self.n = int(n)
+        self.buf[self.n:] = 10
+
+    def upload(self, off, host, length):
+        self.buf[off:off + length] = np.frombuffer(memoryview(host), dtype=np.uint8)[:length] \
+            if not isinstance(host, np.ndarray) else host.reshape(-1).view(np.uint8)[:length]
+
+    def download(self, off, length):
+        return self.buf[off:off + length].copy()
+
+    def free(self):
+        pass
+
+
+class FakeTable(object):
+    def __init__(self, ctx, log2):
+        self.ctx = ctx
+        self.capacity = 1 << int(log2)
+        self.clear()
+
+    def clear(self):
+        self.counts, self.first = {}, {}
+        self.st = {"lines": 0, "empty": 0, "folded": 0, "flags": 0, "hashed": 0, "raw": 0}
+
+    def free(self):
+        pass
+
+    def count(self, tb, lo, hi, mode):
+        from dampr_b200 import device as dev
+        data = tb.buf[:tb.n].tobytes()
+        pos = 0
+        while pos < len(data):
+            end = data.find(b"\n", pos)
+            nxt = len(data) if end < 0 else end + 1
+            line = data[pos:len(data) if end < 0 else end]
+            if lo <= pos < hi:
+                self._line(line, pos, mode, dev)
+            pos = nxt
+        if len(self.counts) * 2 > self.capacity:
+            self.st["flags"] |= dev.TF_TABLEFULL if len(self.counts) >= self.capacity else 0
+
+    def _line(self, line, off, mode, dev):
+        st = self.st
+        st["lines"] += 1
+        if any(b >= 0x80 for b in line):
+            st["flags"] |= dev.TF_NONASCII
+            return
+        text = line.decode("ascii")
+        if mode == dev.TOK_WS:
+            toks, limit = text.split(), 9
+        else:
+            if "\r" in text:
+                st["flags"] |= dev.TF_CR
+            toks, limit = _RX.split(text.lower()), 12
+        st["raw"] += sum(1 for t in toks if t != "")
+        if mode == dev.TOK_NONWORD_LOWER_SET:
+            toks = set(toks)
+        for t in toks:
+            if t == "":
+                st["empty"] += 1
+                continue
+            st["folded"] += 1
+            if len(t) > limit or "\0" in t:
+                st["hashed"] += 1
+            if t not in self.counts:
+                low = text if mode == dev.TOK_WS else text.lower()
+                self.first[t] = off + low.find(t)
+            self.counts[t] = self.counts.get(t, 0) + 1
+
+    def stats(self):
+        d = dict(self.st)
+        d["entries"] = len(self.counts)
+        return d
+
+    def verify(self, tb, lo, hi, mode):
+        pass
+
+    def fetch_words(self, tb, mode, width=32, with_codes=True):
+        toks = list(self.counts)
+        words = np.array([t.encode("ascii")[:width] for t in toks], dtype="S%d" % width) if toks \
+            else np.zeros(0, dtype="S%d" % width)
+        counts = np.array([self.counts[t] for t in toks], dtype=np.uint64)
+        if not with_codes:
+            return words, counts, None, None
+        limit = 9 if mode == 0 else 12
+        codes = np.array([(1 << 63 | i) if (len(t) > limit or "\0" in t) else i + 1 for i, t in enumerate(toks)], dtype=np.uint64)
+        reps = np.array([(self.first[t] << 20) | len(t) for t in toks], dtype=np.uint64)
+        return words, counts, codes, reps
+
+
+class FakeTextCtx(FakeCtx):
+    """FakeCtx plus the text entry points."""
+
+    def textbuf(self, capacity):
+        return FakeTextBuf(self, capacity)
+
+    def table(self, log2):
+        return FakeTable(self, log2)
+
+    def sync_copy_stream(self):
+        pass
+
+
+class FakePinned(object):
+    def __init__(self, nbytes):
+        self.array = np.zeros(int(nbytes), dtype=np.uint8)

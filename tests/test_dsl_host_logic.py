@@ -73,3 +73,34 @@ def test_reference_golden_text_workloads_through_the_host_map_path(fixture, make
     assert [c for _w, c in rows] == sorted((c for _w, c in rows), reverse=True)
     assert W.run_tfidf(str(p), str(tmp_path / "idfs"), len(data) / 8 + 1) == fix["tfidf_lines"]
     assert Dampr.text(str(p)).len().read() == [fix["n_lines"]]
+
+
+from fake_device import FakeTextCtx, FakePinned
+
+TEXT_WORKLOADS = ["test_text_workloads_larger_vs_oracle", "test_gzip_text_inputs_are_lowered",
+                  "test_lines_with_many_distinct_tokens_stay_on_the_device", "test_non_lowerable_text_falls_back_to_host_map"]
+
+
+def _text_fake(monkeypatch):
+    fake = FakeTextCtx()
+    monkeypatch.setattr(runner_mod, "_CTX", {settings.device: fake})
+    monkeypatch.setattr(plan, "_BUFFERS", {})
+    monkeypatch.setattr(plan, "_pinned_ring", lambda nslots, slot_bytes: [FakePinned(slot_bytes) for _ in range(nslots)])
+    return fake
+
+
+@pytest.mark.parametrize("name", TEXT_WORKLOADS)
+def test_text_workload_through_the_scan_plumbing(name, monkeypatch, tmp_path):
+    """plan.TextScan (files laid out in one buffer, chunked uploads, owner ranges, flags, fallbacks, the result
+    frame) with a stand-in tokeniser: the lowered text path minus the kernel."""
+    fake = _text_fake(monkeypatch)
+    fn = getattr(W, name)
+    fn(**{a: (fake if a == "ctx" else tmp_path) for a in inspect.signature(fn).parameters})
+
+
+@pytest.mark.parametrize("fixture,maker", W.test_text_workloads_match_reference_golden.pytestmark[0].args[1],
+                         ids=["text_zipf", "text_dirty"])
+def test_reference_golden_text_workloads_through_the_scan_plumbing(fixture, maker, monkeypatch, tmp_path):
+    """The same golden outputs of the REAL reference, this time through the lowered text path's host side
+    (scan plumbing, line-count by-product, relabel, memoised cross, native sink)."""
+    W.test_text_workloads_match_reference_golden(_text_fake(monkeypatch), tmp_path, fixture, maker)
