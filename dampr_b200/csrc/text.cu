@@ -102,8 +102,11 @@ __device__ __forceinline__ void classify4(u32 x, u32 &wbits, u32 &nlbits, u32 &b
         u32 digit = ge7(x7, 0x30) & ~ge7(x7, 0x3A);
         u32 us = eq7(x7, 0x5F);
         word = (alpha | digit | us);
-        bad |= (eq7(x7, 0x0D) >> 1);  // bit6 marks CR (kept apart from the non-ASCII bit7)
     }
+    // a '\r' ends a line under universal newlines: tokens of the \w modes and the LINE COUNT of every mode then
+    // differ from what this kernel computes -> flag (bit6, kept apart from the non-ASCII bit7); str.split token
+    // counts are unaffected ('\r' is whitespace) and the host ignores the flag for them
+    bad |= (eq7(x7, 0x0D) >> 1);
     word &= ~hi;
     wbits = movemask4(word);
     nlbits = movemask4(nl);

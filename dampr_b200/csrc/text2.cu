@@ -112,8 +112,10 @@ __device__ __forceinline__ void classify4(u32 x, u32 &wbits, u32 &nlbits, u32 &b
         u32 alpha = ge7(y, 0x61) & ~ge7(y, 0x7B);
         u32 digit = ge7(x7, 0x30) & ~ge7(x7, 0x3A);
         word = alpha | digit | eq7(x7, 0x5F);
-        bad |= (eq7(x7, 0x0D) >> 1);
     }
+    // '\r' (universal newlines): flagged in every mode -- the \w tokenisers and the line count depend on it, the
+    // str.split token counts do not and the host ignores the flag for them
+    bad |= (eq7(x7, 0x0D) >> 1);
     word &= ~hi;
     wbits = movemask4(word);
     nlbits = movemask4(nl);

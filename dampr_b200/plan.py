@@ -300,6 +300,7 @@ class TextScan(object):
         self.n_lines = 0
         self.empty = 0
         self.nbytes = 0
+        self.has_cr = False   # '\r' seen: n_lines counts '\n' only and is not the universal-newline line count
 
     def run(self):
         ctx = self.runner.ctx
@@ -390,6 +391,7 @@ class TextScan(object):
         self.counts = counts.view(np.int64)
         self.n_lines = int(st["lines"])
         self.empty = int(st["empty"])
+        self.has_cr = bool(flags & dev.TF_CR)
         return self
 
     def _finish_distributed(self, ctx, tb, tab, st):
@@ -409,8 +411,9 @@ class TextScan(object):
             ws = keycodes.decode_table(codes[hs], reps[hs], self.mode,
                                        lambda off, ln: tb.download(off, ln).tobytes())
             hashed_words = dict(zip(codes[hs].tolist(), ws))
-        lines, empty, anybad, any_hashed = dist.all_reduce_sum_int(
-            [int(st["lines"]), int(st["empty"]), 1 if bad else 0, len(hashed_words)])
+        lines, empty, anybad, any_hashed, any_cr = dist.all_reduce_sum_int(
+            [int(st["lines"]), int(st["empty"]), 1 if bad else 0, len(hashed_words), 1 if flags & dev.TF_CR else 0])
+        self.has_cr = bool(any_cr)
         if anybad:
             raise RuntimeError("distributed text scan cannot be lowered on every rank (flags=%d); the "
                                "host-map path is single-process only" % flags)
@@ -698,7 +701,14 @@ def _lower_map(runner, stage, inputs, si):
             fut = _future_text_count(runner, si, stage.inputs[0])
             mode = fut[1] if fut is not None else dev.TOK_WS
             scan = text_scan(runner, src, mode)
+            if scan.has_cr:
+                # text mode reads with universal newlines (dataset.py:458-476): '\r' and '\r\n' end lines too
+                raise NotLowerable("carriage returns: the line count needs universal-newline semantics")
             runner.stats.add(stage, "device line count (tokenise kernel by-product)", "lines=%d" % scan.n_lines)
+            if scan.nbytes == 0:
+                # no bytes, no chunks, no count record: len() of an empty text input is an empty collection in
+                # the reference (dampr.py:245-275), not [0]
+                return RecordsDataset([], [])
             return RecordsDataset([1], [scan.n_lines])
         if isinstance(ds, (Frame, RecordsDataset)):
             runner.stats.add(stage, "frame length", "records=%d" % len(ds))

@@ -235,11 +235,11 @@ class FakeTable(object):
             st["flags"] |= dev.TF_NONASCII
             return
         text = line.decode("ascii")
+        if "\r" in text:
+            st["flags"] |= dev.TF_CR          # every mode flags it; the host ignores it for str.split token counts
         if mode == dev.TOK_WS:
             toks, limit = text.split(), 9
         else:
-            if "\r" in text:
-                st["flags"] |= dev.TF_CR
             toks, limit = _RX.split(text.lower()), 12
         st["raw"] += sum(1 for t in toks if t != "")
         if mode == dev.TOK_NONWORD_LOWER_SET:

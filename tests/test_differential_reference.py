@@ -128,9 +128,11 @@ def text_pipelines(seed, n_cases, longest):
     return out
 
 
-def test_random_text_pipelines_agree_with_the_reference(monkeypatch, tmp_path):
+@pytest.mark.parametrize("path_kind", ["host-map", "scan-plumbing"])
+def test_random_text_pipelines_agree_with_the_reference(path_kind, monkeypatch, tmp_path):
     """Text inputs with assorted chunk sizes (line ownership at chunk seams, the '' token of re.split,
-    str.split) through the reference and through this engine's host-map path."""
+    str.split) through the reference and through this engine: once with every text stage as a host map, once
+    through the lowered path's plumbing (plan.TextScan) with the stand-in tokeniser of tests/fake_device.py."""
     import math
     import re
     from fake_device import FakeCtx
@@ -156,7 +158,12 @@ def test_random_text_pipelines_agree_with_the_reference(monkeypatch, tmp_path):
                            text=True, env=env, cwd="/tmp", timeout=240)
         assert p.returncode == 0, p.stderr[-2000:]
         ref = json.loads(p.stdout.strip().split("\n")[-1])
-        monkeypatch.setattr(runner_mod, "_CTX", {settings.device: FakeCtx()})
+        if path_kind == "host-map":
+            monkeypatch.setattr(runner_mod, "_CTX", {settings.device: FakeCtx()})
+        else:
+            from fake_device import FakeTextCtx, FakePinned
+            monkeypatch.setattr(runner_mod, "_CTX", {settings.device: FakeTextCtx()})
+            monkeypatch.setattr(plan, "_pinned_ring", lambda n, b: [FakePinned(b) for _ in range(n)])
         monkeypatch.setattr(plan, "_BUFFERS", {})
         for src, exp in zip(srcs, ref):
             got = sorted(repr(x) for x in eval(src, {"Dampr": Dampr, "path": path, "RX": RX, "math": math}).run())
