@@ -516,3 +516,39 @@ def test_lowered_joins_probes_and_sorts_agree_with_the_reference(monkeypatch):
     for needle in ("device join ranges", "device broadcast hash build+probe", "partition+sort of whole records",
                    "device sort of frame rows", "memoised per distinct"):
         assert any(needle in h for h in seen), needle
+
+
+@pytest.mark.parametrize("path_kind", ["host-map", "scan-plumbing"])
+def test_directory_inputs_agree_with_the_reference(path_kind, monkeypatch, tmp_path):
+    """Dampr.text on a directory tree: several files laid out back to back, an empty file, files without a
+    final newline, a .gz member."""
+    import gzip
+    import math
+    import re
+    import fake_device as F
+    from oracle import gen
+    from dampr_b200 import Dampr, settings, plan
+    from dampr_b200 import runner as runner_mod
+    RX = re.compile(r"[^\w]+")
+    d = tmp_path / "corpus"
+    (d / "sub" / "deep").mkdir(parents=True)
+    files = {"a.txt": gen.text(1, 150, V=80), "b.txt": gen.dirty_text(2, 120, 100), "sub/c.txt": b"tail without newline",
+             "sub/deep/d.txt": b"", "sub/e.txt": gen.text(3, 60, V=40)[:-1]}
+    for fn, data in files.items():
+        (d / fn).write_bytes(data)
+    with gzip.open(str(d / "sub" / "f.txt.gz"), "wb") as f:
+        f.write(gen.text(4, 80, V=50))
+    longest = max(len(l) + 1 for data in files.values() for l in data.split(b"\n")) + 5
+    srcs = text_pipelines(900, 12, longest)
+    env = dict(os.environ)
+    env.pop("PYTHONPATH", None)
+    p = subprocess.run([sys.executable, "-c", TEXT_DRIVER, REF, str(d), json.dumps(srcs)], capture_output=True, text=True,
+                       env=env, cwd="/tmp", timeout=300)
+    assert p.returncode == 0, p.stderr[-2000:]
+    ref = json.loads(p.stdout.strip().split("\n")[-1])
+    monkeypatch.setattr(plan, "_pinned_ring", lambda n, b: [F.FakePinned(b) for _ in range(n)])
+    for src, exp in zip(srcs, ref):
+        monkeypatch.setattr(runner_mod, "_CTX", {settings.device: F.FakeCtx() if path_kind == "host-map" else F.FakeTextCtx()})
+        monkeypatch.setattr(plan, "_BUFFERS", {})
+        got = sorted(repr(x) for x in eval(src, {"Dampr": Dampr, "path": str(d), "RX": RX, "math": math}).run())
+        assert got == exp, src
