@@ -6,7 +6,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libdampr_b200.so")
-SOURCES = ["ctx.cu", "text.cu", "text2.cu", "kv.cu", "ops.cu"]
+SOURCES = ["ctx.cu", "text.cu", "text2.cu", "kv.cu", "merge.cu", "ops.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC",
@@ -22,7 +22,7 @@ def build(force=False, verbose=False):
     nvcc = os.environ.get("NVCC", "nvcc")
     objdir = os.path.join(HERE, "build")
     os.makedirs(objdir, exist_ok=True)
-    deps = [os.path.join(CSRC, "common.cuh"), os.path.join(HERE, "..", "include", "dampr_b200.h")]
+    deps = [os.path.join(CSRC, "common.cuh"), os.path.join(CSRC, "leaf.cuh"), os.path.join(HERE, "..", "include", "dampr_b200.h")]
     objs = []
     relink = force or not os.path.exists(LIB)
     for src in SOURCES:

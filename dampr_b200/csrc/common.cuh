@@ -55,6 +55,11 @@ struct dampr_ctx {
     void *stage_slot[STAGE_SLOTS] = {nullptr, nullptr, nullptr, nullptr};
     cudaEvent_t stage_ev[STAGE_SLOTS] = {nullptr, nullptr, nullptr, nullptr};
     int host_threads = 4;
+    // page-locked scratch (descriptor uploads / small downloads that must not synchronise the stream)
+    void *h_pin[2] = {nullptr, nullptr};
+    size_t h_pin_bytes[2] = {0, 0};
+    cudaEvent_t h_pin_ev[2] = {nullptr, nullptr};  // last transfer that used the slot
+    bool h_pin_busy[2] = {false, false};
 };
 
 // Host <-> device copies that stay at PCIe speed for pageable host memory: the bytes go through the
@@ -89,6 +94,13 @@ struct dampr_kv {
     u64 capacity;
     u64 n;
 };
+
+// page-locked scratch slot `which` of at least `bytes` (waits for the last transfer that used it);
+// host_pin_used marks the transfers enqueued so far as users of the slot
+void *host_pin(dampr_ctx *ctx, int which, size_t bytes);
+void host_pin_used(dampr_ctx *ctx, int which);
+// kv.cu internals shared with merge.cu
+int kv_sort_device_range(dampr_ctx *ctx, ulonglong2 *cur, ulonglong2 *alt, u64 n, int xf);
 
 // tuning switches (dampr_set_option)
 extern int g_text_ctas;     // resident CTAs per SM of the v2 tokenise kernel: 2 (double-buffered) or 3

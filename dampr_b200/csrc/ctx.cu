@@ -51,6 +51,38 @@ void *pool_alloc(dampr_ctx *ctx, size_t bytes) {
     return p;
 }
 
+void *host_pin(dampr_ctx *ctx, int which, size_t bytes) {
+    if (ctx->h_pin_busy[which]) {
+        cudaEventSynchronize(ctx->h_pin_ev[which]);
+        ctx->h_pin_busy[which] = false;
+    }
+    if (ctx->h_pin_bytes[which] < bytes) {
+        if (ctx->h_pin[which]) {
+            cudaFreeHost(ctx->h_pin[which]);
+            ctx->h_pin[which] = nullptr;
+            ctx->h_pin_bytes[which] = 0;
+        }
+        size_t cap = std::max<size_t>(bytes + bytes / 4, 1 << 20);
+        if (cudaMallocHost(&ctx->h_pin[which], cap) != cudaSuccess) {
+            cudaGetLastError();
+            return nullptr;
+        }
+        ctx->h_pin_bytes[which] = cap;
+    }
+    return ctx->h_pin[which];
+}
+
+void host_pin_used(dampr_ctx *ctx, int which) {
+    if (!ctx->h_pin_ev[which] &&
+        cudaEventCreateWithFlags(&ctx->h_pin_ev[which], cudaEventDisableTiming) != cudaSuccess) {
+        cudaGetLastError();
+        cudaStreamSynchronize(ctx->stream);  // no event: fall back to a full wait
+        return;
+    }
+    cudaEventRecord(ctx->h_pin_ev[which], ctx->stream);
+    ctx->h_pin_busy[which] = true;
+}
+
 void pool_free(dampr_ctx *ctx, void *p) {
     if (!p) return;
     auto it = ctx->pool_live.find(p);
@@ -314,6 +346,10 @@ int32_t dampr_ctx_destroy(dampr_ctx *ctx) {
     cudaEventDestroy(ctx->upload_done);
     cudaFree(ctx->d_scratch);
     cudaFreeHost(ctx->h_scratch);
+    for (int i = 0; i < 2; ++i) {
+        if (ctx->h_pin[i]) cudaFreeHost(ctx->h_pin[i]);
+        if (ctx->h_pin_ev[i]) cudaEventDestroy(ctx->h_pin_ev[i]);
+    }
     for (int i = 0; i < dampr_ctx::STAGE_SLOTS; ++i) {
         if (ctx->stage_slot[i]) cudaFreeHost(ctx->stage_slot[i]);
         if (ctx->stage_ev[i]) cudaEventDestroy(ctx->stage_ev[i]);

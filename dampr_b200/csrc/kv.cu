@@ -1,40 +1,62 @@
-// kv.cu — K3/K4/K5: radix partition, in-partition sort, segmented reduce over 16-byte records.
+// kv.cu — K3/K4: radix partition, in-partition sort, segmented reduce over 16-byte records.
 //
 // Replaces the reference's shuffle/sort/reduce for (key, value) records:
 //   Splitter.partition            dampr/base.py:6-8          hash(key) % n_partitions
 //   CSDatasetWriter.flush         dampr/dataset.py:236-253   route every record to its partition
 //   SortedWriter._write_to_gzip   dampr/dataset.py:162-164   list.sort(key=itemgetter(0)) (stable)
-//   MergeDataset.read             dampr/dataset.py:571-579   k-way merge of sorted runs
 //   Dataset.grouped_read          dampr/dataset.py:429-433   group adjacent equal keys
 //   ARReduce._reduce / Reduce     dampr/dampr.py:678-683, dampr/base.py:204-207  fold a group
+// (the k-way merge of sorted runs, MergeDataset.read dataset.py:571-579, lives in merge.cu)
 //
-// Design (B200): MSD radix partition on the top bits of the (transformed) key, at most 10 bits
-// per level, two levels for up to ~3e9 records; every level is histogram -> scan -> scatter with
-// per-CTA contiguous record ranges ("pieces") so ranks are stable and no atomics touch HBM. The
-// scatter ranks records inside a warp with one ballot per digit bit, stages a tile in shared memory
-// bucket-major and writes each bucket's run with one TMA bulk store (cp.async.bulk.global.shared::cta)
-// or coalesced 16-byte stores. Leaves (whole segments, <= 4096 records) are sorted in shared memory
-// by a counting sort on the next key bits, after which every record ranks itself inside its bin by
-// (key, input position), which makes the whole sort stable and deterministic; the same kernel
-// optionally folds each key group (segmented reduce, or a shared-memory hash aggregate for commutative
-// integer folds) before anything is written back.
+// Design (B200), second generation:
+//   * ONE partition level of up to 12 key bits (4096 buckets) for up to ~1.1e8 records, then one
+//     leaf pass: two data passes instead of three.  A level is histogram -> scans -> scatter over
+//     per-CTA contiguous record ranges ("pieces"), so a bucket receives its records in input order
+//     (stable) and nothing but the per-piece histogram touches HBM with atomics.
+//   * scatter: every record takes its rank inside (tile, bucket) from ONE shared-memory atomic; the
+//     arbitrary order the atomics hand out is repaired by ranking each record among the (one or two)
+//     tile mates of its bucket by tile index; long runs (skew) are sorted by a warp through a presence
+//     bitmap.  No per-warp histograms, no ballots per digit bit: the per-tile cost no longer grows with
+//     warps x buckets, which is what allows 12 bits.
+//   * leaf: a thread-block CLUSTER of 8 CTAs sorts a whole ~24K-record bucket.  Each CTA loads 1/8 of
+//     the bucket, the 8 CTAs agree on a 256-bin histogram through distributed shared memory, every
+//     record is stored straight into the shared memory of the CTA that owns its bin
+//     (st.shared::cluster), and each CTA finishes with a counting sort + rank-by-(key, original index)
+//     of its ~3K records.  Segments of at most 4096 records use the single-CTA leaf.
+//   * segmented reduce (SUM/COUNT/MIN/MAX/FIRST/LAST) is fused into both leaves.
 #include <algorithm>
+#include <cooperative_groups.h>
 
 #include "common.cuh"
+#include "leaf.cuh"
+
+namespace cg = cooperative_groups;
+
+int g_kv_scatter = 2;   // 2 = atomic-rank scatter (up to 12 bits), 1 = first-generation ballot scatter (10 bits)
+int g_kv_cluster = 1;   // 1 = cluster/DSMEM leaf for segments above one CTA's capacity
+int g_kv_tile = 4096;   // scatter tile: 4096 (512 threads, 2 CTAs/SM) or 8192 (1024 threads, 1 CTA/SM)
+int g_kv_max_bits = 12; // digit bits per partition level (<= 12)
 
 namespace {
 
+// ---- first-generation scatter (kept selectable for A/B measurements) ---------------------------
 constexpr int P_THREADS = 512;
 constexpr int P_WARPS = P_THREADS / 32;
 constexpr int P_TILE = 4096;                 // records per tile
 constexpr int P_PER_WARP = P_TILE / P_WARPS;  // 256
 constexpr int P_ROUNDS = P_PER_WARP / 32;     // 8
-constexpr int P_MAX_BITS = 10;
-constexpr int P_MAX_NB = 1 << P_MAX_BITS;
+constexpr int P1_MAX_BITS = 10;
+constexpr int P1_MAX_NB = 1 << P1_MAX_BITS;
 
-constexpr int L_THREADS = 512;
-constexpr int L_CAP = 4096;    // records per leaf chunk
-constexpr int L_BINS = 8192;   // counting-sort bins
+// ---- second generation ---------------------------------------------------------------------------
+constexpr int P2_MAX_BITS = 12;
+constexpr int P2_MAX_NB = 1 << P2_MAX_BITS;
+constexpr int HOT_L = 32;  // (tile, bucket) runs longer than this are sorted by a warp
+
+
+constexpr u64 C_NMAX = 27500;   // records per cluster chunk (8 x 4096 minus slack for bin granularity)
+constexpr u64 C_TARGET = 25000; // planned average segment size when the cluster leaf is in use
+constexpr u64 S_TARGET = 2600;  // planned average segment size for single-CTA leaves
 
 struct Piece {
     u64 start, end;
@@ -55,12 +77,22 @@ __device__ __forceinline__ u32 digit_of(u64 key, const DigitSpec &d) {
     return (u32)(((key_xform(key, d.xf) - d.base) >> d.shift) & d.mask);
 }
 
-// ---- level histogram --------------------------------------------------------------------------
+// piece p of a uniform decomposition (no descriptor array: used by the single-segment level)
+__device__ __forceinline__ Piece uniform_piece(u32 p, u64 start, u64 n, u64 R) {
+    Piece pc;
+    pc.start = start + min(n, (u64)p * R);
+    pc.end = start + min(n, (u64)(p + 1) * R);
+    pc.seg = 0;
+    pc.pad = 0;
+    return pc;
+}
+
+// ---- level histogram (v1) -----------------------------------------------------------------------
 __global__ void __launch_bounds__(P_THREADS)
 part_hist_kernel(const ulonglong2 *__restrict__ in, const Piece *__restrict__ pieces,
                  const u32 *__restrict__ cta_piece_begin, DigitSpec ds, u32 nb,
                  u32 *__restrict__ piece_hist) {
-    __shared__ u32 sh[P_MAX_NB];
+    __shared__ u32 sh[P1_MAX_NB];
     const u32 pb = cta_piece_begin[blockIdx.x], pe = cta_piece_begin[blockIdx.x + 1];
     for (u32 p = pb; p < pe; ++p) {
         for (u32 b = threadIdx.x; b < nb; b += blockDim.x) sh[b] = 0;
@@ -76,19 +108,57 @@ part_hist_kernel(const ulonglong2 *__restrict__ in, const Piece *__restrict__ pi
     }
 }
 
-// ---- per-segment scan: bucket bases, per-piece offsets, next-level segment offsets ------------
-__global__ void part_scan_kernel(const u32 *__restrict__ piece_hist, const u32 *__restrict__ seg_piece_begin,
-                                 const u64 *__restrict__ seg_off, u32 nb, u64 *__restrict__ piece_off,
-                                 u64 *__restrict__ next_seg_off) {
+// ---- level histogram (v2): HS CTAs per piece, 8 keys in flight per thread, folded into the piece
+// histogram (and the bucket totals when `tot` is given) with global reductions ----------------------
+constexpr int H2_THREADS = 1024;
+constexpr int H2_UNROLL = 8;
+__global__ void __launch_bounds__(H2_THREADS, 2)
+part_hist2_kernel(const ulonglong2 *__restrict__ in, const Piece *__restrict__ pieces, u64 ustart, u64 un,
+                  u64 uR, u32 hs, DigitSpec ds, u32 nb, u32 *__restrict__ piece_hist,
+                  u32 *__restrict__ tot) {
+    __shared__ u32 sh[P2_MAX_NB];
+    const u32 p = blockIdx.x / hs, sub = blockIdx.x % hs;
+    const Piece pc = pieces ? pieces[p] : uniform_piece(p, ustart, un, uR);
+    const u64 len = pc.end - pc.start;
+    const u64 per = ((len + hs - 1) / hs + 15) & ~15ULL;
+    const u64 lo = pc.start + min(len, (u64)sub * per), hi = pc.start + min(len, (u64)(sub + 1) * per);
+    for (u32 b = threadIdx.x; b < nb; b += H2_THREADS) sh[b] = 0;
+    __syncthreads();
+    u64 i = lo + threadIdx.x;
+    for (; i + (u64)(H2_UNROLL - 1) * H2_THREADS < hi; i += (u64)H2_UNROLL * H2_THREADS) {
+        u64 k[H2_UNROLL];
+#pragma unroll
+        for (int u = 0; u < H2_UNROLL; ++u) k[u] = in[i + (u64)u * H2_THREADS].x;
+#pragma unroll
+        for (int u = 0; u < H2_UNROLL; ++u) atomicAdd(&sh[digit_of(k[u], ds)], 1u);
+    }
+    for (; i < hi; i += H2_THREADS) atomicAdd(&sh[digit_of(in[i].x, ds)], 1u);
+    __syncthreads();
+    for (u32 b = threadIdx.x; b < nb; b += H2_THREADS) {
+        const u32 c = sh[b];
+        if (hs == 1) piece_hist[(u64)p * nb + b] = c;
+        else if (c) atomicAdd(&piece_hist[(u64)p * nb + b], c);
+        if (tot && c) atomicAdd(&tot[b], c);
+    }
+}
+
+// ---- per-segment scan (general levels): bucket bases, per-piece offsets, next-level offsets ------
+// one CTA of 1024 threads per segment, nb <= 4096 (up to 4 buckets per thread)
+__global__ void __launch_bounds__(1024)
+part_scan_kernel(const u32 *__restrict__ piece_hist, const u32 *__restrict__ seg_piece_begin,
+                 const u64 *__restrict__ seg_off, u32 nb, u64 *__restrict__ piece_off,
+                 u64 *__restrict__ next_seg_off) {
     __shared__ u64 wsum[32];
     const u32 s = blockIdx.x;
-    const u32 b = threadIdx.x;  // blockDim.x == nb rounded up to 32
+    const u32 bpt = (nb + 1023) / 1024;
+    const u32 b0 = threadIdx.x * bpt;
     const u32 pb = seg_piece_begin[s], pe = seg_piece_begin[s + 1];
-    u64 tot = 0;
-    if (b < nb)
-        for (u32 p = pb; p < pe; ++p) tot += piece_hist[(u64)p * nb + b];
-    // block exclusive scan of tot
-    u64 v = tot;
+    u64 tot[4] = {0, 0, 0, 0};
+    for (u32 p = pb; p < pe; ++p)
+        for (u32 j = 0; j < bpt; ++j)
+            if (b0 + j < nb) tot[j] += piece_hist[(u64)p * nb + b0 + j];
+    u64 sum = tot[0] + tot[1] + tot[2] + tot[3];
+    u64 v = sum;
     for (int d = 1; d < 32; d <<= 1) {
         u64 o = __shfl_up_sync(0xFFFFFFFFu, v, d);
         if ((int)(threadIdx.x & 31) >= d) v += o;
@@ -97,25 +167,82 @@ __global__ void part_scan_kernel(const u32 *__restrict__ piece_hist, const u32 *
     __syncthreads();
     u64 woff = 0;
     for (u32 w = 0; w < (threadIdx.x >> 5); ++w) woff += wsum[w];
-    u64 excl = woff + v - tot;
-    if (b < nb) {
-        u64 run = seg_off[s] + excl;
-        next_seg_off[(u64)s * nb + b] = run;
+    u64 run = seg_off[s] + woff + v - sum;
+    for (u32 j = 0; j < bpt; ++j) {
+        if (b0 + j >= nb) break;
+        next_seg_off[(u64)s * nb + b0 + j] = run;
+        u64 r2 = run;
         for (u32 p = pb; p < pe; ++p) {
-            u32 h = piece_hist[(u64)p * nb + b];
+            u32 h = piece_hist[(u64)p * nb + b0 + j];
+            piece_off[(u64)p * nb + b0 + j] = r2;
+            r2 += h;
+        }
+        run += tot[j];
+    }
+}
+
+// ---- single-segment level: exclusive scan of the bucket totals (one CTA) ... ----------------------
+__global__ void __launch_bounds__(1024)
+bucket_scan_kernel(const u32 *__restrict__ tot, u32 nb, u64 start, u64 n, u64 *__restrict__ seg_off) {
+    __shared__ u64 wsum[32];
+    const u32 bpt = (nb + 1023) / 1024;
+    const u32 b0 = threadIdx.x * bpt;
+    u64 t[4] = {0, 0, 0, 0};
+    for (u32 j = 0; j < bpt; ++j)
+        if (b0 + j < nb) t[j] = tot[b0 + j];
+    u64 sum = t[0] + t[1] + t[2] + t[3];
+    u64 v = sum;
+    for (int d = 1; d < 32; d <<= 1) {
+        u64 o = __shfl_up_sync(0xFFFFFFFFu, v, d);
+        if ((int)(threadIdx.x & 31) >= d) v += o;
+    }
+    if ((threadIdx.x & 31) == 31) wsum[threadIdx.x >> 5] = v;
+    __syncthreads();
+    u64 woff = 0;
+    for (u32 w = 0; w < (threadIdx.x >> 5); ++w) woff += wsum[w];
+    u64 run = start + woff + v - sum;
+    for (u32 j = 0; j < bpt; ++j) {
+        if (b0 + j >= nb) break;
+        seg_off[b0 + j] = run;
+        run += t[j];
+    }
+    if (threadIdx.x == 0) seg_off[nb] = start + n;
+}
+
+// ---- ... and the per-piece offsets inside every bucket: 32 buckets (lanes) x 32 piece groups (warps)
+// per CTA, so both passes over the piece histogram are coalesced --------------------------------------
+__global__ void __launch_bounds__(1024)
+column_offsets_kernel(const u32 *__restrict__ piece_hist, u32 np, u32 nb, const u64 *__restrict__ seg_off,
+                      u64 *__restrict__ piece_off) {
+    __shared__ u64 wtot[32][33];
+    const u32 lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const u32 b = blockIdx.x * 32 + lane;
+    const u32 pg = (np + 31) / 32;
+    const u32 p0 = min(np, w * pg), p1 = min(np, (w + 1) * pg);
+    u64 sum = 0;
+    if (b < nb)
+        for (u32 p = p0; p < p1; ++p) sum += piece_hist[(u64)p * nb + b];
+    wtot[w][lane] = sum;
+    __syncthreads();
+    u64 run = 0;
+    for (u32 k = 0; k < w; ++k) run += wtot[k][lane];
+    if (b < nb) {
+        run += seg_off[b];
+        for (u32 p = p0; p < p1; ++p) {
+            const u32 h = piece_hist[(u64)p * nb + b];
             piece_off[(u64)p * nb + b] = run;
             run += h;
         }
     }
 }
 
-// ---- level scatter ---------------------------------------------------------------------------
+// ---- level scatter (v1: ballots per digit bit, per-warp histograms, TMA bulk stores) --------------
 struct ScatterSmem {
     alignas(16) ulonglong2 stage[P_TILE];
-    u64 run_off[P_MAX_NB];
-    u16 warp_hist[P_WARPS][P_MAX_NB];
-    u32 local_base[P_MAX_NB + 1];
-    u32 tile_cnt[P_MAX_NB];
+    u64 run_off[P1_MAX_NB];
+    u16 warp_hist[P_WARPS][P1_MAX_NB];
+    u32 local_base[P1_MAX_NB + 1];
+    u32 tile_cnt[P1_MAX_NB];
     u32 wsum[32];
 };
 
@@ -137,27 +264,21 @@ part_scatter_kernel(const ulonglong2 *__restrict__ in, ulonglong2 *__restrict__ 
         __syncthreads();
         for (u64 t0 = pc.start; t0 < pc.end; t0 += P_TILE) {
             const u32 tn = (u32)min((u64)P_TILE, pc.end - t0);
-            for (u32 i = tid; i < P_WARPS * nb; i += P_THREADS) (&s.warp_hist[0][0])[(i / nb) * P_MAX_NB + (i % nb)] = 0;
+            for (u32 i = tid; i < P_WARPS * nb; i += P_THREADS) (&s.warp_hist[0][0])[(i / nb) * P1_MAX_NB + (i % nb)] = 0;
             __syncthreads();
-            // ---- load + stable rank inside the warp's contiguous slice -------------------------
             ulonglong2 rec[P_ROUNDS];
             u32 dig[P_ROUNDS];
             u32 rnk[P_ROUNDS];
-            // all loads of the tile first (8 independent 16-byte loads in flight per thread) ...
 #pragma unroll
             for (int r = 0; r < P_ROUNDS; ++r) {
                 u32 li = warp * P_PER_WARP + r * 32 + lane;
                 if (li < tn) rec[r] = in[t0 + li];
             }
-            // the tile after this one: pull it into L2 while this one is ranked and staged
             if (t0 + P_TILE < pc.end) {
                 const char *nxt = reinterpret_cast<const char *>(in + t0 + P_TILE);
                 const u32 nbytes = (u32)min((u64)P_TILE, pc.end - t0 - P_TILE) * 16u;
                 if (tid * 128u < nbytes) asm volatile("prefetch.global.L2 [%0];" ::"l"(nxt + tid * 128u));
             }
-            // ... then the stable ranking. Pass 1 (registers only): digit and same-digit lane set per round,
-            // from one ballot per digit bit (MATCH.ANY costs one pass per distinct value, i.e. ~32 passes
-            // with 10-bit digits).
             // Per round one packed word: digit (10 bits) | leader lane << 10 | rank among the set's lanes << 15
             // | (set size - 1) << 20 | valid << 25.
 #pragma unroll
@@ -176,9 +297,6 @@ part_scatter_kernel(const ulonglong2 *__restrict__ in, ulonglong2 *__restrict__ 
                                   (((u32)__popc(peers) - 1u) << 20) | (1u << 25))
                                : 0u;
             }
-            // Pass 2: the leader of every lane set bumps the warp's digit counter. The eight shared-memory
-            // atomics of a thread do not depend on each other, so they pipeline (same-address ones complete
-            // in issue order); counters are u16 pairs updated through their 32-bit word.
             u32 *wh32 = reinterpret_cast<u32 *>(s.warp_hist[warp]);
 #pragma unroll
             for (int r = 0; r < P_ROUNDS; ++r) {
@@ -198,7 +316,6 @@ part_scatter_kernel(const ulonglong2 *__restrict__ in, ulonglong2 *__restrict__ 
                 dig[r] = (pk >> 25) ? (pk & 1023u) : 0xFFFFFFFFu;
             }
             __syncthreads();
-            // ---- per-bucket exclusive scan over warps, then over buckets ------------------------
             for (u32 b = tid; b < nb; b += P_THREADS) {
                 u32 run = 0;
 #pragma unroll
@@ -211,7 +328,6 @@ part_scatter_kernel(const ulonglong2 *__restrict__ in, ulonglong2 *__restrict__ 
             }
             __syncthreads();
             {
-                // exclusive scan of tile_cnt[0..nb) with 512 threads, 2 buckets per thread
                 u32 c0 = (2 * tid < nb) ? s.tile_cnt[2 * tid] : 0;
                 u32 c1 = (2 * tid + 1 < nb) ? s.tile_cnt[2 * tid + 1] : 0;
                 u32 v = c0 + c1;
@@ -230,7 +346,6 @@ part_scatter_kernel(const ulonglong2 *__restrict__ in, ulonglong2 *__restrict__ 
                 if (2 * tid + 1 < nb) s.local_base[2 * tid + 1] = excl + c0;
             }
             __syncthreads();
-            // ---- stage bucket-major in shared memory ------------------------------------------
 #pragma unroll
             for (int r = 0; r < P_ROUNDS; ++r) {
                 if (dig[r] != 0xFFFFFFFFu) {
@@ -240,7 +355,6 @@ part_scatter_kernel(const ulonglong2 *__restrict__ in, ulonglong2 *__restrict__ 
             }
             if (USE_TMA) fence_proxy_async();
             __syncthreads();
-            // ---- write every bucket's run ------------------------------------------------------
             if (USE_TMA) {
                 for (u32 b = tid; b < nb; b += P_THREADS) {
                     u32 c = s.tile_cnt[b];
@@ -263,76 +377,218 @@ part_scatter_kernel(const ulonglong2 *__restrict__ in, ulonglong2 *__restrict__ 
     if (USE_TMA) tma_store_wait_all();
 }
 
-// ---- leaf: counting sort + fix-up in shared memory, optional segmented reduce -----------------
-struct LeafChunk {
-    u64 start;      // first record
-    u32 n;          // records (<= L_CAP)
-    int bin_shift;  // bin = ((xf(key) - base) >> bin_shift) - bin_base
-    u64 bin_base;
-};
-
-// 104 KB: two CTAs per SM.  Only the transformed key is kept (every transform is a bijection, the stored
-// key is rebuilt with key_unxform on the way out), which is what makes the second CTA fit.
-struct LeafSmem {
-    alignas(16) u64 sk[L_CAP];   // key_xform(key) - base
-    u64 val[L_CAP];
-    u16 cnt[L_BINS];   // counts, then bin starts
-    u16 cur[L_BINS];   // cursors
-    u16 ord[L_CAP];    // sorted order -> record index
+// ---- level scatter (v2): one shared-memory atomic per record + order fix-up -----------------------
+template <int NT, int RPT>
+struct Scatter2Smem {
+    static constexpr int T = NT * RPT;
+    u64 run_off[P2_MAX_NB];
+    alignas(16) u32 cnt[P2_MAX_NB];
+    alignas(16) u32 base[P2_MAX_NB + 4];
+    u32 bitmap[NT / 32][T / 32];
+    u16 sidx[T];
+    u16 hot[T / 32];
+    u32 nhot;
     u32 wsum[32];
-    u32 total_groups;
 };
 
-__device__ __forceinline__ u64 apply_op(int op, u64 acc, u64 v) {
-    switch (op) {
-        case DAMPR_OP_SUM_I64: return acc + v;
-        case DAMPR_OP_COUNT: return acc + v;
-        case DAMPR_OP_SUM_F64: return (u64)__double_as_longlong(__longlong_as_double((long long)acc) + __longlong_as_double((long long)v));
-        case DAMPR_OP_MIN_I64: return ((long long)v < (long long)acc) ? v : acc;
-        case DAMPR_OP_MAX_I64: return ((long long)v > (long long)acc) ? v : acc;
-        case DAMPR_OP_MIN_F64: return (__longlong_as_double((long long)v) < __longlong_as_double((long long)acc)) ? v : acc;
-        case DAMPR_OP_MAX_F64: return (__longlong_as_double((long long)v) > __longlong_as_double((long long)acc)) ? v : acc;
-        case DAMPR_OP_FIRST: return acc;
-        case DAMPR_OP_LAST: return v;
+template <int NT, int RPT>
+__global__ void __launch_bounds__(NT, (NT <= 512 ? 2 : 1))
+part_scatter2_kernel(const ulonglong2 *__restrict__ in, ulonglong2 *__restrict__ out,
+                     const Piece *__restrict__ pieces, const u32 *__restrict__ cta_piece_begin, u64 ustart,
+                     u64 un, u64 uR, DigitSpec ds, u32 nb, const u64 *__restrict__ piece_off) {
+    using Smem = Scatter2Smem<NT, RPT>;
+    constexpr int T = NT * RPT;
+    constexpr int NW = NT / 32;
+    constexpr int WPL = T / 32 / 32;  // bitmap words per lane
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    Smem &s = *reinterpret_cast<Smem *>(smem_raw);
+    const u32 tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const u32 pb = pieces ? cta_piece_begin[blockIdx.x] : blockIdx.x;
+    const u32 pe = pieces ? cta_piece_begin[blockIdx.x + 1] : blockIdx.x + 1;
+    const u32 bpt = max(4u, ((nb + NT - 1) / NT + 3u) & ~3u);  // buckets per thread in the scans: 4 or 8
+
+    for (u32 p = pb; p < pe; ++p) {
+        const Piece pc = pieces ? pieces[p] : uniform_piece(p, ustart, un, uR);
+        for (u32 b = tid; b < (u32)P2_MAX_NB; b += NT) {
+            s.run_off[b] = (b < nb) ? piece_off[(u64)p * nb + b] : 0ULL;
+            s.cnt[b] = 0;
+        }
+        if (tid == 0) s.nhot = 0;
+        __syncthreads();
+        for (u64 t0 = pc.start; t0 < pc.end; t0 += T) {
+            const u32 tn = (u32)min((u64)T, pc.end - t0);
+            ulonglong2 rec[RPT];
+            u32 dg[RPT], sl[RPT];
+#pragma unroll
+            for (int r = 0; r < RPT; ++r) {
+                const u32 li = r * NT + tid;
+                if (li < tn) rec[r] = in[t0 + li];
+            }
+            if (t0 + T < pc.end) {  // the next tile: pull it into L2 while this one is ranked
+                const char *nxt = reinterpret_cast<const char *>(in + t0 + T);
+                const u32 nbytes = (u32)min((u64)T, pc.end - t0 - T) * 16u;
+                for (u32 off = tid * 128u; off < nbytes; off += NT * 128u)
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(nxt + off));
+            }
+#pragma unroll
+            for (int r = 0; r < RPT; ++r) {
+                const u32 li = r * NT + tid;
+                if (li < tn) {
+                    dg[r] = digit_of(rec[r].x, ds);
+                    sl[r] = atomicAdd(&s.cnt[dg[r]], 1u);
+                }
+            }
+            __syncthreads();
+            // ---- exclusive scan of the tile's bucket counts -> base[]; long runs go on the hot list.
+            // 4 or 8 consecutive buckets per thread, read and written as 16-byte vectors (entries past nb
+            // stay zero).
+            {
+                const u32 b0 = tid * bpt;
+                u32 c[8];
+                {
+                    const uint4 a = *reinterpret_cast<const uint4 *>(&s.cnt[b0]);
+                    c[0] = a.x, c[1] = a.y, c[2] = a.z, c[3] = a.w;
+                    uint4 b = make_uint4(0, 0, 0, 0);
+                    if (bpt == 8) b = *reinterpret_cast<const uint4 *>(&s.cnt[b0 + 4]);
+                    c[4] = b.x, c[5] = b.y, c[6] = b.z, c[7] = b.w;
+                }
+                u32 sum = 0;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    sum += c[j];
+                    if (c[j] > HOT_L) s.hot[atomicAdd(&s.nhot, 1u)] = (u16)(b0 + j);
+                }
+                u32 v = sum;
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) {
+                    u32 o = __shfl_up_sync(0xFFFFFFFFu, v, d);
+                    if ((int)lane >= d) v += o;
+                }
+                if (lane == 31) s.wsum[warp] = v;
+                __syncthreads();
+                u32 woff = 0;
+                for (u32 w = 0; w < warp; ++w) woff += s.wsum[w];
+                u32 run = woff + v - sum;
+                u32 e[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    e[j] = run;
+                    run += c[j];
+                }
+                *reinterpret_cast<uint4 *>(&s.base[b0]) = make_uint4(e[0], e[1], e[2], e[3]);
+                if (bpt == 8) *reinterpret_cast<uint4 *>(&s.base[b0 + 4]) = make_uint4(e[4], e[5], e[6], e[7]);
+                if (tid == NT - 1) s.base[NT * bpt] = tn;
+            }
+            __syncthreads();
+#pragma unroll
+            for (int r = 0; r < RPT; ++r) {
+                const u32 li = r * NT + tid;
+                if (li < tn) s.sidx[s.base[dg[r]] + sl[r]] = (u16)li;
+            }
+            __syncthreads();
+            const u32 nh = s.nhot;
+            if (nh) {
+                // skew: a warp sorts the tile indices of a long run through a presence bitmap
+                u32 *bm = s.bitmap[warp];
+                for (u32 hi = warp; hi < nh; hi += NW) {
+                    const u32 h = s.hot[hi];
+                    const u32 st = s.base[h], L = s.base[h + 1] - st;
+                    for (u32 w = lane; w < T / 32; w += 32) bm[w] = 0;
+                    __syncwarp();
+                    for (u32 j = lane; j < L; j += 32) {
+                        const u32 x = s.sidx[st + j];
+                        atomicOr(&bm[x >> 5], 1u << (x & 31));
+                    }
+                    __syncwarp();
+                    u32 words[WPL];
+                    u32 cl = 0;
+#pragma unroll
+                    for (int k = 0; k < WPL; ++k) {
+                        words[k] = bm[lane * WPL + k];
+                        cl += __popc(words[k]);
+                    }
+                    u32 v = cl;
+#pragma unroll
+                    for (int d = 1; d < 32; d <<= 1) {
+                        u32 o = __shfl_up_sync(0xFFFFFFFFu, v, d);
+                        if ((int)lane >= d) v += o;
+                    }
+                    u32 pos = st + v - cl;
+#pragma unroll
+                    for (int k = 0; k < WPL; ++k) {
+                        u32 wd = words[k];
+                        while (wd) {
+                            const u32 bit = __ffs(wd) - 1;
+                            wd &= wd - 1;
+                            s.sidx[pos++] = (u16)((lane * WPL + k) * 32 + bit);
+                        }
+                    }
+                    __syncwarp();
+                }
+                __syncthreads();
+            }
+            // ---- rank inside (tile, bucket) by tile index, then straight to the bucket's run ----------
+#pragma unroll
+            for (int r = 0; r < RPT; ++r) {
+                const u32 li = r * NT + tid;
+                if (li < tn) {
+                    const u32 d = dg[r];
+                    const u32 st = s.base[d], L = s.base[d + 1] - st;
+                    u32 rk = 0;
+                    if (L > HOT_L) {  // sorted by a warp above: lower bound
+                        u32 lo = 0, hi = L;
+                        while (lo < hi) {
+                            const u32 mid = (lo + hi) >> 1;
+                            if (s.sidx[st + mid] < li) lo = mid + 1;
+                            else hi = mid;
+                        }
+                        rk = lo;
+                    } else if (L > 1) {
+                        for (u32 j = 0; j < L; ++j) rk += (s.sidx[st + j] < li) ? 1u : 0u;
+                    }
+                    out[s.run_off[d] + rk] = rec[r];
+                }
+            }
+            __syncthreads();
+            for (u32 b = tid; b < nb; b += NT) {
+                s.run_off[b] += s.cnt[b];
+                s.cnt[b] = 0;
+            }
+            if (tid == 0) s.nhot = 0;
+            __syncthreads();
+        }
     }
-    return acc;
 }
 
-// REDUCE_OP < 0: sort only (records rewritten in place). Otherwise one record per key group is
-// written compacted at the start of the chunk in `out` and the group count to chunk_groups[c].
+// single-CTA leaf. reduce_op < 0: sort only, records written to out[ch.start ..). Otherwise one record
+// per key group is written compacted at out[ch.start ..) and (start, groups) to the entry table.
 __global__ void __launch_bounds__(L_THREADS, 2)
-leaf_sort_kernel(ulonglong2 *__restrict__ data, ulonglong2 *__restrict__ out, const LeafChunk *__restrict__ chunks,
-                 u32 nchunks, int xf, u64 base, int reduce_op, u32 *__restrict__ chunk_groups) {
+leaf_sort_kernel(const ulonglong2 *__restrict__ data, ulonglong2 *__restrict__ out,
+                 const LeafChunk *__restrict__ chunks, u32 nchunks, int xf, u64 base, int reduce_op,
+                 u64 *__restrict__ entry_start, u32 *__restrict__ entry_groups) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     LeafSmem &s = *reinterpret_cast<LeafSmem *>(smem_raw);
-    const u32 tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const u32 tid = threadIdx.x;
     for (u32 c = blockIdx.x; c < nchunks; c += gridDim.x) {
         const LeafChunk ch = chunks[c];
         const u32 n = ch.n;
         if (c + gridDim.x < nchunks) {
             // pull the chunk this CTA handles next into L2 (one 128-byte line per thread per pass)
             const LeafChunk nx = chunks[c + gridDim.x];
-            const char *base = reinterpret_cast<const char *>(data + nx.start);
+            const char *nb = reinterpret_cast<const char *>(data + nx.start);
             for (u32 off = tid * 128u; off < nx.n * 16u; off += L_THREADS * 128u)
-                asm volatile("prefetch.global.L2 [%0];" ::"l"(base + off));
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(nb + off));
         }
         {
-            uint4 *z = reinterpret_cast<uint4 *>(s.cnt);  // 8 counters per 16-byte store
-            for (u32 i = tid; i < L_BINS / 8; i += L_THREADS) z[i] = make_uint4(0, 0, 0, 0);
-        }
-        __syncthreads();
-        // load + histogram
-        {
-            // L_CAP / L_THREADS independent loads in flight per thread
-            ulonglong2 rr[L_CAP / L_THREADS];
+            ulonglong2 rr[L_IPT];
 #pragma unroll
-            for (int k = 0; k < L_CAP / L_THREADS; ++k) {
-                u32 i = tid + k * L_THREADS;
+            for (int k = 0; k < L_IPT; ++k) {
+                const u32 i = tid + k * L_THREADS;
                 if (i < n) rr[k] = data[ch.start + i];
             }
 #pragma unroll
-            for (int k = 0; k < L_CAP / L_THREADS; ++k) {
-                u32 i = tid + k * L_THREADS;
+            for (int k = 0; k < L_IPT; ++k) {
+                const u32 i = tid + k * L_THREADS;
                 if (i < n) {
                     s.val[i] = rr[k].y;
                     s.sk[i] = key_xform(rr[k].x, xf) - base;
@@ -340,206 +596,181 @@ leaf_sort_kernel(ulonglong2 *__restrict__ data, ulonglong2 *__restrict__ out, co
             }
         }
         __syncthreads();
-        // ---- commutative integer folds under the MIX order (a_group_by(...).sum()/count()/min()/max()):
-        // no sort at all. Every record looks its key up in a shared-memory index (slot -> first record
-        // holding the key) and folds its value into that record with a shared-memory atomic: O(1) per
-        // record however many duplicates a key has (the sort path ranks inside bins: O(duplicates)).
-        if (xf == DAMPR_KEY_MIX && (reduce_op == DAMPR_OP_SUM_I64 || reduce_op == DAMPR_OP_COUNT ||
-                                    reduce_op == DAMPR_OP_MIN_I64 || reduce_op == DAMPR_OP_MAX_I64)) {
-            for (u32 i = tid; i < L_BINS; i += L_THREADS) s.cur[i] = 0;  // cnt[] is the index (zeroed above)
-            if (reduce_op == DAMPR_OP_COUNT)
-                for (u32 i = tid; i < n; i += L_THREADS) s.val[i] = 1ULL;
-            __syncthreads();
-            for (u32 i = tid; i < n; i += L_THREADS) {
-                const u64 ki = s.sk[i];
-                u32 slot = (u32)(ki >> 13) & (L_BINS - 1);  // the partition consumed the top bits
-                slot = (slot ^ (u32)(ki >> 37)) & (L_BINS - 1);
-                for (;;) {
-                    u32 cur = s.cnt[slot];
-                    if (cur == 0) {
-                        cur = atomicCAS(&s.cnt[slot], (unsigned short)0, (unsigned short)(i + 1));
-                        if (cur == 0) {
-                            s.cur[i] = 1;  // this record represents its key
-                            break;
-                        }
-                    }
-                    if (s.sk[cur - 1] == ki) {
-                        unsigned long long *acc = &s.val[cur - 1];
-                        const u64 v = s.val[i];
-                        if (reduce_op == DAMPR_OP_MIN_I64) atomicMin((long long *)acc, (long long)v);
-                        else if (reduce_op == DAMPR_OP_MAX_I64) atomicMax((long long *)acc, (long long)v);
-                        else atomicAdd(acc, v);
-                        break;
-                    }
-                    slot = (slot + 1) & (L_BINS - 1);
-                }
+        if (reduce_op >= 0 && hash_fold_op(xf, reduce_op)) {
+            const u32 g = leaf_hash_fold(s, n, reduce_op, xf, base, out + ch.start);
+            if (tid == 0) {
+                entry_start[ch.entry] = ch.start;
+                entry_groups[ch.entry] = g;
             }
-            __syncthreads();
-            // compact the representatives (in record order)
-            constexpr int IPT = L_CAP / L_THREADS;
-            u32 flags = 0;
-#pragma unroll
-            for (int k = 0; k < IPT; ++k) {
-                u32 p = tid * IPT + k;
-                if (p < n && s.cur[p]) flags |= 1u << k;
-            }
-            u32 cntl = __popc(flags), v = cntl;
-#pragma unroll
-            for (int d = 1; d < 32; d <<= 1) {
-                u32 o = __shfl_up_sync(0xFFFFFFFFu, v, d);
-                if ((int)lane >= d) v += o;
-            }
-            if (lane == 31) s.wsum[warp] = v;
-            __syncthreads();
-            u32 woff = 0;
-            for (u32 w = 0; w < warp; ++w) woff += s.wsum[w];
-            u32 gidx = woff + v - cntl;
-            if (tid == L_THREADS - 1) s.total_groups = woff + v;
-#pragma unroll
-            for (int k = 0; k < IPT; ++k)
-                if (flags & (1u << k)) {
-                    const u32 p = tid * IPT + k;
-                    out[ch.start + gidx++] = make_ulonglong2(key_unxform(s.sk[p] + base, xf), s.val[p]);
-                }
-            __syncthreads();
-            if (tid == 0) chunk_groups[c] = s.total_groups;
             __syncthreads();
             continue;
         }
-        // counting with u16 counters packed two per u32 word: use 32-bit atomics on the pair
-        u32 *cnt32 = reinterpret_cast<u32 *>(s.cnt);
-        for (u32 i = tid; i < n; i += L_THREADS) {
-            u64 bin64 = (s.sk[i] >> ch.bin_shift) - ch.bin_base;
-            u32 bin = (u32)min(bin64, (u64)(L_BINS - 1));
-            atomicAdd(&cnt32[bin >> 1], (bin & 1) ? 0x10000u : 1u);
-        }
-        __syncthreads();
-        // exclusive scan of cnt[0..L_BINS): 16 bins per thread
-        {
-            u32 loc[16];
-            u32 sum = 0;
-            {
-                const uint4 *c4 = reinterpret_cast<const uint4 *>(s.cnt) + tid * 2;
-                const uint4 a = c4[0], b = c4[1];
-                const u32 w[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
-#pragma unroll
-                for (int k = 0; k < 8; ++k) {
-                    loc[2 * k] = w[k] & 0xFFFFu;
-                    loc[2 * k + 1] = w[k] >> 16;
-                    sum += loc[2 * k] + loc[2 * k + 1];
-                }
-            }
-            u32 v = sum;
-#pragma unroll
-            for (int d = 1; d < 32; d <<= 1) {
-                u32 o = __shfl_up_sync(0xFFFFFFFFu, v, d);
-                if ((int)lane >= d) v += o;
-            }
-            if (lane == 31) s.wsum[warp] = v;
-            __syncthreads();
-            u32 woff = 0;
-            for (u32 w = 0; w < warp; ++w) woff += s.wsum[w];
-            u32 run = woff + v - sum;
-            {
-                u32 w[8];
-#pragma unroll
-                for (int k = 0; k < 8; ++k) {
-                    const u32 lo = run;
-                    run += loc[2 * k];
-                    w[k] = lo | (run << 16);
-                    run += loc[2 * k + 1];
-                }
-                const uint4 a = make_uint4(w[0], w[1], w[2], w[3]), b = make_uint4(w[4], w[5], w[6], w[7]);
-                uint4 *c4 = reinterpret_cast<uint4 *>(s.cnt) + tid * 2;  // bin starts
-                uint4 *u4 = reinterpret_cast<uint4 *>(s.cur) + tid * 2;  // cursors
-                c4[0] = a;
-                c4[1] = b;
-                u4[0] = a;
-                u4[1] = b;
-            }
-        }
-        __syncthreads();
-        // scatter indices (order inside a bin is fixed below)
-        u32 *cur32 = reinterpret_cast<u32 *>(s.cur);
-        for (u32 i = tid; i < n; i += L_THREADS) {
-            u64 bin64 = (s.sk[i] >> ch.bin_shift) - ch.bin_base;
-            u32 bin = (u32)min(bin64, (u64)(L_BINS - 1));
-            u32 old = atomicAdd(&cur32[bin >> 1], (bin & 1) ? 0x10000u : 1u);
-            u32 pos = (bin & 1) ? (old >> 16) : (old & 0xFFFFu);
-            s.ord[pos] = (u16)i;
-        }
-        __syncthreads();
-        // order inside every bin by (key, input position): each record counts the members of its own
-        // bin that precede it (thread per record: all lanes busy, loop length = bin population) and
-        // takes that rank. cur[] is free after the scatter and receives the final order.
-        for (u32 i = tid; i < n; i += L_THREADS) {
-            const u64 ki = s.sk[i];
-            u64 bin64 = (ki >> ch.bin_shift) - ch.bin_base;
-            u32 bin = (u32)min(bin64, (u64)(L_BINS - 1));
-            u32 st = s.cnt[bin];
-            u32 en = (bin + 1 < L_BINS) ? s.cnt[bin + 1] : n;
-            u32 r = 0;
-            for (u32 j = st; j < en; ++j) {
-                u32 o = s.ord[j];
-                u64 ko = s.sk[o];
-                r += (ko < ki || (ko == ki && o < i)) ? 1u : 0u;
-            }
-            s.cur[st + r] = (u16)i;
-        }
-        __syncthreads();
-        const u16 *fin = s.cur;   // final order: position -> record index
+        leaf_sort_core<false>(s, n, ch.bin_shift, ch.bin_base);
         if (reduce_op < 0) {
             for (u32 i = tid; i < n; i += L_THREADS) {
-                const u32 o = fin[i];
+                const u32 o = s.fin[i];
                 out[ch.start + i] = make_ulonglong2(key_unxform(s.sk[o] + base, xf), s.val[o]);
+            }
+        } else {
+            const u32 g = leaf_seg_reduce(s, n, reduce_op, xf, base, out + ch.start);
+            if (tid == 0) {
+                entry_start[ch.entry] = ch.start;
+                entry_groups[ch.entry] = g;
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// cluster leaf: 8 CTAs sort one chunk of up to C_NMAX records (see the file header).
+// An exchange that would overflow a CTA (a fine bin larger than its capacity: heavy duplicates / skew
+// inside the chunk) writes nothing and reports the chunk in ovf_list; the host re-sorts those chunks with
+// further partition levels.
+__global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(L_THREADS, 2)
+cluster_leaf_kernel(const ulonglong2 *__restrict__ data, ulonglong2 *__restrict__ out,
+                    const LeafChunk *__restrict__ chunks, u32 nchunks, int xf, u64 base, int reduce_op,
+                    u64 *__restrict__ entry_start, u32 *__restrict__ entry_groups, u32 *__restrict__ ovf_count,
+                    u32 *__restrict__ ovf_list) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    LeafSmem &s = *reinterpret_cast<LeafSmem *>(smem_raw);
+    cg::cluster_group cluster = cg::this_cluster();
+    const u32 tid = threadIdx.x;
+    const u32 rank = cluster.block_rank();
+    const u32 ncl = gridDim.x / CL, cid = blockIdx.x / CL;
+    for (u32 c = cid; c < nchunks; c += ncl) {
+        const LeafChunk ch = chunks[c];
+        const u32 n = ch.n;
+        const u32 S = (n + CL - 1) / CL;  // slice per CTA, <= L_CAP
+        const u32 lo = min(n, rank * S), hi = min(n, lo + S);
+        if (c + ncl < nchunks) {
+            const LeafChunk nx = chunks[c + ncl];
+            const u32 S2 = (nx.n + CL - 1) / CL;
+            const u32 lo2 = min(nx.n, rank * S2), hi2 = min(nx.n, lo2 + S2);
+            const char *nb = reinterpret_cast<const char *>(data + nx.start + lo2);
+            for (u32 off = tid * 128u; off < (hi2 - lo2) * 16u; off += L_THREADS * 128u)
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(nb + off));
+        }
+        if (tid < CF) s.fh[tid] = 0;
+        if (tid < CL) {
+            s.firstg[tid] = 0;
+            s.endg[tid] = 0;
+            s.firstbin[tid] = 0;
+            s.lastbin[tid] = 0;
+        }
+        if (tid == 0) s.ovf = 0;
+        __syncthreads();
+        // ---- my slice: fine-bin histogram, the atomic's return value is the record's slot --------------
+        ulonglong2 rec[L_IPT];
+        u32 pk[L_IPT];
+#pragma unroll
+        for (int k = 0; k < L_IPT; ++k) {
+            const u32 i = tid + k * L_THREADS;
+            if (lo + i < hi) rec[k] = data[ch.start + lo + i];
+        }
+#pragma unroll
+        for (int k = 0; k < L_IPT; ++k) {
+            const u32 i = tid + k * L_THREADS;
+            pk[k] = 0;
+            if (lo + i < hi) {
+                const u64 skv = key_xform(rec[k].x, xf) - base;
+                rec[k].x = skv;
+                const u32 f = (u32)min((skv >> ch.bin_shift) - ch.bin_base, (u64)(CF - 1));
+                pk[k] = f | (atomicAdd(&s.fh[f], 1u) << 8);
+            }
+        }
+        cluster.sync();
+        // ---- all CTAs derive the same bin -> CTA assignment from the 8 histograms ---------------------
+        u32 tot = 0, before = 0;
+        if (tid < CF) {
+#pragma unroll
+            for (u32 r = 0; r < CL; ++r) {
+                const u32 *rfh = cluster.map_shared_rank(s.fh, r);
+                const u32 cnt = rfh[tid];
+                before += (r < rank) ? cnt : 0u;
+                tot += cnt;
+            }
+        }
+        u32 total;
+        const u32 g0 = block_excl_scan(s, tot, &total);
+        const u32 Q = (n + CL - 1) / CL;
+        u32 own = 0;
+        if (tid < CF) {
+            s.gpos[tid] = g0;
+            own = min((u32)CL - 1, g0 / Q);
+            s.down[tid] = (u8)own;
+        }
+        __syncthreads();
+        if (tid < CF) {
+            if (tid == 0 || s.down[tid - 1] != own) {
+                s.firstbin[own] = tid;
+                s.firstg[own] = g0;
+            }
+            if (tid == CF - 1 || s.down[tid + 1] != own) {
+                s.lastbin[own] = tid;
+                s.endg[own] = g0 + tot;
+            }
+        }
+        __syncthreads();
+        if (tid < CF) s.dpos[tid] = (u16)(g0 - s.firstg[own] + before);
+        if (tid < CL && s.endg[tid] - s.firstg[tid] > (u32)L_CAP) s.ovf = 1;
+        __syncthreads();
+        const bool ovf = s.ovf != 0;
+        // ---- exchange: every record goes straight into the owner's shared memory ------------------------
+        if (!ovf) {
+#pragma unroll
+            for (int k = 0; k < L_IPT; ++k) {
+                const u32 i = tid + k * L_THREADS;
+                if (lo + i < hi) {
+                    const u32 f = pk[k] & 255u;
+                    const u32 o = s.down[f];
+                    const u32 p = (u32)s.dpos[f] + (pk[k] >> 8);
+                    u64 *rsk = cluster.map_shared_rank(s.sk, o);
+                    u64 *rval = cluster.map_shared_rank(s.val, o);
+                    u16 *raux = cluster.map_shared_rank(s.aux, o);
+                    rsk[p] = rec[k].x;
+                    rval[p] = rec[k].y;
+                    raux[p] = (u16)(lo + i);
+                }
+            }
+        }
+        cluster.sync();
+        if (ovf) {
+            if (rank == 0 && tid == 0) ovf_list[atomicAdd(ovf_count, 1u)] = c;
+            if (reduce_op >= 0 && tid == 0) {
+                entry_start[ch.entry + rank] = ch.start;
+                entry_groups[ch.entry + rank] = 0;
+            }
+            continue;
+        }
+        // ---- local finish ------------------------------------------------------------------------------------
+        const u32 m = s.endg[rank] - s.firstg[rank];
+        const u64 ostart = ch.start + s.firstg[rank];
+        if (reduce_op >= 0 && hash_fold_op(xf, reduce_op)) {
+            const u32 g = leaf_hash_fold(s, m, reduce_op, xf, base, out + ostart);
+            if (tid == 0) {
+                entry_start[ch.entry + rank] = ostart;
+                entry_groups[ch.entry + rank] = g;
             }
             __syncthreads();
             continue;
         }
-        // ---- segmented reduce: one thread per group head walks its group ----------------------
-        {
-            // heads per thread-strided position; ranks via block scan over 8 consecutive positions
-            constexpr int IPT = L_CAP / L_THREADS;  // 8
-            u32 headbits = 0;
-#pragma unroll
-            for (int k = 0; k < IPT; ++k) {
-                u32 p = tid * IPT + k;
-                if (p < n) {
-                    bool head = (p == 0) || (s.sk[fin[p]] != s.sk[fin[p - 1]]);
-                    headbits |= head ? (1u << k) : 0u;
-                }
+        const u32 nbo = s.lastbin[rank] - s.firstbin[rank] + 1;
+        int k = 0;
+        while (((nbo << (k + 1)) <= (u32)L_BINS) && (k + 1) <= ch.bin_shift) ++k;
+        leaf_sort_core<true>(s, m, ch.bin_shift - k, (ch.bin_base + s.firstbin[rank]) << k);
+        if (reduce_op < 0) {
+            for (u32 i = tid; i < m; i += L_THREADS) {
+                const u32 o = s.fin[i];
+                out[ostart + i] = make_ulonglong2(key_unxform(s.sk[o] + base, xf), s.val[o]);
             }
-            u32 cntl = __popc(headbits);
-            u32 v = cntl;
-#pragma unroll
-            for (int d = 1; d < 32; d <<= 1) {
-                u32 o = __shfl_up_sync(0xFFFFFFFFu, v, d);
-                if ((int)lane >= d) v += o;
+        } else {
+            const u32 g = leaf_seg_reduce(s, m, reduce_op, xf, base, out + ostart);
+            if (tid == 0) {
+                entry_start[ch.entry + rank] = ostart;
+                entry_groups[ch.entry + rank] = g;
             }
-            if (lane == 31) s.wsum[warp] = v;
-            __syncthreads();
-            u32 woff = 0;
-            for (u32 w = 0; w < warp; ++w) woff += s.wsum[w];
-            u32 gidx = woff + v - cntl;
-            if (tid == L_THREADS - 1) s.total_groups = woff + v;
-#pragma unroll
-            for (int k = 0; k < IPT; ++k) {
-                if (headbits & (1u << k)) {
-                    u32 p = tid * IPT + k;
-                    u64 ksk = s.sk[fin[p]];
-                    u64 acc = (reduce_op == DAMPR_OP_COUNT) ? 1ULL : s.val[fin[p]];
-                    for (u32 q = p + 1; q < n && s.sk[fin[q]] == ksk; ++q) {
-                        u64 val = (reduce_op == DAMPR_OP_COUNT) ? 1ULL : s.val[fin[q]];
-                        acc = apply_op(reduce_op, acc, val);
-                    }
-                    out[ch.start + gidx] = make_ulonglong2(key_unxform(ksk + base, xf), acc);
-                    ++gidx;
-                }
-            }
-            __syncthreads();
-            if (tid == 0) chunk_groups[c] = s.total_groups;
-            __syncthreads();
         }
+        __syncthreads();
     }
 }
 
@@ -625,38 +856,13 @@ __global__ void copy_records_kernel(const ulonglong2 *__restrict__ in, ulonglong
     for (u64 i = blockIdx.x * (u64)blockDim.x + threadIdx.x; i < n; i += (u64)gridDim.x * blockDim.x) out[i] = in[i];
 }
 
-// exclusive scan of chunk group counts (single CTA, sequential over blocks of 1024)
-__global__ void scan_u32_to_u64_kernel(const u32 *__restrict__ in, u64 *__restrict__ out, u32 n) {
-    __shared__ u64 wsum[32];
-    __shared__ u64 carry;
-    if (threadIdx.x == 0) carry = 0;
-    __syncthreads();
-    for (u32 base = 0; base < n + 1; base += blockDim.x) {
-        u32 i = base + threadIdx.x;
-        u64 x = (i < n) ? in[i] : 0;
-        u64 v = x;
-        for (int d = 1; d < 32; d <<= 1) {
-            u64 o = __shfl_up_sync(0xFFFFFFFFu, v, d);
-            if ((int)(threadIdx.x & 31) >= d) v += o;
-        }
-        if ((threadIdx.x & 31) == 31) wsum[threadIdx.x >> 5] = v;
-        __syncthreads();
-        u64 woff = 0;
-        for (u32 w = 0; w < (threadIdx.x >> 5); ++w) woff += wsum[w];
-        u64 excl = carry + woff + v - x;
-        if (i <= n) out[i] = excl;
-        __syncthreads();
-        if (threadIdx.x == blockDim.x - 1) carry = excl + x;
-        __syncthreads();
-    }
-}
-
-__global__ void gather_groups_kernel(const ulonglong2 *__restrict__ tmp, const LeafChunk *__restrict__ chunks,
-                                     const u32 *__restrict__ chunk_groups, const u64 *__restrict__ chunk_out_off,
-                                     u32 nchunks, ulonglong2 *__restrict__ out) {
-    for (u32 c = blockIdx.x; c < nchunks; c += gridDim.x) {
-        u32 g = chunk_groups[c];
-        u64 src = chunks[c].start, dst = chunk_out_off[c];
+// copies the groups of every entry (start, count) of the table to its offset in the output
+__global__ void gather_groups_kernel(const ulonglong2 *__restrict__ tmp, const u64 *__restrict__ entry_start,
+                                     const u32 *__restrict__ entry_groups, const u64 *__restrict__ entry_out_off,
+                                     u32 nentries, ulonglong2 *__restrict__ out) {
+    for (u32 c = blockIdx.x; c < nentries; c += gridDim.x) {
+        const u32 g = entry_groups[c];
+        const u64 src = entry_start[c], dst = entry_out_off[c];
         for (u32 i = threadIdx.x; i < g; i += blockDim.x) out[dst + i] = tmp[src + i];
     }
 }
@@ -705,24 +911,94 @@ static int bits_for(u64 n, u64 leaf_avg) {
     return b;
 }
 
-struct SortOut {
-    // sort only: result lives in `cur`. reduce: groups appended to `groups` (device) in key order
-    ulonglong2 *groups = nullptr;
-    u64 n_groups = 0;
-};
-
 static int g_use_tma = 1;
+
+static int scatter_ctas(dampr_ctx *ctx) { return (g_kv_tile == 8192) ? ctx->num_sms : ctx->num_sms * 2; }
+static u64 scatter_tile() { return (g_kv_scatter == 2) ? (u64)g_kv_tile : (u64)P_TILE; }
+
+template <int NT, int RPT>
+static cudaError_t launch_scatter2(dampr_ctx *ctx, int G, const ulonglong2 *src, ulonglong2 *dst, const Piece *pieces,
+                                   const u32 *cta_pb, u64 ustart, u64 un, u64 uR, DigitSpec ds, u32 nb,
+                                   const u64 *poff) {
+    const size_t smem = sizeof(Scatter2Smem<NT, RPT>);
+    cudaError_t e = cudaFuncSetAttribute(part_scatter2_kernel<NT, RPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    part_scatter2_kernel<NT, RPT><<<G, NT, smem, ctx->stream>>>(src, dst, pieces, cta_pb, ustart, un, uR, ds, nb, poff);
+    return cudaGetLastError();
+}
+
+static int run_scatter(dampr_ctx *ctx, int G, const ulonglong2 *src, ulonglong2 *dst, const Piece *pieces,
+                       const u32 *cta_pb, u64 ustart, u64 un, u64 uR, DigitSpec ds, u32 nb, const u64 *poff) {
+    ScopedTimer tm(ctx, DAMPR_K_PART_SCATTER);
+    if (g_kv_scatter == 2) {
+        if (g_kv_tile == 8192) CUDA_TRY(ctx, (launch_scatter2<1024, 8>(ctx, G, src, dst, pieces, cta_pb, ustart, un, uR, ds, nb, poff)));
+        else CUDA_TRY(ctx, (launch_scatter2<512, 8>(ctx, G, src, dst, pieces, cta_pb, ustart, un, uR, ds, nb, poff)));
+        return DAMPR_OK;
+    }
+    const size_t smem = sizeof(ScatterSmem);
+    if (g_use_tma) {
+        cudaFuncSetAttribute(part_scatter_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        part_scatter_kernel<true><<<G, P_THREADS, smem, ctx->stream>>>(src, dst, pieces, cta_pb, ds, nb, poff);
+    } else {
+        cudaFuncSetAttribute(part_scatter_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        part_scatter_kernel<false><<<G, P_THREADS, smem, ctx->stream>>>(src, dst, pieces, cta_pb, ds, nb, poff);
+    }
+    CUDA_TRY(ctx, cudaGetLastError());
+    return DAMPR_OK;
+}
 
 // One partition level over records [start, start+n) of `src` into `dst`: every segment of
 // seg_off is split by the digit `ds` into nb sub-segments (stable). seg_off is replaced by the
-// (S*nb + 1) offsets of the next level.
+// (S*nb + 1) offsets of the next level. The offsets travel to the host while the scatter runs.
 static int partition_level(dampr_ctx *ctx, const ulonglong2 *src, ulonglong2 *dst, u64 start, u64 n,
                            std::vector<u64> &seg_off, DigitSpec ds, u32 nb) {
-    const int G = ctx->num_sms * 2;
+    const int G = scatter_ctas(ctx);
     const u64 S = seg_off.size() - 1;
-    // pieces: split [start, start+n) at CTA-range boundaries and at segment boundaries
+    const u64 T = scatter_tile();
     u64 R = (n + G - 1) / G;
-    R = ((R + P_TILE - 1) / P_TILE) * P_TILE;
+    R = ((R + T - 1) / T) * T;
+    cudaEvent_t ev;
+    CUDA_TRY(ctx, cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    struct EvGuard {
+        cudaEvent_t e;
+        ~EvGuard() { cudaEventDestroy(e); }
+    } evg{ev};
+
+    if (S == 1 && g_kv_scatter == 2) {
+        // ---- single segment: uniform pieces computed on the device, nothing uploaded ----------------------
+        const u32 NP = (u32)G;
+        DevBuf d_hist, d_tot, d_seg, d_poff;
+        CUDA_TRY(ctx, d_hist.alloc((u64)NP * nb * 4));
+        CUDA_TRY(ctx, d_tot.alloc((u64)nb * 4));
+        CUDA_TRY(ctx, d_seg.alloc((u64)(nb + 1) * 8));
+        CUDA_TRY(ctx, d_poff.alloc((u64)NP * nb * 8));
+        const u32 hs = (u32)std::max(1, (2 * ctx->num_sms + (int)NP - 1) / (int)NP);
+        CUDA_TRY(ctx, cudaMemsetAsync(d_tot.p, 0, (u64)nb * 4, ctx->stream));
+        if (hs > 1) CUDA_TRY(ctx, cudaMemsetAsync(d_hist.p, 0, (u64)NP * nb * 4, ctx->stream));
+        {
+            ScopedTimer tm(ctx, DAMPR_K_PART_HIST);
+            part_hist2_kernel<<<NP * hs, H2_THREADS, 0, ctx->stream>>>(src, nullptr, start, n, R, hs, ds, nb,
+                                                                     (u32 *)d_hist.p, (u32 *)d_tot.p);
+        }
+        {
+            ScopedTimer tm(ctx, DAMPR_K_MISC);
+            bucket_scan_kernel<<<1, 1024, 0, ctx->stream>>>((const u32 *)d_tot.p, nb, start, n, (u64 *)d_seg.p);
+            column_offsets_kernel<<<(nb + 31) / 32, 1024, 0, ctx->stream>>>((const u32 *)d_hist.p, NP, nb,
+                                                                           (const u64 *)d_seg.p, (u64 *)d_poff.p);
+        }
+        CUDA_TRY(ctx, cudaGetLastError());
+        u64 *h_next = (u64 *)host_pin(ctx, 0, (u64)(nb + 1) * 8);
+        if (!h_next) return set_err(ctx, DAMPR_ERR_NOMEM, "%s", "pinned scratch allocation failed");
+        CUDA_TRY(ctx, cudaMemcpyAsync(h_next, d_seg.p, (u64)(nb + 1) * 8, cudaMemcpyDeviceToHost, ctx->stream));
+        CUDA_TRY(ctx, cudaEventRecord(ev, ctx->stream));
+        int rc = run_scatter(ctx, G, src, dst, nullptr, nullptr, start, n, R, ds, nb, (const u64 *)d_poff.p);
+        if (rc) return rc;
+        CUDA_TRY(ctx, cudaEventSynchronize(ev));  // the scatter is still running
+        seg_off.assign(h_next, h_next + nb + 1);
+        return DAMPR_OK;
+    }
+
+    // ---- general level: pieces split at CTA-range boundaries and at segment boundaries ---------------
     std::vector<Piece> pieces;
     std::vector<u32> cta_pb(G + 1, 0), seg_pb(S + 1, 0);
     {
@@ -759,51 +1035,68 @@ static int partition_level(dampr_ctx *ctx, const ulonglong2 *src, ulonglong2 *ds
     CUDA_TRY(ctx, d_hist.alloc(NP * nb * 4));
     CUDA_TRY(ctx, d_poff.alloc(NP * nb * 8));
     CUDA_TRY(ctx, d_next.alloc((S * nb + 1) * 8));
-    CUDA_TRY(ctx, cudaMemcpyAsync(d_pieces.p, pieces.data(), NP * sizeof(Piece), cudaMemcpyHostToDevice, ctx->stream));
-    CUDA_TRY(ctx, cudaMemcpyAsync(d_cta_pb.p, cta_pb.data(), (G + 1) * 4, cudaMemcpyHostToDevice, ctx->stream));
-    CUDA_TRY(ctx, cudaMemcpyAsync(d_seg_pb.p, seg_pb.data(), (S + 1) * 4, cudaMemcpyHostToDevice, ctx->stream));
-    CUDA_TRY(ctx, cudaMemcpyAsync(d_seg_off.p, seg_off.data(), (S + 1) * 8, cudaMemcpyHostToDevice, ctx->stream));
+    {
+        // descriptors go up through page-locked scratch (a pageable source synchronises the stream)
+        const size_t b0 = NP * sizeof(Piece), b1 = (G + 1) * 4, b2 = (S + 1) * 4, b3 = (S + 1) * 8;
+        const size_t o1 = (b0 + 15) & ~(size_t)15, o2 = o1 + ((b1 + 15) & ~(size_t)15), o3 = o2 + ((b2 + 15) & ~(size_t)15);
+        char *hp = (char *)host_pin(ctx, 1, o3 + b3);
+        if (!hp) return set_err(ctx, DAMPR_ERR_NOMEM, "%s", "pinned scratch allocation failed");
+        memcpy(hp, pieces.data(), b0);
+        memcpy(hp + o1, cta_pb.data(), b1);
+        memcpy(hp + o2, seg_pb.data(), b2);
+        memcpy(hp + o3, seg_off.data(), b3);
+        CUDA_TRY(ctx, cudaMemcpyAsync(d_pieces.p, hp, b0, cudaMemcpyHostToDevice, ctx->stream));
+        CUDA_TRY(ctx, cudaMemcpyAsync(d_cta_pb.p, hp + o1, b1, cudaMemcpyHostToDevice, ctx->stream));
+        CUDA_TRY(ctx, cudaMemcpyAsync(d_seg_pb.p, hp + o2, b2, cudaMemcpyHostToDevice, ctx->stream));
+        CUDA_TRY(ctx, cudaMemcpyAsync(d_seg_off.p, hp + o3, b3, cudaMemcpyHostToDevice, ctx->stream));
+        host_pin_used(ctx, 1);
+    }
     {
         ScopedTimer tm(ctx, DAMPR_K_PART_HIST);
-        part_hist_kernel<<<G, P_THREADS, 0, ctx->stream>>>(src, (const Piece *)d_pieces.p, (const u32 *)d_cta_pb.p, ds,
-                                                          nb, (u32 *)d_hist.p);
+        if (g_kv_scatter == 2)
+            part_hist2_kernel<<<(unsigned)NP, H2_THREADS, 0, ctx->stream>>>(src, (const Piece *)d_pieces.p, 0, 0, 0, 1, ds, nb,
+                                                                           (u32 *)d_hist.p, nullptr);
+        else
+            part_hist_kernel<<<G, P_THREADS, 0, ctx->stream>>>(src, (const Piece *)d_pieces.p, (const u32 *)d_cta_pb.p, ds,
+                                                              nb, (u32 *)d_hist.p);
     }
     {
         ScopedTimer tm(ctx, DAMPR_K_MISC);
-        u32 thr = ((nb + 31) / 32) * 32;
-        part_scan_kernel<<<(unsigned)S, thr, 0, ctx->stream>>>((const u32 *)d_hist.p, (const u32 *)d_seg_pb.p,
-                                                              (const u64 *)d_seg_off.p, nb, (u64 *)d_poff.p,
-                                                              (u64 *)d_next.p);
-    }
-    {
-        size_t smem = sizeof(ScatterSmem);
-        ScopedTimer tm(ctx, DAMPR_K_PART_SCATTER);
-        if (g_use_tma) {
-            cudaFuncSetAttribute(part_scatter_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-            part_scatter_kernel<true><<<G, P_THREADS, smem, ctx->stream>>>(
-                src, dst, (const Piece *)d_pieces.p, (const u32 *)d_cta_pb.p, ds, nb, (const u64 *)d_poff.p);
-        } else {
-            cudaFuncSetAttribute(part_scatter_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-            part_scatter_kernel<false><<<G, P_THREADS, smem, ctx->stream>>>(
-                src, dst, (const Piece *)d_pieces.p, (const u32 *)d_cta_pb.p, ds, nb, (const u64 *)d_poff.p);
-        }
+        part_scan_kernel<<<(unsigned)S, 1024, 0, ctx->stream>>>((const u32 *)d_hist.p, (const u32 *)d_seg_pb.p,
+                                                               (const u64 *)d_seg_off.p, nb, (u64 *)d_poff.p,
+                                                               (u64 *)d_next.p);
     }
     CUDA_TRY(ctx, cudaGetLastError());
-    // next level's segment offsets
-    std::vector<u64> next(S * nb + 1);
-    CUDA_TRY(ctx, cudaMemcpyAsync(next.data(), d_next.p, S * nb * 8, cudaMemcpyDeviceToHost, ctx->stream));
-    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
-    next[S * nb] = start + n;
-    seg_off.swap(next);
+    u64 *h_next = (u64 *)host_pin(ctx, 0, (S * nb + 1) * 8);
+    if (!h_next) return set_err(ctx, DAMPR_ERR_NOMEM, "%s", "pinned scratch allocation failed");
+    CUDA_TRY(ctx, cudaMemcpyAsync(h_next, d_next.p, S * nb * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(ctx, cudaEventRecord(ev, ctx->stream));
+    int rc = run_scatter(ctx, G, src, dst, (const Piece *)d_pieces.p, (const u32 *)d_cta_pb.p, 0, 0, 0, ds, nb,
+                         (const u64 *)d_poff.p);
+    if (rc) return rc;
+    CUDA_TRY(ctx, cudaEventSynchronize(ev));
+    h_next[S * nb] = start + n;
+    seg_off.assign(h_next, h_next + S * nb + 1);
+    // the device buffers of this level are released to the pool with the stream's position recorded,
+    // so nothing reuses them before the scatter has finished
+    return DAMPR_OK;
+}
+
+static int copy_range(dampr_ctx *ctx, const ulonglong2 *from, ulonglong2 *to, u64 start, u64 n) {
+    if (from == to || n == 0) return DAMPR_OK;
+    ScopedTimer tm(ctx, DAMPR_K_MISC);
+    copy_records_kernel<<<ctx->num_sms * 4, 256, 0, ctx->stream>>>(from + start, to + start, n);
+    CUDA_TRY(ctx, cudaGetLastError());
     return DAMPR_OK;
 }
 
 // Sort records [start, start+n) that currently live in `cur` (scratch = `alt`, same indexing).
-// Digits are taken from bit `top` downwards of (xf(key) - base). On return the sorted range is in
-// `cur` (copied back if an odd number of levels ran). If reduce_op >= 0 the key groups of the range
-// are appended, in order, to gout[*gcount...] and nothing is guaranteed about `cur`.
+// Digits are taken from bit `top` downwards of (xf(key) - base). reduce_op < 0: on return the sorted
+// range is in `target` (either buffer; the last pass writes there, nothing is copied). reduce_op >= 0:
+// the key groups of the range are appended, in order, to gout[*gcount...] and both buffers are scratch.
 static int sort_range(dampr_ctx *ctx, ulonglong2 *cur, ulonglong2 *alt, u64 start, u64 n, int xf, u64 base,
-                      int top, int reduce_op, ulonglong2 *gout, u64 *gcount, int depth) {
+                      int top, int reduce_op, ulonglong2 *gout, u64 *gcount, int depth, ulonglong2 *target,
+                      bool allow_cluster) {
     if (n == 0) return DAMPR_OK;
     if (top <= 0 || depth > 12) {
         // all keys equal: already "sorted" (stable); a single group when reducing
@@ -811,13 +1104,16 @@ static int sort_range(dampr_ctx *ctx, ulonglong2 *cur, ulonglong2 *alt, u64 star
             ScopedTimer tm(ctx, DAMPR_K_SEG_REDUCE);
             single_group_reduce_kernel<<<1, 1024, 0, ctx->stream>>>(cur, start, n, reduce_op, gout + *gcount);
             *gcount += 1;
+            CUDA_TRY(ctx, cudaGetLastError());
+            return DAMPR_OK;
         }
-        CUDA_TRY(ctx, cudaGetLastError());
-        return DAMPR_OK;
+        return copy_range(ctx, cur, target, start, n);
     }
+    const bool use_cluster = allow_cluster && g_kv_cluster && n > (u64)L_CAP;
+    const int max_bits = (g_kv_scatter == 2) ? std::min(g_kv_max_bits, P2_MAX_BITS) : P1_MAX_BITS;
     // ---- plan the levels ---------------------------------------------------------------------
-    int total_bits = std::min(top, bits_for(n, 2600));
-    int nlev = (total_bits + P_MAX_BITS - 1) / P_MAX_BITS;
+    int total_bits = std::min(top, bits_for(n, use_cluster ? C_TARGET : S_TARGET));
+    int nlev = (total_bits + max_bits - 1) / max_bits;
     std::vector<int> lev_bits;
     {
         int left = total_bits;
@@ -827,7 +1123,6 @@ static int sort_range(dampr_ctx *ctx, ulonglong2 *cur, ulonglong2 *alt, u64 star
             left -= b;
         }
     }
-    // segment offsets of the current level (host copy), relative to absolute record index
     std::vector<u64> seg_off{start, start + n};
     ulonglong2 *src = cur, *dst = alt;
     int consumed = 0;
@@ -840,129 +1135,193 @@ static int sort_range(dampr_ctx *ctx, ulonglong2 *cur, ulonglong2 *alt, u64 star
         std::swap(src, dst);
         consumed += bits;
     }
-    // data now in `src`
+    // data now in `src`; `dst` is free
     // ---- leaves --------------------------------------------------------------------------------
     const int rem_top = top - consumed;  // bits left below the partition digits
     const u64 S = seg_off.size() - 1;
-    std::vector<LeafChunk> chunks;
+    // sort only: leaves read src and write the target (in place when they are the same buffer).
+    // reduce: leaves write their compacted groups into the free buffer, src stays intact.
+    ulonglong2 *leaf_out = (reduce_op >= 0) ? dst : target;
+    std::vector<LeafChunk> small, clus;
     struct Big {
         u64 start, n;
-        size_t after_chunk;  // chunks.size() when encountered (ordering of reduce output)
-        u64 seg;             // flattened digit value of the segment
+        u32 after_entry;  // entries emitted before it (ordering of the reduce output)
+        u64 seg;          // flattened digit value of the segment
     };
     std::vector<Big> bigs;
+    u32 nentries = 0;
     {
         u64 s0 = 0;
         while (s0 < S) {
-            u64 sz = seg_off[s0 + 1] - seg_off[s0];
+            const u64 sz = seg_off[s0 + 1] - seg_off[s0];
             if (sz == 0) {
                 ++s0;
                 continue;
             }
-            if (sz > L_CAP) {
-                bigs.push_back(Big{seg_off[s0], sz, chunks.size(), s0});
+            const u64 cap = use_cluster ? C_NMAX : (u64)L_CAP;
+            if (sz > cap) {
+                bigs.push_back(Big{seg_off[s0], sz, nentries, s0});
                 ++s0;
                 continue;
             }
             u64 s1 = s0 + 1;
             u64 tot = sz;
-            while (s1 < S && tot + (seg_off[s1 + 1] - seg_off[s1]) <= L_CAP && (s1 - s0) < (u64)L_BINS) {
-                tot += seg_off[s1 + 1] - seg_off[s1];
+            // a chunk stays "small" (single CTA, up to L_BINS segments) while it fits one CTA; beyond that it
+            // becomes a cluster chunk of at most CF segments
+            while (s1 < S) {
+                const u64 nx = seg_off[s1 + 1] - seg_off[s1];
+                const u64 nseg = s1 - s0 + 1;
+                if (tot + nx <= (u64)L_CAP && nseg <= (u64)L_BINS) {
+                } else if (use_cluster && tot + nx <= C_NMAX && nseg <= (u64)CF && tot + nx > (u64)L_CAP) {
+                } else
+                    break;
+                tot += nx;
                 ++s1;
             }
-            // bins: (segment index relative to s0) << k | next k key bits
-            u64 nseg = s1 - s0;
-            int k = 0;
-            while (((nseg << (k + 1)) <= (u64)L_BINS) && (k + 1) <= rem_top) ++k;
+            const u64 nseg = s1 - s0;
             LeafChunk lc;
             lc.start = seg_off[s0];
             lc.n = (u32)tot;
+            lc.pad = 0;
+            lc.entry = nentries;
+            const bool is_cluster = tot > (u64)L_CAP;
+            const u64 nbins = is_cluster ? (u64)CF : (u64)L_BINS;
+            // bins: (segment index relative to s0) << k | next k key bits.  The segment index of a record is
+            // ((sk - base) >> rem_top); recursive calls pass a base that clears the bits above `top`.
+            int k = 0;
+            while (((nseg << (k + 1)) <= nbins) && (k + 1) <= rem_top) ++k;
             lc.bin_shift = rem_top - k;
-            // value of ((sk - base) >> rem_top) for segment s0 is its index in the flattened
-            // digit space; the whole range shares the bits above `top` (zero after subtracting base
-            // for the outermost call, or equal for recursive calls), so take the low `consumed` bits
-            lc.bin_base = 0;  // filled below from s0 (needs the digit prefix)
             lc.bin_base = ((u64)s0) << k;
-            chunks.push_back(lc);
+            if (is_cluster) {
+                clus.push_back(lc);
+                nentries += CL;
+            } else {
+                small.push_back(lc);
+                nentries += 1;
+            }
             s0 = s1;
         }
     }
-    // the segment index of a record is ((sk-base) >> rem_top) & (2^consumed - 1) only if the bits
-    // above `top` are zero; recursive calls pass a base that makes them zero (see below).
-    const size_t nchunks = chunks.size();
-    DevBuf d_chunks, d_cgroups, d_coff;
-    ulonglong2 *leaf_out = (reduce_op >= 0) ? dst : src;  // reduce writes compact groups into dst
-    if (nchunks) {
-        CUDA_TRY(ctx, d_chunks.alloc(nchunks * sizeof(LeafChunk)));
-        CUDA_TRY(ctx, cudaMemcpyAsync(d_chunks.p, chunks.data(), nchunks * sizeof(LeafChunk), cudaMemcpyHostToDevice,
-                                      ctx->stream));
-        if (reduce_op >= 0) {
-            CUDA_TRY(ctx, d_cgroups.alloc(nchunks * 4));
-            CUDA_TRY(ctx, d_coff.alloc((nchunks + 1) * 8));
-        }
-        size_t smem = sizeof(LeafSmem);
-        CUDA_TRY(ctx, cudaFuncSetAttribute(leaf_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        u32 grid = (u32)std::min<size_t>(nchunks, (size_t)ctx->num_sms * 2);
-        {
+    DevBuf d_small, d_clus, d_estart, d_egroups, d_ovf;
+    const size_t nsmall = small.size(), nclus = clus.size();
+    if (reduce_op >= 0 && nentries) {
+        CUDA_TRY(ctx, d_estart.alloc((u64)nentries * 8));
+        CUDA_TRY(ctx, d_egroups.alloc((u64)nentries * 4));
+    }
+    u32 *h_ovf = nullptr;
+    if (nsmall || nclus) {
+        const size_t bs = nsmall * sizeof(LeafChunk), bc = nclus * sizeof(LeafChunk);
+        char *hp = (char *)host_pin(ctx, 1, bs + bc + 16);
+        if (!hp) return set_err(ctx, DAMPR_ERR_NOMEM, "%s", "pinned scratch allocation failed");
+        if (bs) memcpy(hp, small.data(), bs);
+        if (bc) memcpy(hp + bs, clus.data(), bc);
+        const size_t smem = sizeof(LeafSmem);
+        if (nsmall) {
+            CUDA_TRY(ctx, d_small.alloc(bs));
+            CUDA_TRY(ctx, cudaMemcpyAsync(d_small.p, hp, bs, cudaMemcpyHostToDevice, ctx->stream));
+            CUDA_TRY(ctx, cudaFuncSetAttribute(leaf_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            const u32 grid = (u32)std::min<size_t>(nsmall, (size_t)ctx->num_sms * 2);
             ScopedTimer tm(ctx, DAMPR_K_LEAF_SORT);
-            leaf_sort_kernel<<<grid, L_THREADS, smem, ctx->stream>>>(src, leaf_out, (const LeafChunk *)d_chunks.p,
-                                                                    (u32)nchunks, xf, base, reduce_op,
-                                                                    (u32 *)d_cgroups.p);
+            leaf_sort_kernel<<<grid, L_THREADS, smem, ctx->stream>>>(src, leaf_out, (const LeafChunk *)d_small.p, (u32)nsmall,
+                                                                    xf, base, reduce_op, (u64 *)d_estart.p,
+                                                                    (u32 *)d_egroups.p);
+        }
+        if (nclus) {
+            CUDA_TRY(ctx, d_clus.alloc(bc));
+            CUDA_TRY(ctx, d_ovf.alloc((nclus + 1) * 4));
+            CUDA_TRY(ctx, cudaMemcpyAsync(d_clus.p, hp + bs, bc, cudaMemcpyHostToDevice, ctx->stream));
+            CUDA_TRY(ctx, cudaMemsetAsync(d_ovf.p, 0, 4, ctx->stream));
+            CUDA_TRY(ctx, cudaFuncSetAttribute(cluster_leaf_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            const u32 maxcl = (u32)std::max(1, ctx->num_sms * 2 / CL);
+            const u32 grid = (u32)std::min<size_t>(nclus, (size_t)maxcl) * CL;
+            ScopedTimer tm(ctx, DAMPR_K_LEAF_SORT);
+            cluster_leaf_kernel<<<grid, L_THREADS, smem, ctx->stream>>>(src, leaf_out, (const LeafChunk *)d_clus.p, (u32)nclus,
+                                                                       xf, base, reduce_op, (u64 *)d_estart.p,
+                                                                       (u32 *)d_egroups.p, (u32 *)d_ovf.p,
+                                                                       (u32 *)d_ovf.p + 1);
         }
         CUDA_TRY(ctx, cudaGetLastError());
+        host_pin_used(ctx, 1);
+        if (nclus) {
+            h_ovf = (u32 *)host_pin(ctx, 0, (nclus + 1) * 4);
+            if (!h_ovf) return set_err(ctx, DAMPR_ERR_NOMEM, "%s", "pinned scratch allocation failed");
+            CUDA_TRY(ctx, cudaMemcpyAsync(h_ovf, d_ovf.p, (nclus + 1) * 4, cudaMemcpyDeviceToHost, ctx->stream));
+        }
+    }
+    // chunks the cluster leaf could not balance (read before anything else reuses the pinned slot)
+    std::vector<u32> ov;
+    if (nclus) {
+        CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+        ov.assign(h_ovf + 1, h_ovf + 1 + std::min<u32>(h_ovf[0], (u32)nclus));
     }
     if (reduce_op < 0) {
-        // big segments: recurse in place (their data is in `src`; scratch is `dst`)
+        // big segments: recurse (their data is in `src`; scratch is `dst`)
         for (auto &b : bigs) {
             // keys in the segment share all bits >= rem_top: new base clears them
             int rc = sort_range(ctx, src, dst, b.start, b.n, xf, base + (b.seg << rem_top), rem_top, -1, nullptr, nullptr,
-                                depth + 1);
+                                depth + 1, target, allow_cluster);
             if (rc) return rc;
         }
-        if (src != cur) {
-            ScopedTimer tm(ctx, DAMPR_K_MISC);
-            copy_records_kernel<<<ctx->num_sms * 4, 256, 0, ctx->stream>>>(src + start, cur + start, n);
-            CUDA_TRY(ctx, cudaGetLastError());
+        {
+            for (u32 ci : ov) {
+                // a chunk the cluster could not balance (skew inside it): its records are untouched in `src`.
+                // They share every bit above bin_shift + 8 of (sk - base): sort them on the bits below.
+                const LeafChunk &lc = clus[ci];
+                const int sub_top = std::min(top, lc.bin_shift + 8);
+                const u64 sub_base = base + ((lc.bin_base << lc.bin_shift));
+                int rc = sort_range(ctx, src, dst, lc.start, lc.n, xf, sub_base, sub_top, -1, nullptr, nullptr, depth + 1,
+                                    target, false);
+                if (rc) return rc;
+            }
         }
         return DAMPR_OK;
     }
-    // ---- reduce: gather chunk groups in order, interleaving the big segments --------------------
-    std::vector<u32> cg(nchunks);
-    if (nchunks) {
-        CUDA_TRY(ctx, cudaMemcpyAsync(cg.data(), d_cgroups.p, nchunks * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    // ---- reduce: gather entry groups in order, interleaving the big segments ---------------------------
+    std::vector<u32> eg(nentries);
+    if (nentries) {
+        CUDA_TRY(ctx, cudaMemcpyAsync(eg.data(), d_egroups.p, (u64)nentries * 4, cudaMemcpyDeviceToHost, ctx->stream));
         CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
     }
-    // output offsets per chunk (host scan; big segments produce a variable number -> processed in order)
-    size_t ci = 0;
+    if (!ov.empty()) {
+        // rare: redo the leaf stage of this range without the cluster leaf (src is intact)
+        for (u64 s0 = 0; s0 < S; ++s0) {
+            const u64 sz = seg_off[s0 + 1] - seg_off[s0];
+            if (sz == 0) continue;
+            int rc = sort_range(ctx, src, dst, seg_off[s0], sz, xf, base + (s0 << rem_top), rem_top, reduce_op, gout, gcount,
+                                depth + 1, nullptr, false);
+            if (rc) return rc;
+        }
+        return DAMPR_OK;
+    }
+    u32 ei = 0;
     size_t bi = 0;
-    while (ci < nchunks || bi < bigs.size()) {
-        size_t run_end = (bi < bigs.size()) ? bigs[bi].after_chunk : nchunks;
-        if (ci < run_end) {
-            // gather chunks [ci, run_end)
-            std::vector<u64> off(run_end - ci);
+    while (ei < nentries || bi < bigs.size()) {
+        const u32 run_end = (bi < bigs.size()) ? bigs[bi].after_entry : nentries;
+        if (ei < run_end) {
+            const u32 cntE = run_end - ei;
+            u64 *off = (u64 *)host_pin(ctx, 1, (u64)cntE * 8);
+            if (!off) return set_err(ctx, DAMPR_ERR_NOMEM, "%s", "pinned scratch allocation failed");
             u64 run = *gcount;
-            for (size_t c = ci; c < run_end; ++c) {
-                off[c - ci] = run;
-                run += cg[c];
+            for (u32 e = ei; e < run_end; ++e) {
+                off[e - ei] = run;
+                run += eg[e];
             }
             DevBuf d_off;
-            CUDA_TRY(ctx, d_off.alloc(off.size() * 8));
-            CUDA_TRY(ctx, cudaMemcpyAsync(d_off.p, off.data(), off.size() * 8, cudaMemcpyHostToDevice, ctx->stream));
+            CUDA_TRY(ctx, d_off.alloc((u64)cntE * 8));
+            CUDA_TRY(ctx, cudaMemcpyAsync(d_off.p, off, (u64)cntE * 8, cudaMemcpyHostToDevice, ctx->stream));
             {
                 ScopedTimer tm(ctx, DAMPR_K_SEG_REDUCE);
-                gather_groups_kernel<<<(unsigned)std::min<size_t>(run_end - ci, (size_t)ctx->num_sms * 8), 256, 0, ctx->stream>>>(
-                    leaf_out, (const LeafChunk *)d_chunks.p + ci, (const u32 *)d_cgroups.p + ci, (const u64 *)d_off.p,
-                    (u32)(run_end - ci), gout);
+                gather_groups_kernel<<<(unsigned)std::min<size_t>(cntE, (size_t)ctx->num_sms * 8), 256, 0, ctx->stream>>>(
+                    leaf_out, (const u64 *)d_estart.p + ei, (const u32 *)d_egroups.p + ei, (const u64 *)d_off.p, cntE, gout);
             }
             CUDA_TRY(ctx, cudaGetLastError());
-            CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));  // d_off lifetime
+            CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));  // pinned `off` is reused by the next run
             *gcount = run;
-            ci = run_end;
+            ei = run_end;
         }
-        if (bi < bigs.size() && bigs[bi].after_chunk == ci) {
+        if (bi < bigs.size() && bigs[bi].after_entry == ei) {
             int rc = sort_range(ctx, src, dst, bigs[bi].start, bigs[bi].n, xf, base + (bigs[bi].seg << rem_top), rem_top,
-                                reduce_op, gout, gcount,
-                                depth + 1);
+                                reduce_op, gout, gcount, depth + 1, nullptr, allow_cluster);
             if (rc) return rc;
             ++bi;
         }
@@ -982,22 +1341,24 @@ static int ensure_alt(dampr_ctx *ctx, dampr_kv *kv) {
 }
 
 // key range -> (base, top)
-static int key_range(dampr_ctx *ctx, dampr_kv *kv, int xf, u64 *base, int *top) {
+static int key_range(dampr_ctx *ctx, const ulonglong2 *rec, u64 n, int xf, u64 *base, int *top) {
     if (xf == DAMPR_KEY_MIX) {
         *base = 0;
         *top = 64;
         return DAMPR_OK;
     }
     u64 init[2] = {~0ULL, 0ULL};
-    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_scratch, init, 16, cudaMemcpyHostToDevice, ctx->stream));
+    ctx->h_scratch[0] = init[0];
+    ctx->h_scratch[1] = init[1];
+    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_scratch, ctx->h_scratch, 16, cudaMemcpyHostToDevice, ctx->stream));
     {
         ScopedTimer tm(ctx, DAMPR_K_MISC);
-        minmax_kernel<<<ctx->num_sms * 4, 256, 0, ctx->stream>>>(kv->rec, kv->n, xf, ctx->d_scratch);
+        minmax_kernel<<<ctx->num_sms * 4, 256, 0, ctx->stream>>>(rec, n, xf, ctx->d_scratch);
     }
     CUDA_TRY(ctx, cudaGetLastError());
-    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->h_scratch, ctx->d_scratch, 16, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->h_scratch + 2, ctx->d_scratch, 16, cudaMemcpyDeviceToHost, ctx->stream));
     CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
-    u64 mn = ctx->h_scratch[0], mx = ctx->h_scratch[1];
+    u64 mn = ctx->h_scratch[2], mx = ctx->h_scratch[3];
     *base = mn;
     u64 span = mx - mn;
     int t = 0;
@@ -1008,12 +1369,41 @@ static int key_range(dampr_ctx *ctx, dampr_kv *kv, int xf, u64 *base, int *top) 
 
 }  // namespace
 
+// shared with merge.cu: sort-only entry over a raw device range (data in `cur`, result in `cur`)
+int kv_sort_device_range(dampr_ctx *ctx, ulonglong2 *cur, ulonglong2 *alt, u64 n, int xf) {
+    if (n < 2) return DAMPR_OK;
+    u64 base;
+    int top;
+    int rc = key_range(ctx, cur, n, xf, &base, &top);
+    if (rc) return rc;
+    return sort_range(ctx, cur, alt, 0, n, xf, base, top, -1, nullptr, nullptr, 0, cur, true);
+}
+
 extern "C" {
 
 int32_t dampr_set_option(const char *name, int64_t value) {
     if (!name) return DAMPR_ERR_ARG;
     if (!strcmp(name, "scatter_tma")) {
         g_use_tma = value != 0;
+        return DAMPR_OK;
+    }
+    if (!strcmp(name, "kv_scatter")) {
+        if (value != 1 && value != 2) return DAMPR_ERR_ARG;
+        g_kv_scatter = (int)value;
+        return DAMPR_OK;
+    }
+    if (!strcmp(name, "kv_cluster")) {
+        g_kv_cluster = value != 0;
+        return DAMPR_OK;
+    }
+    if (!strcmp(name, "kv_tile")) {
+        if (value != 4096 && value != 8192) return DAMPR_ERR_ARG;
+        g_kv_tile = (int)value;
+        return DAMPR_OK;
+    }
+    if (!strcmp(name, "kv_max_bits")) {
+        if (value < 4 || value > P2_MAX_BITS) return DAMPR_ERR_ARG;
+        g_kv_max_bits = (int)value;
         return DAMPR_OK;
     }
     if (!strcmp(name, "text_ctas")) {
@@ -1040,9 +1430,9 @@ int32_t dampr_kv_sort(dampr_ctx *ctx, dampr_kv *kv, int32_t key_xf) {
     if (rc) return rc;
     u64 base;
     int top;
-    rc = key_range(ctx, kv, key_xf, &base, &top);
+    rc = key_range(ctx, kv->rec, kv->n, key_xf, &base, &top);
     if (rc) return rc;
-    return sort_range(ctx, kv->rec, kv->alt, 0, kv->n, key_xf, base, top, -1, nullptr, nullptr, 0);
+    return sort_range(ctx, kv->rec, kv->alt, 0, kv->n, key_xf, base, top, -1, nullptr, nullptr, 0, kv->rec, true);
 }
 
 int32_t dampr_kv_sort_reduce(dampr_ctx *ctx, dampr_kv *kv, int32_t key_xf, int32_t op, dampr_kv **out) {
@@ -1059,40 +1449,16 @@ int32_t dampr_kv_sort_reduce(dampr_ctx *ctx, dampr_kv *kv, int32_t key_xf, int32
     if (rc) return rc;
     u64 base;
     int top;
-    rc = key_range(ctx, kv, key_xf, &base, &top);
+    rc = key_range(ctx, kv->rec, kv->n, key_xf, &base, &top);
     if (rc) return rc;
     u64 g = 0;
-    rc = sort_range(ctx, kv->rec, kv->alt, 0, kv->n, key_xf, base, top, op, (*out)->rec, &g, 0);
+    rc = sort_range(ctx, kv->rec, kv->alt, 0, kv->n, key_xf, base, top, op, (*out)->rec, &g, 0, nullptr, true);
     if (rc) return rc;
     (*out)->n = g;
     // the partition levels ping-pong between the two buffers of `kv` and the leaves stage their group
     // records in whichever is free: the input is consumed
     kv->n = 0;
     return DAMPR_OK;
-}
-
-int32_t dampr_kv_reduce_by_key(dampr_ctx *ctx, dampr_kv *sorted, int32_t op, dampr_kv **out) {
-    ARG_CHECK(ctx, ctx && sorted && out, "null");
-    // a key-sorted run is reduced by the same machinery in RAW key order (the levels only re-discover
-    // the order the input already has), on a copy: the caller keeps its sorted run
-    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
-    wait_uploads(ctx);
-    dampr_kv *tmp = nullptr;
-    int rc = dampr_kv_create(ctx, sorted->n, &tmp);
-    if (rc) return rc;
-    if (sorted->n) {
-        cudaError_t e = cudaMemcpyAsync(tmp->rec, sorted->rec, sorted->n * sizeof(ulonglong2), cudaMemcpyDeviceToDevice,
-                                        ctx->stream);
-        if (e != cudaSuccess) {
-            dampr_kv_destroy(ctx, tmp);
-            ctx->err = std::string("reduce_by_key copy failed: ") + cudaGetErrorString(e);
-            return DAMPR_ERR_CUDA;
-        }
-    }
-    tmp->n = sorted->n;
-    rc = dampr_kv_sort_reduce(ctx, tmp, DAMPR_KEY_RAW, op, out);
-    dampr_kv_destroy(ctx, tmp);
-    return rc;
 }
 
 int32_t dampr_kv_group_offsets(dampr_ctx *ctx, dampr_kv *sorted, uint64_t *offsets, uint64_t cap,
@@ -1139,16 +1505,12 @@ int32_t dampr_kv_group_offsets(dampr_ctx *ctx, dampr_kv *sorted, uint64_t *offse
     return DAMPR_OK;
 }
 
-}  // extern "C"
-
-extern "C" {
-
 // destination-contiguous split for the exchange: owner = mix64(key) % n_dest
 int32_t dampr_kv_partition_by_owner(dampr_ctx *ctx, dampr_kv *kv, int32_t n_dest, dampr_kv **out,
                                     uint64_t *counts_host) {
     ARG_CHECK(ctx, ctx && kv && out && counts_host, "null");
     CtxScope scope_(ctx);
-    ARG_CHECK(ctx, n_dest >= 1 && n_dest <= P_MAX_NB, "n_dest out of range");
+    ARG_CHECK(ctx, n_dest >= 1 && n_dest <= P1_MAX_NB, "n_dest out of range");
     CUDA_TRY(ctx, cudaSetDevice(ctx->device));
     wait_uploads(ctx);
     int rc = dampr_kv_create(ctx, kv->n, out);
@@ -1164,44 +1526,6 @@ int32_t dampr_kv_partition_by_owner(dampr_ctx *ctx, dampr_kv *kv, int32_t n_dest
     if (rc) return rc;
     for (int i = 0; i < n_dest; ++i) counts_host[i] = seg_off[i + 1] - seg_off[i];
     return DAMPR_OK;
-}
-
-// k-way merge of key-sorted runs (+ optional segmented reduce). The runs are concatenated in run
-// order and pushed through the stable partition+leaf pipeline, which yields exactly the stable
-// merge (ties by run order, then by position) that heapq.merge produces (dataset.py:571-579).
-int32_t dampr_kv_merge(dampr_ctx *ctx, dampr_kv **runs, int32_t n_runs, int32_t key_xf, int32_t op,
-                       dampr_kv **out) {
-    ARG_CHECK(ctx, ctx && runs && out && n_runs >= 0, "null");
-    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
-    wait_uploads(ctx);
-    u64 total = 0;
-    for (int i = 0; i < n_runs; ++i) {
-        ARG_CHECK(ctx, runs[i] != nullptr, "null run");
-        total += runs[i]->n;
-    }
-    dampr_kv *cat = nullptr;
-    int rc = dampr_kv_create(ctx, total, &cat);
-    if (rc) return rc;
-    u64 off = 0;
-    for (int i = 0; i < n_runs; ++i) {
-        if (runs[i]->n)
-            CUDA_TRY(ctx, cudaMemcpyAsync(cat->rec + off, runs[i]->rec, runs[i]->n * sizeof(ulonglong2),
-                                          cudaMemcpyDeviceToDevice, ctx->stream));
-        off += runs[i]->n;
-    }
-    cat->n = total;
-    if (op < 0) {
-        rc = dampr_kv_sort(ctx, cat, key_xf);
-        if (rc) {
-            dampr_kv_destroy(ctx, cat);
-            return rc;
-        }
-        *out = cat;
-        return DAMPR_OK;
-    }
-    rc = dampr_kv_sort_reduce(ctx, cat, key_xf, op, out);
-    dampr_kv_destroy(ctx, cat);
-    return rc;
 }
 
 }  // extern "C"

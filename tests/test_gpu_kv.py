@@ -232,3 +232,148 @@ def test_synth_kv_matches_numpy(ctx):
     k2, v2 = kv.columns()
     ek, ev = gen.kv(42, 10000, 777)
     assert np.array_equal(k2, ek) and np.array_equal(v2.view(np.int64), ev)
+
+
+# ---- second-generation sort path: 12-bit atomic-rank scatter + cluster/DSMEM leaf + K5 merge ----------------
+@pytest.mark.parametrize("n", [4097, 9000, 27000, 27600, 60000, 1_000_000])
+def test_cluster_leaf_sizes(ctx, n):
+    """sizes around the single-CTA / cluster / one-level boundaries, unique-ish and duplicated keys"""
+    for nk in (max(1, n // 3), 10 * n):
+        keys, vals = gen.kv(77, n, nk)
+        check_sort(ctx, keys, vals, dev.KEY_MIX)
+        check_sort(ctx, keys, vals, dev.KEY_RAW)
+
+
+def test_cluster_leaf_overflow_falls_back(ctx):
+    """a chunk the cluster cannot balance (one key holds most of a 20K-record bucket) is re-sorted exactly"""
+    rng = np.random.default_rng(5)
+    n = 20000
+    keys = rng.integers(0, 1 << 62, size=n).astype(np.uint64)
+    keys[rng.random(n) < 0.7] = np.uint64(123456789)
+    vals = np.arange(n, dtype=np.int64)
+    check_sort(ctx, keys, vals, dev.KEY_MIX)
+    check_sort(ctx, keys, vals, dev.KEY_RAW)
+    kv = ctx.kv_from_columns(keys, vals)
+    out = kv.sort_reduce(dev.OP_COUNT, dev.KEY_RAW)
+    k2, v2 = out.columns()
+    assert dict(zip(k2.tolist(), v2.tolist())) == refsem.group_count(keys)
+    kv = ctx.kv_from_columns(keys, vals)
+    out = kv.sort_reduce(dev.OP_FIRST, dev.KEY_MIX)
+    k2, v2 = out.columns()
+    assert dict(zip(k2.tolist(), v2.view(np.int64).tolist())) == refsem.group_fold(keys, vals, lambda a, b: a)
+
+
+@pytest.mark.parametrize("opts", [{"kv_scatter": 1}, {"kv_cluster": 0}, {"kv_tile": 8192}, {"kv_max_bits": 8}])
+def test_sort_variants_agree(ctx, opts):
+    """every selectable kernel variant gives the same stable order (and leaves the defaults restored)"""
+    defaults = {"kv_scatter": 2, "kv_cluster": 1, "kv_tile": 4096, "kv_max_bits": 12}
+    try:
+        for k, v in opts.items():
+            dev.set_option(k, v)
+        keys, vals = gen.kv(13, 2_500_000, 700_000)
+        check_sort(ctx, keys, vals, dev.KEY_MIX)
+        keys = (np.random.default_rng(3).zipf(1.2, size=600_000) % 5000).astype(np.uint64)
+        check_sort(ctx, keys, np.arange(len(keys), dtype=np.int64), dev.KEY_RAW)
+        kv = ctx.kv_from_columns(keys, np.ones(len(keys), dtype=np.int64))
+        out = kv.sort_reduce(dev.OP_SUM_I64, dev.KEY_MIX)
+        k2, v2 = out.columns()
+        assert dict(zip(k2.tolist(), v2.tolist())) == refsem.group_count(keys)
+    finally:
+        for k, v in defaults.items():
+            dev.set_option(k, v)
+
+
+def test_low_cardinality_keys_hot_runs(ctx):
+    """few distinct keys: every (tile, bucket) run of the scatter is long (the warp-sorted path)"""
+    rng = np.random.default_rng(17)
+    n = 1_500_000
+    for nk in (1, 3, 200, 5000):
+        keys = (rng.integers(0, nk, size=n).astype(np.uint64) * np.uint64(0x9E3779B97F4A7C15))
+        vals = np.arange(n, dtype=np.int64)
+        check_sort(ctx, keys, vals, dev.KEY_RAW)
+        check_sort(ctx, keys, vals, dev.KEY_MIX)
+
+
+def _merge_oracle(runs_k, runs_v, xf):
+    """stable k-way merge = stable sort of the concatenation in run order (heapq.merge, dataset.py:571-579)"""
+    ak, av = np.concatenate(runs_k), np.concatenate(runs_v)
+    sk = mix64(ak) if xf == dev.KEY_MIX else xf_key(ak, xf)
+    order = np.argsort(sk, kind="stable")
+    return ak[order], av[order]
+
+
+@pytest.mark.parametrize("k,n,nk", [(2, 50000, 300), (3, 1000, 10 ** 9), (8, 200000, 40000), (8, 5000, 3), (20, 30000, 1000),
+                                    (70, 3000, 500)])
+def test_merge_kway_stable(ctx, k, n, nk):
+    for xf in (dev.KEY_RAW, dev.KEY_MIX):
+        runs, rk, rv = [], [], []
+        for s in range(k):
+            kk, _ = gen.kv(1000 + s, n + 37 * s, nk)
+            vv = (np.arange(len(kk), dtype=np.int64) << 8) | s  # value encodes (input position, run)
+            kv = ctx.kv_from_columns(kk, vv).sort(xf)
+            a, b = kv.columns()
+            runs.append(kv)
+            rk.append(a.copy())
+            rv.append(b.view(np.int64).copy())
+        merged = dev.kv_merge(ctx, runs, xf)
+        mk, mv = merged.columns()
+        ek, ev = _merge_oracle(rk, rv, xf)
+        assert np.array_equal(mk, ek)
+        assert np.array_equal(mv.view(np.int64), ev)  # ties: run order, then position
+        allk, allv = np.concatenate(rk), np.concatenate(rv)
+        for op, exp in ((dev.OP_SUM_I64, refsem.group_sum(allk, allv)), (dev.OP_COUNT, refsem.group_count(allk))):
+            red = dev.kv_merge(ctx, runs, xf, op)
+            gk, gv = red.columns()
+            assert len(set(gk.tolist())) == len(gk)
+            assert dict(zip(gk.tolist(), gv.view(np.int64).tolist())) == exp
+        # FIRST / LAST follow the merge order
+        first = dev.kv_merge(ctx, runs, xf, dev.OP_FIRST)
+        fk, fv = first.columns()
+        heads = np.concatenate(([True], ek[1:] != ek[:-1]))
+        assert np.array_equal(fk, ek[heads]) and np.array_equal(fv.view(np.int64), ev[heads])
+        last = dev.kv_merge(ctx, runs, xf, dev.OP_LAST)
+        lk, lv = last.columns()
+        tails = np.concatenate((ek[1:] != ek[:-1], [True]))
+        assert np.array_equal(lk, ek[tails]) and np.array_equal(lv.view(np.int64), ev[tails])
+
+
+def test_merge_edge_cases(ctx):
+    empty = ctx.kv_from_columns(np.zeros(0, dtype=np.uint64), np.zeros(0, dtype=np.int64))
+    one = ctx.kv_from_columns(np.array([5], dtype=np.uint64), np.array([7], dtype=np.int64))
+    assert len(dev.kv_merge(ctx, [], dev.KEY_RAW)) == 0
+    assert len(dev.kv_merge(ctx, [empty, empty], dev.KEY_RAW, dev.OP_SUM_I64)) == 0
+    m = dev.kv_merge(ctx, [empty, one, empty, one], dev.KEY_RAW)
+    assert m.columns()[0].tolist() == [5, 5]
+    r = dev.kv_merge(ctx, [empty, one, empty, one], dev.KEY_RAW, dev.OP_SUM_I64)
+    assert [x.tolist() for x in r.columns()] == [[5], [14]]
+    # one key spanning many partitions and runs
+    n = 40000
+    runs = [ctx.kv_from_columns(np.full(n, 9, dtype=np.uint64), np.arange(n, dtype=np.int64) + s * n) for s in range(4)]
+    r = dev.kv_merge(ctx, runs, dev.KEY_RAW, dev.OP_SUM_I64)
+    assert [x.tolist() for x in r.columns()] == [[9], [sum(range(4 * n))]]
+    r = dev.kv_merge(ctx, runs, dev.KEY_RAW, dev.OP_LAST)
+    assert [x.tolist() for x in r.columns()] == [[9], [4 * n - 1]]
+    m = dev.kv_merge(ctx, runs, dev.KEY_RAW)
+    assert np.array_equal(m.columns()[1].view(np.int64), np.arange(4 * n))
+
+
+def test_reduce_by_key_single_pass(ctx):
+    rng = np.random.default_rng(23)
+    for n, nk in ((1, 1), (4096, 4096), (4097, 2), (300_000, 7), (2_000_000, 900_000)):
+        keys = np.sort(rng.integers(0, nk, size=n).astype(np.uint64))
+        vals = rng.integers(-1000, 1000, size=n).astype(np.int64)
+        kv = ctx.kv_from_columns(keys, vals)
+        for op, f in ((dev.OP_SUM_I64, None), (dev.OP_MIN_I64, min), (dev.OP_FIRST, lambda a, b: a), (dev.OP_LAST, lambda a, b: b)):
+            red = kv.reduce_by_key(op)
+            gk, gv = red.columns()
+            exp = refsem.group_sum(keys, vals) if f is None else refsem.group_fold(keys, vals, f)
+            assert np.array_equal(gk, np.unique(keys))
+            assert dict(zip(gk.tolist(), gv.view(np.int64).tolist())) == exp
+    fl = rng.standard_normal(100000)
+    keys = np.sort(rng.integers(0, 20, size=100000).astype(np.uint64))
+    red = ctx.kv_from_columns(keys, fl.view(np.uint64)).reduce_by_key(dev.OP_SUM_F64)
+    gk, gv = red.columns()
+    import math
+    for k, got in zip(gk.tolist(), gv.view(np.float64).tolist()):
+        sel = fl[keys == k]
+        assert abs(got - math.fsum(sel.tolist())) <= 4 * len(sel) * 2.0 ** -53 * float(np.abs(sel).sum())

