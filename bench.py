@@ -3,20 +3,28 @@
 on synthetic Zipf text, through the Dampr DSL on the B200 engine.
 
     python bench.py --gpus 1 --steps K --warmup W            # this engine
-    python bench.py --impl reference --gpus 1 ...             # CPU port of the reference's runner
+    python bench.py --impl reference --gpus 1 ...             # the reference's own CPU runner
 
 A step = one complete run of the TF-IDF graph (len + tokenise/count + fold + cross + sink_tsv) over
 the whole corpus (10 GB, V = 1e6, split evenly over the ranks: strong scaling).
-  value  whole-job MB/s with the text resident in HBM when the step starts (max over ranks).
-  e2e    the same job from page-locked host memory: host->device copies of the text and the
-         device->host fetch of the result table are inside the timed region.
-  roofline  the tokenise+combine kernel (dominant): algorithmic bytes = 1 B per input byte
-         (SURVEY §8(d)), CUDA-event duration measured inside the timed steps, peak = measured HBM
-         copy bandwidth (MEASURED_PEAKS.json).
-  cpu_baseline  oracle/cpu_runner.py (multi-process Python port of the reference's runner) on a
-         bounded prefix of the same corpus, all host cores.
+  value / e2e   whole-job MB/s END TO END: the text starts in page-locked HOST memory, the host->device copies,
+                every kernel, the exchange, the device->host fetch of the result table and the sink files
+                are inside the timed region (max over ranks). This is BASELINE.json's metric.
+  device_resident  the same job with the text already resident in HBM when the step starts (explains e2e:
+                the difference is PCIe).
+  roofline      the tokenise+combine kernel (dominant): algorithmic bytes = 1 B per input byte
+                (SURVEY §8(d)), CUDA-event duration measured inside the timed steps, peak = measured HBM
+                copy bandwidth (MEASURED_PEAKS.json).
+  parity        after the timed loops the SAME graph runs on a line-aligned sample of the same corpus on the
+                GPU(s) and through the CPU checker (the real reference from oracle/_ref when present, else
+                oracle/cpu_runner.py); the sorted sink lines must be byte-identical or the run fails.
+  extra         (1 GPU) the north-star's own stage and the other BASELINE configs: partition+sort of 1e8 and
+                6.25e8 16-byte records (32*N/t against the HBM peak), merge / reduce, config 2 end to end,
+                config 5 joins, the file-path e2e.
+  cpu_baseline  the CPU arm on a bounded sample of the same corpus, all host cores.
 """
 import argparse
+import hashlib
 import json
 import math
 import os
@@ -35,6 +43,8 @@ import numpy as np
 
 RX = re.compile(r"[^\w]+")
 MB = 1e6
+METRIC = "MB/s ingested end-to-end, TF-IDF 10 GB synthetic text, 1/2/4/8 GPU"
+MEAN_LINE = 99.94  # mean synthetic line: 99.94 B at V = 1e6 (measured)
 
 
 def parse_args():
@@ -47,6 +57,8 @@ def parse_args():
                     help="corpus size in GB (10 = the BASELINE config)")
     ap.add_argument("--vocab", type=int, default=1000000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extra", action="store_true", help="skip the kv / join / file-path extras (1 GPU)")
+    ap.add_argument("--no-parity", action="store_true")
     return ap.parse_args()
 
 
@@ -137,21 +149,44 @@ def measured_peak():
         return 6650.0, "fallback"
 
 
-def cpu_baseline(sample_bytes_arr, n_procs):
-    """Time the oracle CPU port on a prefix of the corpus (rank 0 only)."""
+# ---- the CPU arms: the real reference (oracle/_ref, a separate process) or the oracle port ------------------------
+def have_reference():
+    return os.path.isdir(os.path.join(ROOT, "oracle", "_ref", "dampr"))
+
+
+def run_cpu_tfidf(path, out_dir, n_procs, kind):
+    """One TF-IDF run of the CPU arm on `path`; returns wall seconds (process start -> exit for the reference,
+    like benchmarks/run.sh times it)."""
+    shutil.rmtree(out_dir, ignore_errors=True)
+    if kind == "reference":
+        t0 = time.time()
+        r = subprocess.run([sys.executable, os.path.join(ROOT, "oracle", "ref_tfidf.py"), path, out_dir, str(n_procs)],
+                           cwd=tempfile.gettempdir(), capture_output=True, text=True)
+        sec = time.time() - t0
+        if r.returncode != 0:
+            raise RuntimeError("reference run failed: %s" % r.stderr[-2000:])
+        return sec
     from oracle import cpu_runner
-    tmp = tempfile.mkdtemp(prefix="dampr_cpu_")
-    path = os.path.join(tmp, "sample.txt")
-    try:
-        with open(path, "wb") as f:
-            f.write(sample_bytes_arr.tobytes())
-        with open(path, "rb") as f:  # warm the page cache like benchmarks/run.sh:3
-            while f.read(1 << 24):
-                pass
-        sec, n_terms, n_lines = cpu_runner.timed_tfidf(path, os.path.join(tmp, "idfs"), n_procs)
-        return sec, n_terms, n_lines
-    finally:
-        shutil.rmtree(tmp, ignore_errors=True)
+    sec, _n_terms, _n_lines = cpu_runner.timed_tfidf(path, out_dir, n_procs)
+    return sec
+
+
+def read_sink_lines(out_dir):
+    lines = []
+    for fn in sorted(os.listdir(out_dir)):
+        with open(os.path.join(out_dir, fn), "rb") as f:
+            lines.extend(f.read().split(b"\n"))
+    return sorted(l for l in lines if l)
+
+
+def warm_page_cache(path):
+    with open(path, "rb") as f:  # like benchmarks/run.sh:3
+        while f.read(1 << 24):
+            pass
+
+
+def lcm(a, b):
+    return a * b // math.gcd(a, b)
 
 
 def cut_at_line(arr, nbytes):
@@ -165,31 +200,218 @@ def cut_at_line(arr, nbytes):
     return arr[:cut]
 
 
+def pad_sample(sample, before, mult):
+    """bytes: `sample` with its last line extended by the generator's filler words so that before + len is a
+    multiple of `mult` (the reference's float chunk size must be integral)."""
+    from oracle import gen
+    tail, _ = gen.pad_tail(before + len(sample), mult)
+    data = sample.tobytes() if hasattr(sample, "tobytes") else bytes(sample)
+    return data[:-1] + tail if tail else data
+
+
+def reference_arm(args):
+    """--impl reference: the reference's own CPU implementation of the path on the host cores, on a bounded
+    sample of the same workload per step. Loads nothing of this repository's native code."""
+    from oracle import gen
+    ncores = os.cpu_count() or 1
+    kind = "reference" if have_reference() else "port"
+    total_bytes = int(args.gb * 1e9)
+    sample_target = int(min(total_bytes, max(32e6, 4e6 * ncores)))
+    tmp = tempfile.mkdtemp(prefix="dampr_refarm_")
+    try:
+        path = os.path.join(tmp, "sample.txt")
+        n_lines = max(1, int(sample_target / MEAN_LINE))
+        gen.text_to_file(path, 1234, n_lines, V=args.vocab, procs=ncores)
+        # the reference chunks by st_size / cpu_count (a float): make it integral
+        with open(path, "rb") as f:
+            data = np.frombuffer(f.read(), dtype=np.uint8)
+        with open(path, "wb") as f:
+            f.write(pad_sample(data, 0, lcm(64, ncores)))
+        del data
+        nbytes = os.path.getsize(path)
+        warm_page_cache(path)
+        times = []
+        budget = 240.0
+        for i in range(args.warmup + args.steps):
+            sec = run_cpu_tfidf(path, os.path.join(tmp, "idfs"), ncores, kind)
+            if i == 0 and sec * (args.warmup + args.steps) > budget and nbytes > 48e6:
+                # the box is slower than planned: shrink the per-step sample so the whole run stays bounded
+                keep = int(max(32e6, nbytes * budget / (sec * (args.warmup + args.steps))))
+                with open(path, "rb") as f:
+                    data = np.frombuffer(f.read(), dtype=np.uint8)
+                with open(path, "wb") as f:
+                    f.write(pad_sample(cut_at_line(data, keep), 0, lcm(64, ncores)))
+                del data
+                nbytes = os.path.getsize(path)
+                warm_page_cache(path)
+            if i >= args.warmup:
+                times.append(sec)
+        val = nbytes * len(times) / sum(times) / MB
+        sample = "%d-byte line-aligned prefix of the synthetic corpus per step (oracle/gen.py, seed 1234, V=%d), %d processes" % (
+            nbytes, args.vocab, ncores)
+        how = ("the unmodified reference (pip install of /root/reference under oracle/_ref), benchmarks/tf-idf-dampr.py "
+               "statements, wall time of the whole python process" if kind == "reference"
+               else "oracle/cpu_runner.py (port of the reference's runner; oracle/_ref is absent)")
+        line = {"impl": "reference", "metric": METRIC, "value": val, "unit": "MB/s", "n_gpus": args.gpus,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * sum(times) / len(times),
+                "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+                "config": {"workload": "benchmarks/tf-idf-dampr.py on synthetic Zipf(1.1) text, V=%d: %s" % (args.vocab, sample),
+                           "sample": sample, "how": how},
+                "cpu_baseline": {"value": val, "unit": "MB/s", "cores": ncores, "kind": kind, "sample": sample},
+                "e2e": {"value": val, "unit": "MB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(line))
+    finally:
+        shutil.rmtree(tmp, ignore_errors=True)
+    return 0
+
+
+# ---- parity of the timed graph: GPU result vs the CPU checker on a sample of the same corpus ---------------------
+def parity_check(Dampr, MemoryText, host_text, rank, world, use_dist, dist, out_root):
+    """Runs the TF-IDF graph on a line-aligned sample (every rank takes a prefix of its shard) through the
+    engine — all ranks, with the exchange — and through the CPU checker on the concatenation of the samples;
+    the sorted sink lines must be byte-identical. Returns the `parity` object (rank 0) or None."""
+    ncores = os.cpu_count() or 1
+    mult = lcm(64, ncores)
+    per_rank = int(min(len(host_text), (48e6 if world == 1 else 24e6)))
+    sample = cut_at_line(host_text, per_rank)
+    lens = [len(sample)]
+    if use_dist:
+        lens = [None] * world
+        dist.all_gather_object(lens, len(sample))
+    before = sum(lens[:rank])
+    if rank == world - 1:
+        data = pad_sample(sample, before, mult)
+    else:
+        data = sample.tobytes()
+    arr = np.frombuffer(data, dtype=np.uint8)
+    shared = os.path.join(tempfile.gettempdir(), "dampr_parity_%s" % os.environ.get("MASTER_PORT", str(os.getppid())))
+    if rank == 0:
+        shutil.rmtree(shared, ignore_errors=True)
+        os.makedirs(shared)
+    if use_dist:
+        dist.barrier()
+    with open(os.path.join(shared, "sample-%03d.txt" % rank), "wb") as f:
+        f.write(data)
+    out_dir = os.path.join(shared, "gpu_idfs")
+    tfidf_job(Dampr, MemoryText(arr), out_dir)
+    if use_dist:
+        dist.barrier()
+    if rank != 0:
+        return None
+    corpus = os.path.join(shared, "corpus.txt")
+    with open(corpus, "wb") as f:
+        for r in range(world):
+            with open(os.path.join(shared, "sample-%03d.txt" % r), "rb") as g:
+                shutil.copyfileobj(g, f)
+    nbytes = os.path.getsize(corpus)
+    got = read_sink_lines(out_dir)
+    kind = "reference" if have_reference() else "port"
+    run_cpu_tfidf(corpus, os.path.join(shared, "cpu_idfs"), ncores, kind)
+    exp = read_sink_lines(os.path.join(shared, "cpu_idfs"))
+    equal = got == exp
+    second = None
+    if kind == "reference":
+        # the port is the second checker (independent of the reference's float chunking)
+        run_cpu_tfidf(corpus, os.path.join(shared, "cpu2_idfs"), ncores, "port")
+        second = read_sink_lines(os.path.join(shared, "cpu2_idfs")) == got
+    res = {"checked_bytes": nbytes, "equal": bool(equal and (second is not False)), "n_terms": len(got),
+           "sha256_sorted_lines": hashlib.sha256(b"\n".join(got)).hexdigest(),
+           "checker": ("the unmodified reference (oracle/_ref)" if kind == "reference" else "oracle/cpu_runner.py"),
+           "second_checker_equal": second, "ranks": world,
+           "what": "sorted sink_tsv lines of the same TF-IDF graph on a %d-byte line-aligned sample "
+                   "(prefix of every rank's shard), byte-identical" % nbytes}
+    if not res["equal"]:
+        bad = [l for l in got if l not in set(exp)][:5]
+        res["first_differences"] = [b.decode("utf-8", "replace") for b in bad]
+    shutil.rmtree(shared, ignore_errors=True)
+    return res
+
+
+# ---- extras (1 GPU): the north-star's own stage and the other BASELINE configs ------------------------------------
+def kv_extras(ctx_unused, args):
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import kv_bench
+    from dampr_b200 import device as dev
+    from dampr_b200 import runner as runner_mod
+    ctx = runner_mod.get_ctx()
+    extra = {}
+
+    def guarded(name, fn):
+        try:
+            t0 = time.time()
+            extra[name] = fn()
+            if isinstance(extra[name], dict):
+                extra[name]["bench_wall_s"] = round(time.time() - t0, 2)
+        except Exception as e:  # an extra must never take the headline line down
+            extra[name] = {"error": "%s: %s" % (type(e).__name__, str(e)[:300])}
+
+    guarded("kv_partition_sort_1e8_K=N", lambda: kv_bench.sort_case(ctx, 100_000_000, 100_000_000, label="K=N"))
+    guarded("kv_partition_sort_1e8_K=1e7", lambda: kv_bench.sort_case(ctx, 100_000_000, 10_000_000, label="K=1e7"))
+    guarded("kv_partition_sort_6.25e8_K=N", lambda: kv_bench.sort_case(ctx, 625_000_000, 625_000_000, label="K=N"))
+    guarded("kv_partition_sort_6.25e8_K=1e7", lambda: kv_bench.sort_case(ctx, 625_000_000, 10_000_000, label="K=1e7"))
+    guarded("kv_sort_reduce_6.25e8_K=1e7", lambda: kv_bench.reduce_case(ctx, 625_000_000, 10_000_000, label="config 2 on device"))
+    guarded("kv_merge_8runs_1e8", lambda: kv_bench.merge_case(ctx, 100_000_000, 100_000_000, 8, -1))
+    guarded("kv_merge_reduce_8runs_1e8_K=1e7", lambda: kv_bench.merge_case(ctx, 100_000_000, 10_000_000, 8, dev.OP_SUM_I64))
+    guarded("kv_reduce_by_key_sorted_1e8_K=1e7", lambda: kv_bench.reduce_sorted_case(ctx, 100_000_000, 10_000_000))
+    guarded("config2_e2e", lambda: kv_bench.config2_e2e(ctx))
+    guarded("config5", lambda: kv_bench.config5(ctx))
+    return extra
+
+
+def file_e2e(Dampr, host_text, out_root, steps=2):
+    """The script under test takes a PATH: Dampr.text(path) -> page cache -> pinned ring -> device. Timed on a
+    file holding a 2.5 GB line-aligned prefix of the corpus (written and page-cache-warmed before timing)."""
+    part = cut_at_line(host_text, int(2.5e9))
+    path = os.path.join(out_root, "corpus_prefix.txt")
+    part.tofile(path)
+    warm_page_cache(path)
+    nbytes = os.path.getsize(path)
+
+    def one(i):
+        out_dir = os.path.join(out_root, "file_idfs_%d" % i)
+        docs = Dampr.text(path, nbytes / (os.cpu_count() or 1) + 1)
+        doc_freq = docs.flat_map(lambda x: set(RX.split(x.lower()))).count(reduce_buffer=float("inf"))
+        idf = doc_freq.cross_right(docs.len(), lambda df, total: (df[0], df[1], math.log(1 + (float(total) / df[1]))),
+                                   memory=True)
+        idf.sink_tsv(out_dir).run()
+        shutil.rmtree(out_dir, ignore_errors=True)
+
+    one(-1)
+    t0 = time.perf_counter()
+    for i in range(steps):
+        one(i)
+    sec = (time.perf_counter() - t0) / steps
+    os.remove(path)
+    return {"value": nbytes / sec / MB, "unit": "MB/s", "bytes": nbytes, "ms_per_step": 1e3 * sec,
+            "what": "Dampr.text(path, st_size/cpu_count + 1) ... sink_tsv(dir).run(): file in the page cache -> "
+                    "reader threads -> pinned ring -> device -> sink files"}
+
+
 def main():
     args = parse_args()
     rank, world, local = dist_env()
     if world != max(1, args.gpus) and world > 1:
         args.gpus = world
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        return reference_arm(args)
+
     total_bytes = int(args.gb * 1e9)
     shard_bytes = total_bytes // world
-    n_lines = int(shard_bytes / 99.94)  # mean synthetic line: 99.94 B at V = 1e6 (measured)
+    n_lines = int(shard_bytes / MEAN_LINE)
 
     from dampr_b200 import device as dev
     from dampr_b200 import synth, settings
 
-    if args.impl == "reference" and rank != 0:
-        return 0
-
     settings.device = local
-    ctx_err = None
     try:
         ctx = dev.Ctx(local)
     except dev.DeviceError as e:
-        ctx, ctx_err = None, e
-    if ctx is None:
-        raise SystemExit("bench.py needs a CUDA device (no CPU fallback): %s" % ctx_err)
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback): %s" % e)
 
-    use_dist = world > 1 and args.impl == "ours"
+    use_dist = world > 1
+    dist = None
     if use_dist:
         import torch
         import torch.distributed as dist
@@ -208,29 +430,6 @@ def main():
     ncores = os.cpu_count() or 1
     workload = "benchmarks/tf-idf-dampr.py on %.2f GB synthetic Zipf(1.1) text, V=%d, %d GPU(s)" % (
         nbytes * world / 1e9, args.vocab, world)
-
-    if args.impl == "reference":
-        # CPU port of the reference's runner, bounded sample per step (a few seconds of CPU work)
-        per_core = 6e6
-        sample = cut_at_line(host_text, int(min(nbytes, per_core * ncores * 3)))
-        tb.free()
-        times = []
-        for i in range(args.warmup + args.steps):
-            sec, n_terms, n_lines_s = cpu_baseline(sample, ncores)
-            if i >= args.warmup:
-                times.append(sec)
-        val = len(sample) * len(times) / sum(times) / MB
-        line = {"impl": "reference", "metric": "MB/s ingested end-to-end, TF-IDF 10 GB synthetic text, 1/2/4/8 GPU", "value": val,
-                "unit": "MB/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-                "ms_per_step": 1e3 * sum(times) / len(times), "higher_is_better": True, "scaling": "strong",
-                "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-                "config": {"workload": workload, "sample": "%d-byte line-aligned prefix per step" % len(sample)},
-                "cpu_baseline": {"value": val, "unit": "MB/s", "cores": ncores, "kind": "port",
-                                 "sample": "%d-byte prefix of the corpus, %d processes (oracle/cpu_runner.py)" % (
-                                     len(sample), ncores)},
-                "e2e": {"value": val, "unit": "MB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-        print(json.dumps(line))
-        return 0
 
     from dampr_b200 import Dampr
     from dampr_b200 import runner as runner_mod
@@ -256,6 +455,16 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
+    def sink_digest(out_dir):
+        """order-independent digest of this rank's sink lines: (lines, sum of 64-bit line hashes mod 2^64)"""
+        n, acc = 0, 0
+        for fn in os.listdir(out_dir):
+            with open(os.path.join(out_dir, fn), "rb") as f:
+                for l in f:
+                    n += 1
+                    acc = (acc + int.from_bytes(hashlib.blake2b(l, digest_size=8).digest(), "little")) & 0xFFFFFFFFFFFFFFFF
+        return n, acc
+
     # ---- warm-up immediately before each timed loop (no host-side pause in between) -------------------
     sampler = ClockSampler(local)
     if not os.environ.get("DAMPR_BENCH_NOSAMPLER"):
@@ -268,21 +477,20 @@ def main():
             print("warmup resident %d: %.1f ms %s" % (i, 1e3 * (time.perf_counter() - ts),
                                                       [round(ms, 1) for _s, ms in runner_mod.LAST_STATS.ms]), file=sys.stderr)
 
-    # ---- timed: device-resident input ("value") ------------------------------------------------------------
+    # ---- timed: device-resident input ("device_resident") ------------------------------------------------
     runner_ctx = runner_mod.get_ctx(local)
     barrier()
     runner_ctx.timings_reset()
-    l0 = runner_ctx.launches()
     t0 = time.perf_counter()
     dev_steps = []
+    d_dev = None
     for i in range(args.steps):
         ts = time.perf_counter()
-        d = step(True, i)
+        d_dev = step(True, i)
         dev_steps.append([round(1e3 * (time.perf_counter() - ts), 1)] +
                          [round(ms, 1) for _s, ms in runner_mod.LAST_STATS.ms])
     barrier()
     t_dev = max_over_ranks(time.perf_counter() - t0)
-    launches = runner_ctx.launches() - l0
     ktimes = runner_ctx.timings()
     for i in range(args.warmup):
         ts = time.perf_counter()
@@ -291,10 +499,12 @@ def main():
             print("warmup e2e %d: %.1f ms %s" % (i, 1e3 * (time.perf_counter() - ts),
                                                  [round(ms, 1) for _s, ms in runner_mod.LAST_STATS.ms]), file=sys.stderr)
 
-    # ---- timed: host-resident input ("e2e") ----------------------------------------------------------------
+    # ---- timed: host-resident input (the metric) -----------------------------------------------------------
     barrier()
+    l0 = runner_ctx.launches()
     t0 = time.perf_counter()
     e2e_steps = []
+    d = None
     for i in range(args.steps):
         ts = time.perf_counter()
         d = step(False, i)
@@ -302,7 +512,9 @@ def main():
                          [round(ms, 1) for _s, ms in runner_mod.LAST_STATS.ms])
     barrier()
     t_e2e = max_over_ranks(time.perf_counter() - t0)
+    launches = runner_ctx.launches() - l0
     stats = runner_mod.LAST_STATS.stages if runner_mod.LAST_STATS else []
+    e2e_stage_ms = [round(ms, 2) for _s, ms in (runner_mod.LAST_STATS.ms if runner_mod.LAST_STATS else [])]
     sampler.stop_flag.set()
     if sampler.is_alive():
         sampler.join(timeout=5)
@@ -324,17 +536,21 @@ def main():
         for i in range(5):
             step(True, 100 + i)
 
-    # result size fetched from the device per step
-    n_terms = 0
-    try:
-        for fn in os.listdir(d):
-            with open(os.path.join(d, fn)) as f:
-                n_terms += sum(1 for _ in f)
-    except Exception:
-        pass
+    # ---- full-size consistency: both timed variants produced the same result on every rank, the line
+    # totals add up over the ranks -------------------------------------------------------------------------
+    n_terms, dig_host = sink_digest(d)
+    n_terms_dev, dig_dev = sink_digest(d_dev)
+    full = {"rank_terms": n_terms, "host_vs_resident_equal": bool(dig_host == dig_dev and n_terms == n_terms_dev)}
+    if use_dist:
+        t = torch.tensor([n_terms, int(full["host_vs_resident_equal"])], dtype=torch.int64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        full = {"terms_all_ranks": int(t[0].item()), "host_vs_resident_equal": bool(int(t[1].item()) == world)}
+        n_terms_total = int(t[0].item())
+    else:
+        n_terms_total = n_terms
 
     total = nbytes * world
-    value = total * args.steps / t_dev / MB
+    value_dev = total * args.steps / t_dev / MB
     e2e = total * args.steps / t_e2e / MB
     tc = [ms for name, ms in ktimes if name == "text_count"]
     peak, peak_kind = measured_peak()
@@ -345,8 +561,13 @@ def main():
         ach = per_launch_bytes / (per_launch_ms * 1e-3) / 1e9
         traffic, traffic_src, issue = None, None, None
         try:
-            with open(os.path.join(ROOT, "profiles", "r01_text_traffic.json")) as f:
-                tj = json.load(f)
+            tj = None
+            for fn in ("text_traffic.json", "r01_text_traffic.json"):
+                fp = os.path.join(ROOT, "profiles", fn)
+                if os.path.exists(fp):
+                    with open(fp) as f:
+                        tj = json.load(f)
+                    break
             # dram__bytes_read+write of one ncu --set full capture of this kernel, scaled from the
             # captured launch (250 MB of the same corpus) to this launch's bytes
             traffic = tj["dram_bytes_per_input_byte"] * per_launch_bytes
@@ -367,38 +588,74 @@ def main():
                 "algorithmic_bytes_per_launch": per_launch_bytes, "ms_per_launch": per_launch_ms,
                 "peak_source": peak_kind + " (MEASURED_PEAKS.json hbm_gbs)", "issue_roofline": issue}
 
-    line = {"metric": "MB/s ingested end-to-end, TF-IDF 10 GB synthetic text, 1/2/4/8 GPU", "value": value, "unit": "MB/s",
+    # ---- parity of the timed graph against the CPU checker (all ranks take part) ----------------------------
+    parity = None
+    if not args.no_parity:
+        try:
+            parity = parity_check(Dampr, MemoryText, host_text, rank, world, use_dist, dist, out_root)
+        except Exception as e:
+            parity = {"equal": False, "error": "%s: %s" % (type(e).__name__, str(e)[:500])}
+        if parity is not None:
+            parity["full_size"] = full
+
+    d2h = int(n_terms_total) * (24 if world == 1 else 32)
+    line = {"metric": METRIC, "value": e2e, "unit": "MB/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": 1e3 * t_dev / args.steps, "higher_is_better": True, "scaling": "strong",
+            "ms_per_step": 1e3 * t_e2e / args.steps, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "u8", "data": "synthetic",
             "config": {"workload": workload, "bytes_per_rank": nbytes, "lines_per_rank": n_lines,
                        "l2": "inputs (%.1f GB per rank) are larger than L2" % (nbytes / 1e9),
-                       "resident_step_ms_total_then_stages": dev_steps,
+                       "value_is": "end to end: text in page-locked host memory -> H2D -> kernels -> exchange -> result "
+                                   "table D2H -> sink files, all inside the timed region",
                        "stages": [[s.split("`")[1][:40] if "`" in s else s, h] for s, h, _d in stats],
-                       "e2e_stage_ms": [round(ms, 2) for _s, ms in (runner_mod.LAST_STATS.ms if runner_mod.LAST_STATS else [])]},
+                       "e2e_stage_ms": e2e_stage_ms},
             "e2e": {"value": e2e, "unit": "MB/s", "h2d_bytes_per_step": nbytes * world,
                     # result table per term: 16-byte key string + 8-byte count (single GPU; the synthetic
                     # corpus has no hashed tokens), plus the 8-byte code after the exchange (multi GPU)
-                    "d2h_bytes_per_step": int(n_terms) * (24 if world == 1 else 32),
-                    "ms_per_step": 1e3 * t_e2e / args.steps,
-                    "step_ms": e2e_steps},
-            "gpu_launches": int(launches), "clocks": sampler.summary(), "roofline": roof}
+                    "d2h_bytes_per_step": d2h, "ms_per_step": 1e3 * t_e2e / args.steps, "step_ms": e2e_steps},
+            "device_resident": {"value": value_dev, "unit": "MB/s", "ms_per_step": 1e3 * t_dev / args.steps,
+                                "step_ms_total_then_stages": dev_steps,
+                                "what": "the same job with the text already in HBM when the step starts"},
+            "gpu_launches": int(launches), "clocks": sampler.summary(), "roofline": roof, "parity": parity}
+
+    if rank == 0 and world == 1 and not args.no_extra:
+        tb.free()
+        extra = kv_extras(ctx, args)
+        try:
+            extra["file_e2e"] = file_e2e(Dampr, host_text, out_root)
+        except Exception as e:
+            extra["file_e2e"] = {"error": "%s: %s" % (type(e).__name__, str(e)[:300])}
+        line["extra"] = extra
 
     if rank == 0 and not args.no_cpu_baseline:
-        sample = cut_at_line(host_text, int(min(nbytes, 6e6 * ncores * 3)))
-        cpu_baseline(sample[:min(len(sample), 4 << 20)], ncores)  # warm-up (imports, fork)
-        sec, _t, _l = cpu_baseline(sample, ncores)
-        line["cpu_baseline"] = {"value": len(sample) / sec / MB, "unit": "MB/s", "cores": ncores, "kind": "port",
-                                "sample": "%d-byte line-aligned prefix of the corpus, %d processes "
-                                          "(oracle/cpu_runner.py, a leaner port of the reference's runner)" % (
-                                              len(sample), ncores)}
+        kind = "reference" if have_reference() else "port"
+        tmp = tempfile.mkdtemp(prefix="dampr_cpu_")
+        try:
+            sample = cut_at_line(host_text, int(min(nbytes, max(32e6, 4e6 * ncores))))
+            path = os.path.join(tmp, "sample.txt")
+            with open(path, "wb") as f:
+                f.write(pad_sample(sample, 0, lcm(64, ncores)))
+            sbytes = os.path.getsize(path)
+            warm_page_cache(path)
+            run_cpu_tfidf(path, os.path.join(tmp, "idfs"), ncores, kind)  # warm-up (imports, fork, page cache)
+            sec = run_cpu_tfidf(path, os.path.join(tmp, "idfs"), ncores, kind)
+            line["cpu_baseline"] = {"value": sbytes / sec / MB, "unit": "MB/s", "cores": ncores, "kind": kind,
+                                    "sample": "%d-byte line-aligned prefix of the corpus, %d processes (%s)" % (
+                                        sbytes, ncores, "the unmodified reference, oracle/_ref" if kind == "reference"
+                                        else "oracle/cpu_runner.py, a leaner port of the reference's runner")}
+        finally:
+            shutil.rmtree(tmp, ignore_errors=True)
     shutil.rmtree(out_root, ignore_errors=True)
     if rank == 0:
         print(json.dumps(line))
+    ok = True
+    if parity is not None and not parity.get("equal", False):
+        ok = False
+        print("PARITY FAILURE: %s" % json.dumps(parity)[:2000], file=sys.stderr)
     if use_dist:
         dist.barrier()
         dist.destroy_process_group()
-    return 0
+    return 0 if ok else 3
 
 
 if __name__ == "__main__":

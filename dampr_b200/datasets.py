@@ -136,13 +136,14 @@ class ColumnDataset(Dataset):
 
 
 # ---- text inputs ---------------------------------------------------------------------------------
-def _iter_lines(buf, base):
+def _iter_lines(buf, base, universal=True):
     """(byte offset, str) for every line of `buf` (bytes). '\\n', '\\r\\n' and lone '\\r' end lines,
-    a trailing unterminated piece is a line, like Python's universal-newline text mode."""
+    a trailing unterminated piece is a line, like Python's universal-newline text mode. universal=False:
+    binary-mode iteration (only '\\n' ends a line, a '\\r' stays in it) as the reference reads .gz files."""
     pos = 0
     n = len(buf)
     find = buf.find
-    has_cr = find(b"\r") >= 0
+    has_cr = universal and find(b"\r") >= 0
     while pos < n:
         if has_cr:
             i_n = find(b"\n", pos)
@@ -242,9 +243,11 @@ class GzipLineDataset(Dataset):
         self.path = path
 
     def read(self):
+        # binary mode like the reference (dataset.py:488-493): split on '\n' only, rstrip(os.linesep) strips
+        # just the '\n', so the '\r' of a CRLF file stays in the line
         with gzip.open(self.path, "rb") as f:
             data = f.read()
-        return _iter_lines(data, 0)
+        return _iter_lines(data, 0, universal=False)
 
     def __str__(self):
         return "GzipFile[path=%s]" % self.path

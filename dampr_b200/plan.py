@@ -312,6 +312,12 @@ class TextScan(object):
             self.nbytes = tb.n
         else:
             gz = [p for kind, p in self.sources if kind == "gz"]
+            # the reference reads .gz files in BINARY mode (GzipLineDataset, dataset.py:488-493): only '\n' ends a
+            # line and a '\r' stays in it, where it is an ordinary separator of the \w tokenisers and whitespace
+            # for str.split. The kernels treat it exactly like that; the CR flag (universal newlines of text-mode
+            # files) does not apply when every source of the scan is a .gz file.
+            if gz and len(gz) == len(self.sources):
+                self._cr_is_data = True
             if gz:
                 if dist.active():
                     raise NotLowerable("gzip inputs are not sharded across ranks")
@@ -332,6 +338,9 @@ class TextScan(object):
         tab = self._tab
         st = tab.stats()
         flags = st["flags"]
+        if getattr(self, "_cr_is_data", False):
+            flags &= ~dev.TF_CR
+            st = dict(st, flags=flags)
         if dist.active():
             return self._finish_distributed(ctx, tb, tab, st)
         if (flags & dev.TF_TABLEFULL or st["entries"] * 2 > tab.capacity) and settings.text_table_log2 < 28 \
@@ -711,8 +720,12 @@ def _lower_map(runner, stage, inputs, si):
                 return RecordsDataset([], [])
             return RecordsDataset([1], [scan.n_lines])
         if isinstance(ds, (Frame, RecordsDataset)):
-            runner.stats.add(stage, "frame length", "records=%d" % len(ds))
-            return RecordsDataset([1], [len(ds)])
+            n = len(ds)
+            if dist.active():
+                # results are owner-partitioned over the ranks: the length is the sum of the shards
+                n = int(dist.all_reduce_sum_int([n])[0])
+            runner.stats.add(stage, "frame length", "records=%d" % n)
+            return RecordsDataset([1], [n])
         return None
     kv = _lower_kv_map(runner, stage, inputs)
     if kv is not None:

@@ -66,6 +66,10 @@ def _chunks_of(ds):
     return list(ds)
 
 
+class DistributedUnsupported(RuntimeError):
+    """A stage that is not lowered would give a per-rank (wrong) result under torch.distributed."""
+
+
 class StageStats(object):
     """What ran where: the judge-facing answer to 'was this stage lowered?'"""
 
@@ -113,6 +117,8 @@ class B200Runner(object):
             inputs = [data[s] for s in stage.inputs]
             t_stage = time.perf_counter()
             lowered = plan.try_lower(self, stage, inputs, si, data)
+            if lowered is None and dist.active():
+                self._check_distributed_generic(stage, inputs)
             if lowered is not None:
                 out = lowered
             elif isinstance(stage, GMap):
@@ -146,6 +152,25 @@ class B200Runner(object):
                         pass
         LAST_STATS = self.stats
         return ret
+
+    def _check_distributed_generic(self, stage, inputs):
+        """Under torch.distributed only the lowered stages exchange records between the ranks (text scans, kv
+        folds, the frame length). A stage that falls back to the host path would silently work on this rank's
+        shard (frames are owner-partitioned) or, for an original input, on the whole input on every rank. The
+        only host stages that stay correct are record-wise ones over rank-local results: a plain map / filter
+        chain (no combiner, no supplementary input) and the sink, which writes rank-numbered parts."""
+        from . import plan
+        local = all(isinstance(d, (plan.Frame, RecordsDataset)) for d in inputs) and \
+            not any(src in self.graph.inputs for src in stage.inputs)
+        recordwise = isinstance(stage, GSink) or (
+            isinstance(stage, GMap) and len(inputs) == 1 and
+            not isinstance(stage.combiner, ops.PartialReduceCombiner) and
+            isinstance(stage.mapper, (ops.Map, ops.FusedMapper)) and
+            not isinstance(stage.mapper, (ops.MapCrossJoin, ops.MapAllJoin)))
+        if not (local and recordwise):
+            raise DistributedUnsupported(
+                "stage %s is not lowered to the device and cannot run under torch.distributed (world size %d): "
+                "only lowered stages exchange records between ranks; run it on one GPU" % (stage, dist.world()[1]))
 
     # ---- device helpers ---------------------------------------------------------------------
     def device_order(self, codes):
@@ -321,8 +346,10 @@ class B200Runner(object):
         parts = []
         main, supp = inputs[0], inputs[1:]
         n = 0
+        # one process per GPU: results are rank-local, part numbers follow the rank like the lowered sink's
+        first = 4096 * dist.world()[0] if dist.active() else 0
         for i, ch in enumerate(_chunks_of(main)):
-            fname = os.path.join(path, "part-%d" % i)
+            fname = os.path.join(path, "part-%d" % (first + i))
             with open(fname, "w", encoding="utf-8") as f:
                 for _k, v in stage.mapper.map(ch, *supp):
                     f.write("%s\n" % (v,))

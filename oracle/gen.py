@@ -29,14 +29,36 @@ def splitmix64(x):
         return x ^ (x >> np.uint64(31))
 
 
-from dampr_b200.synth import make_vocab, make_cdf  # noqa: E402,F401  (same tables as the device generator)
+def make_vocab(V, seed=1234):
+    """(vocab_bytes uint8[], vocab_off uint32[V+1]) — V lowercase ASCII words, lengths U[2,11].
+    The product's bench tooling (dampr_b200/synth.py) builds the same tables for the device generator;
+    tests/test_oracle_golden.py pins the two against each other. The oracle imports nothing of the product."""
+    rng = np.random.default_rng(seed)
+    lens = rng.integers(2, 12, size=V).astype(np.uint32)
+    off = np.zeros(V + 1, dtype=np.uint32)
+    np.cumsum(lens, out=off[1:])
+    letters = rng.integers(0, 26, size=int(off[-1])).astype(np.uint8) + np.uint8(ord("a"))
+    return letters, off
 
 
-def pad_tail(total):
-    """bytes appended in place of the final newline so that the size is a multiple of 64."""
-    pad = (64 - (total % 64)) % 64
+def make_cdf(V, s=1.1):
+    """uint64[V]: cdf[i] = floor(2^64 * P(rank <= i+1)) for Zipf(s), last entry 2^64-1."""
+    p = np.arange(1, V + 1, dtype=np.float64) ** (-float(s))
+    c = np.cumsum(p)
+    c /= c[-1]
+    scaled = np.minimum(np.floor(c * 18446744073709551616.0), 18446744073709549568.0)
+    cdf = scaled.astype(np.uint64)
+    cdf[-1] = np.uint64(0xFFFFFFFFFFFFFFFF)
+    return cdf
+
+
+def pad_tail(total, mult=64):
+    """bytes appended in place of the final newline so that the size is a multiple of `mult` (64 in the
+    generator; the bench's CPU arms use lcm(64, cpu count) so that the reference's st_size / cpu_count
+    chunk size is integral)."""
+    pad = (mult - (total % mult)) % mult
     if pad == 1:
-        pad = 65
+        pad = mult + 1
     if pad == 0 or total == 0:
         return b"", 0
     tail = b""
@@ -51,21 +73,14 @@ def pad_tail(total):
     return tail + b"\n", pad
 
 
-def text(seed, n_lines, V=50000, s=1.1, vocab=None, cdf=None, pad=True):
-    """Synthetic corpus as bytes (numpy implementation; fine up to a few hundred MB)."""
-    if vocab is None:
-        vocab = make_vocab(V)
-    if cdf is None:
-        cdf = make_cdf(V, s)
-    vbytes, voff = vocab
+BLOCK = 1 << 18
+_POOL_STATE = None
+
+
+def _block(seed, lo, hi, vbytes, voff, cdf):
+    """bytes of lines [lo, hi) (every line '\n' terminated)"""
     V = len(voff) - 1
-    if n_lines == 0:
-        return b""
-    out_parts = []
-    total = 0
-    BLOCK = 1 << 18
-    for lo in range(0, n_lines, BLOCK):
-        hi = min(n_lines, lo + BLOCK)
+    if True:
         i = np.arange(lo, hi, dtype=np.uint64)
         with np.errstate(over="ignore"):
             r0 = splitmix64(np.uint64(seed) ^ (i * GOLD))
@@ -97,14 +112,64 @@ def text(seed, n_lines, V=50000, s=1.1, vocab=None, cdf=None, pad=True):
         np.cumsum(wl[:-1], out=wfirst[1:])
         k = np.arange(W, dtype=np.int64) - wfirst[tok_of]
         out[tok_out[tok_of] + k] = vbytes[voff[w][tok_of].astype(np.int64) + k]
-        out_parts.append(out.tobytes())
-        total += nbytes
-    data = b"".join(out_parts)
+        return out.tobytes()
+
+
+def text(seed, n_lines, V=50000, s=1.1, vocab=None, cdf=None, pad=True):
+    """Synthetic corpus as bytes (numpy implementation; fine up to a few hundred MB)."""
+    if vocab is None:
+        vocab = make_vocab(V)
+    if cdf is None:
+        cdf = make_cdf(V, s)
+    vbytes, voff = vocab
+    if n_lines == 0:
+        return b""
+    data = b"".join(_block(seed, lo, min(n_lines, lo + BLOCK), vbytes, voff, cdf) for lo in range(0, n_lines, BLOCK))
     if pad:
         tail, _ = pad_tail(len(data))
         if tail:
             data = data[:-1] + tail
     return data
+
+
+def _pool_block(rng):
+    seed, vbytes, voff, cdf = _POOL_STATE
+    return _block(seed, rng[0], rng[1], vbytes, voff, cdf)
+
+
+def text_to_file(path, seed, n_lines, V=50000, s=1.1, procs=None, pad=True):
+    """The same corpus written to `path`, blocks of lines generated by forked workers (the bench's CPU arms
+    need ~1 GB samples on the GPU box's many host cores). Returns the byte count."""
+    import multiprocessing as mp
+    global _POOL_STATE
+    vocab, cdf = make_vocab(V), make_cdf(V, s)
+    _POOL_STATE = (seed, vocab[0], vocab[1], cdf)
+    ranges = [(lo, min(n_lines, lo + BLOCK)) for lo in range(0, n_lines, BLOCK)]
+    procs = max(1, min(procs or (mp.cpu_count() or 1), len(ranges)))
+    total = 0
+    with open(path, "wb") as f:
+        if procs == 1:
+            it = map(_pool_block, ranges)
+            pool = None
+        else:
+            pool = mp.get_context("fork").Pool(procs)
+            it = pool.imap(_pool_block, ranges)
+        try:
+            for blk in it:
+                f.write(blk)
+                total += len(blk)
+        finally:
+            if pool is not None:
+                pool.close()
+                pool.join()
+        if pad and total:
+            tail, _ = pad_tail(total)
+            if tail:
+                f.seek(total - 1)
+                f.write(tail)
+                total += len(tail) - 1
+    _POOL_STATE = None
+    return total
 
 
 def kv(seed, n, n_keys):

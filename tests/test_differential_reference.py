@@ -552,3 +552,50 @@ def test_directory_inputs_agree_with_the_reference(path_kind, monkeypatch, tmp_p
         monkeypatch.setattr(plan, "_BUFFERS", {})
         got = sorted(repr(x) for x in eval(src, {"Dampr": Dampr, "path": str(d), "RX": RX, "math": math}).run())
         assert got == exp, src
+
+
+@pytest.mark.parametrize("path_kind", ["host-map", "scan-plumbing"])
+def test_crlf_gzip_inputs_agree_with_the_reference(path_kind, monkeypatch, tmp_path):
+    """.gz text is read in BINARY mode by the reference (dataset.py:488-493): only '\\n' ends a line, the '\\r'
+    of a CRLF file stays in the line (so the tf-idf tokeniser yields a '' token per line and 'hello world\\r'
+    is the line), a lone '\\r' does not end a line. Both as a gz-only directory (stays lowered: the CR flag is
+    data there) and next to a plain CRLF file (universal newlines apply to that one)."""
+    import gzip
+    import math
+    import re
+    import fake_device as F
+    from dampr_b200 import Dampr, settings, plan
+    from dampr_b200 import runner as runner_mod
+    RX = re.compile(r"[^\w]+")
+    crlf = b"hello world\r\nfoo bar\r\nlone\rcr inside\r\n\r\nlast line no cr\nunterminated\r"
+    for layout in ("gz-only", "mixed"):
+        d = tmp_path / layout
+        d.mkdir()
+        with gzip.open(str(d / "a.txt.gz"), "wb") as f:
+            f.write(crlf)
+        with gzip.open(str(d / "b.txt.gz"), "wb") as f:
+            f.write(b"plain gz\nno carriage returns\n")
+        if layout == "mixed":
+            (d / "c.txt").write_bytes(b"text mode\r\nuniversal newlines\rhere\n")
+        srcs = ["Dampr.text(path, 1 << 20)" + tail for tail in (
+            ".flat_map(lambda x: x.split()).count()",
+            ".flat_map(lambda x: set(RX.split(x.lower()))).count()",
+            ".flat_map(lambda x: RX.split(x.lower())).count()",
+            ".len()",
+            ".map(lambda x: x)",
+        )]
+        env = dict(os.environ)
+        env.pop("PYTHONPATH", None)
+        p = subprocess.run([sys.executable, "-c", TEXT_DRIVER, REF, str(d), json.dumps(srcs)], capture_output=True, text=True,
+                           env=env, cwd="/tmp", timeout=300)
+        assert p.returncode == 0, p.stderr[-2000:]
+        ref = json.loads(p.stdout.strip().split("\n")[-1])
+        assert repr("hello world\r") in ref[4] if layout == "gz-only" else True
+        monkeypatch.setattr(plan, "_pinned_ring", lambda n, b: [F.FakePinned(b) for _ in range(n)])
+        for src, exp in zip(srcs, ref):
+            monkeypatch.setattr(runner_mod, "_CTX", {settings.device: F.FakeCtx() if path_kind == "host-map" else F.FakeTextCtx()})
+            monkeypatch.setattr(plan, "_BUFFERS", {})
+            got = sorted(repr(x) for x in eval(src, {"Dampr": Dampr, "path": str(d), "RX": RX, "math": math}).run())
+            assert got == exp, (layout, src)
+            if path_kind == "scan-plumbing" and layout == "gz-only" and "count" in src:
+                assert any("device text tokenise+combine" in h for _s, h, _d in runner_mod.LAST_STATS.stages), src

@@ -89,3 +89,29 @@ def test_text_lines_semantics():
     assert [l for _p, l in tl(b"a\r\nb\rc\n")] == ["a", "b", "c"]
     assert refsem.docfreq(b"...\n a\nb.\n\n")[0] == {"": 4, "a": 1, "b": 1}
     assert refsem.termfreq_nonset(b"...\n")[""] == 2
+
+
+def test_generator_tables_agree_between_oracle_and_bench_tooling():
+    """oracle/gen.py imports nothing of the product; its vocabulary / Zipf tables and the ones the device
+    generator is fed with (dampr_b200/synth.py) are two independent statements of the same definition"""
+    import numpy as np
+    from dampr_b200 import synth
+    from oracle import gen
+    for V in (7, 5000, 50000):
+        a, b = gen.make_vocab(V), synth.make_vocab(V)
+        assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
+        assert np.array_equal(gen.make_cdf(V), synth.make_cdf(V))
+    import oracle.gen as g
+    assert "dampr_b200" not in open(g.__file__).read().replace("dampr_b200/", "")
+
+
+def test_parallel_generator_and_padding(tmp_path):
+    from oracle import gen
+    data = gen.text(99, 30000, V=2000)
+    p = str(tmp_path / "c.txt")
+    assert gen.text_to_file(p, 99, 30000, V=2000, procs=3) == len(data)
+    assert open(p, "rb").read() == data and len(data) % 64 == 0
+    for total in (1000, 1023, 4097, 12345):
+        for mult in (64, 192, 640):
+            tail, _ = gen.pad_tail(total, mult)
+            assert (total - 1 + len(tail)) % mult == 0 if tail else total % mult == 0
