@@ -410,6 +410,24 @@ int32_t dampr_kv_merge(dampr_ctx *ctx, dampr_kv **runs, int32_t n_runs, int32_t 
     return rc;
 }
 
+// the same merge over runs that are CONSECUTIVE SLICES of one kv: run i = records [offsets[i], offsets[i+1]).
+// This is how sorted runs arrive from the all-to-all (one run per source rank, back to back in the receive
+// buffer) and from the spill uploads (one run per batch).
+int32_t dampr_kv_merge_ranges(dampr_ctx *ctx, dampr_kv *kv, const uint64_t *offsets, int32_t n_runs,
+                              int32_t key_xf, int32_t op, dampr_kv **out) {
+    ARG_CHECK(ctx, ctx && kv && out && n_runs >= 0 && (offsets || n_runs == 0), "null");
+    std::vector<dampr_kv> views((size_t)n_runs);
+    std::vector<dampr_kv *> ptrs((size_t)n_runs);
+    for (int i = 0; i < n_runs; ++i) {
+        ARG_CHECK(ctx, offsets[i] <= offsets[i + 1] && offsets[i + 1] <= kv->n, "run offsets out of range");
+        views[i].rec = kv->rec + offsets[i];
+        views[i].alt = nullptr;
+        views[i].capacity = views[i].n = offsets[i + 1] - offsets[i];
+        ptrs[i] = &views[i];
+    }
+    return dampr_kv_merge(ctx, ptrs.data(), n_runs, key_xf, op, out);
+}
+
 // segmented reduce of a key-sorted kv in ONE pass over it: tiles of 4096 records, head flags, fold, then the
 // groups are compacted (a key that straddles tiles is folded across them in order). `sorted` is not modified.
 int32_t dampr_kv_reduce_by_key(dampr_ctx *ctx, dampr_kv *sorted, int32_t op, dampr_kv **out) {

@@ -109,6 +109,7 @@ def load_library():
     _sig(lib, "dampr_kv_reduce_by_key", vp, vp, i32, pvp)
     _sig(lib, "dampr_kv_group_offsets", vp, vp, vp, u64, pu64)
     _sig(lib, "dampr_kv_merge", vp, pvp, i32, i32, i32, pvp)
+    _sig(lib, "dampr_kv_merge_ranges", vp, vp, vp, i32, i32, i32, pvp)
     _sig(lib, "dampr_kv_sort_reduce", vp, vp, i32, i32, pvp)
     _sig(lib, "dampr_kv_join_ranges", vp, vp, vp, i32, vp, u64, pu64)
     _sig(lib, "dampr_kv_hash_probe", vp, vp, vp, pvp, vp)
@@ -262,6 +263,21 @@ class Ctx(object):
                                              _ptr(vocab_off), len(vocab_off) - 1, _ptr(cdf), C.byref(out)))
         tb.n = out.value
         return tb
+
+    def kv_merge(self, runs, xform, op=-1):
+        """k-way merge (op < 0) or merge + fold of key-sorted KVs -> new KV (stable: run order, then position)"""
+        arr = (C.c_void_p * len(runs))(*[r.h for r in runs])
+        h = C.c_void_p()
+        self.check(self.lib.dampr_kv_merge(self.h, arr, len(runs), int(xform), int(op), C.byref(h)))
+        return KV(self, None, handle=h)
+
+    def kv_merge_ranges(self, kv, offsets, xform, op=-1):
+        """the same over the sorted runs kv[offsets[i]:offsets[i+1]] of one KV"""
+        offs = np.ascontiguousarray(offsets, dtype=np.uint64)
+        h = C.c_void_p()
+        self.check(self.lib.dampr_kv_merge_ranges(self.h, kv.h, offs.ctypes.data_as(C.c_void_p), len(offs) - 1,
+                                                  int(xform), int(op), C.byref(h)))
+        return KV(self, None, handle=h)
 
     def synth_kv(self, seed, n, n_keys):
         kv = KV(self, n)
@@ -456,10 +472,17 @@ class KV(object):
         self.ctx.check(self.ctx.lib.dampr_kv_sort(self.ctx.h, self.h, int(xform)))
         return self
 
-    def sort_reduce(self, op, xform=KEY_MIX):
+    def sort_reduce(self, op, xform=KEY_MIX, sorted_run=False):
+        """One record per key. The groups come out in key order under `xform`, except for the commutative
+        integer folds under KEY_MIX (SUM / COUNT / MIN / MAX), which the leaves fold through a shared-memory
+        hash table: there the order is by bucket of the mixed key only. sorted_run=True sorts those too, so
+        the result can feed the k-way merge as a sorted run."""
         h = C.c_void_p()
         self.ctx.check(self.ctx.lib.dampr_kv_sort_reduce(self.ctx.h, self.h, int(xform), int(op), C.byref(h)))
-        return KV(self.ctx, None, handle=h)
+        out = KV(self.ctx, None, handle=h)
+        if sorted_run and xform == KEY_MIX and op in (OP_SUM_I64, OP_COUNT, OP_MIN_I64, OP_MAX_I64):
+            out.sort(xform)
+        return out
 
     def reduce_by_key(self, op):
         h = C.c_void_p()
@@ -605,8 +628,9 @@ def host_unique_small(col, table=1 << 20, with_rows=False):
     return (uniq, inv, rows) if with_rows else (uniq, inv)
 
 
+def kv_merge_ranges(ctx, kv, offsets, xform, op=-1):
+    return ctx.kv_merge_ranges(kv, offsets, xform, op)
+
+
 def kv_merge(ctx, runs, xform, op=-1):
-    arr = (C.c_void_p * len(runs))(*[r.h for r in runs])
-    h = C.c_void_p()
-    ctx.check(ctx.lib.dampr_kv_merge(ctx.h, arr, len(runs), int(xform), int(op), C.byref(h)))
-    return KV(ctx, None, handle=h)
+    return ctx.kv_merge(runs, xform, op)

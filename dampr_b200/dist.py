@@ -74,8 +74,9 @@ def all_gather_objects(obj):
 
 
 def shuffle_kv(ctx, kv):
-    """Exchange a device kv so that every key lives on its owner rank. Returns the received kv
-    (concatenation of one run per source rank)."""
+    """Exchange a device kv so that every key lives on its owner rank. Returns (received kv, offsets): the
+    records of source rank s are recv[offsets[s]:offsets[s+1]]. The split by owner is stable, so a kv that is
+    key-sorted arrives as one SORTED RUN per source rank — the input of the k-way merge (csrc/merge.cu)."""
     import torch
     _rank, n = world()
     parts, counts = kv.partition_by_owner(n)
@@ -89,4 +90,5 @@ def shuffle_kv(ctx, kv):
     all_to_all_bytes(send_t, counts, recv_t, recv_counts)
     torch.cuda.synchronize()
     parts.free()
-    return out
+    offsets = np.concatenate(([0], np.cumsum(recv_counts))).astype(np.uint64)
+    return out, offsets

@@ -431,10 +431,14 @@ class TextScan(object):
             for c, w in d.items():
                 if merged.setdefault(c, w) != w:
                     raise RuntimeError("64-bit key-code collision between two long tokens across ranks")
+        # the local table as ONE SORTED RUN, one exchange, then the owner merges the sorted runs of all source
+        # ranks and folds equal keys while merging (MergeDataset.read + the combiner, dataset.py:571-579,
+        # base.py:393-402): one read + one write of the received records instead of a second sort
         local = tab.to_kv()
-        recv = dist.shuffle_kv(ctx, local)
+        local.sort(dev.KEY_MIX)
+        recv, offs = dist.shuffle_kv(ctx, local)
         local.free()
-        red = recv.sort_reduce(dev.OP_SUM_I64, dev.KEY_MIX)
+        red = ctx.kv_merge_ranges(recv, offs, dev.KEY_MIX, dev.OP_SUM_I64)
         recv.free()
         codes, counts = red.columns()
         W = 32 if any_hashed else 16             # exact codes hold at most 12 characters
@@ -900,13 +904,13 @@ def _device_group(runner, keys, vals, op, xform):
         lo, hi = n * r // w, n * (r + 1) // w
         kv = ctx.kv_from_columns(keys[lo:hi], vals[lo:hi])
         try:
-            part = kv.sort_reduce(op, dev.KEY_MIX)
+            part = kv.sort_reduce(op, dev.KEY_MIX, sorted_run=True)
         finally:
             kv.free()
-        recv = dist.shuffle_kv(ctx, part)
+        recv, offs = dist.shuffle_kv(ctx, part)   # `part` is sorted by the mixed key: sorted runs arrive
         part.free()
         op2 = dev.OP_SUM_I64 if op == dev.OP_COUNT else op
-        red = recv.sort_reduce(op2, dev.KEY_MIX)
+        red = ctx.kv_merge_ranges(recv, offs, dev.KEY_MIX, op2)   # runs in rank order: FIRST / LAST keep their meaning
         recv.free()
         try:
             rk, rv = red.columns()

@@ -42,8 +42,10 @@ typedef struct dampr_kv dampr_kv;           /* device array of 16-byte (u64 key,
 /* ---- library ------------------------------------------------------------------------- */
 int32_t dampr_abi_version(void);
 int32_t dampr_device_count(int32_t *out_n);
-/* process-wide tuning switches: "scatter_tma" (1 = TMA bulk stores in the partition scatter,
- * 0 = coalesced 16-byte stores); "text_ctas" (3 = single-window 3 CTAs/SM variant of the v2
+/* process-wide tuning switches: "kv_scatter" (2 = atomic-rank scatter, up to 12 digit bits per level,
+ * default; 1 = first-generation ballot scatter, 10 bits), "kv_cluster" (1 = thread-block-cluster leaf over
+ * distributed shared memory, default), "kv_tile" (4096 | 8192 records per scatter tile), "kv_max_bits";
+ * "scatter_tma" (first-generation scatter only: 1 = TMA bulk stores, 0 = coalesced 16-byte stores); "text_ctas" (3 = single-window 3 CTAs/SM variant of the v2
  * tokenise kernel, default; 2 = double-buffered 2 CTAs/SM); "text_kernel" (2 = warp-autonomous tokenise kernel, default;
  * 1 = first-generation kernel, also the fallback for lines longer than 2 KB) */
 int32_t dampr_set_option(const char *name, int64_t value);
@@ -221,7 +223,8 @@ int32_t dampr_kv_sort(dampr_ctx *ctx, dampr_kv *kv, int32_t key_xform);
 
 /* segmented reduce of a key-sorted kv: one output record per key. Replaces
  * Dataset.grouped_read + Reduce.reduce (dataset.py:429-433, base.py:204-207). out is created; `sorted`
- * is left untouched (the reduction runs on a device copy). */
+ * is left untouched. ONE pass over the input: tiles of 4096 records, head flags, fold; a key that straddles
+ * tiles is folded across them in order. */
 int32_t dampr_kv_reduce_by_key(dampr_ctx *ctx, dampr_kv *sorted, int32_t op, dampr_kv **out);
 /* group boundaries of a key-sorted kv: offsets[g] = first record of group g, offsets[G] = n.
  * two-phase: pass offsets=NULL to get *n_groups. */
@@ -229,9 +232,18 @@ int32_t dampr_kv_group_offsets(dampr_ctx *ctx, dampr_kv *sorted, uint64_t *offse
                                uint64_t *n_groups);
 
 /* k-way merge of key-sorted runs + optional segmented reduce: replaces MergeDataset.read
- * (dataset.py:571-579) + PartialReduceCombiner._combine (base.py:397-399). op < 0 = merge only. */
+ * (dataset.py:571-579) + PartialReduceCombiner._combine (base.py:397-399). op < 0 = merge only.
+ * One read of the runs, one write of the result: sampled splitters -> merge-path style cut vectors ->
+ * one CTA per <= 4096-record partition (csrc/merge.cu). Stable: equal keys come out in run order, then in
+ * position order (heapq.merge's order); any number of runs (more than 64 are merged in two levels). */
 int32_t dampr_kv_merge(dampr_ctx *ctx, dampr_kv **runs, int32_t n_runs, int32_t key_xform,
                        int32_t op, dampr_kv **out);
+
+/* the same merge over runs given as consecutive slices of ONE kv: run i = records [offsets[i], offsets[i+1])
+ * (offsets has n_runs + 1 entries). The shape sorted runs have after the all-to-all (one run per source
+ * rank) and after a spill upload (one run per batch). */
+int32_t dampr_kv_merge_ranges(dampr_ctx *ctx, dampr_kv *kv, const uint64_t *offsets, int32_t n_runs,
+                              int32_t key_xform, int32_t op, dampr_kv **out);
 
 /* fused sort + reduce for associative ops (a_group_by(...).sum()/count()/...). CONSUMES `kv`: the
  * partition levels and the leaves use both of its buffers as scratch, so its contents are undefined

@@ -62,7 +62,7 @@ class FakeKV(object):
         out.n = self.n
         return out, np.bincount(own.astype(np.int64), minlength=nb).astype(np.uint64)
 
-    def sort_reduce(self, op, xform):
+    def sort_reduce(self, op, xform, sorted_run=False):
         from dampr_b200 import device as dev
         self.sort(xform)
         k, v = self.columns()
@@ -94,6 +94,26 @@ class FakeKV(object):
         out.rec[:len(heads), 1] = np.asarray(r, dtype=np.int64).view(np.uint64)
         out.n = len(heads)
         self.n = 0
+        return out
+
+    def reduce_by_key(self, op):
+        """dampr_kv_reduce_by_key: fold adjacent equal keys of a key-sorted kv; the input is left alone"""
+        from dampr_b200 import device as dev
+        k, v = self.columns()
+        heads = np.flatnonzero(np.concatenate(([True], k[1:] != k[:-1]))) if len(k) else np.zeros(0, dtype=np.int64)
+        assert len(set(k[heads].tolist())) == len(heads), "reduce_by_key: equal keys are not adjacent"
+        tmp = FakeKV(self.ctx, max(1, self.n))
+        tmp.rec[:self.n] = self.rec[:self.n]
+        tmp.n = self.n
+        # group order must stay the input's: reduce in RAW order, then restore the order of first appearance
+        red = tmp.sort_reduce(op, dev.KEY_RAW)
+        rk, rv = red.columns()
+        pos = {int(key): i for i, key in enumerate(k[heads].tolist())}
+        order = np.argsort(np.array([pos[int(x)] for x in rk.tolist()], dtype=np.int64), kind="stable")
+        out = FakeKV(self.ctx, max(1, len(rk)))
+        out.rec[:len(rk), 0] = rk[order]
+        out.rec[:len(rk), 1] = rv[order]
+        out.n = len(rk)
         return out
 
     def free(self):
@@ -138,6 +158,34 @@ class FakeKV(object):
 class FakeCtx(object):
     def kv(self, capacity):
         return FakeKV(self, capacity)
+
+    def kv_merge(self, runs, xform, op=-1):
+        """dampr_kv_merge: the runs MUST be key-sorted under xform (checked here: the device kernel relies on
+        it); the result is the stable sort of their concatenation in run order, optionally folded."""
+        from dampr_b200 import device as dev
+        recs = []
+        for r in runs:
+            o = FakeKV._order(r.rec[:r.n, 0], xform)
+            assert np.all(o[1:] >= o[:-1]), "kv_merge: a run is not sorted under the key transform"
+            recs.append(r.rec[:r.n])
+        cat = FakeKV(self, max(1, sum(len(x) for x in recs)))
+        if recs:
+            allr = np.concatenate(recs)
+            cat.rec[:len(allr)] = allr
+            cat.n = len(allr)
+        if op < 0:
+            return cat.sort(xform)
+        return cat.sort_reduce(op, xform)
+
+    def kv_merge_ranges(self, kv, offsets, xform, op=-1):
+        views = []
+        offs = [int(x) for x in offsets]
+        for a, b in zip(offs[:-1], offs[1:]):
+            v = FakeKV(self, max(1, b - a))
+            v.rec[:b - a] = kv.rec[a:b]
+            v.n = b - a
+            views.append(v)
+        return self.kv_merge(views, xform, op)
 
     def sync(self):
         pass
