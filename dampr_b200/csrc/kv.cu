@@ -1090,6 +1090,8 @@ static int copy_range(dampr_ctx *ctx, const ulonglong2 *from, ulonglong2 *to, u6
     return DAMPR_OK;
 }
 
+static int key_range(dampr_ctx *ctx, const ulonglong2 *rec, u64 n, int xf, u64 *base, int *top, bool scan_mix);
+
 // Sort records [start, start+n) that currently live in `cur` (scratch = `alt`, same indexing).
 // Digits are taken from bit `top` downwards of (xf(key) - base). reduce_op < 0: on return the sorted
 // range is in `target` (either buffer; the last pass writes there, nothing is copied). reduce_op >= 0:
@@ -1098,7 +1100,19 @@ static int sort_range(dampr_ctx *ctx, ulonglong2 *cur, ulonglong2 *alt, u64 star
                       int top, int reduce_op, ulonglong2 *gout, u64 *gcount, int depth, ulonglong2 *target,
                       bool allow_cluster) {
     if (n == 0) return DAMPR_OK;
-    if (top <= 0 || depth > 12) {
+    if (depth > 0 && top > 0) {
+        // a segment that is still too large after a level (skew / heavy hitters): its keys usually occupy a
+        // small part of the remaining key range. Re-basing on the segment's own minimum and maximum makes the
+        // next digits split it (the top bit of the new span is set), so every recursion makes progress and a
+        // segment whose keys are all equal is recognised at once.
+        u64 b2;
+        int t2;
+        int rc = key_range(ctx, cur + start, n, xf, &b2, &t2, true);
+        if (rc) return rc;
+        base = b2;
+        top = t2;
+    }
+    if (top <= 0 || depth > 70) {
         // all keys equal: already "sorted" (stable); a single group when reducing
         if (reduce_op >= 0) {
             ScopedTimer tm(ctx, DAMPR_K_SEG_REDUCE);
@@ -1112,7 +1126,11 @@ static int sort_range(dampr_ctx *ctx, ulonglong2 *cur, ulonglong2 *alt, u64 star
     const bool use_cluster = allow_cluster && g_kv_cluster && n > (u64)L_CAP;
     const int max_bits = (g_kv_scatter == 2) ? std::min(g_kv_max_bits, P2_MAX_BITS) : P1_MAX_BITS;
     // ---- plan the levels ---------------------------------------------------------------------
-    int total_bits = std::min(top, bits_for(n, use_cluster ? C_TARGET : S_TARGET));
+    // at least 8 bits per call when a level is needed at all: surplus buckets cost nothing (small segments
+    // are packed into shared leaf chunks) and skewed inputs need the resolution
+    int total_bits = bits_for(n, use_cluster ? C_TARGET : S_TARGET);
+    if (total_bits > 0) total_bits = std::max(total_bits, 8);
+    total_bits = std::min(top, total_bits);
     int nlev = (total_bits + max_bits - 1) / max_bits;
     std::vector<int> lev_bits;
     {
@@ -1341,8 +1359,8 @@ static int ensure_alt(dampr_ctx *ctx, dampr_kv *kv) {
 }
 
 // key range -> (base, top)
-static int key_range(dampr_ctx *ctx, const ulonglong2 *rec, u64 n, int xf, u64 *base, int *top) {
-    if (xf == DAMPR_KEY_MIX) {
+static int key_range(dampr_ctx *ctx, const ulonglong2 *rec, u64 n, int xf, u64 *base, int *top, bool scan_mix) {
+    if (xf == DAMPR_KEY_MIX && !scan_mix) {
         *base = 0;
         *top = 64;
         return DAMPR_OK;
@@ -1374,7 +1392,7 @@ int kv_sort_device_range(dampr_ctx *ctx, ulonglong2 *cur, ulonglong2 *alt, u64 n
     if (n < 2) return DAMPR_OK;
     u64 base;
     int top;
-    int rc = key_range(ctx, cur, n, xf, &base, &top);
+    int rc = key_range(ctx, cur, n, xf, &base, &top, false);
     if (rc) return rc;
     return sort_range(ctx, cur, alt, 0, n, xf, base, top, -1, nullptr, nullptr, 0, cur, true);
 }
@@ -1430,7 +1448,7 @@ int32_t dampr_kv_sort(dampr_ctx *ctx, dampr_kv *kv, int32_t key_xf) {
     if (rc) return rc;
     u64 base;
     int top;
-    rc = key_range(ctx, kv->rec, kv->n, key_xf, &base, &top);
+    rc = key_range(ctx, kv->rec, kv->n, key_xf, &base, &top, false);
     if (rc) return rc;
     return sort_range(ctx, kv->rec, kv->alt, 0, kv->n, key_xf, base, top, -1, nullptr, nullptr, 0, kv->rec, true);
 }
@@ -1449,7 +1467,7 @@ int32_t dampr_kv_sort_reduce(dampr_ctx *ctx, dampr_kv *kv, int32_t key_xf, int32
     if (rc) return rc;
     u64 base;
     int top;
-    rc = key_range(ctx, kv->rec, kv->n, key_xf, &base, &top);
+    rc = key_range(ctx, kv->rec, kv->n, key_xf, &base, &top, false);
     if (rc) return rc;
     u64 g = 0;
     rc = sort_range(ctx, kv->rec, kv->alt, 0, kv->n, key_xf, base, top, op, (*out)->rec, &g, 0, nullptr, true);
