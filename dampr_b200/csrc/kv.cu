@@ -34,7 +34,7 @@ namespace cg = cooperative_groups;
 
 int g_kv_scatter = 2;   // 2 = atomic-rank scatter (up to 12 bits), 1 = first-generation ballot scatter (10 bits)
 int g_kv_cluster = 1;   // 1 = cluster/DSMEM leaf for segments above one CTA's capacity
-int g_kv_tile = 4096;   // scatter tile: 4096 (512 threads, 2 CTAs/SM) or 8192 (1024 threads, 1 CTA/SM)
+int g_kv_hints = 1;     // L2 eviction-priority hints in the table scatter (evict-first loads, evict-last stores)
 int g_kv_max_bits = 12; // digit bits per partition level (<= 12)
 
 namespace {
@@ -377,52 +377,97 @@ part_scatter_kernel(const ulonglong2 *__restrict__ in, ulonglong2 *__restrict__ 
     if (USE_TMA) tma_store_wait_all();
 }
 
-// ---- level scatter (v2): one shared-memory atomic per record + order fix-up -----------------------
-template <int NT, int RPT>
-struct Scatter2Smem {
-    static constexpr int T = NT * RPT;
-    u64 run_off[P2_MAX_NB];
-    alignas(16) u32 cnt[P2_MAX_NB];
-    alignas(16) u32 base[P2_MAX_NB + 4];
-    u32 bitmap[NT / 32][T / 32];
-    u16 sidx[T];
-    u16 hot[T / 32];
-    u32 nhot;
+// ---- level scatter (v2): one shared-memory atomic per record + an 8-slot index table per bucket ------
+// Tile = 4096 records (512 threads x 8), up to 4096 buckets. Every record takes its (arbitrary) slot
+// inside (tile, bucket) from ONE packed 16-bit shared-memory atomic and drops its tile index into the
+// bucket's row of an 8-slot table; after one barrier it reads the row back with a single 16-byte load and
+// ranks itself among its tile mates with SWAR halfword compares (stable: by tile index = input order),
+// then stores its 16 bytes straight into the bucket's run. Two barriers per tile; the counters are
+// double buffered so the bucket cursors are advanced while the next tile is already loading.
+// A tile in which some bucket receives more than 8 records (fewer buckets than records per tile, skew,
+// duplicates) takes the general path: exclusive scan of the tile's bucket counts, a compact index list
+// per bucket, long runs sorted by a warp through a presence bitmap (O(T) per tile whatever the skew).
+// Streaming loads carry an L2 evict-first policy and the scattered stores evict-last, so half-written
+// sectors of the 296 x 4096 write fronts stay in L2 until their neighbours arrive (the first build,
+// without hints, read 2.1x and wrote 1.5x the algorithmic bytes from DRAM: profiles/r02_kv_a_*).
+constexpr int S3_NT = 512;
+constexpr int S3_RPT = 8;
+constexpr int S3_T = S3_NT * S3_RPT;  // 4096
+constexpr int S3_W = 8;               // table slots per bucket
+
+struct Scatter3Smem {
+    u32 run_off[P2_MAX_NB];                     // cursor of every bucket, relative to the level's first record
+    alignas(16) u32 cnt[2][P2_MAX_NB / 2];      // packed 16-bit counters, double buffered
+    alignas(16) u16 tab[P2_MAX_NB][S3_W];       // tile indices by (bucket, slot); the general path overlays it
+    u32 ovf[2];
     u32 wsum[32];
 };
+// overlay of the general path inside `tab` (64 KB)
+struct Scatter3Slow {
+    alignas(16) u32 base[P2_MAX_NB + 4];
+    u32 bitmap[S3_NT / 32][S3_T / 32];
+    u16 sidx[S3_T];
+    u16 hot[S3_T / 32];
+    u32 nhot;
+};
+static_assert(sizeof(Scatter3Slow) <= sizeof(u16) * P2_MAX_NB * S3_W, "slow-path overlay must fit the table");
 
-template <int NT, int RPT>
-__global__ void __launch_bounds__(NT, (NT <= 512 ? 2 : 1))
+__device__ __forceinline__ u64 l2_policy_evict_first() {
+    u64 p;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ u64 l2_policy_evict_last() {
+    u64 p;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ ulonglong2 ld_rec_hint(const ulonglong2 *p, u64 pol) {
+    ulonglong2 r;
+    asm volatile("ld.global.L2::cache_hint.v2.u64 {%0, %1}, [%2], %3;" : "=l"(r.x), "=l"(r.y) : "l"(p), "l"(pol));
+    return r;
+}
+__device__ __forceinline__ void st_rec_hint(ulonglong2 *p, const ulonglong2 &r, u64 pol) {
+    asm volatile("st.global.L2::cache_hint.v2.u64 [%0], {%1, %2}, %3;" ::"l"(p), "l"(r.x), "l"(r.y), "l"(pol) : "memory");
+}
+
+template <bool HINTS>
+__global__ void __launch_bounds__(S3_NT, 2)
 part_scatter2_kernel(const ulonglong2 *__restrict__ in, ulonglong2 *__restrict__ out,
                      const Piece *__restrict__ pieces, const u32 *__restrict__ cta_piece_begin, u64 ustart,
-                     u64 un, u64 uR, DigitSpec ds, u32 nb, const u64 *__restrict__ piece_off) {
-    using Smem = Scatter2Smem<NT, RPT>;
-    constexpr int T = NT * RPT;
-    constexpr int NW = NT / 32;
-    constexpr int WPL = T / 32 / 32;  // bitmap words per lane
+                     u64 un, u64 uR, u64 out_base, DigitSpec ds, u32 nb, const u64 *__restrict__ piece_off) {
+    constexpr int NT = S3_NT, RPT = S3_RPT, T = S3_T, NW = NT / 32, WPL = T / 32 / 32;
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    Smem &s = *reinterpret_cast<Smem *>(smem_raw);
+    Scatter3Smem &s = *reinterpret_cast<Scatter3Smem *>(smem_raw);
+    Scatter3Slow &sl_ = *reinterpret_cast<Scatter3Slow *>(&s.tab[0][0]);
     const u32 tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const u32 pb = pieces ? cta_piece_begin[blockIdx.x] : blockIdx.x;
     const u32 pe = pieces ? cta_piece_begin[blockIdx.x + 1] : blockIdx.x + 1;
-    const u32 bpt = max(4u, ((nb + NT - 1) / NT + 3u) & ~3u);  // buckets per thread in the scans: 4 or 8
+    u64 pol_in = 0, pol_out = 0;
+    if (HINTS) {
+        pol_in = l2_policy_evict_first();
+        pol_out = l2_policy_evict_last();
+    }
+    ulonglong2 *const obase = out + out_base;
+    u32 tile_no = 0;
 
     for (u32 p = pb; p < pe; ++p) {
         const Piece pc = pieces ? pieces[p] : uniform_piece(p, ustart, un, uR);
-        for (u32 b = tid; b < (u32)P2_MAX_NB; b += NT) {
-            s.run_off[b] = (b < nb) ? piece_off[(u64)p * nb + b] : 0ULL;
-            s.cnt[b] = 0;
-        }
-        if (tid == 0) s.nhot = 0;
+        __syncthreads();  // the previous piece's last tile is done with the cursors
+        for (u32 b = tid; b < (u32)P2_MAX_NB; b += NT) s.run_off[b] = (b < nb) ? (u32)(piece_off[(u64)p * nb + b] - out_base) : 0u;
+        for (u32 b = tid; b < (u32)P2_MAX_NB; b += NT) (&s.cnt[0][0])[b] = 0;  // both counter buffers
+        if (tid < 2) s.ovf[tid] = 0;
         __syncthreads();
-        for (u64 t0 = pc.start; t0 < pc.end; t0 += T) {
+        for (u64 t0 = pc.start; t0 < pc.end; t0 += T, ++tile_no) {
             const u32 tn = (u32)min((u64)T, pc.end - t0);
+            const u32 buf = tile_no & 1u;
+            u32 *cnt32 = s.cnt[buf];
             ulonglong2 rec[RPT];
-            u32 dg[RPT], sl[RPT];
+            u32 dsl[RPT];  // digit | slot << 16
 #pragma unroll
             for (int r = 0; r < RPT; ++r) {
                 const u32 li = r * NT + tid;
-                if (li < tn) rec[r] = in[t0 + li];
+                if (li < tn) rec[r] = HINTS ? ld_rec_hint(in + t0 + li, pol_in) : in[t0 + li];
             }
             if (t0 + T < pc.end) {  // the next tile: pull it into L2 while this one is ranked
                 const char *nxt = reinterpret_cast<const char *>(in + t0 + T);
@@ -430,132 +475,176 @@ part_scatter2_kernel(const ulonglong2 *__restrict__ in, ulonglong2 *__restrict__
                 for (u32 off = tid * 128u; off < nbytes; off += NT * 128u)
                     asm volatile("prefetch.global.L2 [%0];" ::"l"(nxt + off));
             }
+            bool over = false;
 #pragma unroll
             for (int r = 0; r < RPT; ++r) {
                 const u32 li = r * NT + tid;
+                dsl[r] = 0;
                 if (li < tn) {
-                    dg[r] = digit_of(rec[r].x, ds);
-                    sl[r] = atomicAdd(&s.cnt[dg[r]], 1u);
+                    const u32 d = digit_of(rec[r].x, ds);
+                    const u32 old = atomicAdd(&cnt32[d >> 1], (d & 1u) ? 0x10000u : 1u);
+                    const u32 slot = (d & 1u) ? (old >> 16) : (old & 0xFFFFu);
+                    dsl[r] = d | (slot << 16);
+                    if (slot < (u32)S3_W) s.tab[d][slot] = (u16)li;
+                    else over = true;
                 }
             }
+            if (over) s.ovf[buf] = 1;
             __syncthreads();
-            // ---- exclusive scan of the tile's bucket counts -> base[]; long runs go on the hot list.
-            // 4 or 8 consecutive buckets per thread, read and written as 16-byte vectors (entries past nb
-            // stay zero).
-            {
-                const u32 b0 = tid * bpt;
-                u32 c[8];
-                {
-                    const uint4 a = *reinterpret_cast<const uint4 *>(&s.cnt[b0]);
-                    c[0] = a.x, c[1] = a.y, c[2] = a.z, c[3] = a.w;
-                    uint4 b = make_uint4(0, 0, 0, 0);
-                    if (bpt == 8) b = *reinterpret_cast<const uint4 *>(&s.cnt[b0 + 4]);
-                    c[4] = b.x, c[5] = b.y, c[6] = b.z, c[7] = b.w;
-                }
-                u32 sum = 0;
+            if (!s.ovf[buf]) {
+                // ---- fast path: rank among the <= 8 tile mates of the bucket, SWAR on halfwords -------------
+                const u16 *cnt16 = reinterpret_cast<const u16 *>(cnt32);
 #pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    sum += c[j];
-                    if (c[j] > HOT_L) s.hot[atomicAdd(&s.nhot, 1u)] = (u16)(b0 + j);
+                for (int r = 0; r < RPT; ++r) {
+                    const u32 li = r * NT + tid;
+                    if (li < tn) {
+                        const u32 d = dsl[r] & 0xFFFFu;
+                        const u32 L = cnt16[d];
+                        u32 rk = 0;
+                        if (L > 1) {
+                            const uint4 row = *reinterpret_cast<const uint4 *>(&s.tab[d][0]);
+                            const u64 lo = (u64)row.x | ((u64)row.y << 32), hi = (u64)row.z | ((u64)row.w << 32);
+                            const u64 H = 0x8000800080008000ULL, lim = (u64)li * 0x0001000100010001ULL;
+                            const u64 lt0 = ~((lo | H) - lim) & H, lt1 = ~((hi | H) - lim) & H;  // bit 15: entry < li
+                            const u64 m0 = (L >= 4) ? ~0ULL : ((1ULL << (16 * L)) - 1ULL);
+                            const u64 m1 = (L >= 8) ? ~0ULL : ((L > 4) ? ((1ULL << (16 * (L - 4))) - 1ULL) : 0ULL);
+                            rk = (u32)__popcll(lt0 & m0) + (u32)__popcll(lt1 & m1);
+                        }
+                        ulonglong2 *dst = obase + s.run_off[d] + rk;
+                        if (HINTS) st_rec_hint(dst, rec[r], pol_out);
+                        else *dst = rec[r];
+                    }
                 }
-                u32 v = sum;
-#pragma unroll
-                for (int d = 1; d < 32; d <<= 1) {
-                    u32 o = __shfl_up_sync(0xFFFFFFFFu, v, d);
-                    if ((int)lane >= d) v += o;
-                }
-                if (lane == 31) s.wsum[warp] = v;
                 __syncthreads();
-                u32 woff = 0;
-                for (u32 w = 0; w < warp; ++w) woff += s.wsum[w];
-                u32 run = woff + v - sum;
-                u32 e[8];
-#pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    e[j] = run;
-                    run += c[j];
-                }
-                *reinterpret_cast<uint4 *>(&s.base[b0]) = make_uint4(e[0], e[1], e[2], e[3]);
-                if (bpt == 8) *reinterpret_cast<uint4 *>(&s.base[b0 + 4]) = make_uint4(e[4], e[5], e[6], e[7]);
-                if (tid == NT - 1) s.base[NT * bpt] = tn;
-            }
-            __syncthreads();
-#pragma unroll
-            for (int r = 0; r < RPT; ++r) {
-                const u32 li = r * NT + tid;
-                if (li < tn) s.sidx[s.base[dg[r]] + sl[r]] = (u16)li;
-            }
-            __syncthreads();
-            const u32 nh = s.nhot;
-            if (nh) {
-                // skew: a warp sorts the tile indices of a long run through a presence bitmap
-                u32 *bm = s.bitmap[warp];
-                for (u32 hi = warp; hi < nh; hi += NW) {
-                    const u32 h = s.hot[hi];
-                    const u32 st = s.base[h], L = s.base[h + 1] - st;
-                    for (u32 w = lane; w < T / 32; w += 32) bm[w] = 0;
-                    __syncwarp();
-                    for (u32 j = lane; j < L; j += 32) {
-                        const u32 x = s.sidx[st + j];
-                        atomicOr(&bm[x >> 5], 1u << (x & 31));
+            } else {
+                // ---- general path (the table is overlaid): scan, compact index lists, hot runs -----------------
+                const u16 *cnt16 = reinterpret_cast<const u16 *>(cnt32);
+                {
+                    const u32 b0 = tid * 8u;
+                    u32 c[8];
+                    {
+                        const uint4 a = *reinterpret_cast<const uint4 *>(&cnt32[b0 >> 1]);
+                        c[0] = a.x & 0xFFFFu, c[1] = a.x >> 16, c[2] = a.y & 0xFFFFu, c[3] = a.y >> 16;
+                        c[4] = a.z & 0xFFFFu, c[5] = a.z >> 16, c[6] = a.w & 0xFFFFu, c[7] = a.w >> 16;
                     }
-                    __syncwarp();
-                    u32 words[WPL];
-                    u32 cl = 0;
+                    __syncthreads();  // every thread has read its counters: the table may be overwritten
+                    if (tid == 0) sl_.nhot = 0;
+                    __syncthreads();
+                    u32 sum = 0;
 #pragma unroll
-                    for (int k = 0; k < WPL; ++k) {
-                        words[k] = bm[lane * WPL + k];
-                        cl += __popc(words[k]);
+                    for (int j = 0; j < 8; ++j) {
+                        sum += c[j];
+                        if (c[j] > HOT_L) sl_.hot[atomicAdd(&sl_.nhot, 1u)] = (u16)(b0 + j);
                     }
-                    u32 v = cl;
+                    u32 v = sum;
 #pragma unroll
                     for (int d = 1; d < 32; d <<= 1) {
                         u32 o = __shfl_up_sync(0xFFFFFFFFu, v, d);
                         if ((int)lane >= d) v += o;
                     }
-                    u32 pos = st + v - cl;
+                    if (lane == 31) s.wsum[warp] = v;
+                    __syncthreads();
+                    u32 woff = 0;
+                    for (u32 w = 0; w < warp; ++w) woff += s.wsum[w];
+                    u32 run = woff + v - sum;
+                    u32 e[8];
 #pragma unroll
-                    for (int k = 0; k < WPL; ++k) {
-                        u32 wd = words[k];
-                        while (wd) {
-                            const u32 bit = __ffs(wd) - 1;
-                            wd &= wd - 1;
-                            s.sidx[pos++] = (u16)((lane * WPL + k) * 32 + bit);
-                        }
+                    for (int j = 0; j < 8; ++j) {
+                        e[j] = run;
+                        run += c[j];
                     }
-                    __syncwarp();
+                    *reinterpret_cast<uint4 *>(&sl_.base[b0]) = make_uint4(e[0], e[1], e[2], e[3]);
+                    *reinterpret_cast<uint4 *>(&sl_.base[b0 + 4]) = make_uint4(e[4], e[5], e[6], e[7]);
+                    if (tid == NT - 1) sl_.base[P2_MAX_NB] = tn;
                 }
                 __syncthreads();
-            }
-            // ---- rank inside (tile, bucket) by tile index, then straight to the bucket's run ----------
 #pragma unroll
-            for (int r = 0; r < RPT; ++r) {
-                const u32 li = r * NT + tid;
-                if (li < tn) {
-                    const u32 d = dg[r];
-                    const u32 st = s.base[d], L = s.base[d + 1] - st;
-                    u32 rk = 0;
-                    if (L > HOT_L) {  // sorted by a warp above: lower bound
-                        u32 lo = 0, hi = L;
-                        while (lo < hi) {
-                            const u32 mid = (lo + hi) >> 1;
-                            if (s.sidx[st + mid] < li) lo = mid + 1;
-                            else hi = mid;
-                        }
-                        rk = lo;
-                    } else if (L > 1) {
-                        for (u32 j = 0; j < L; ++j) rk += (s.sidx[st + j] < li) ? 1u : 0u;
-                    }
-                    out[s.run_off[d] + rk] = rec[r];
+                for (int r = 0; r < RPT; ++r) {
+                    const u32 li = r * NT + tid;
+                    if (li < tn) sl_.sidx[sl_.base[dsl[r] & 0xFFFFu] + (dsl[r] >> 16)] = (u16)li;
                 }
+                __syncthreads();
+                const u32 nh = sl_.nhot;
+                if (nh) {
+                    u32 *bm = sl_.bitmap[warp];
+                    for (u32 hi = warp; hi < nh; hi += NW) {
+                        const u32 h = sl_.hot[hi];
+                        const u32 st = sl_.base[h], L = sl_.base[h + 1] - st;
+                        for (u32 w = lane; w < T / 32; w += 32) bm[w] = 0;
+                        __syncwarp();
+                        for (u32 j = lane; j < L; j += 32) {
+                            const u32 x = sl_.sidx[st + j];
+                            atomicOr(&bm[x >> 5], 1u << (x & 31));
+                        }
+                        __syncwarp();
+                        u32 words[WPL];
+                        u32 cl = 0;
+#pragma unroll
+                        for (int k = 0; k < WPL; ++k) {
+                            words[k] = bm[lane * WPL + k];
+                            cl += __popc(words[k]);
+                        }
+                        u32 v = cl;
+#pragma unroll
+                        for (int d = 1; d < 32; d <<= 1) {
+                            u32 o = __shfl_up_sync(0xFFFFFFFFu, v, d);
+                            if ((int)lane >= d) v += o;
+                        }
+                        u32 pos = st + v - cl;
+#pragma unroll
+                        for (int k = 0; k < WPL; ++k) {
+                            u32 wd = words[k];
+                            while (wd) {
+                                const u32 bit = __ffs(wd) - 1;
+                                wd &= wd - 1;
+                                sl_.sidx[pos++] = (u16)((lane * WPL + k) * 32 + bit);
+                            }
+                        }
+                        __syncwarp();
+                    }
+                    __syncthreads();
+                }
+#pragma unroll
+                for (int r = 0; r < RPT; ++r) {
+                    const u32 li = r * NT + tid;
+                    if (li < tn) {
+                        const u32 d = dsl[r] & 0xFFFFu;
+                        const u32 st = sl_.base[d], L = sl_.base[d + 1] - st;
+                        u32 rk = 0;
+                        if (L > HOT_L) {  // sorted by a warp above: lower bound
+                            u32 lo = 0, hi = L;
+                            while (lo < hi) {
+                                const u32 mid = (lo + hi) >> 1;
+                                if (sl_.sidx[st + mid] < li) lo = mid + 1;
+                                else hi = mid;
+                            }
+                            rk = lo;
+                        } else if (L > 1) {
+                            for (u32 j = 0; j < L; ++j) rk += (sl_.sidx[st + j] < li) ? 1u : 0u;
+                        }
+                        ulonglong2 *dst = obase + s.run_off[d] + rk;
+                        if (HINTS) st_rec_hint(dst, rec[r], pol_out);
+                        else *dst = rec[r];
+                    }
+                }
+                (void)cnt16;
+                __syncthreads();
             }
-            __syncthreads();
-            for (u32 b = tid; b < nb; b += NT) {
-                s.run_off[b] += s.cnt[b];
-                s.cnt[b] = 0;
+            // ---- advance the cursors, clear this tile's counters (8 consecutive buckets per thread). No barrier:
+            // the next tile counts into the other buffer and its own barrier orders everything else.
+            {
+                const u32 b0 = tid * 8u;
+                uint4 *cp = reinterpret_cast<uint4 *>(&cnt32[b0 >> 1]);
+                const uint4 a = *cp;
+                uint4 *rp = reinterpret_cast<uint4 *>(&s.run_off[b0]);
+                uint4 r0 = rp[0], r1 = rp[1];
+                r0.x += a.x & 0xFFFFu, r0.y += a.x >> 16, r0.z += a.y & 0xFFFFu, r0.w += a.y >> 16;
+                r1.x += a.z & 0xFFFFu, r1.y += a.z >> 16, r1.z += a.w & 0xFFFFu, r1.w += a.w >> 16;
+                rp[0] = r0;
+                rp[1] = r1;
+                *cp = make_uint4(0, 0, 0, 0);
+                if (tid == 0) s.ovf[buf] = 0;
             }
-            if (tid == 0) s.nhot = 0;
-            __syncthreads();
         }
     }
 }
@@ -651,12 +740,6 @@ cluster_leaf_kernel(const ulonglong2 *__restrict__ data, ulonglong2 *__restrict_
                 asm volatile("prefetch.global.L2 [%0];" ::"l"(nb + off));
         }
         if (tid < CF) s.fh[tid] = 0;
-        if (tid < CL) {
-            s.firstg[tid] = 0;
-            s.endg[tid] = 0;
-            s.firstbin[tid] = 0;
-            s.lastbin[tid] = 0;
-        }
         if (tid == 0) s.ovf = 0;
         __syncthreads();
         // ---- my slice: fine-bin histogram, the atomic's return value is the record's slot --------------
@@ -692,27 +775,17 @@ cluster_leaf_kernel(const ulonglong2 *__restrict__ data, ulonglong2 *__restrict_
         }
         u32 total;
         const u32 g0 = block_excl_scan(s, tot, &total);
-        const u32 Q = (n + CL - 1) / CL;
-        u32 own = 0;
-        if (tid < CF) {
-            s.gpos[tid] = g0;
-            own = min((u32)CL - 1, g0 / Q);
-            s.down[tid] = (u8)own;
-        }
+        // CTA o owns the fine bins [32 o, 32 o + 32): with hashed (or locally uniform) keys every CTA receives
+        // n/8 +- a few dozen records, and exactly 32 bins per CTA give the local sort 8192 bins
+        if (tid < CF) s.gpos[tid] = g0;
+        if (tid == CF - 1) s.gpos[CF] = g0 + tot;
         __syncthreads();
-        if (tid < CF) {
-            if (tid == 0 || s.down[tid - 1] != own) {
-                s.firstbin[own] = tid;
-                s.firstg[own] = g0;
-            }
-            if (tid == CF - 1 || s.down[tid + 1] != own) {
-                s.lastbin[own] = tid;
-                s.endg[own] = g0 + tot;
-            }
+        if (tid < CF) s.dpos[tid] = (u16)(g0 - s.gpos[tid & ~(CF / CL - 1)] + before);
+        if (tid < CL) {
+            s.firstg[tid] = s.gpos[tid * (CF / CL)];
+            s.endg[tid] = s.gpos[(tid + 1) * (CF / CL)];
+            if (s.gpos[(tid + 1) * (CF / CL)] - s.gpos[tid * (CF / CL)] > (u32)L_CAP) s.ovf = 1;
         }
-        __syncthreads();
-        if (tid < CF) s.dpos[tid] = (u16)(g0 - s.firstg[own] + before);
-        if (tid < CL && s.endg[tid] - s.firstg[tid] > (u32)L_CAP) s.ovf = 1;
         __syncthreads();
         const bool ovf = s.ovf != 0;
         // ---- exchange: every record goes straight into the owner's shared memory ------------------------
@@ -722,7 +795,7 @@ cluster_leaf_kernel(const ulonglong2 *__restrict__ data, ulonglong2 *__restrict_
                 const u32 i = tid + k * L_THREADS;
                 if (lo + i < hi) {
                     const u32 f = pk[k] & 255u;
-                    const u32 o = s.down[f];
+                    const u32 o = f / (u32)(CF / CL);
                     const u32 p = (u32)s.dpos[f] + (pk[k] >> 8);
                     u64 *rsk = cluster.map_shared_rank(s.sk, o);
                     u64 *rval = cluster.map_shared_rank(s.val, o);
@@ -754,10 +827,10 @@ cluster_leaf_kernel(const ulonglong2 *__restrict__ data, ulonglong2 *__restrict_
             __syncthreads();
             continue;
         }
-        const u32 nbo = s.lastbin[rank] - s.firstbin[rank] + 1;
+        const u32 nbo = CF / CL;
         int k = 0;
         while (((nbo << (k + 1)) <= (u32)L_BINS) && (k + 1) <= ch.bin_shift) ++k;
-        leaf_sort_core<true>(s, m, ch.bin_shift - k, (ch.bin_base + s.firstbin[rank]) << k);
+        leaf_sort_core<true>(s, m, ch.bin_shift - k, (ch.bin_base + (u64)rank * nbo) << k);
         if (reduce_op < 0) {
             for (u32 i = tid; i < m; i += L_THREADS) {
                 const u32 o = s.fin[i];
@@ -913,26 +986,26 @@ static int bits_for(u64 n, u64 leaf_avg) {
 
 static int g_use_tma = 1;
 
-static int scatter_ctas(dampr_ctx *ctx) { return (g_kv_tile == 8192) ? ctx->num_sms : ctx->num_sms * 2; }
-static u64 scatter_tile() { return (g_kv_scatter == 2) ? (u64)g_kv_tile : (u64)P_TILE; }
-
-template <int NT, int RPT>
-static cudaError_t launch_scatter2(dampr_ctx *ctx, int G, const ulonglong2 *src, ulonglong2 *dst, const Piece *pieces,
-                                   const u32 *cta_pb, u64 ustart, u64 un, u64 uR, DigitSpec ds, u32 nb,
-                                   const u64 *poff) {
-    const size_t smem = sizeof(Scatter2Smem<NT, RPT>);
-    cudaError_t e = cudaFuncSetAttribute(part_scatter2_kernel<NT, RPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    part_scatter2_kernel<NT, RPT><<<G, NT, smem, ctx->stream>>>(src, dst, pieces, cta_pb, ustart, un, uR, ds, nb, poff);
-    return cudaGetLastError();
-}
+static int scatter_ctas(dampr_ctx *ctx) { return ctx->num_sms * 2; }
+static u64 scatter_tile() { return (u64)P_TILE; }  // both scatter generations use 4096-record tiles
+static_assert(P_TILE == S3_T, "tile sizes");
 
 static int run_scatter(dampr_ctx *ctx, int G, const ulonglong2 *src, ulonglong2 *dst, const Piece *pieces,
-                       const u32 *cta_pb, u64 ustart, u64 un, u64 uR, DigitSpec ds, u32 nb, const u64 *poff) {
+                       const u32 *cta_pb, u64 ustart, u64 un, u64 uR, u64 out_base, DigitSpec ds, u32 nb,
+                       const u64 *poff, bool v2) {
     ScopedTimer tm(ctx, DAMPR_K_PART_SCATTER);
-    if (g_kv_scatter == 2) {
-        if (g_kv_tile == 8192) CUDA_TRY(ctx, (launch_scatter2<1024, 8>(ctx, G, src, dst, pieces, cta_pb, ustart, un, uR, ds, nb, poff)));
-        else CUDA_TRY(ctx, (launch_scatter2<512, 8>(ctx, G, src, dst, pieces, cta_pb, ustart, un, uR, ds, nb, poff)));
+    if (v2) {
+        const size_t smem = sizeof(Scatter3Smem);
+        if (g_kv_hints) {
+            CUDA_TRY(ctx, cudaFuncSetAttribute(part_scatter2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            part_scatter2_kernel<true><<<G, S3_NT, smem, ctx->stream>>>(src, dst, pieces, cta_pb, ustart, un, uR, out_base, ds,
+                                                                       nb, poff);
+        } else {
+            CUDA_TRY(ctx, cudaFuncSetAttribute(part_scatter2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            part_scatter2_kernel<false><<<G, S3_NT, smem, ctx->stream>>>(src, dst, pieces, cta_pb, ustart, un, uR, out_base, ds,
+                                                                        nb, poff);
+        }
+        CUDA_TRY(ctx, cudaGetLastError());
         return DAMPR_OK;
     }
     const size_t smem = sizeof(ScatterSmem);
@@ -945,6 +1018,14 @@ static int run_scatter(dampr_ctx *ctx, int G, const ulonglong2 *src, ulonglong2 
     }
     CUDA_TRY(ctx, cudaGetLastError());
     return DAMPR_OK;
+}
+
+// which scatter a level of nb buckets over n records uses: the table scatter wants at least as many buckets as
+// a tile has records... it is still correct below that (every tile takes its general path), the ballot scatter
+// is faster there and handles at most 1024 buckets; cursors of the table scatter are 32-bit
+static bool use_v2_scatter(u32 nb, u64 n) {
+    if (g_kv_scatter != 2 || n >= (1ULL << 32)) return false;
+    return nb > (u32)P1_MAX_NB || nb >= 2048u;
 }
 
 // One partition level over records [start, start+n) of `src` into `dst`: every segment of
@@ -964,7 +1045,8 @@ static int partition_level(dampr_ctx *ctx, const ulonglong2 *src, ulonglong2 *ds
         ~EvGuard() { cudaEventDestroy(e); }
     } evg{ev};
 
-    if (S == 1 && g_kv_scatter == 2) {
+    const bool v2 = use_v2_scatter(nb, n);
+    if (S == 1 && v2) {
         // ---- single segment: uniform pieces computed on the device, nothing uploaded ----------------------
         const u32 NP = (u32)G;
         DevBuf d_hist, d_tot, d_seg, d_poff;
@@ -991,7 +1073,7 @@ static int partition_level(dampr_ctx *ctx, const ulonglong2 *src, ulonglong2 *ds
         if (!h_next) return set_err(ctx, DAMPR_ERR_NOMEM, "%s", "pinned scratch allocation failed");
         CUDA_TRY(ctx, cudaMemcpyAsync(h_next, d_seg.p, (u64)(nb + 1) * 8, cudaMemcpyDeviceToHost, ctx->stream));
         CUDA_TRY(ctx, cudaEventRecord(ev, ctx->stream));
-        int rc = run_scatter(ctx, G, src, dst, nullptr, nullptr, start, n, R, ds, nb, (const u64 *)d_poff.p);
+        int rc = run_scatter(ctx, G, src, dst, nullptr, nullptr, start, n, R, start, ds, nb, (const u64 *)d_poff.p, true);
         if (rc) return rc;
         CUDA_TRY(ctx, cudaEventSynchronize(ev));  // the scatter is still running
         seg_off.assign(h_next, h_next + nb + 1);
@@ -1071,8 +1153,8 @@ static int partition_level(dampr_ctx *ctx, const ulonglong2 *src, ulonglong2 *ds
     if (!h_next) return set_err(ctx, DAMPR_ERR_NOMEM, "%s", "pinned scratch allocation failed");
     CUDA_TRY(ctx, cudaMemcpyAsync(h_next, d_next.p, S * nb * 8, cudaMemcpyDeviceToHost, ctx->stream));
     CUDA_TRY(ctx, cudaEventRecord(ev, ctx->stream));
-    int rc = run_scatter(ctx, G, src, dst, (const Piece *)d_pieces.p, (const u32 *)d_cta_pb.p, 0, 0, 0, ds, nb,
-                         (const u64 *)d_poff.p);
+    int rc = run_scatter(ctx, G, src, dst, (const Piece *)d_pieces.p, (const u32 *)d_cta_pb.p, 0, 0, 0, start, ds, nb,
+                         (const u64 *)d_poff.p, v2);
     if (rc) return rc;
     CUDA_TRY(ctx, cudaEventSynchronize(ev));
     h_next[S * nb] = start + n;
@@ -1080,6 +1162,32 @@ static int partition_level(dampr_ctx *ctx, const ulonglong2 *src, ulonglong2 *ds
     // the device buffers of this level are released to the pool with the stream's position recorded,
     // so nothing reuses them before the scatter has finished
     return DAMPR_OK;
+}
+
+// clusters of the leaf kernel the device keeps resident at once (the kernel is persistent: a cluster that does
+// not fit the first wave would start only after another one has finished ALL its chunks)
+static int cluster_leaf_max_active(dampr_ctx *ctx, size_t smem) {
+    static int cached[64] = {0};
+    int &c = cached[ctx->device & 63];
+    if (c > 0) return c;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(ctx->num_sms * 2 / CL * CL), 1, 1);
+    cfg.blockDim = dim3(L_THREADS, 1, 1);
+    cfg.dynamicSmemBytes = smem;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CL;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    int n = 0;
+    if (cudaOccupancyMaxActiveClusters(&n, cluster_leaf_kernel, &cfg) != cudaSuccess || n <= 0) {
+        cudaGetLastError();
+        n = std::max(1, ctx->num_sms * 2 / CL * 3 / 4);
+    }
+    c = n;
+    return c;
 }
 
 static int copy_range(dampr_ctx *ctx, const ulonglong2 *from, ulonglong2 *to, u64 start, u64 n) {
@@ -1124,23 +1232,33 @@ static int sort_range(dampr_ctx *ctx, ulonglong2 *cur, ulonglong2 *alt, u64 star
         return copy_range(ctx, cur, target, start, n);
     }
     const bool use_cluster = allow_cluster && g_kv_cluster && n > (u64)L_CAP;
-    const int max_bits = (g_kv_scatter == 2) ? std::min(g_kv_max_bits, P2_MAX_BITS) : P1_MAX_BITS;
     // ---- plan the levels ---------------------------------------------------------------------
     // at least 8 bits per call when a level is needed at all: surplus buckets cost nothing (small segments
-    // are packed into shared leaf chunks) and skewed inputs need the resolution
+    // are packed into shared leaf chunks) and skewed inputs need the resolution. With the table scatter the
+    // first level takes 12 bits whenever the key has them (its fast path wants buckets >= records per tile);
+    // further levels (more than ~1.1e8 records) use the ballot scatter with at most 10 bits each.
     int total_bits = bits_for(n, use_cluster ? C_TARGET : S_TARGET);
     if (total_bits > 0) total_bits = std::max(total_bits, 8);
     total_bits = std::min(top, total_bits);
-    int nlev = (total_bits + max_bits - 1) / max_bits;
     std::vector<int> lev_bits;
     {
         int left = total_bits;
-        for (int l = 0; l < nlev; ++l) {
-            int b = (left + (nlev - l) - 1) / (nlev - l);
-            lev_bits.push_back(b);
-            left -= b;
+        const bool table = g_kv_scatter == 2 && n < (1ULL << 32) && n >= 65536 && top >= g_kv_max_bits &&
+                           g_kv_max_bits > P1_MAX_BITS;
+        if (table && left > 0) {
+            lev_bits.push_back(g_kv_max_bits);
+            left = std::max(0, left - g_kv_max_bits);
+        }
+        if (left > 0) {
+            const int nl = (left + P1_MAX_BITS - 1) / P1_MAX_BITS;
+            for (int l = 0; l < nl; ++l) {
+                int bq = (left + (nl - l) - 1) / (nl - l);
+                lev_bits.push_back(bq);
+                left -= bq;
+            }
         }
     }
+    const int nlev = (int)lev_bits.size();
     std::vector<u64> seg_off{start, start + n};
     ulonglong2 *src = cur, *dst = alt;
     int consumed = 0;
@@ -1250,7 +1368,7 @@ static int sort_range(dampr_ctx *ctx, ulonglong2 *cur, ulonglong2 *alt, u64 star
             CUDA_TRY(ctx, cudaMemcpyAsync(d_clus.p, hp + bs, bc, cudaMemcpyHostToDevice, ctx->stream));
             CUDA_TRY(ctx, cudaMemsetAsync(d_ovf.p, 0, 4, ctx->stream));
             CUDA_TRY(ctx, cudaFuncSetAttribute(cluster_leaf_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            const u32 maxcl = (u32)std::max(1, ctx->num_sms * 2 / CL);
+            const u32 maxcl = (u32)cluster_leaf_max_active(ctx, smem);
             const u32 grid = (u32)std::min<size_t>(nclus, (size_t)maxcl) * CL;
             ScopedTimer tm(ctx, DAMPR_K_LEAF_SORT);
             cluster_leaf_kernel<<<grid, L_THREADS, smem, ctx->stream>>>(src, leaf_out, (const LeafChunk *)d_clus.p, (u32)nclus,
@@ -1414,9 +1532,8 @@ int32_t dampr_set_option(const char *name, int64_t value) {
         g_kv_cluster = value != 0;
         return DAMPR_OK;
     }
-    if (!strcmp(name, "kv_tile")) {
-        if (value != 4096 && value != 8192) return DAMPR_ERR_ARG;
-        g_kv_tile = (int)value;
+    if (!strcmp(name, "kv_hints")) {
+        g_kv_hints = value != 0;
         return DAMPR_OK;
     }
     if (!strcmp(name, "kv_max_bits")) {

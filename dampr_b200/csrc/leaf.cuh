@@ -35,8 +35,7 @@ struct LeafSmem {
     u32 fh[CF];
     u32 gpos[CF + 1];
     u16 dpos[CF];
-    u8 down[CF];
-    u32 firstg[CL], endg[CL], firstbin[CL], lastbin[CL];
+    u32 firstg[CL], endg[CL];
     u32 wsum[32];
     u32 total_groups;
     u32 ovf;
@@ -239,38 +238,50 @@ __device__ __forceinline__ u32 leaf_hash_fold(LeafSmem &s, u32 n, int reduce_op,
     return total;
 }
 
-// segmented reduce over the sorted order s.fin: one thread per group head walks its group
+// segmented reduce over the sorted order s.fin: one thread per group head walks its group. Positions are dealt
+// to the threads warp by warp, 32 consecutive positions per round (conflict-free shared-memory reads; the
+// blocked layout of the first build cost 16-way bank conflicts), head ranks come from ballots.
 __device__ __forceinline__ u32 leaf_seg_reduce(LeafSmem &s, u32 n, int reduce_op, int xf, u64 base,
                                                ulonglong2 *__restrict__ out) {
-    const u32 tid = threadIdx.x;
+    const u32 lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const u32 lt = (1u << lane) - 1u;
     const u16 *fin = s.fin;
-    u32 headbits = 0;
+    u32 headbits = 0, run = 0;
+    u32 rank[L_IPT];
 #pragma unroll
     for (int k = 0; k < L_IPT; ++k) {
-        const u32 p = tid * L_IPT + k;
-        if (p < n) {
-            const bool head = (p == 0) || (s.sk[fin[p]] != s.sk[fin[p - 1]]);
-            headbits |= head ? (1u << k) : 0u;
-        }
+        const u32 p = warp * (32u * L_IPT) + k * 32u + lane;
+        bool head = false;
+        if (p < n) head = (p == 0) || (s.sk[fin[p]] != s.sk[fin[p - 1]]);
+        const u32 b = __ballot_sync(0xFFFFFFFFu, head);
+        rank[k] = run + (u32)__popc(b & lt);
+        run += (u32)__popc(b);
+        headbits |= head ? (1u << k) : 0u;
     }
-    u32 total;
-    u32 gidx = block_excl_scan(s, __popc(headbits), &total);
+    __syncthreads();  // wsum may still be read by an earlier scan
+    if (lane == 0) s.wsum[warp] = run;
+    __syncthreads();
+    u32 woff = 0, total = 0;
+    for (u32 w = 0; w < L_THREADS / 32; ++w) {
+        const u32 ws = s.wsum[w];
+        if (w < warp) woff += ws;
+        total += ws;
+    }
 #pragma unroll
     for (int k = 0; k < L_IPT; ++k) {
         if (headbits & (1u << k)) {
-            const u32 p = tid * L_IPT + k;
+            const u32 p = warp * (32u * L_IPT) + k * 32u + lane;
             const u64 ksk = s.sk[fin[p]];
             u64 acc = (reduce_op == DAMPR_OP_COUNT) ? 1ULL : s.val[fin[p]];
             for (u32 q = p + 1; q < n && s.sk[fin[q]] == ksk; ++q) {
                 const u64 val = (reduce_op == DAMPR_OP_COUNT) ? 1ULL : s.val[fin[q]];
                 acc = apply_op(reduce_op, acc, val);
             }
-            out[gidx++] = make_ulonglong2(key_unxform(ksk + base, xf), acc);
+            out[woff + rank[k]] = make_ulonglong2(key_unxform(ksk + base, xf), acc);
         }
     }
     return total;
 }
-
 
 // exclusive scan of u32 counts into u64 offsets (single CTA, sequential over blocks of 1024)
 __global__ void scan_u32_to_u64_kernel(const u32 *__restrict__ in, u64 *__restrict__ out, u32 n) {

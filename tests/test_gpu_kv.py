@@ -263,10 +263,10 @@ def test_cluster_leaf_overflow_falls_back(ctx):
     assert dict(zip(k2.tolist(), v2.view(np.int64).tolist())) == refsem.group_fold(keys, vals, lambda a, b: a)
 
 
-@pytest.mark.parametrize("opts", [{"kv_scatter": 1}, {"kv_cluster": 0}, {"kv_tile": 8192}, {"kv_max_bits": 8}])
+@pytest.mark.parametrize("opts", [{"kv_scatter": 1}, {"kv_cluster": 0}, {"kv_hints": 0}, {"kv_max_bits": 11}, {"kv_scatter": 1, "kv_cluster": 0}])
 def test_sort_variants_agree(ctx, opts):
     """every selectable kernel variant gives the same stable order (and leaves the defaults restored)"""
-    defaults = {"kv_scatter": 2, "kv_cluster": 1, "kv_tile": 4096, "kv_max_bits": 12}
+    defaults = {"kv_scatter": 2, "kv_cluster": 1, "kv_hints": 1, "kv_max_bits": 12}
     try:
         for k, v in opts.items():
             dev.set_option(k, v)

@@ -228,17 +228,17 @@ def main():
     for m in sizes:
         n = int(m * 1e6)
         if variants:
-            for opts, label in (({"kv_scatter": 1, "kv_cluster": 0}, "v1 scatter(10b) + CTA leaf"),
-                                ({"kv_scatter": 2, "kv_cluster": 0}, "v2 scatter + CTA leaf"),
-                                ({"kv_scatter": 2, "kv_cluster": 1, "kv_max_bits": 11}, "v2 11 bits + cluster leaf"),
-                                ({"kv_scatter": 2, "kv_cluster": 1, "kv_tile": 8192}, "v2 tile 8192 + cluster leaf"),
-                                ({"kv_scatter": 2, "kv_cluster": 1}, "v2 scatter(12b) + cluster leaf")):
-                for a, b in {"kv_scatter": 2, "kv_cluster": 1, "kv_tile": 4096, "kv_max_bits": 12}.items():
+            for opts, label in (({"kv_scatter": 1, "kv_cluster": 0}, "v1 scatter(10b x2) + CTA leaf"),
+                                ({"kv_scatter": 1, "kv_cluster": 1}, "v1 scatter(10b) + cluster leaf"),
+                                ({"kv_scatter": 2, "kv_cluster": 0}, "table scatter(12b) + v1 scatter(4b) + CTA leaf"),
+                                ({"kv_scatter": 2, "kv_cluster": 1, "kv_hints": 0}, "table scatter(12b, no L2 hints) + cluster leaf"),
+                                ({"kv_scatter": 2, "kv_cluster": 1}, "table scatter(12b) + cluster leaf")):
+                for a, b in {"kv_scatter": 2, "kv_cluster": 1, "kv_hints": 1, "kv_max_bits": 12}.items():
                     dev.set_option(a, b)
                 for a, b in opts.items():
                     dev.set_option(a, b)
                 print(json.dumps(sort_case(ctx, n, n, label=label)), flush=True)
-            for a, b in {"kv_scatter": 2, "kv_cluster": 1, "kv_tile": 4096, "kv_max_bits": 12}.items():
+            for a, b in {"kv_scatter": 2, "kv_cluster": 1, "kv_hints": 1, "kv_max_bits": 12}.items():
                 dev.set_option(a, b)
         print(json.dumps(sort_case(ctx, n, n, label="K=N")), flush=True)
         print(json.dumps(sort_case(ctx, n, 10_000_000, label="K=1e7")), flush=True)
