@@ -32,10 +32,11 @@
 
 namespace cg = cooperative_groups;
 
-int g_kv_scatter = 2;   // 2 = atomic-rank scatter (up to 12 bits), 1 = first-generation ballot scatter (10 bits)
-int g_kv_cluster = 1;   // 1 = cluster/DSMEM leaf for segments above one CTA's capacity
+int g_kv_scatter = 3;   // 3 = staged runs + atomic/SWAR ranking, 10 bits per level (default); 2 = 12-bit table scatter
+                        // for the first level; 1 = first-generation ballot scatter
+int g_kv_cluster = 0;   // 1 = cluster/DSMEM leaf for segments above one CTA's capacity (measured slower)
 int g_kv_hints = 1;     // L2 eviction-priority hints in the table scatter (evict-first loads, evict-last stores)
-int g_kv_max_bits = 12; // digit bits per partition level (<= 12)
+int g_kv_max_bits = 12; // digit bits of the table scatter's level (kv_scatter = 2)
 
 namespace {
 
@@ -649,6 +650,207 @@ part_scatter2_kernel(const ulonglong2 *__restrict__ in, ulonglong2 *__restrict__
     }
 }
 
+// ---- level scatter (v3): staged bucket runs (like v1) ranked with ONE atomic per record (like v2) ---------
+// What the measurements of this round say (profiles/r02_kv_*): the fan-out of a level is bounded by the L2,
+// not by the SM — every (piece, bucket) pair is a write front that occupies a 128-byte line until its
+// neighbours arrive, and 296 pieces x 4096 buckets do not fit (DRAM reads 2.1x, writes 1.5x the algorithmic
+// bytes: ECC read-modify-write of half-written sectors); 296 x 1024 do, if every tile hands each bucket a
+// contiguous run. So: 10 bits per level, the tile staged bucket-major in shared memory and every bucket's run
+// written by one TMA bulk store (v1's data path), but the rank of a record inside (tile, bucket) comes from one
+// packed 16-bit atomic plus a SWAR compare against the tile indices of its bucket mates (v1 spent ~120 of its
+// 231 warp-instructions per 32 records on one ballot per digit bit and per-warp histograms).
+constexpr int S4_NT = 512;
+constexpr int S4_RPT = 8;
+constexpr int S4_T = S4_NT * S4_RPT;           // 4096
+constexpr int S4_NB = P1_MAX_NB;               // 1024
+constexpr int S4_SIDX = S4_T + 7 * S4_NB + 8;  // bucket index lists, each padded to a multiple of 8 entries
+
+struct Scatter4Smem {
+    alignas(16) ulonglong2 stage[S4_T];
+    u64 run_off[S4_NB];
+    alignas(16) u16 sidx[S4_SIDX];
+    alignas(16) u32 cnt[2][S4_NB / 2];   // packed 16-bit counters, double buffered
+    u32 base[S4_NB + 2];                 // padded list start << 16 | staging start
+    u32 bitmap[S4_NT / 32][S4_T / 32];   // hot runs only
+    u16 hot[S4_T / 32];
+    u32 nhot;
+    u32 wsum[32];
+};
+
+__global__ void __launch_bounds__(S4_NT, 2)
+part_scatter3_kernel(const ulonglong2 *__restrict__ in, ulonglong2 *__restrict__ out,
+                     const Piece *__restrict__ pieces, const u32 *__restrict__ cta_piece_begin, u64 ustart,
+                     u64 un, u64 uR, DigitSpec ds, u32 nb, const u64 *__restrict__ piece_off) {
+    constexpr int NT = S4_NT, RPT = S4_RPT, T = S4_T, NW = NT / 32, WPL = T / 32 / 32;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    Scatter4Smem &s = *reinterpret_cast<Scatter4Smem *>(smem_raw);
+    const u32 tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const u32 pb = pieces ? cta_piece_begin[blockIdx.x] : blockIdx.x;
+    const u32 pe = pieces ? cta_piece_begin[blockIdx.x + 1] : blockIdx.x + 1;
+    u32 tile_no = 0;
+
+    for (u32 p = pb; p < pe; ++p) {
+        const Piece pc = pieces ? pieces[p] : uniform_piece(p, ustart, un, uR);
+        __syncthreads();
+        for (u32 b = tid; b < (u32)S4_NB; b += NT) {
+            s.run_off[b] = (b < nb) ? piece_off[(u64)p * nb + b] : 0ULL;
+            (&s.cnt[0][0])[b] = 0;
+        }
+        __syncthreads();
+        for (u64 t0 = pc.start; t0 < pc.end; t0 += T, ++tile_no) {
+            const u32 tn = (u32)min((u64)T, pc.end - t0);
+            const u32 buf = tile_no & 1u;
+            u32 *cnt32 = s.cnt[buf];
+            ulonglong2 rec[RPT];
+            u32 dsl[RPT];  // digit | slot << 16
+#pragma unroll
+            for (int r = 0; r < RPT; ++r) {
+                const u32 li = r * NT + tid;
+                if (li < tn) rec[r] = in[t0 + li];
+            }
+            if (t0 + T < pc.end) {  // the next tile: pull it into L2 while this one is ranked and staged
+                const char *nxt = reinterpret_cast<const char *>(in + t0 + T);
+                const u32 nbytes = (u32)min((u64)T, pc.end - t0 - T) * 16u;
+                for (u32 off = tid * 128u; off < nbytes; off += NT * 128u)
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(nxt + off));
+            }
+#pragma unroll
+            for (int r = 0; r < RPT; ++r) {
+                const u32 li = r * NT + tid;
+                dsl[r] = 0;
+                if (li < tn) {
+                    const u32 d = digit_of(rec[r].x, ds);
+                    const u32 old = atomicAdd(&cnt32[d >> 1], (d & 1u) ? 0x10000u : 1u);
+                    dsl[r] = d | (((d & 1u) ? (old >> 16) : (old & 0xFFFFu)) << 16);
+                }
+            }
+            if (tid == 0) s.nhot = 0;
+            __syncthreads();
+            // ---- scan of the bucket counts (2 buckets per thread): staging offsets and padded list offsets ----
+            {
+                const u32 w = cnt32[tid];  // buckets 2 tid, 2 tid + 1
+                const u32 c0 = w & 0xFFFFu, c1 = w >> 16;
+                if (c0 > HOT_L) s.hot[atomicAdd(&s.nhot, 1u)] = (u16)(2 * tid);
+                if (c1 > HOT_L) s.hot[atomicAdd(&s.nhot, 1u)] = (u16)(2 * tid + 1);
+                const u32 p0 = (c0 + 7u) & ~7u, p1 = (c1 + 7u) & ~7u;
+                const u32 mine = (c0 + c1) | ((p0 + p1) << 16);  // both sums stay below 2^16
+                u32 v = mine;
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) {
+                    u32 o = __shfl_up_sync(0xFFFFFFFFu, v, d);
+                    if ((int)lane >= d) v += o;
+                }
+                if (lane == 31) s.wsum[warp] = v;
+                __syncthreads();
+                u32 woff = 0;
+                for (u32 ww = 0; ww < warp; ++ww) woff += s.wsum[ww];
+                const u32 ex = woff + v - mine;
+                s.base[2 * tid] = ex;
+                s.base[2 * tid + 1] = ex + (c0 | (p0 << 16));
+                if (tid == NT - 1) s.base[S4_NB] = ex + mine;
+            }
+            __syncthreads();
+#pragma unroll
+            for (int r = 0; r < RPT; ++r) {
+                const u32 li = r * NT + tid;
+                if (li < tn) s.sidx[(s.base[dsl[r] & 0xFFFFu] >> 16) + (dsl[r] >> 16)] = (u16)li;
+            }
+            __syncthreads();
+            const u32 nh = s.nhot;
+            if (nh) {
+                // skew: a warp sorts the tile indices of a long run through a presence bitmap
+                u32 *bm = s.bitmap[warp];
+                for (u32 hi = warp; hi < nh; hi += NW) {
+                    const u32 h = s.hot[hi];
+                    const u32 st = s.base[h] >> 16, L = (s.base[h + 1] & 0xFFFFu) - (s.base[h] & 0xFFFFu);
+                    for (u32 w = lane; w < T / 32; w += 32) bm[w] = 0;
+                    __syncwarp();
+                    for (u32 j = lane; j < L; j += 32) {
+                        const u32 x = s.sidx[st + j];
+                        atomicOr(&bm[x >> 5], 1u << (x & 31));
+                    }
+                    __syncwarp();
+                    u32 words[WPL];
+                    u32 cl = 0;
+#pragma unroll
+                    for (int k = 0; k < WPL; ++k) {
+                        words[k] = bm[lane * WPL + k];
+                        cl += __popc(words[k]);
+                    }
+                    u32 v = cl;
+#pragma unroll
+                    for (int d = 1; d < 32; d <<= 1) {
+                        u32 o = __shfl_up_sync(0xFFFFFFFFu, v, d);
+                        if ((int)lane >= d) v += o;
+                    }
+                    u32 pos = st + v - cl;
+#pragma unroll
+                    for (int k = 0; k < WPL; ++k) {
+                        u32 wd = words[k];
+                        while (wd) {
+                            const u32 bit = __ffs(wd) - 1;
+                            wd &= wd - 1;
+                            s.sidx[pos++] = (u16)((lane * WPL + k) * 32 + bit);
+                        }
+                    }
+                    __syncwarp();
+                }
+                __syncthreads();
+            }
+            // ---- rank inside (tile, bucket) by tile index, stage bucket-major -----------------------------------
+#pragma unroll
+            for (int r = 0; r < RPT; ++r) {
+                const u32 li = r * NT + tid;
+                if (li < tn) {
+                    const u32 d = dsl[r] & 0xFFFFu;
+                    const u32 b0 = s.base[d], b1 = s.base[d + 1];
+                    const u32 lst = b0 >> 16, L = (b1 & 0xFFFFu) - (b0 & 0xFFFFu);
+                    u32 rk = 0;
+                    if (L > HOT_L) {  // sorted by a warp above: lower bound
+                        u32 lo = 0, hi = L;
+                        while (lo < hi) {
+                            const u32 mid = (lo + hi) >> 1;
+                            if (s.sidx[lst + mid] < li) lo = mid + 1;
+                            else hi = mid;
+                        }
+                        rk = lo;
+                    } else if (L > 1) {
+                        // 8 tile indices per 16-byte row; halfword-wise "entry < li" by SWAR (entries < 2^15)
+                        const u64 H = 0x8000800080008000ULL, lim = (u64)li * 0x0001000100010001ULL;
+                        for (u32 j = 0; j < L; j += 8) {
+                            const uint4 row = *reinterpret_cast<const uint4 *>(&s.sidx[lst + j]);
+                            const u64 lo = (u64)row.x | ((u64)row.y << 32), hi = (u64)row.z | ((u64)row.w << 32);
+                            const u32 left = L - j;
+                            const u64 m0 = (left >= 4) ? ~0ULL : ((1ULL << (16 * left)) - 1ULL);
+                            const u64 m1 = (left >= 8) ? ~0ULL : ((left > 4) ? ((1ULL << (16 * (left - 4))) - 1ULL) : 0ULL);
+                            rk += (u32)__popcll(~((lo | H) - lim) & H & m0) + (u32)__popcll(~((hi | H) - lim) & H & m1);
+                        }
+                    }
+                    s.stage[(b0 & 0xFFFFu) + rk] = rec[r];
+                }
+            }
+            fence_proxy_async();
+            __syncthreads();
+            // ---- every bucket's run leaves with one TMA bulk store; cursors advance, counters clear -----------------
+            {
+                const u32 w = cnt32[tid];
+                const u32 c0 = w & 0xFFFFu, c1 = w >> 16;
+                const u32 s0 = s.base[2 * tid] & 0xFFFFu;
+                u64 r0 = s.run_off[2 * tid], r1 = s.run_off[2 * tid + 1];
+                if (c0) tma_store_1d(out + r0, &s.stage[s0], c0 * 16u);
+                if (c1) tma_store_1d(out + r1, &s.stage[s0 + c0], c1 * 16u);
+                tma_store_commit();
+                s.run_off[2 * tid] = r0 + c0;
+                s.run_off[2 * tid + 1] = r1 + c1;
+                cnt32[tid] = 0;
+                tma_store_wait_read();  // the staging area is reused by the next tile
+            }
+            __syncthreads();
+        }
+    }
+    tma_store_wait_all();
+}
+
 // single-CTA leaf. reduce_op < 0: sort only, records written to out[ch.start ..). Otherwise one record
 // per key group is written compacted at out[ch.start ..) and (start, groups) to the entry table.
 __global__ void __launch_bounds__(L_THREADS, 2)
@@ -994,6 +1196,13 @@ static int run_scatter(dampr_ctx *ctx, int G, const ulonglong2 *src, ulonglong2 
                        const u32 *cta_pb, u64 ustart, u64 un, u64 uR, u64 out_base, DigitSpec ds, u32 nb,
                        const u64 *poff, bool v2) {
     ScopedTimer tm(ctx, DAMPR_K_PART_SCATTER);
+    if (!v2 && g_kv_scatter >= 2 && nb <= (u32)S4_NB) {
+        const size_t smem = sizeof(Scatter4Smem);
+        CUDA_TRY(ctx, cudaFuncSetAttribute(part_scatter3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        part_scatter3_kernel<<<G, S4_NT, smem, ctx->stream>>>(src, dst, pieces, cta_pb, ustart, un, uR, ds, nb, poff);
+        CUDA_TRY(ctx, cudaGetLastError());
+        return DAMPR_OK;
+    }
     if (v2) {
         const size_t smem = sizeof(Scatter3Smem);
         if (g_kv_hints) {
@@ -1024,8 +1233,8 @@ static int run_scatter(dampr_ctx *ctx, int G, const ulonglong2 *src, ulonglong2 
 // a tile has records... it is still correct below that (every tile takes its general path), the ballot scatter
 // is faster there and handles at most 1024 buckets; cursors of the table scatter are 32-bit
 static bool use_v2_scatter(u32 nb, u64 n) {
-    if (g_kv_scatter != 2 || n >= (1ULL << 32)) return false;
-    return nb > (u32)P1_MAX_NB || nb >= 2048u;
+    if (g_kv_scatter < 2 || n >= (1ULL << 32)) return false;
+    return nb > (u32)P1_MAX_NB;
 }
 
 // One partition level over records [start, start+n) of `src` into `dst`: every segment of
@@ -1046,7 +1255,7 @@ static int partition_level(dampr_ctx *ctx, const ulonglong2 *src, ulonglong2 *ds
     } evg{ev};
 
     const bool v2 = use_v2_scatter(nb, n);
-    if (S == 1 && v2) {
+    if (S == 1 && g_kv_scatter >= 2 && (v2 || nb <= (u32)S4_NB)) {
         // ---- single segment: uniform pieces computed on the device, nothing uploaded ----------------------
         const u32 NP = (u32)G;
         DevBuf d_hist, d_tot, d_seg, d_poff;
@@ -1073,7 +1282,7 @@ static int partition_level(dampr_ctx *ctx, const ulonglong2 *src, ulonglong2 *ds
         if (!h_next) return set_err(ctx, DAMPR_ERR_NOMEM, "%s", "pinned scratch allocation failed");
         CUDA_TRY(ctx, cudaMemcpyAsync(h_next, d_seg.p, (u64)(nb + 1) * 8, cudaMemcpyDeviceToHost, ctx->stream));
         CUDA_TRY(ctx, cudaEventRecord(ev, ctx->stream));
-        int rc = run_scatter(ctx, G, src, dst, nullptr, nullptr, start, n, R, start, ds, nb, (const u64 *)d_poff.p, true);
+        int rc = run_scatter(ctx, G, src, dst, nullptr, nullptr, start, n, R, start, ds, nb, (const u64 *)d_poff.p, v2);
         if (rc) return rc;
         CUDA_TRY(ctx, cudaEventSynchronize(ev));  // the scatter is still running
         seg_off.assign(h_next, h_next + nb + 1);
@@ -1135,7 +1344,7 @@ static int partition_level(dampr_ctx *ctx, const ulonglong2 *src, ulonglong2 *ds
     }
     {
         ScopedTimer tm(ctx, DAMPR_K_PART_HIST);
-        if (g_kv_scatter == 2)
+        if (g_kv_scatter >= 2)
             part_hist2_kernel<<<(unsigned)NP, H2_THREADS, 0, ctx->stream>>>(src, (const Piece *)d_pieces.p, 0, 0, 0, 1, ds, nb,
                                                                            (u32 *)d_hist.p, nullptr);
         else
@@ -1524,7 +1733,7 @@ int32_t dampr_set_option(const char *name, int64_t value) {
         return DAMPR_OK;
     }
     if (!strcmp(name, "kv_scatter")) {
-        if (value != 1 && value != 2) return DAMPR_ERR_ARG;
+        if (value < 1 || value > 3) return DAMPR_ERR_ARG;
         g_kv_scatter = (int)value;
         return DAMPR_OK;
     }

@@ -237,11 +237,17 @@ def test_synth_kv_matches_numpy(ctx):
 # ---- second-generation sort path: 12-bit atomic-rank scatter + cluster/DSMEM leaf + K5 merge ----------------
 @pytest.mark.parametrize("n", [4097, 9000, 27000, 27600, 60000, 1_000_000])
 def test_cluster_leaf_sizes(ctx, n):
-    """sizes around the single-CTA / cluster / one-level boundaries, unique-ish and duplicated keys"""
-    for nk in (max(1, n // 3), 10 * n):
-        keys, vals = gen.kv(77, n, nk)
-        check_sort(ctx, keys, vals, dev.KEY_MIX)
-        check_sort(ctx, keys, vals, dev.KEY_RAW)
+    """sizes around the single-CTA / cluster / one-level boundaries, unique-ish and duplicated keys, with the
+    default leaves and with the cluster (DSMEM) leaf"""
+    for cluster in (0, 1):
+        dev.set_option("kv_cluster", cluster)
+        try:
+            for nk in (max(1, n // 3), 10 * n):
+                keys, vals = gen.kv(77, n, nk)
+                check_sort(ctx, keys, vals, dev.KEY_MIX)
+                check_sort(ctx, keys, vals, dev.KEY_RAW)
+        finally:
+            dev.set_option("kv_cluster", 0)
 
 
 def test_cluster_leaf_overflow_falls_back(ctx):
@@ -251,6 +257,14 @@ def test_cluster_leaf_overflow_falls_back(ctx):
     keys = rng.integers(0, 1 << 62, size=n).astype(np.uint64)
     keys[rng.random(n) < 0.7] = np.uint64(123456789)
     vals = np.arange(n, dtype=np.int64)
+    dev.set_option("kv_cluster", 1)
+    try:
+        _overflow_checks(ctx, keys, vals)
+    finally:
+        dev.set_option("kv_cluster", 0)
+
+
+def _overflow_checks(ctx, keys, vals):
     check_sort(ctx, keys, vals, dev.KEY_MIX)
     check_sort(ctx, keys, vals, dev.KEY_RAW)
     kv = ctx.kv_from_columns(keys, vals)
@@ -263,10 +277,11 @@ def test_cluster_leaf_overflow_falls_back(ctx):
     assert dict(zip(k2.tolist(), v2.view(np.int64).tolist())) == refsem.group_fold(keys, vals, lambda a, b: a)
 
 
-@pytest.mark.parametrize("opts", [{"kv_scatter": 1}, {"kv_cluster": 0}, {"kv_hints": 0}, {"kv_max_bits": 11}, {"kv_scatter": 1, "kv_cluster": 0}])
+@pytest.mark.parametrize("opts", [{"kv_scatter": 1}, {"kv_scatter": 2}, {"kv_cluster": 1}, {"kv_scatter": 2, "kv_cluster": 1, "kv_hints": 0},
+                                  {"kv_scatter": 2, "kv_max_bits": 11}, {"kv_scatter": 1, "kv_cluster": 1}])
 def test_sort_variants_agree(ctx, opts):
     """every selectable kernel variant gives the same stable order (and leaves the defaults restored)"""
-    defaults = {"kv_scatter": 2, "kv_cluster": 1, "kv_hints": 1, "kv_max_bits": 12}
+    defaults = {"kv_scatter": 3, "kv_cluster": 0, "kv_hints": 1, "kv_max_bits": 12}
     try:
         for k, v in opts.items():
             dev.set_option(k, v)

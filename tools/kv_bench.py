@@ -228,17 +228,17 @@ def main():
     for m in sizes:
         n = int(m * 1e6)
         if variants:
-            for opts, label in (({"kv_scatter": 1, "kv_cluster": 0}, "v1 scatter(10b x2) + CTA leaf"),
-                                ({"kv_scatter": 1, "kv_cluster": 1}, "v1 scatter(10b) + cluster leaf"),
-                                ({"kv_scatter": 2, "kv_cluster": 0}, "table scatter(12b) + v1 scatter(4b) + CTA leaf"),
-                                ({"kv_scatter": 2, "kv_cluster": 1, "kv_hints": 0}, "table scatter(12b, no L2 hints) + cluster leaf"),
-                                ({"kv_scatter": 2, "kv_cluster": 1}, "table scatter(12b) + cluster leaf")):
-                for a, b in {"kv_scatter": 2, "kv_cluster": 1, "kv_hints": 1, "kv_max_bits": 12}.items():
+            for opts, label in (({"kv_scatter": 1, "kv_cluster": 0}, "v1: ballot scatter 2 x 8b + CTA leaf"),
+                                ({"kv_scatter": 2, "kv_cluster": 1}, "v2: table scatter 12b + cluster leaf"),
+                                ({"kv_scatter": 2, "kv_cluster": 0}, "v2: table scatter 12b + staged scatter 4b + CTA leaf"),
+                                ({"kv_scatter": 3, "kv_cluster": 1}, "v3: staged scatter 2 x 6b + cluster leaf"),
+                                ({"kv_scatter": 3, "kv_cluster": 0}, "v3: staged scatter 2 x 8b + CTA leaf (default)")):
+                for a, b in {"kv_scatter": 3, "kv_cluster": 0, "kv_hints": 1, "kv_max_bits": 12}.items():
                     dev.set_option(a, b)
                 for a, b in opts.items():
                     dev.set_option(a, b)
                 print(json.dumps(sort_case(ctx, n, n, label=label)), flush=True)
-            for a, b in {"kv_scatter": 2, "kv_cluster": 1, "kv_hints": 1, "kv_max_bits": 12}.items():
+            for a, b in {"kv_scatter": 3, "kv_cluster": 0, "kv_hints": 1, "kv_max_bits": 12}.items():
                 dev.set_option(a, b)
         print(json.dumps(sort_case(ctx, n, n, label="K=N")), flush=True)
         print(json.dumps(sort_case(ctx, n, 10_000_000, label="K=1e7")), flush=True)
