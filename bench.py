@@ -45,6 +45,15 @@ RX = re.compile(r"[^\w]+")
 MB = 1e6
 METRIC = "MB/s ingested end-to-end, TF-IDF 10 GB synthetic text, 1/2/4/8 GPU"
 MEAN_LINE = 99.94  # mean synthetic line: 99.94 B at V = 1e6 (measured)
+REF_TIMEOUT = 300  # seconds one run of the reference may take before the arm gives up on it
+
+
+_T0 = time.time()
+
+
+def progress(msg):
+    """phase log on stderr (the JSON line is the only thing on stdout)"""
+    print("[bench %7.1fs] %s" % (time.time() - _T0, msg), file=sys.stderr, flush=True)
 
 
 def parse_args():
@@ -160,8 +169,9 @@ def run_cpu_tfidf(path, out_dir, n_procs, kind):
     shutil.rmtree(out_dir, ignore_errors=True)
     if kind == "reference":
         t0 = time.time()
+        # the reference hangs when one of its workers dies: bound the run
         r = subprocess.run([sys.executable, os.path.join(ROOT, "oracle", "ref_tfidf.py"), path, out_dir, str(n_procs)],
-                           cwd=tempfile.gettempdir(), capture_output=True, text=True)
+                           cwd=tempfile.gettempdir(), capture_output=True, text=True, timeout=REF_TIMEOUT)
         sec = time.time() - t0
         if r.returncode != 0:
             raise RuntimeError("reference run failed: %s" % r.stderr[-2000:])
@@ -306,7 +316,9 @@ def parity_check(Dampr, MemoryText, host_text, rank, world, use_dist, dist, out_
     nbytes = os.path.getsize(corpus)
     got = read_sink_lines(out_dir)
     kind = "reference" if have_reference() else "port"
+    progress("parity: GPU side done (%d lines), running the CPU checker (%s) on %d bytes" % (len(got), kind, nbytes))
     run_cpu_tfidf(corpus, os.path.join(shared, "cpu_idfs"), ncores, kind)
+    progress("parity: checker done")
     exp = read_sink_lines(os.path.join(shared, "cpu_idfs"))
     equal = got == exp
     second = None
@@ -337,6 +349,7 @@ def kv_extras(ctx_unused, args):
     extra = {}
 
     def guarded(name, fn):
+        progress("extra: " + name)
         try:
             t0 = time.time()
             extra[name] = fn()
@@ -361,6 +374,7 @@ def kv_extras(ctx_unused, args):
 def file_e2e(Dampr, host_text, out_root, steps=2):
     """The script under test takes a PATH: Dampr.text(path) -> page cache -> pinned ring -> device. Timed on a
     file holding a 2.5 GB line-aligned prefix of the corpus (written and page-cache-warmed before timing)."""
+    progress("extra: file_e2e")
     part = cut_at_line(host_text, int(2.5e9))
     path = os.path.join(out_root, "corpus_prefix.txt")
     part.tofile(path)
@@ -419,6 +433,7 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
     # ---- synthetic corpus: generated on the device, mirrored into page-locked host memory -------------
+    progress("rank %d/%d: generating %.2f GB of text" % (rank, world, shard_bytes / 1e9))
     vocab = synth.make_vocab(args.vocab)
     cdf = synth.make_cdf(args.vocab)
     tb = ctx.synth_text(1234 + rank, n_lines, vocab[0], vocab[1], cdf)
@@ -470,6 +485,7 @@ def main():
     if not os.environ.get("DAMPR_BENCH_NOSAMPLER"):
         sampler.start()
     verbose = bool(os.environ.get("DAMPR_BENCH_VERBOSE"))
+    progress("warm-up + timed loops")
     for i in range(args.warmup):
         ts = time.perf_counter()
         shutil.rmtree(step(True, -1 - i), ignore_errors=True)
@@ -590,7 +606,9 @@ def main():
 
     # ---- parity of the timed graph against the CPU checker (all ranks take part) ----------------------------
     parity = None
+    progress("timed loops done: e2e %.1f ms/step, resident %.1f ms/step" % (1e3 * t_e2e / args.steps, 1e3 * t_dev / args.steps))
     if not args.no_parity:
+        progress("parity check")
         try:
             parity = parity_check(Dampr, MemoryText, host_text, rank, world, use_dist, dist, out_root)
         except Exception as e:
@@ -629,6 +647,7 @@ def main():
 
     if rank == 0 and not args.no_cpu_baseline:
         kind = "reference" if have_reference() else "port"
+        progress("cpu_baseline (%s)" % kind)
         tmp = tempfile.mkdtemp(prefix="dampr_cpu_")
         try:
             sample = cut_at_line(host_text, int(min(nbytes, max(32e6, 4e6 * ncores))))
@@ -646,6 +665,7 @@ def main():
         finally:
             shutil.rmtree(tmp, ignore_errors=True)
     shutil.rmtree(out_root, ignore_errors=True)
+    progress("done")
     if rank == 0:
         print(json.dumps(line))
     ok = True

@@ -32,8 +32,9 @@
 
 namespace cg = cooperative_groups;
 
-int g_kv_scatter = 3;   // 3 = staged runs + atomic/SWAR ranking, 10 bits per level (default); 2 = 12-bit table scatter
-                        // for the first level; 1 = first-generation ballot scatter
+int g_kv_scatter = 1;   // 1 = staged runs ranked by ballots, TMA bulk stores, 10 bits per level (default: fastest measured);
+                        // 3 = staged runs ranked by one atomic + SWAR compares; 2 = 12-bit table scatter for the first level
+int g_kv_hist = 2;      // 2 = unrolled histogram, several CTAs per piece (default); 1 = first generation
 int g_kv_cluster = 0;   // 1 = cluster/DSMEM leaf for segments above one CTA's capacity (measured slower)
 int g_kv_hints = 1;     // L2 eviction-priority hints in the table scatter (evict-first loads, evict-last stores)
 int g_kv_max_bits = 12; // digit bits of the table scatter's level (kv_scatter = 2)
@@ -250,17 +251,18 @@ struct ScatterSmem {
 template <bool USE_TMA>
 __global__ void __launch_bounds__(P_THREADS, 2)
 part_scatter_kernel(const ulonglong2 *__restrict__ in, ulonglong2 *__restrict__ out,
-                    const Piece *__restrict__ pieces, const u32 *__restrict__ cta_piece_begin,
-                    DigitSpec ds, u32 nb, const u64 *__restrict__ piece_off) {
+                    const Piece *__restrict__ pieces, const u32 *__restrict__ cta_piece_begin, u64 ustart, u64 un,
+                    u64 uR, DigitSpec ds, u32 nb, const u64 *__restrict__ piece_off) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     ScatterSmem &s = *reinterpret_cast<ScatterSmem *>(smem_raw);
     const u32 tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const u32 pb = cta_piece_begin[blockIdx.x], pe = cta_piece_begin[blockIdx.x + 1];
+    const u32 pb = pieces ? cta_piece_begin[blockIdx.x] : blockIdx.x;
+    const u32 pe = pieces ? cta_piece_begin[blockIdx.x + 1] : blockIdx.x + 1;
     u32 dbits = 0;
     while ((1u << dbits) < nb) ++dbits;
 
     for (u32 p = pb; p < pe; ++p) {
-        const Piece pc = pieces[p];
+        const Piece pc = pieces ? pieces[p] : uniform_piece(p, ustart, un, uR);
         for (u32 b = tid; b < nb; b += P_THREADS) s.run_off[b] = piece_off[(u64)p * nb + b];
         __syncthreads();
         for (u64 t0 = pc.start; t0 < pc.end; t0 += P_TILE) {
@@ -870,23 +872,34 @@ leaf_sort_kernel(const ulonglong2 *__restrict__ data, ulonglong2 *__restrict__ o
             for (u32 off = tid * 128u; off < nx.n * 16u; off += L_THREADS * 128u)
                 asm volatile("prefetch.global.L2 [%0];" ::"l"(nb + off));
         }
-        {
-            ulonglong2 rr[L_IPT];
+        ulonglong2 rr[L_IPT];
 #pragma unroll
-            for (int k = 0; k < L_IPT; ++k) {
-                const u32 i = tid + k * L_THREADS;
-                if (i < n) rr[k] = data[ch.start + i];
-            }
+        for (int k = 0; k < L_IPT; ++k) {
+            const u32 i = tid + k * L_THREADS;
+            if (i < n) rr[k] = data[ch.start + i];
+        }
 #pragma unroll
-            for (int k = 0; k < L_IPT; ++k) {
-                const u32 i = tid + k * L_THREADS;
-                if (i < n) {
-                    s.val[i] = rr[k].y;
-                    s.sk[i] = key_xform(rr[k].x, xf) - base;
-                }
+        for (int k = 0; k < L_IPT; ++k) {
+            const u32 i = tid + k * L_THREADS;
+            if (i < n) {
+                if (reduce_op >= 0) s.val[i] = rr[k].y;
+                s.sk[i] = key_xform(rr[k].x, xf) - base;
             }
         }
         __syncthreads();
+        if (reduce_op < 0) {
+            // sort only: the records stay in registers; each one computes its final position and leaves
+            // directly (no gather pass over shared memory, no inverse key transform)
+            u32 slot[L_IPT];
+            leaf_bin_records(s, n, ch.bin_shift, ch.bin_base, slot);
+#pragma unroll
+            for (int k = 0; k < L_IPT; ++k) {
+                const u32 i = tid + k * L_THREADS;
+                if (i < n) out[ch.start + leaf_final_pos<false>(s, n, i, slot[k])] = rr[k];
+            }
+            __syncthreads();
+            continue;
+        }
         if (reduce_op >= 0 && hash_fold_op(xf, reduce_op)) {
             const u32 g = leaf_hash_fold(s, n, reduce_op, xf, base, out + ch.start);
             if (tid == 0) {
@@ -897,12 +910,7 @@ leaf_sort_kernel(const ulonglong2 *__restrict__ data, ulonglong2 *__restrict__ o
             continue;
         }
         leaf_sort_core<false>(s, n, ch.bin_shift, ch.bin_base);
-        if (reduce_op < 0) {
-            for (u32 i = tid; i < n; i += L_THREADS) {
-                const u32 o = s.fin[i];
-                out[ch.start + i] = make_ulonglong2(key_unxform(s.sk[o] + base, xf), s.val[o]);
-            }
-        } else {
+        {
             const u32 g = leaf_seg_reduce(s, n, reduce_op, xf, base, out + ch.start);
             if (tid == 0) {
                 entry_start[ch.entry] = ch.start;
@@ -1196,7 +1204,7 @@ static int run_scatter(dampr_ctx *ctx, int G, const ulonglong2 *src, ulonglong2 
                        const u32 *cta_pb, u64 ustart, u64 un, u64 uR, u64 out_base, DigitSpec ds, u32 nb,
                        const u64 *poff, bool v2) {
     ScopedTimer tm(ctx, DAMPR_K_PART_SCATTER);
-    if (!v2 && g_kv_scatter >= 2 && nb <= (u32)S4_NB) {
+    if (!v2 && g_kv_scatter == 3 && nb <= (u32)S4_NB) {
         const size_t smem = sizeof(Scatter4Smem);
         CUDA_TRY(ctx, cudaFuncSetAttribute(part_scatter3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         part_scatter3_kernel<<<G, S4_NT, smem, ctx->stream>>>(src, dst, pieces, cta_pb, ustart, un, uR, ds, nb, poff);
@@ -1220,10 +1228,10 @@ static int run_scatter(dampr_ctx *ctx, int G, const ulonglong2 *src, ulonglong2 
     const size_t smem = sizeof(ScatterSmem);
     if (g_use_tma) {
         cudaFuncSetAttribute(part_scatter_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        part_scatter_kernel<true><<<G, P_THREADS, smem, ctx->stream>>>(src, dst, pieces, cta_pb, ds, nb, poff);
+        part_scatter_kernel<true><<<G, P_THREADS, smem, ctx->stream>>>(src, dst, pieces, cta_pb, ustart, un, uR, ds, nb, poff);
     } else {
         cudaFuncSetAttribute(part_scatter_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        part_scatter_kernel<false><<<G, P_THREADS, smem, ctx->stream>>>(src, dst, pieces, cta_pb, ds, nb, poff);
+        part_scatter_kernel<false><<<G, P_THREADS, smem, ctx->stream>>>(src, dst, pieces, cta_pb, ustart, un, uR, ds, nb, poff);
     }
     CUDA_TRY(ctx, cudaGetLastError());
     return DAMPR_OK;
@@ -1255,7 +1263,7 @@ static int partition_level(dampr_ctx *ctx, const ulonglong2 *src, ulonglong2 *ds
     } evg{ev};
 
     const bool v2 = use_v2_scatter(nb, n);
-    if (S == 1 && g_kv_scatter >= 2 && (v2 || nb <= (u32)S4_NB)) {
+    if (S == 1 && g_kv_hist == 2) {
         // ---- single segment: uniform pieces computed on the device, nothing uploaded ----------------------
         const u32 NP = (u32)G;
         DevBuf d_hist, d_tot, d_seg, d_poff;
@@ -1344,7 +1352,7 @@ static int partition_level(dampr_ctx *ctx, const ulonglong2 *src, ulonglong2 *ds
     }
     {
         ScopedTimer tm(ctx, DAMPR_K_PART_HIST);
-        if (g_kv_scatter >= 2)
+        if (g_kv_hist == 2)
             part_hist2_kernel<<<(unsigned)NP, H2_THREADS, 0, ctx->stream>>>(src, (const Piece *)d_pieces.p, 0, 0, 0, 1, ds, nb,
                                                                            (u32 *)d_hist.p, nullptr);
         else
@@ -1735,6 +1743,11 @@ int32_t dampr_set_option(const char *name, int64_t value) {
     if (!strcmp(name, "kv_scatter")) {
         if (value < 1 || value > 3) return DAMPR_ERR_ARG;
         g_kv_scatter = (int)value;
+        return DAMPR_OK;
+    }
+    if (!strcmp(name, "kv_hist")) {
+        if (value != 1 && value != 2) return DAMPR_ERR_ARG;
+        g_kv_hist = (int)value;
         return DAMPR_OK;
     }
     if (!strcmp(name, "kv_cluster")) {

@@ -84,21 +84,19 @@ __device__ __forceinline__ u32 block_excl_scan(LeafSmem &s, u32 x, u32 *total) {
     return woff + v - x;
 }
 
-// Sort the n records held in s.sk / s.val: counting sort on `bin`, then every record ranks itself inside
-// its bin by (key, tie-break) where the tie-break is the record's smem index (input position) or, in
-// the cluster leaf, its index inside the chunk (s.aux). Result: s.fin[position] = record index.
-template <bool HAS_AUX>
-__device__ __forceinline__ void leaf_sort_core(LeafSmem &s, u32 n, int bin_shift, u64 bin_base) {
+// Counting sort of the n records held in s.sk (+ s.val): the first half — one atomic per record whose return
+// value is the record's (arbitrary) slot inside its bin, exclusive scan of the bin counts (s.cnt then holds the
+// bin starts), every record's index dropped into its bin's range of s.ord. slot[k] = bin << 16 | slot for the
+// thread's records i = tid + k * L_THREADS. Ends with a barrier.
+__device__ __forceinline__ void leaf_bin_records(LeafSmem &s, u32 n, int bin_shift, u64 bin_base, u32 (&slot)[L_IPT]) {
     const u32 tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     {
         uint4 *z = reinterpret_cast<uint4 *>(s.cnt);  // 8 counters per 16-byte store
         for (u32 i = tid; i < L_BINS / 8; i += L_THREADS) z[i] = make_uint4(0, 0, 0, 0);
     }
     __syncthreads();
-    // one atomic per record: the count it returns is the record's (arbitrary) slot inside its bin.
-    // u16 counters packed two per u32 word, updated through the word.
+    // u16 counters packed two per u32 word, updated through the word
     u32 *cnt32 = reinterpret_cast<u32 *>(s.cnt);
-    u32 slot[L_IPT];
 #pragma unroll
     for (int k = 0; k < L_IPT; ++k) {
         const u32 i = tid + k * L_THREADS;
@@ -156,26 +154,40 @@ __device__ __forceinline__ void leaf_sort_core(LeafSmem &s, u32 n, int bin_shift
         if (i < n) s.ord[s.cnt[slot[k] >> 16] + (slot[k] & 0xFFFFu)] = (u16)i;
     }
     __syncthreads();
+}
+
+// second half: the final position of record i — its bin's start plus its rank inside the bin by (key, tie-break),
+// the tie-break being the record's smem index (input position) or, in the cluster leaf, its index inside the
+// chunk (s.aux)
+template <bool HAS_AUX>
+__device__ __forceinline__ u32 leaf_final_pos(const LeafSmem &s, u32 n, u32 i, u32 slotinfo) {
+    const u32 bin = slotinfo >> 16;
+    const u32 st = s.cnt[bin];
+    const u32 en = (bin + 1 < L_BINS) ? s.cnt[bin + 1] : n;
+    u32 r = 0;
+    if (en - st > 1) {
+        const u64 ki = s.sk[i];
+        const u32 ti = HAS_AUX ? s.aux[i] : i;
+        for (u32 j = st; j < en; ++j) {
+            const u32 o = s.ord[j];
+            const u64 ko = s.sk[o];
+            const u32 to = HAS_AUX ? s.aux[o] : o;
+            r += (ko < ki || (ko == ki && to < ti)) ? 1u : 0u;
+        }
+    }
+    return st + r;
+}
+
+// Sort the n records held in s.sk / s.val. Result: s.fin[position] = record index.
+template <bool HAS_AUX>
+__device__ __forceinline__ void leaf_sort_core(LeafSmem &s, u32 n, int bin_shift, u64 bin_base) {
+    const u32 tid = threadIdx.x;
+    u32 slot[L_IPT];
+    leaf_bin_records(s, n, bin_shift, bin_base, slot);
 #pragma unroll
     for (int k = 0; k < L_IPT; ++k) {
         const u32 i = tid + k * L_THREADS;
-        if (i < n) {
-            const u32 bin = slot[k] >> 16;
-            const u32 st = s.cnt[bin];
-            const u32 en = (bin + 1 < L_BINS) ? s.cnt[bin + 1] : n;
-            u32 r = 0;
-            if (en - st > 1) {
-                const u64 ki = s.sk[i];
-                const u32 ti = HAS_AUX ? s.aux[i] : i;
-                for (u32 j = st; j < en; ++j) {
-                    const u32 o = s.ord[j];
-                    const u64 ko = s.sk[o];
-                    const u32 to = HAS_AUX ? s.aux[o] : o;
-                    r += (ko < ki || (ko == ki && to < ti)) ? 1u : 0u;
-                }
-            }
-            s.fin[st + r] = (u16)i;
-        }
+        if (i < n) s.fin[leaf_final_pos<HAS_AUX>(s, n, i, slot[k])] = (u16)i;
     }
     __syncthreads();
 }

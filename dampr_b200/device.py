@@ -489,6 +489,12 @@ class KV(object):
         self.ctx.check(self.ctx.lib.dampr_kv_reduce_by_key(self.ctx.h, self.h, int(op), C.byref(h)))
         return KV(self.ctx, None, handle=h)
 
+    def count_groups(self):
+        """number of key groups of a key-sorted kv (nothing but the count leaves the device)"""
+        g = C.c_uint64(0)
+        self.ctx.check(self.ctx.lib.dampr_kv_group_offsets(self.ctx.h, self.h, None, 0, C.byref(g)))
+        return int(g.value)
+
     def group_offsets(self):
         g = C.c_uint64(0)
         self.ctx.check(self.ctx.lib.dampr_kv_group_offsets(self.ctx.h, self.h, None, 0, C.byref(g)))

@@ -277,11 +277,12 @@ def _overflow_checks(ctx, keys, vals):
     assert dict(zip(k2.tolist(), v2.view(np.int64).tolist())) == refsem.group_fold(keys, vals, lambda a, b: a)
 
 
-@pytest.mark.parametrize("opts", [{"kv_scatter": 1}, {"kv_scatter": 2}, {"kv_cluster": 1}, {"kv_scatter": 2, "kv_cluster": 1, "kv_hints": 0},
-                                  {"kv_scatter": 2, "kv_max_bits": 11}, {"kv_scatter": 1, "kv_cluster": 1}])
+@pytest.mark.parametrize("opts", [{"kv_hist": 1}, {"kv_scatter": 3}, {"kv_scatter": 2}, {"kv_cluster": 1},
+                                  {"kv_scatter": 2, "kv_cluster": 1, "kv_hints": 0}, {"kv_scatter": 2, "kv_max_bits": 11},
+                                  {"kv_scatter": 3, "kv_cluster": 1}])
 def test_sort_variants_agree(ctx, opts):
     """every selectable kernel variant gives the same stable order (and leaves the defaults restored)"""
-    defaults = {"kv_scatter": 3, "kv_cluster": 0, "kv_hints": 1, "kv_max_bits": 12}
+    defaults = {"kv_scatter": 1, "kv_hist": 2, "kv_cluster": 0, "kv_hints": 1, "kv_max_bits": 12}
     try:
         for k, v in opts.items():
             dev.set_option(k, v)

@@ -17,6 +17,9 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from dampr_b200 import device as dev
 
 
+DEFAULTS = {"kv_scatter": 1, "kv_hist": 2, "kv_cluster": 0, "kv_hints": 1, "kv_max_bits": 12}
+
+
 def peak():
     try:
         with open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "MEASURED_PEAKS.json")) as f:
@@ -67,13 +70,13 @@ def sort_case(ctx, n, nk, xf=dev.KEY_MIX, label=""):
 
     tot, wall, k, _ = timed(ctx, run)
     # check: sorted under the transform (count inversions on a sample on the host is too slow: use the library)
-    offs = kv.group_offsets()
-    ok = bool(len(offs) >= 2)
+    groups = kv.count_groups()
+    ok = groups >= 1
     kv.free()
     pk = peak()
     return {"what": "partition+sort", "label": label, "n": n, "keys": nk, "ms": round(tot, 4), "wall_ms": round(wall, 3),
             "kernels_ms": {a: round(b, 4) for a, b in k.items()}, "algorithmic_GBps": round(32.0 * n / tot / 1e6, 1),
-            "frac_of_hbm_peak": round(32.0 * n / tot / 1e6 / pk, 4), "groups": int(len(offs) - 1), "ok": ok}
+            "frac_of_hbm_peak": round(32.0 * n / tot / 1e6 / pk, 4), "groups": int(groups), "ok": ok}
 
 
 def reduce_case(ctx, n, nk, label=""):
@@ -228,17 +231,16 @@ def main():
     for m in sizes:
         n = int(m * 1e6)
         if variants:
-            for opts, label in (({"kv_scatter": 1, "kv_cluster": 0}, "v1: ballot scatter 2 x 8b + CTA leaf"),
-                                ({"kv_scatter": 2, "kv_cluster": 1}, "v2: table scatter 12b + cluster leaf"),
-                                ({"kv_scatter": 2, "kv_cluster": 0}, "v2: table scatter 12b + staged scatter 4b + CTA leaf"),
-                                ({"kv_scatter": 3, "kv_cluster": 1}, "v3: staged scatter 2 x 6b + cluster leaf"),
-                                ({"kv_scatter": 3, "kv_cluster": 0}, "v3: staged scatter 2 x 8b + CTA leaf (default)")):
-                for a, b in {"kv_scatter": 3, "kv_cluster": 0, "kv_hints": 1, "kv_max_bits": 12}.items():
+            for opts, label in (({"kv_scatter": 1, "kv_hist": 1}, "round 1: ballot scatter 2 x 8b + first histogram + CTA leaf"),
+                                ({"kv_scatter": 2, "kv_cluster": 1}, "table scatter 12b + cluster (DSMEM) leaf"),
+                                ({"kv_scatter": 3}, "staged scatter, atomic + SWAR ranking, 2 x 8b + CTA leaf"),
+                                ({}, "default: ballot scatter 2 x 8b + unrolled histogram + CTA leaf (direct emit)")):
+                for a, b in DEFAULTS.items():
                     dev.set_option(a, b)
                 for a, b in opts.items():
                     dev.set_option(a, b)
                 print(json.dumps(sort_case(ctx, n, n, label=label)), flush=True)
-            for a, b in {"kv_scatter": 3, "kv_cluster": 0, "kv_hints": 1, "kv_max_bits": 12}.items():
+            for a, b in DEFAULTS.items():
                 dev.set_option(a, b)
         print(json.dumps(sort_case(ctx, n, n, label="K=N")), flush=True)
         print(json.dumps(sort_case(ctx, n, 10_000_000, label="K=1e7")), flush=True)
