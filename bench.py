@@ -45,7 +45,7 @@ RX = re.compile(r"[^\w]+")
 MB = 1e6
 METRIC = "MB/s ingested end-to-end, TF-IDF 10 GB synthetic text, 1/2/4/8 GPU"
 MEAN_LINE = 99.94  # mean synthetic line: 99.94 B at V = 1e6 (measured)
-REF_TIMEOUT = 300  # seconds one run of the reference may take before the arm gives up on it
+REF_TIMEOUT = 120  # seconds one run of the reference may take before the arm gives up on it
 
 
 _T0 = time.time()
@@ -170,15 +170,42 @@ def run_cpu_tfidf(path, out_dir, n_procs, kind):
     if kind == "reference":
         t0 = time.time()
         # the reference hangs when one of its workers dies: bound the run
-        r = subprocess.run([sys.executable, os.path.join(ROOT, "oracle", "ref_tfidf.py"), path, out_dir, str(n_procs)],
-                           cwd=tempfile.gettempdir(), capture_output=True, text=True, timeout=REF_TIMEOUT)
+        # own process group: on a timeout the reference's forked workers are killed with it
+        proc = subprocess.Popen([sys.executable, os.path.join(ROOT, "oracle", "ref_tfidf.py"), path, out_dir, str(n_procs)],
+                                cwd=tempfile.gettempdir(), stdout=subprocess.DEVNULL, stderr=subprocess.PIPE, text=True,
+                                start_new_session=True)
+        try:
+            _out, err = proc.communicate(timeout=REF_TIMEOUT)
+        except subprocess.TimeoutExpired:
+            import signal
+            try:
+                os.killpg(proc.pid, signal.SIGKILL)
+            except Exception:
+                proc.kill()
+            proc.wait()
+            raise RuntimeError("the reference did not finish within %d s on this box" % REF_TIMEOUT)
         sec = time.time() - t0
-        if r.returncode != 0:
-            raise RuntimeError("reference run failed: %s" % r.stderr[-2000:])
+        if proc.returncode != 0:
+            raise RuntimeError("reference run failed: %s" % (err or "")[-2000:])
         return sec
     from oracle import cpu_runner
     sec, _n_terms, _n_lines = cpu_runner.timed_tfidf(path, out_dir, n_procs)
     return sec
+
+
+_REF_STATE = {"broken": None}
+
+
+def cpu_arm(path, out_dir, n_procs):
+    """The CPU arm on `path`: the unmodified reference when oracle/_ref is present and finishes on this box, else the
+    oracle port. Returns (seconds, kind, note)."""
+    if have_reference() and not _REF_STATE["broken"]:
+        try:
+            return run_cpu_tfidf(path, out_dir, n_procs, "reference"), "reference", None
+        except Exception as e:
+            _REF_STATE["broken"] = str(e)[:300]
+            progress("the reference failed here (%s): falling back to the oracle port" % _REF_STATE["broken"])
+    return run_cpu_tfidf(path, out_dir, n_procs, "port"), "port", _REF_STATE["broken"]
 
 
 def read_sink_lines(out_dir):
@@ -242,8 +269,9 @@ def reference_arm(args):
         warm_page_cache(path)
         times = []
         budget = 240.0
+        note = None
         for i in range(args.warmup + args.steps):
-            sec = run_cpu_tfidf(path, os.path.join(tmp, "idfs"), ncores, kind)
+            sec, kind, note = cpu_arm(path, os.path.join(tmp, "idfs"), ncores)
             if i == 0 and sec * (args.warmup + args.steps) > budget and nbytes > 48e6:
                 # the box is slower than planned: shrink the per-step sample so the whole run stays bounded
                 keep = int(max(32e6, nbytes * budget / (sec * (args.warmup + args.steps))))
@@ -261,7 +289,8 @@ def reference_arm(args):
             nbytes, args.vocab, ncores)
         how = ("the unmodified reference (pip install of /root/reference under oracle/_ref), benchmarks/tf-idf-dampr.py "
                "statements, wall time of the whole python process" if kind == "reference"
-               else "oracle/cpu_runner.py (port of the reference's runner; oracle/_ref is absent)")
+               else "oracle/cpu_runner.py (port of the reference's runner; %s)" % (
+                   ("the reference under oracle/_ref failed on this box: " + note) if note else "oracle/_ref is absent"))
         line = {"impl": "reference", "metric": METRIC, "value": val, "unit": "MB/s", "n_gpus": args.gpus,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * sum(times) / len(times),
                 "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
@@ -315,10 +344,9 @@ def parity_check(Dampr, MemoryText, host_text, rank, world, use_dist, dist, out_
                 shutil.copyfileobj(g, f)
     nbytes = os.path.getsize(corpus)
     got = read_sink_lines(out_dir)
-    kind = "reference" if have_reference() else "port"
-    progress("parity: GPU side done (%d lines), running the CPU checker (%s) on %d bytes" % (len(got), kind, nbytes))
-    run_cpu_tfidf(corpus, os.path.join(shared, "cpu_idfs"), ncores, kind)
-    progress("parity: checker done")
+    progress("parity: GPU side done (%d lines), running the CPU checker on %d bytes" % (len(got), nbytes))
+    _sec, kind, _note = cpu_arm(corpus, os.path.join(shared, "cpu_idfs"), ncores)
+    progress("parity: checker (%s) done" % kind)
     exp = read_sink_lines(os.path.join(shared, "cpu_idfs"))
     equal = got == exp
     second = None
@@ -357,6 +385,7 @@ def kv_extras(ctx_unused, args):
                 extra[name]["bench_wall_s"] = round(time.time() - t0, 2)
         except Exception as e:  # an extra must never take the headline line down
             extra[name] = {"error": "%s: %s" % (type(e).__name__, str(e)[:300])}
+            progress("extra %s failed: %s: %s" % (name, type(e).__name__, str(e)[:300]))
 
     guarded("kv_partition_sort_1e8_K=N", lambda: kv_bench.sort_case(ctx, 100_000_000, 100_000_000, label="K=N"))
     guarded("kv_partition_sort_1e8_K=1e7", lambda: kv_bench.sort_case(ctx, 100_000_000, 10_000_000, label="K=1e7"))
@@ -646,8 +675,7 @@ def main():
         line["extra"] = extra
 
     if rank == 0 and not args.no_cpu_baseline:
-        kind = "reference" if have_reference() else "port"
-        progress("cpu_baseline (%s)" % kind)
+        progress("cpu_baseline")
         tmp = tempfile.mkdtemp(prefix="dampr_cpu_")
         try:
             sample = cut_at_line(host_text, int(min(nbytes, max(32e6, 4e6 * ncores))))
@@ -656,8 +684,8 @@ def main():
                 f.write(pad_sample(sample, 0, lcm(64, ncores)))
             sbytes = os.path.getsize(path)
             warm_page_cache(path)
-            run_cpu_tfidf(path, os.path.join(tmp, "idfs"), ncores, kind)  # warm-up (imports, fork, page cache)
-            sec = run_cpu_tfidf(path, os.path.join(tmp, "idfs"), ncores, kind)
+            cpu_arm(path, os.path.join(tmp, "idfs"), ncores)  # warm-up (imports, fork, page cache)
+            sec, kind, _note = cpu_arm(path, os.path.join(tmp, "idfs"), ncores)
             line["cpu_baseline"] = {"value": sbytes / sec / MB, "unit": "MB/s", "cores": ncores, "kind": kind,
                                     "sample": "%d-byte line-aligned prefix of the corpus, %d processes (%s)" % (
                                         sbytes, ncores, "the unmodified reference, oracle/_ref" if kind == "reference"

@@ -84,6 +84,8 @@ struct dampr_table {
     u64 *counts;
     u64 *reps;    // offset<<20 | len, min over occurrences (hashed tokens only); ~0 = none
     u64 *stats;   // device, 8 x u64
+    u64 *fb;      // device: lines handed back to the host, (offset << 16) | length (count in stats[7])
+    u32 fb_cap;
     u32 cap_log2;
     u64 cap;
 };

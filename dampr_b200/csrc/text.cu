@@ -648,13 +648,16 @@ int32_t dampr_table_create(dampr_ctx *ctx, uint32_t capacity_log2, dampr_table *
     dampr_table *t = new dampr_table();
     t->cap_log2 = capacity_log2;
     t->cap = 1ULL << capacity_log2;
-    t->keys = t->counts = t->reps = t->stats = nullptr;
+    t->keys = t->counts = t->reps = t->stats = t->fb = nullptr;
+    t->fb_cap = 1u << 16;
     if (cudaMalloc(&t->keys, t->cap * 8) != cudaSuccess || cudaMalloc(&t->counts, t->cap * 8) != cudaSuccess ||
-        cudaMalloc(&t->reps, t->cap * 8) != cudaSuccess || cudaMalloc(&t->stats, 8 * 8) != cudaSuccess) {
+        cudaMalloc(&t->reps, t->cap * 8) != cudaSuccess || cudaMalloc(&t->stats, 8 * 8) != cudaSuccess ||
+        cudaMalloc(&t->fb, (size_t)t->fb_cap * 8) != cudaSuccess) {
         cudaFree(t->keys);
         cudaFree(t->counts);
         cudaFree(t->reps);
         cudaFree(t->stats);
+        cudaFree(t->fb);
         delete t;
         ctx->err = "cudaMalloc(table) failed";
         cudaGetLastError();
@@ -674,6 +677,7 @@ int32_t dampr_table_destroy(dampr_ctx *ctx, dampr_table *t) {
     cudaFree(t->counts);
     cudaFree(t->reps);
     cudaFree(t->stats);
+    cudaFree(t->fb);
     delete t;
     return DAMPR_OK;
 }
@@ -695,6 +699,7 @@ int32_t dampr_text_count(dampr_ctx *ctx, dampr_table *t, dampr_textbuf *tb, uint
     ARG_CHECK(ctx, own_lo <= own_hi && own_hi <= tb->n, "ownership range outside the text");
     ARG_CHECK(ctx, (own_lo % 16) == 0, "own_lo must be a multiple of 16");
     if (g_text_kernel == 2) return launch_text_count_v2(ctx, t, tb, own_lo, own_hi, mode);
+    mode &= ~DAMPR_TOK_FLAG_CR_DATA;  // the first-generation kernel flags every '\r' scan-wide; the host decides
     switch (mode) {
         case DAMPR_TOK_WS: return launch_text<DAMPR_TOK_WS, false>(ctx, t, tb, own_lo, own_hi);
         case DAMPR_TOK_NONWORD_LOWER_SET:
@@ -727,6 +732,22 @@ int32_t dampr_table_stats(dampr_ctx *ctx, dampr_table *t, uint64_t stats[8]) {
     CUDA_TRY(ctx, cudaMemcpyAsync(ctx->h_scratch, t->stats, 64, cudaMemcpyDeviceToHost, ctx->stream));
     CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
     memcpy(stats, ctx->h_scratch, 64);
+    return DAMPR_OK;
+}
+
+int32_t dampr_table_fallback_lines(dampr_ctx *ctx, dampr_table *t, uint64_t *lines, uint64_t cap, uint64_t *n) {
+    ARG_CHECK(ctx, ctx && t && n, "null");
+    uint64_t st[8];
+    int rc = dampr_table_stats(ctx, t, st);
+    if (rc) return rc;
+    *n = st[7];
+    if (!lines) return DAMPR_OK;
+    ARG_CHECK(ctx, st[7] <= (uint64_t)t->fb_cap, "fallback list overflowed (DAMPR_TF_NONASCII is set)");
+    ARG_CHECK(ctx, cap >= st[7], "lines array too small");
+    if (st[7]) {
+        CUDA_TRY(ctx, cudaMemcpyAsync(lines, t->fb, st[7] * 8, cudaMemcpyDeviceToHost, ctx->stream));
+        CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    }
     return DAMPR_OK;
 }
 

@@ -26,6 +26,8 @@
 #define DAMPR_TEXT_USE_MATCH 0
 #endif
 
+static bool g_text_cr_is_data = false;  // set per launch from the mode flags (one host thread drives a ctx)
+
 namespace {
 
 constexpr int V_THREADS = 256;
@@ -53,8 +55,12 @@ struct TableView2 {
     u64 *stats;
     u64 mask;
     u64 seed;
+    u64 *fb;      // fallback list: (global offset of the line << 16) | length, lines the host must tokenise
+    u32 fb_cap;
+    u32 cr_is_data;  // 1: '\r' is an ordinary byte (binary-mode .gz sources); 0: it ends lines (text mode)
 };
-enum { S_ENTRIES = 0, S_LINES = 1, S_EMPTY = 2, S_FOLDED = 3, S_FLAGS = 4, S_LONG = 5, S_RAW = 6 };
+enum { S_ENTRIES = 0, S_LINES = 1, S_EMPTY = 2, S_FOLDED = 3, S_FLAGS = 4, S_LONG = 5, S_RAW = 6, S_FALLBACK = 7 };
+constexpr int V_MAXBAD = 8;  // lines per warp region that may go to the host before the whole scan gives up
 
 // WS (str.split mode): no per-line history; the miss queue also carries the representative of a long token
 template <int HCAP, bool WS>
@@ -64,6 +70,7 @@ struct WarpScratchT {
     alignas(8) u64 missr[WS ? 64 : 1];
     u32 dtab[WS ? 1 : 64];  // set() de-duplication of a round: lanes per hash slot
     u16 tpos[V_TPOS];
+    u16 badterm[V_MAXBAD];  // terminators of the lines of this region that were handed to the host
 };
 constexpr u32 V_REP_UNPUB = 0xFFFFFFFFu;
 
@@ -81,6 +88,7 @@ struct Smem2T {
     alignas(16) u8 text[NBUF][V_WIN];
     u32 w[NBUF][V_WORDS + 3];
     u32 nl[NBUF][V_WORDS + 3];
+    u32 badw[NBUF][((V_WORDS + V_THREADS - 1) / V_THREADS) * V_WARPS];  // bit per 32-byte window word: holds a byte the device cannot tokenise
     alignas(8) u64 tabk[STAB];
     u32 tabc[STAB];
     // str.split mode: last occurrence (byte offset from own_lo - V_LEAD) of the long token an entry holds
@@ -348,23 +356,39 @@ text_count2_kernel(const u8 *__restrict__ text, u64 n, u64 own_lo, u64 own_hi, u
         phase[buf] ^= 1;
 
         // ---- classify the whole window (all threads) ------------------------------------------------
+        // A byte the device cannot tokenise like Python does (non-ASCII; '\r' where it ends lines) marks its
+        // 32-byte word in badw. [^\w]+ modes hand just the LINES holding such bytes to the host (per-line
+        // fallback, below); str.split mode keeps the scan-wide flags.
         u32 bad = 0;
-        for (int i = tid; i < V_WORDS; i += V_THREADS) {
-            const uint4 *p = reinterpret_cast<const uint4 *>(tx + 32 * i);
-            uint4 a = p[0], b = p[1];
-            u32 wmk = 0, nmk = 0, wb, nb;
-            classify4<MODE>(a.x, wb, nb, bad); wmk |= wb;        nmk |= nb;
-            classify4<MODE>(a.y, wb, nb, bad); wmk |= wb << 4;   nmk |= nb << 4;
-            classify4<MODE>(a.z, wb, nb, bad); wmk |= wb << 8;   nmk |= nb << 8;
-            classify4<MODE>(a.w, wb, nb, bad); wmk |= wb << 12;  nmk |= nb << 12;
-            classify4<MODE>(b.x, wb, nb, bad); wmk |= wb << 16;  nmk |= nb << 16;
-            classify4<MODE>(b.y, wb, nb, bad); wmk |= wb << 20;  nmk |= nb << 20;
-            classify4<MODE>(b.z, wb, nb, bad); wmk |= wb << 24;  nmk |= nb << 24;
-            classify4<MODE>(b.w, wb, nb, bad); wmk |= wb << 28;  nmk |= nb << 28;
-            wm[i] = wmk;
-            nm[i] = nmk;
+        u32 *bw = s.badw[buf];
+#pragma unroll 1
+        for (int kk = 0; kk < (V_WORDS + V_THREADS - 1) / V_THREADS; ++kk) {
+            const int i = tid + kk * V_THREADS;
+            u32 wbad = 0;
+            if (i < V_WORDS) {
+                const uint4 *p = reinterpret_cast<const uint4 *>(tx + 32 * i);
+                uint4 a = p[0], b = p[1];
+                u32 wmk = 0, nmk = 0, wb, nb;
+                classify4<MODE>(a.x, wb, nb, wbad); wmk |= wb;        nmk |= nb;
+                classify4<MODE>(a.y, wb, nb, wbad); wmk |= wb << 4;   nmk |= nb << 4;
+                classify4<MODE>(a.z, wb, nb, wbad); wmk |= wb << 8;   nmk |= nb << 8;
+                classify4<MODE>(a.w, wb, nb, wbad); wmk |= wb << 12;  nmk |= nb << 12;
+                classify4<MODE>(b.x, wb, nb, wbad); wmk |= wb << 16;  nmk |= nb << 16;
+                classify4<MODE>(b.y, wb, nb, wbad); wmk |= wb << 20;  nmk |= nb << 20;
+                classify4<MODE>(b.z, wb, nb, wbad); wmk |= wb << 24;  nmk |= nb << 24;
+                classify4<MODE>(b.w, wb, nb, wbad); wmk |= wb << 28;  nmk |= nb << 28;
+                wm[i] = wmk;
+                nm[i] = nmk;
+                if (tab.cr_is_data) wbad &= 0x80808080u;
+            }
+            bad |= wbad;
+            if (!WS) {
+                // the 32 words a warp classifies in one pass are consecutive: one ballot is their flag word
+                const u32 bb = __ballot_sync(0xFFFFFFFFu, wbad != 0);
+                if (lane == 0) bw[kk * V_WARPS + warp] = bb;
+            }
         }
-        if (bad) my_flags |= ((bad & 0x80808080u) ? DAMPR_TF_NONASCII : 0u) | ((bad & 0x40404040u) ? DAMPR_TF_CR : 0u);
+        if (WS && bad) my_flags |= ((bad & 0x80808080u) ? DAMPR_TF_NONASCII : 0u) | ((bad & 0x40404040u) ? DAMPR_TF_CR : 0u);
         __syncthreads();
         // every warp is past tile-1: its buffer may be refilled while this tile is processed
         if (NBUF == 2 && tid == 0) {
@@ -414,6 +438,72 @@ text_count2_kernel(const u8 *__restrict__ text, u64 n, u64 own_lo, u64 own_hi, u
             }
             rlo = q + 1;
             rhi = tl + 1;
+        }
+
+        // ---- per-line fallback ([^\w]+ modes): lines of this region that hold a byte the device cannot tokenise
+        // produce no tokens here; their (offset, length) goes to the fallback list and the host tokenises them
+        // with Python's own rules (universal newlines, Unicode \w, str.lower) and merges the counts.
+        u32 nbad = 0;  // warp-uniform
+        if (!WS) {
+            const u32 fw0 = rlo >> 5, fw1 = (rhi - 1) >> 5;
+            bool anyb = false;
+            for (u32 g = fw0 >> 5; g <= (fw1 >> 5); ++g) {
+                u32 fl = s.badw[buf][g];
+                if (g == (fw0 >> 5)) fl &= ~((1u << (fw0 & 31)) - 1u);
+                if (g == (fw1 >> 5) && (fw1 & 31) != 31) fl &= (1u << ((fw1 & 31) + 1)) - 1u;
+                anyb |= fl != 0;
+            }
+            if (anyb) {
+                u32 pos = rlo;
+                while (pos < rhi) {
+                    // next bad byte at or after pos (32 bytes per step, one per lane)
+                    u32 bpos = 0xFFFFFFFFu;
+                    for (u32 wq = pos >> 5; wq * 32 < rhi && bpos == 0xFFFFFFFFu; ++wq) {
+                        if (!((s.badw[buf][wq >> 5] >> (wq & 31)) & 1u)) continue;
+                        const u32 bp = wq * 32 + lane;
+                        const u32 c = tx[bp];
+                        const bool isb = bp >= pos && bp < rhi && (c >= 0x80u || (c == 0x0Du && !tab.cr_is_data));
+                        const u32 bm = __ballot_sync(0xFFFFFFFFu, isb);
+                        if (bm) bpos = wq * 32 + (u32)__ffs(bm) - 1u;
+                    }
+                    if (bpos == 0xFFFFFFFFu) break;
+                    // its line: q = first byte (after the previous newline), p = terminator
+                    u32 q;
+                    {
+                        int w2 = (int)(bpos >> 5);
+                        u32 m = nm[w2] & (((bpos & 31) == 0) ? 0u : ((1u << (bpos & 31)) - 1u));
+                        while (!m && w2 > (int)(rlo >> 5)) {
+                            --w2;
+                            m = nm[w2];
+                        }
+                        q = m ? (32u * w2 + (31u - (u32)__clz(m)) + 1u) : rlo;
+                        if (q < rlo) q = rlo;
+                    }
+                    const u32 pterm = warp_find_first(nm, bpos, V_WORDS, lane);
+                    if (pterm == 0xFFFFFFFFu || pterm >= rhi || nbad >= (u32)V_MAXBAD) {
+                        // cannot be isolated here (line leaves the window / too many of them): scan-wide fallback
+                        my_flags |= DAMPR_TF_NONASCII;
+                        break;
+                    }
+                    if (lane == 0) {
+                        ws.badterm[nbad] = (u16)pterm;
+                        const u64 goff = base_offset + (sgl - V_LEAD) + q;
+                        if (goff < n) {  // a start at or past n is the virtual terminator padding, not a line
+                            const u64 ix = atomicAdd(&tab.stats[S_FALLBACK], 1ULL);
+                            if (ix < (u64)tab.fb_cap) tab.fb[ix] = (goff << 16) | (u64)(pterm - q);
+                            else my_flags |= DAMPR_TF_NONASCII;
+                            acc_lines--;  // the host counts the lines of this range (universal newlines)
+                        }
+                    }
+                    for (u32 w = (q >> 5) + lane; w * 32 < pterm; w += 32) {
+                        const u32 km = range_mask(w * 32, q, pterm);
+                        if (km) atomicAnd(&wm[w], ~km);
+                    }
+                    ++nbad;
+                    pos = pterm + 1;
+                }
+                __syncwarp();
+            }
         }
 
         // ---- batches of 32 mask words -----------------------------------------------------------------
@@ -677,6 +767,11 @@ text_count2_kernel(const u8 *__restrict__ text, u64 n, u64 own_lo, u64 own_hi, u
                     u32 b = (u32)__ffs(terms) - 1u;
                     terms &= terms - 1;
                     u32 p = wi * 32 + b;
+                    if (nbad) {
+                        bool gone = false;
+                        for (u32 j = 0; j < nbad; ++j) gone |= ws.badterm[j] == (u16)p;
+                        if (gone) continue;
+                    }
                     u32 q;
                     {
                         int w2 = (int)(p >> 5);
@@ -769,7 +864,8 @@ int launch2n(dampr_ctx *ctx, dampr_table *t, dampr_textbuf *tb, u64 lo, u64 hi) 
     u64 ntiles = (hi - lo + V_OWN - 1) / V_OWN;
     u64 grid = (u64)ctx->num_sms * VAR;
     if (grid > ntiles) grid = ntiles;
-    TableView2 tv{t->keys, t->counts, t->reps, t->stats, t->cap - 1, 0x243F6A8885A308D3ULL};
+    TableView2 tv{t->keys, t->counts, t->reps, t->stats, t->cap - 1, 0x243F6A8885A308D3ULL, t->fb, t->fb_cap,
+                  (u32)(g_text_cr_is_data ? 1 : 0)};
     wait_uploads(ctx);
     {
         ScopedTimer tm(ctx, DAMPR_K_TEXT_COUNT);
@@ -797,6 +893,8 @@ int launch2(dampr_ctx *ctx, dampr_table *t, dampr_textbuf *tb, u64 lo, u64 hi) {
 }  // namespace
 
 int launch_text_count_v2(dampr_ctx *ctx, dampr_table *t, dampr_textbuf *tb, u64 lo, u64 hi, int mode) {
+    g_text_cr_is_data = (mode & DAMPR_TOK_FLAG_CR_DATA) != 0;
+    mode &= ~DAMPR_TOK_FLAG_CR_DATA;
     switch (mode) {
         case DAMPR_TOK_WS: return launch2<DAMPR_TOK_WS>(ctx, t, tb, lo, hi);
         case DAMPR_TOK_NONWORD_LOWER_SET: return launch2<DAMPR_TOK_NONWORD_LOWER_SET>(ctx, t, tb, lo, hi);

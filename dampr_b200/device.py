@@ -26,6 +26,7 @@ KEY_RAW, KEY_MIX, KEY_I64, KEY_F64 = 0, 1, 2, 3
 OP_SUM_I64, OP_SUM_F64, OP_COUNT, OP_MIN_I64, OP_MAX_I64, OP_MIN_F64, OP_MAX_F64, OP_FIRST, OP_LAST = range(9)
 # table flags
 TF_NONASCII, TF_CR, TF_LONGLINE, TF_TABLEFULL, TF_LONGTOKEN, TF_COLLISION = 1, 2, 4, 8, 16, 32
+TOK_FLAG_CR_DATA = 0x100
 
 KERNEL_NAMES = {
     1: "text_count", 2: "table_extract", 3: "text_verify", 4: "part_hist", 5: "part_scatter",
@@ -88,6 +89,7 @@ def load_library():
     _sig(lib, "dampr_text_count", vp, vp, vp, u64, u64, i32)
     _sig(lib, "dampr_text_verify", vp, vp, vp, u64, u64, i32)
     _sig(lib, "dampr_table_stats", vp, vp, pu64)
+    _sig(lib, "dampr_table_fallback_lines", vp, vp, vp, u64, pu64)
     _sig(lib, "dampr_table_fetch", vp, vp, vp, vp, vp, u64, pu64)
     _sig(lib, "dampr_table_to_kv", vp, vp, pvp)
     _sig(lib, "dampr_table_fetch_words", vp, vp, vp, i32, u32, vp, vp, vp, vp, u64, pu64)
@@ -351,8 +353,19 @@ class Table(object):
     def clear(self):
         self.ctx.check(self.ctx.lib.dampr_table_clear(self.ctx.h, self.h))
 
-    def count(self, tb, lo, hi, mode):
-        self.ctx.check(self.ctx.lib.dampr_text_count(self.ctx.h, self.h, tb.h, int(lo), int(hi), int(mode)))
+    def count(self, tb, lo, hi, mode, cr_is_data=False):
+        """cr_is_data: '\\r' is an ordinary byte (the reference's binary-mode .gz reader) instead of a line end"""
+        m = int(mode) | (TOK_FLAG_CR_DATA if cr_is_data else 0)
+        self.ctx.check(self.ctx.lib.dampr_text_count(self.ctx.h, self.h, tb.h, int(lo), int(hi), m))
+
+    def fallback_lines(self):
+        """uint64[]: (byte offset << 16) | length of every line the [^\\w]+ tokenisers handed back to the host"""
+        n = C.c_uint64(0)
+        self.ctx.check(self.ctx.lib.dampr_table_fallback_lines(self.ctx.h, self.h, None, 0, C.byref(n)))
+        out = np.empty(n.value, dtype=np.uint64)
+        if n.value:
+            self.ctx.check(self.ctx.lib.dampr_table_fallback_lines(self.ctx.h, self.h, _ptr(out), len(out), C.byref(n)))
+        return out
 
     def verify(self, tb, lo, hi, mode):
         self.ctx.check(self.ctx.lib.dampr_text_verify(self.ctx.h, self.h, tb.h, int(lo), int(hi), int(mode)))
@@ -361,7 +374,7 @@ class Table(object):
         st = (C.c_uint64 * 8)()
         self.ctx.check(self.ctx.lib.dampr_table_stats(self.ctx.h, self.h, st))
         return {"entries": st[0], "lines": st[1], "empty": st[2], "folded": st[3], "flags": st[4],
-                "hashed": st[5], "raw": st[6]}
+                "hashed": st[5], "raw": st[6], "fallback": st[7]}
 
     def fetch(self):
         """(codes, counts, reps) numpy uint64 arrays (unordered)."""

@@ -17,6 +17,7 @@ Lowered pipelines and the reference code they replace:
 import logging
 import math
 import os
+import re
 import threading
 
 import numpy as np
@@ -213,6 +214,63 @@ def _text_files(ds):
     return [("gz" if f.endswith(".gz") else "file", f) for f in files]
 
 
+_NONWORD_RX = re.compile(r"[^\w]+")   # what lowering.tokenizer_mode matched ([^\w]+ or \W+, default flags)
+
+
+def _tokens_present(words, tokens):
+    """the subset of `tokens` (str) that the token table `words` holds"""
+    if isinstance(words, np.ndarray):
+        W = words.dtype.itemsize
+        fit = [k for k in tokens if k.isascii() and 0 < len(k) <= W and "\0" not in k]
+        if not fit or not len(words):
+            return set()
+        arr = np.array([k.encode("ascii") for k in fit], dtype=words.dtype)
+        return set(b.decode("ascii") for b in arr[np.isin(arr, words)].tolist())
+    have = set(words)
+    return set(k for k in tokens if k in have)
+
+
+def merge_token_counts(words, counts, extra):
+    """(words, counts) of a device token table plus {token: count} of host-tokenised lines. `words` is a
+    fixed-width 'S' array (ASCII tokens) or a list of str; tokens the array cannot hold (non-ASCII, longer than
+    its width) turn it into a list."""
+    if not extra:
+        return words, counts
+    counts = np.array(counts, dtype=np.int64, copy=True)
+    keys = list(extra)
+    if isinstance(words, np.ndarray):
+        W = words.dtype.itemsize
+        fit = [k for k in keys if k.isascii() and 0 < len(k) <= W and "\0" not in k]
+        pos = {}
+        if fit and len(words):
+            arr = np.array([k.encode("ascii") for k in fit], dtype=words.dtype)
+            hit = np.flatnonzero(np.isin(words, arr))
+            pos = {w: int(i) for w, i in zip(words[hit].tolist(), hit.tolist())}
+        new = []
+        for k in keys:
+            i = pos.get(k.encode("ascii")) if (k.isascii() and len(k) <= W) else None
+            if i is not None:
+                counts[i] += extra[k]
+            else:
+                new.append(k)
+        if not new:
+            return words, counts
+        if all(k.isascii() and 0 < len(k) <= W and "\0" not in k for k in new):
+            words = np.concatenate((words, np.array([k.encode("ascii") for k in new], dtype=words.dtype)))
+        else:
+            words = [b.decode("ascii") for b in words.tolist()] + new
+        return words, np.concatenate((counts, np.array([extra[k] for k in new], dtype=np.int64)))
+    pos = {w: i for i, w in enumerate(words)}
+    new = []
+    for k in keys:
+        i = pos.get(k)
+        if i is not None:
+            counts[i] += extra[k]
+        else:
+            new.append(k)
+    return list(words) + new, np.concatenate((counts, np.array([extra[k] for k in new], dtype=np.int64)))
+
+
 def _inflate(paths):
     """Decompressed bytes of gzip files as uint8 arrays (zlib releases the GIL: one thread per file)."""
     import gzip
@@ -318,6 +376,7 @@ class TextScan(object):
             # files) does not apply when every source of the scan is a .gz file.
             if gz and len(gz) == len(self.sources):
                 self._cr_is_data = True
+            self._binary_src = [kind == "gz" for kind, _p in self.sources]
             if gz:
                 if dist.active():
                     raise NotLowerable("gzip inputs are not sharded across ranks")
@@ -332,7 +391,7 @@ class TextScan(object):
         # buffers are cached per context (see _cached_textbuf): nothing to release here
         if resident:
             self._tab = _cached_table(ctx)
-            self._tab.count(tb, 0, tb.n, self.mode)
+            self._tab.count(tb, 0, tb.n, self.mode, getattr(self, "_cr_is_data", False))
         else:
             self._upload_and_count(ctx, tb, sizes)
         tab = self._tab
@@ -401,7 +460,46 @@ class TextScan(object):
         self.n_lines = int(st["lines"])
         self.empty = int(st["empty"])
         self.has_cr = bool(flags & dev.TF_CR)
+        extra, extra_empty, extra_lines = self._host_lines(tb, tab, st)
+        if extra_lines:
+            self.words, self.counts = merge_token_counts(self.words, self.counts, extra)
+            self.empty += extra_empty
+            self.n_lines += extra_lines
+        self.host_lines = extra_lines
         return self
+
+    def _host_lines(self, tb, tab, st):
+        """Per-line fallback: the lines the kernel could not tokenise the way
+        Python does — a non-ASCII byte (Unicode \\w and lower()), a '\\r' in a text-mode source (universal
+        newlines split the line) — were left out of the table; they are read back, split and tokenised here with
+        the reference's own rules (TextLineDataset.read dataset.py:458-476, the matched tokeniser idiom) and the
+        counts are merged. Returns ({token: count}, count of the '' token, number of lines)."""
+        if self.mode == dev.TOK_WS or not st.get("fallback"):
+            return {}, 0, 0
+        from .datasets import _iter_lines
+        import bisect
+        fb = np.sort(tab.fallback_lines())
+        starts = getattr(self, "_layout_starts", None)
+        binary = getattr(self, "_binary_src", None)
+        extra, empty, nlines = {}, 0, 0
+        dedup = self.mode == dev.TOK_NONWORD_LOWER_SET
+        for e in fb.tolist():
+            off, ln = e >> 16, e & 0xFFFF
+            raw = tb.download(off, ln).tobytes()
+            # a .gz source is read in binary mode by the reference ('\r' stays in the line), a text file with
+            # universal newlines: the line's offset tells which source it came from
+            universal = not getattr(self, "_cr_is_data", False)
+            if starts and binary and len(binary) == len(starts):
+                universal = not binary[max(0, bisect.bisect_right(starts, off) - 1)]
+            for _o, line in _iter_lines(raw, off, universal=universal):
+                nlines += 1
+                toks = _NONWORD_RX.split(line.lower())
+                for t in (set(toks) if dedup else toks):
+                    if t == "":
+                        empty += 1
+                    else:
+                        extra[t] = extra.get(t, 0) + 1
+        return extra, empty, nlines
 
     def _finish_distributed(self, ctx, tb, tab, st):
         """world > 1: this rank scanned its shard; move every term to its owner with one all-to-all
@@ -420,8 +518,9 @@ class TextScan(object):
             ws = keycodes.decode_table(codes[hs], reps[hs], self.mode,
                                        lambda off, ln: tb.download(off, ln).tobytes())
             hashed_words = dict(zip(codes[hs].tolist(), ws))
-        lines, empty, anybad, any_hashed, any_cr = dist.all_reduce_sum_int(
-            [int(st["lines"]), int(st["empty"]), 1 if bad else 0, len(hashed_words), 1 if flags & dev.TF_CR else 0])
+        lines, empty, anybad, any_hashed, any_cr, any_fb = dist.all_reduce_sum_int(
+            [int(st["lines"]), int(st["empty"]), 1 if bad else 0, len(hashed_words), 1 if flags & dev.TF_CR else 0,
+             int(st.get("fallback", 0))])
         self.has_cr = bool(any_cr)
         if anybad:
             raise RuntimeError("distributed text scan cannot be lowered on every rank (flags=%d); the "
@@ -458,6 +557,27 @@ class TextScan(object):
         self.counts = counts.view(np.int64)
         self.n_lines = int(lines)
         self.empty = int(empty) if rank == 0 else 0
+        # per-line fallback across ranks: every rank tokenises the lines its shard handed back; the counts of all
+        # ranks are added up, a token goes to the rank whose table already holds it, otherwise to rank 0
+        self.host_lines = 0
+        if any_fb:   # (known from the all-reduce above: no extra collective when no rank handed lines back)
+            extra, extra_empty, extra_lines = self._host_lines(tb, tab, st)
+            tot = dist.all_reduce_sum_int([extra_lines, extra_empty])
+            self.host_lines = int(tot[0])
+            merged_extra = {}
+            for d in dist.all_gather_objects(extra):
+                for k, v in d.items():
+                    merged_extra[k] = merged_extra.get(k, 0) + v
+            mine = _tokens_present(self.words, list(merged_extra))
+            owners = dist.all_gather_objects(sorted(mine))
+            taken = set()
+            for o in owners:
+                taken.update(o)
+            take = {k: v for k, v in merged_extra.items() if k in mine or (rank == 0 and k not in taken)}
+            self.words, self.counts = merge_token_counts(self.words, self.counts, take)
+            self.n_lines += int(tot[0])
+            if rank == 0:
+                self.empty += int(tot[1])
         return self
 
     def _upload_and_count(self, ctx, tb, sizes):
@@ -484,6 +604,7 @@ class TextScan(object):
             layout.append((pos, sz, need_nl))
             pos += sz + (1 if need_nl else 0)
         total = pos
+        self._layout_starts = [a for a, _sz, _nl in layout]
         tb.set_length(total)
         # files are a global input: under torch.distributed every rank owns one 4 KB-aligned byte range
         # of the concatenation (line ownership at the seams is the kernel's rule); in-memory texts are
@@ -526,7 +647,7 @@ class TextScan(object):
         if hi > counted:
             a, b = max(counted, self._own[0]), min(hi, self._own[1])
             if b > a:
-                tab.count(tb, a, b, self.mode)
+                tab.count(tb, a, b, self.mode, getattr(self, "_cr_is_data", False))
             counted = hi
         self._counted = counted
         return counted

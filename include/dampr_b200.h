@@ -115,6 +115,10 @@ int32_t dampr_textbuf_devptr(dampr_ctx *ctx, dampr_textbuf *tb, uint64_t *out_pt
 #define DAMPR_TOK_NONWORD_LOWER 2     /* re.split(r'[^\w]+', line.lower()) without set():
                                          every token counts, '' tokens as re.split yields    */
 
+/* OR-ed into `mode`: '\r' is an ordinary byte, as in the reference's binary-mode .gz reader
+ * (GzipLineDataset, dataset.py:488-493). Without it '\r' ends lines (text mode, universal newlines). */
+#define DAMPR_TOK_FLAG_CR_DATA 0x100
+
 int32_t dampr_table_create(dampr_ctx *ctx, uint32_t capacity_log2, dampr_table **out);
 int32_t dampr_table_destroy(dampr_ctx *ctx, dampr_table *t);
 int32_t dampr_table_clear(dampr_ctx *ctx, dampr_table *t);
@@ -129,7 +133,8 @@ int32_t dampr_text_verify(dampr_ctx *ctx, dampr_table *t, dampr_textbuf *tb, uin
                           uint64_t own_hi, int32_t mode);
 
 /* stats[0]=entries stats[1]=lines stats[2]=count of the '' token stats[3]=tokens folded
- * stats[4]=flags (DAMPR_TF_*) stats[5]=hashed(long) tokens stats[6]=raw tokens seen stats[7]=reserved */
+ * stats[4]=flags (DAMPR_TF_*) stats[5]=hashed(long) tokens stats[6]=raw tokens seen
+ * stats[7]=lines handed back to the host (per-line fallback, see dampr_table_fallback_lines) */
 #define DAMPR_TF_NONASCII 1u
 #define DAMPR_TF_CR 2u
 #define DAMPR_TF_LONGLINE 4u
@@ -137,6 +142,14 @@ int32_t dampr_text_verify(dampr_ctx *ctx, dampr_table *t, dampr_textbuf *tb, uin
 #define DAMPR_TF_LONGTOKEN 16u
 #define DAMPR_TF_COLLISION 32u
 int32_t dampr_table_stats(dampr_ctx *ctx, dampr_table *t, uint64_t stats[8]);
+/* Per-line fallback of the [^\w]+ tokenisers: a line that holds a byte the device cannot tokenise the way
+ * Python does (non-ASCII: Unicode \w / lower(); '\r' in text mode: universal newlines) contributes NOTHING to
+ * the table, the line count or the '' token count; instead lines[i] = (byte offset of the line << 16) | length
+ * (without its '\n') is reported here and the caller tokenises just those lines (TextLineDataset.read,
+ * dataset.py:458-476 + the user's lambda) and adds the results. Order unspecified. Two-phase: lines == NULL
+ * returns *n only. More than 65536 such lines, or one that cannot be isolated inside the kernel's window, set
+ * DAMPR_TF_NONASCII instead (the whole scan is then the caller's). str.split mode keeps scan-wide flags. */
+int32_t dampr_table_fallback_lines(dampr_ctx *ctx, dampr_table *t, uint64_t *lines, uint64_t cap, uint64_t *n);
 /* compact the table into caller memory: codes[i], counts[i], reps[i] (rep = offset<<20 | len of the
  * lowest-offset occurrence, hashed tokens only, else 0). cap = array capacity; *n = entries written.
  * Pass all three arrays NULL to query *n only. Order is unspecified (dampr_table_to_kv +

@@ -26,6 +26,16 @@ REF = os.path.join(HERE, "_ref")
 
 def main(argv):
     path, out = argv[1], argv[2]
+    try:
+        # environment, not reference code: the reference's reduce stage opens one run file per map task and
+        # partition (dataset.py:571-579); with ~100 host cores that exceeds the usual soft limit of 1024 open
+        # files, a worker dies with EMFILE and the reference's parent then waits forever
+        import resource
+        soft, hard = resource.getrlimit(resource.RLIMIT_NOFILE)
+        if os.environ.get("DAMPR_REF_RAISE_NOFILE", "1") == "1" and (hard == resource.RLIM_INFINITY or soft < hard):
+            resource.setrlimit(resource.RLIMIT_NOFILE, (hard if hard != resource.RLIM_INFINITY else 1 << 20, hard))
+    except Exception:
+        pass
     sys.path[:] = [REF] + [p for p in sys.path if os.path.abspath(p or ".") not in (os.path.dirname(HERE), HERE)]
     import dampr
     assert os.path.abspath(dampr.__file__).startswith(REF), "not the reference: %s" % dampr.__file__

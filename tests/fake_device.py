@@ -257,13 +257,18 @@ class FakeTable(object):
 
     def clear(self):
         self.counts, self.first = {}, {}
-        self.st = {"lines": 0, "empty": 0, "folded": 0, "flags": 0, "hashed": 0, "raw": 0}
+        self.fb = []
+        self.st = {"lines": 0, "empty": 0, "folded": 0, "flags": 0, "hashed": 0, "raw": 0, "fallback": 0}
 
     def free(self):
         pass
 
-    def count(self, tb, lo, hi, mode):
+    def fallback_lines(self):
+        return np.array(self.fb, dtype=np.uint64)
+
+    def count(self, tb, lo, hi, mode, cr_is_data=False):
         from dampr_b200 import device as dev
+        self.cr_is_data = cr_is_data
         data = tb.buf[:tb.n].tobytes()
         pos = 0
         while pos < len(data):
@@ -278,13 +283,23 @@ class FakeTable(object):
 
     def _line(self, line, off, mode, dev):
         st = self.st
+        nonascii = any(b >= 0x80 for b in line)
+        cr = (b"\r" in line) and not getattr(self, "cr_is_data", False)
+        if mode != dev.TOK_WS and (nonascii or cr):
+            # per-line fallback of the [^\w]+ tokenisers: the line contributes nothing here and is handed back
+            if len(line) < (1 << 16) and len(self.fb) < (1 << 16):
+                self.fb.append((off << 16) | len(line))
+                st["fallback"] += 1
+            else:
+                st["flags"] |= dev.TF_NONASCII
+            return
         st["lines"] += 1
-        if any(b >= 0x80 for b in line):
+        if nonascii:
             st["flags"] |= dev.TF_NONASCII
             return
         text = line.decode("ascii")
-        if "\r" in text:
-            st["flags"] |= dev.TF_CR          # every mode flags it; the host ignores it for str.split token counts
+        if "\r" in text and mode == dev.TOK_WS:
+            st["flags"] |= dev.TF_CR          # str.split mode flags it scan-wide; the host ignores it for the token counts
         if mode == dev.TOK_WS:
             toks, limit = text.split(), 9
         else:

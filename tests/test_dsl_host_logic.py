@@ -78,7 +78,8 @@ def test_reference_golden_text_workloads_through_the_host_map_path(fixture, make
 from fake_device import FakeTextCtx, FakePinned
 
 TEXT_WORKLOADS = ["test_text_workloads_larger_vs_oracle", "test_gzip_text_inputs_are_lowered",
-                  "test_lines_with_many_distinct_tokens_stay_on_the_device", "test_non_lowerable_text_falls_back_to_host_map"]
+                  "test_lines_with_many_distinct_tokens_stay_on_the_device", "test_non_lowerable_text_falls_back_to_host_map",
+                  "test_one_cr_line_in_a_large_text_stays_on_the_device"]
 
 
 def _text_fake(monkeypatch):

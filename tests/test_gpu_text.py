@@ -132,8 +132,10 @@ def test_flags(ctx, text_kernel):
         pytest.skip("limits below are those of the v2 kernel")
     _, st = run_count(ctx, "café au lait\n".encode("utf-8"), dev.TOK_WS)
     assert st["flags"] & dev.TF_NONASCII
+    _, st = run_count(ctx, b"a\r\nb\r\n", dev.TOK_WS)
+    assert st["flags"] & dev.TF_CR          # str.split: scan-wide flag (token counts do not depend on it)
     _, st = run_count(ctx, b"a\r\nb\r\n", dev.TOK_NONWORD_LOWER_SET)
-    assert st["flags"] & dev.TF_CR
+    assert st["flags"] == 0 and st["fallback"] == 2   # [^\w]+ modes: the two lines go to the host, nothing else
     long_line = b"x " * 20000 + b"\n"
     _, st = run_count(ctx, b"a\n" * 4000 + long_line + b"b\n" * 4000, dev.TOK_NONWORD_LOWER_SET)
     assert st["flags"] & dev.TF_LONGLINE
@@ -173,3 +175,83 @@ def test_synth_text_matches_numpy_generator(ctx):
     tb.n = out.value
     got = tb.download(0, out.value).tobytes()
     assert got == ref
+
+
+def _bad_line_corpus(seed=3, n_lines=6000):
+    """ASCII lines with, every so often, a line the device must hand back: non-ASCII bytes (accents, a dotted
+    capital I whose lower() grows, a non-breaking space), '\\r\\n', a lone '\\r' inside, a long line with one
+    accent at its very end, bad lines next to each other and as first / last line."""
+    rng = np.random.default_rng(seed)
+    base = gen.text(seed, n_lines, V=3000).rstrip(b"\n").split(b"\n")
+    special = ["naïve café".encode(), b"cr inside\rline two", b"crlf line\r", "ÜBER İstanbul straße".encode(),
+               "nbsp\u00a0separated words".encode(), b"x " * 700 + "é".encode(), b"\r", "é".encode(), b"a\rb\rc\r"]
+    lines = []
+    for i, l in enumerate(base):
+        if i % 97 == 0:
+            lines.append(special[(i // 97) % len(special)])
+            if i % (97 * 4) == 0:
+                lines.append(special[(i // 97 + 3) % len(special)])   # two bad lines in a row
+        lines.append(l)
+    lines.append(special[0])                                            # ... and one as the last line
+    return lines
+
+
+def test_per_line_fallback_lists_exactly_the_bad_lines(ctx, text_kernel):
+    """[^\\w]+ tokenisers: a line holding a byte the device cannot tokenise like Python (non-ASCII, '\\r' in text
+    mode) contributes nothing to the table / line count / '' count and is reported with its offset and length;
+    everything else is counted as if those lines were not there."""
+    if text_kernel == 1:
+        pytest.skip("the first-generation kernel keeps scan-wide flags")
+    lines = _bad_line_corpus()
+    data = b"\n".join(lines) + b"\n"
+    for cr_is_data in (False, True):
+        def is_bad(l):
+            return any(b >= 0x80 for b in l) or (b"\r" in l and not cr_is_data)
+        exp_fb, off = [], 0
+        for l in lines:
+            if is_bad(l):
+                exp_fb.append((off << 16) | len(l))
+            off += len(l) + 1
+        rest = b"".join(l + b"\n" for l in lines if not is_bad(l))
+        for mode, oracle in ((dev.TOK_NONWORD_LOWER_SET, lambda d: refsem.docfreq(d)[0]),
+                             (dev.TOK_NONWORD_LOWER, refsem.termfreq_nonset)):
+            for chunk in (None, 4096 + 16, 100000):
+                tb = ctx.textbuf(len(data) + 64)
+                tb.upload_all(np.frombuffer(data, dtype=np.uint8))
+                tab = ctx.table(20)
+                lo = 0
+                step = len(data) if chunk is None else chunk
+                while lo < len(data):
+                    hi = min(len(data), lo + step)
+                    tab.count(tb, lo, hi, mode, cr_is_data)
+                    lo = hi
+                st = tab.stats()
+                assert st["flags"] == 0, st
+                assert sorted(tab.fallback_lines().tolist()) == exp_fb
+                codes, counts, reps = tab.fetch()
+                words = keycodes.decode_table(codes, reps, mode, lambda o, n: data[o:o + n])
+                got = dict(zip(words, counts.tolist()))
+                if cr_is_data:
+                    # '\\r' is an ordinary separator byte here (binary-mode .gz): only '\\n' ends lines
+                    exp = {}
+                    nl = 0
+                    for l in rest.split(b"\n")[:-1]:
+                        nl += 1
+                        toks = refsem.RX.split(l.decode("ascii").lower())
+                        for t in (set(toks) if mode == dev.TOK_NONWORD_LOWER_SET else toks):
+                            exp[t] = exp.get(t, 0) + 1
+                else:
+                    exp = dict(oracle(rest))
+                    nl = len(refsem.text_lines(rest))
+                empty = exp.pop("", 0)
+                assert got == exp and st["empty"] == empty and st["lines"] == nl
+                tb.free()
+                tab.free()
+
+
+def test_fallback_list_overflow_sets_the_scan_wide_flag(ctx, text_kernel):
+    if text_kernel == 1:
+        pytest.skip("v2 kernel only")
+    data = "é\n".encode() * 70000      # more bad lines than the list holds (and than a warp region may isolate)
+    _, st = run_count(ctx, data, dev.TOK_NONWORD_LOWER_SET, verify=False)
+    assert st["flags"] & dev.TF_NONASCII
