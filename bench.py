@@ -193,19 +193,60 @@ def run_cpu_tfidf(path, out_dir, n_procs, kind):
     return sec
 
 
-_REF_STATE = {"broken": None}
+_REF_STATE = {"broken": None, "procs": None}
+
+
+def reference_procs(ncores):
+    """settings.max_processes the unmodified reference finishes with on this box. Measured on the 128-core GPU boxes
+    (gpurun_out/r2_refdiag.log): with its default (= all cores) the reference never returns — 48 MB of text, no output,
+    no error, the open-file limit raised — while 32 and 8 worker processes finish in about a second. So the arm
+    probes, on an 8 MB sample and with a short timeout, all cores first and then 64 / 32 / 16 / 8, and keeps the
+    largest count that finishes. (The chunking of the script still follows cpu_count(); only the worker pool is capped.)"""
+    global REF_TIMEOUT
+    if _REF_STATE["procs"] is not None or _REF_STATE["broken"]:
+        return _REF_STATE["procs"]
+    from oracle import gen
+    tmp = tempfile.mkdtemp(prefix="dampr_refprobe_")
+    try:
+        path = os.path.join(tmp, "probe.txt")
+        data = np.frombuffer(gen.text(4321, 80000, V=50000), dtype=np.uint8)
+        with open(path, "wb") as f:
+            f.write(pad_sample(data, 0, lcm(64, ncores)))
+        cands = []
+        for c in (ncores, 64, 32, 16, 8, 1):
+            if c <= ncores and c not in cands:
+                cands.append(c)
+        saved = REF_TIMEOUT
+        REF_TIMEOUT = 25
+        try:
+            for c in cands:
+                try:
+                    run_cpu_tfidf(path, os.path.join(tmp, "idfs"), c, "reference")
+                    _REF_STATE["procs"] = c
+                    break
+                except Exception as e:
+                    progress("reference with %d worker processes: %s" % (c, str(e)[:120]))
+        finally:
+            REF_TIMEOUT = saved
+        if _REF_STATE["procs"] is None:
+            _REF_STATE["broken"] = "the reference finished with no worker count tried (%s)" % cands
+    finally:
+        shutil.rmtree(tmp, ignore_errors=True)
+    return _REF_STATE["procs"]
 
 
 def cpu_arm(path, out_dir, n_procs):
     """The CPU arm on `path`: the unmodified reference when oracle/_ref is present and finishes on this box, else the
-    oracle port. Returns (seconds, kind, note)."""
+    oracle port. Returns (seconds, kind, note, processes used)."""
     if have_reference() and not _REF_STATE["broken"]:
-        try:
-            return run_cpu_tfidf(path, out_dir, n_procs, "reference"), "reference", None
-        except Exception as e:
-            _REF_STATE["broken"] = str(e)[:300]
-            progress("the reference failed here (%s): falling back to the oracle port" % _REF_STATE["broken"])
-    return run_cpu_tfidf(path, out_dir, n_procs, "port"), "port", _REF_STATE["broken"]
+        procs = reference_procs(n_procs)
+        if procs:
+            try:
+                return run_cpu_tfidf(path, out_dir, procs, "reference"), "reference", None, procs
+            except Exception as e:
+                _REF_STATE["broken"] = str(e)[:300]
+                progress("the reference failed here (%s): falling back to the oracle port" % _REF_STATE["broken"])
+    return run_cpu_tfidf(path, out_dir, n_procs, "port"), "port", _REF_STATE["broken"], n_procs
 
 
 def read_sink_lines(out_dir):
@@ -271,7 +312,7 @@ def reference_arm(args):
         budget = 240.0
         note = None
         for i in range(args.warmup + args.steps):
-            sec, kind, note = cpu_arm(path, os.path.join(tmp, "idfs"), ncores)
+            sec, kind, note, used = cpu_arm(path, os.path.join(tmp, "idfs"), ncores)
             if i == 0 and sec * (args.warmup + args.steps) > budget and nbytes > 48e6:
                 # the box is slower than planned: shrink the per-step sample so the whole run stays bounded
                 keep = int(max(32e6, nbytes * budget / (sec * (args.warmup + args.steps))))
@@ -285,8 +326,8 @@ def reference_arm(args):
             if i >= args.warmup:
                 times.append(sec)
         val = nbytes * len(times) / sum(times) / MB
-        sample = "%d-byte line-aligned prefix of the synthetic corpus per step (oracle/gen.py, seed 1234, V=%d), %d processes" % (
-            nbytes, args.vocab, ncores)
+        sample = "%d-byte line-aligned prefix of the synthetic corpus per step (oracle/gen.py, seed 1234, V=%d), %d worker processes on %d cores" % (
+            nbytes, args.vocab, used, ncores)
         how = ("the unmodified reference (pip install of /root/reference under oracle/_ref), benchmarks/tf-idf-dampr.py "
                "statements, wall time of the whole python process" if kind == "reference"
                else "oracle/cpu_runner.py (port of the reference's runner; %s)" % (
@@ -296,7 +337,7 @@ def reference_arm(args):
                 "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
                 "config": {"workload": "benchmarks/tf-idf-dampr.py on synthetic Zipf(1.1) text, V=%d: %s" % (args.vocab, sample),
                            "sample": sample, "how": how},
-                "cpu_baseline": {"value": val, "unit": "MB/s", "cores": ncores, "kind": kind, "sample": sample},
+                "cpu_baseline": {"value": val, "unit": "MB/s", "cores": used, "kind": kind, "sample": sample},
                 "e2e": {"value": val, "unit": "MB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
         print(json.dumps(line))
     finally:
@@ -345,7 +386,7 @@ def parity_check(Dampr, MemoryText, host_text, rank, world, use_dist, dist, out_
     nbytes = os.path.getsize(corpus)
     got = read_sink_lines(out_dir)
     progress("parity: GPU side done (%d lines), running the CPU checker on %d bytes" % (len(got), nbytes))
-    _sec, kind, _note = cpu_arm(corpus, os.path.join(shared, "cpu_idfs"), ncores)
+    _sec, kind, _note, _used = cpu_arm(corpus, os.path.join(shared, "cpu_idfs"), ncores)
     progress("parity: checker (%s) done" % kind)
     exp = read_sink_lines(os.path.join(shared, "cpu_idfs"))
     equal = got == exp
@@ -397,6 +438,7 @@ def kv_extras(ctx_unused, args):
     guarded("kv_reduce_by_key_sorted_1e8_K=1e7", lambda: kv_bench.reduce_sorted_case(ctx, 100_000_000, 10_000_000))
     guarded("config2_e2e", lambda: kv_bench.config2_e2e(ctx))
     guarded("config5", lambda: kv_bench.config5(ctx))
+    guarded("config5_dsl", lambda: kv_bench.config5_dsl(ctx))
     return extra
 
 
@@ -685,10 +727,11 @@ def main():
             sbytes = os.path.getsize(path)
             warm_page_cache(path)
             cpu_arm(path, os.path.join(tmp, "idfs"), ncores)  # warm-up (imports, fork, page cache)
-            sec, kind, _note = cpu_arm(path, os.path.join(tmp, "idfs"), ncores)
-            line["cpu_baseline"] = {"value": sbytes / sec / MB, "unit": "MB/s", "cores": ncores, "kind": kind,
-                                    "sample": "%d-byte line-aligned prefix of the corpus, %d processes (%s)" % (
-                                        sbytes, ncores, "the unmodified reference, oracle/_ref" if kind == "reference"
+            sec, kind, _note, used = cpu_arm(path, os.path.join(tmp, "idfs"), ncores)
+            line["cpu_baseline"] = {"value": sbytes / sec / MB, "unit": "MB/s", "cores": used, "kind": kind,
+                                    "sample": "%d-byte line-aligned prefix of the corpus, %d worker processes on %d cores (%s)" % (
+                                        sbytes, used, ncores, "the unmodified reference, oracle/_ref; with all cores as workers "
+                                        "it never returns on this box" if kind == "reference"
                                         else "oracle/cpu_runner.py, a leaner port of the reference's runner")}
         finally:
             shutil.rmtree(tmp, ignore_errors=True)

@@ -340,6 +340,46 @@ def group_reducer_kind(fn):
     return None
 
 
+def _iter_fold_kind(e, argi):
+    """kind of sum(arg) / min(arg) / max(arg) / len(list(arg)) over argument `argi`, else None"""
+    if not (isinstance(e, E) and e.op == "call" and isinstance(e.a, E) and e.a.op == "obj" and len(e.b) == 1):
+        return None
+    f, a = e.a.a, e.b[0]
+    if _is_arg(a, argi):
+        return {sum: SUM, min: MIN, max: MAX}.get(f) if f in (sum, min, max) else None
+    if f is len and isinstance(a, E) and a.op == "call" and isinstance(a.a, E) and a.a.op == "obj" \
+            and a.a.a in (list, tuple) and len(a.b) == 1 and _is_arg(a.b[0], argi):
+        return COUNT
+    return None
+
+
+PRODUCT = "product"
+
+
+def join_aggregate_kind(fn):
+    """Shape of a join aggregate f(left_values_iter, right_values_iter) (dampr.py:780-820):
+      ("folds", kl, kr)   lambda l, r: (K(l), K'(r)) with K, K' in sum / min / max / len(list(.))
+      ("product",)        lambda l, r: itertools.product(l, r)   (one output per pair: use with many=True)
+    None for anything else (the join then walks Python lists on the host)."""
+    import itertools
+    e = analyze(fn)
+    if e is None or getattr(fn, "__code__", None) is None or fn.__code__.co_argcount != 2:
+        return None
+    if e.op == "tuple" and len(e.a) == 2:
+        kl, kr = _iter_fold_kind(e.a[0], 0), _iter_fold_kind(e.a[1], 1)
+        if kl is not None and kr is not None:
+            return ("folds", kl, kr)
+        return None
+    if e.op == "call" and isinstance(e.a, E) and len(e.b) == 2 and _is_arg(e.b[0], 0) and _is_arg(e.b[1], 1):
+        f = e.a
+        callee = f.a if f.op == "obj" else (
+            getattr(f.a.a, f.b, None) if (f.op == "attr" and isinstance(f.a, E) and f.a.op == "obj" and
+                                          isinstance(f.a.a, types.ModuleType)) else None)
+        if callee is itertools.product:
+            return (PRODUCT,)
+    return None
+
+
 def depends_on(e, argi, fields=None):
     """Which fields of argument `argi` an expression reads: set of ints, or None when the argument is
     used whole (or in a way the analysis does not follow)."""

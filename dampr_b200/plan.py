@@ -803,6 +803,8 @@ def try_lower(runner, stage, inputs, si, data):
         if isinstance(stage, GMap):
             return _lower_map(runner, stage, inputs, si)
         if isinstance(stage, GReduce):
+            if len(inputs) == 2:
+                return _lower_join(runner, stage, inputs)
             return _lower_reduce(runner, stage, inputs)
         if isinstance(stage, GSink):
             return _lower_sink(runner, stage, inputs)
@@ -1498,6 +1500,125 @@ def _lower_reduce(runner, stage, inputs):
                 runner.stats.add(stage, "device segmented reduce of sorted kv" + how, "records=%d groups=%d" % (fr.n, len(rk)))
                 return out
     return None
+
+
+# ---- reduce-side joins -----------------------------------------------------------------------------------------
+def _exchange_raw(runner, keys, vals):
+    """world > 1: this rank's record range of a global kv input, every record moved to the owner of its key
+    (the same owner function on both join sides = the reference's requirement that both sides use one Splitter
+    and partition count, base.py:264-283). Returns host columns of the records this rank owns."""
+    ctx = runner.ctx
+    r, w = dist.world()
+    n = len(keys)
+    lo, hi = n * r // w, n * (r + 1) // w
+    kv = ctx.kv_from_columns(keys[lo:hi], np.asarray(vals[lo:hi]).view(np.uint64))
+    try:
+        recv, _offs = dist.shuffle_kv(ctx, kv)
+    finally:
+        kv.free()
+    try:
+        k, v = recv.columns()
+    finally:
+        recv.free()
+    return k.view(keys.dtype), v.view(vals.dtype)
+
+
+def _lower_join(runner, stage, inputs):
+    """Columnar reduce-side join (InnerJoin / LeftJoin, base.py:264-315; PJoin.reduce dampr.py:780-820) of two
+    grouped binary-kv inputs when the aggregate is one of the idioms of lowering.join_aggregate_kind:
+      folds    lambda l, r: (sum(l), len(list(r)))...  both sides are folded per key on the device
+               (partition + sort + segmented reduce; across ranks: local fold, all-to-all, owner fold) and the two
+               sets of unique keys are matched by the hash build + probe kernels;
+      product  lambda l, r: itertools.product(l, r) with many=True and unique right keys (a dimension table): every
+               left record looks its partner up in the hash table built from the right side — no sort at all.
+    Records never become Python objects; the result is a frame (K, (fl, fr)) / (K, (lv, rv))."""
+    red = stage.reducer
+    if not isinstance(red, (ops.InnerJoin, ops.LeftJoin)) or not getattr(red, "keyed", False):
+        return None
+    agg = getattr(red, "user_aggregate", None)
+    L, R = inputs
+    if agg is None or not (isinstance(L, LazyKVFrame) and isinstance(R, LazyKVFrame)) or L._done or R._done:
+        return None
+    kind = lowering.join_aggregate_kind(agg)
+    if kind is None:
+        return None
+    lk, lv = L.raw()
+    rk, rv = R.raw()
+    if lk.dtype != rk.dtype or lv.dtype.kind not in "iu" or rv.dtype.kind not in "iu":
+        return None
+    left_outer = isinstance(red, ops.LeftJoin)
+    ctx = runner.ctx
+    opmap = {lowering.SUM: dev.OP_SUM_I64, lowering.COUNT: dev.OP_COUNT, lowering.MIN: dev.OP_MIN_I64,
+             lowering.MAX: dev.OP_MAX_I64}
+    if kind[0] == "folds":
+        if bool(getattr(red, "many", False)):
+            return None
+        _k, kl, kr = kind
+        if left_outer and kr not in (lowering.SUM, lowering.COUNT):
+            return None   # min / max of an empty right group raise in Python
+        for col, kk in ((lv, kl), (rv, kr)):
+            if kk == lowering.SUM and len(col) and _may_overflow(col):
+                raise NotLowerable("64-bit sum could overflow (SURVEY B12)")
+        gk_l, gv_l, how = _device_group(runner, lk, lv, opmap[kl], dev.KEY_MIX)
+        gk_r, gv_r, _h = _device_group(runner, rk, rv, opmap[kr], dev.KEY_MIX)
+        build = ctx.kv_from_columns(gk_r, gv_r)
+        probe = ctx.kv_from_columns(gk_l, gv_l)
+        try:
+            vals, hit = build.hash_probe(probe)
+            try:
+                _pk, fr = vals.columns()
+            finally:
+                vals.free()
+        finally:
+            build.free()
+            probe.free()
+        hit = hit.astype(bool)
+        if left_outer:
+            keys = gk_l.view(lk.dtype)
+            fl = gv_l.view(np.int64)
+            fr = np.where(hit, fr.view(np.int64), 0)   # sum / len of an empty right group
+        else:
+            keys = gk_l.view(lk.dtype)[hit]
+            fl = gv_l.view(np.int64)[hit]
+            fr = fr.view(np.int64)[hit]
+        out = Frame(keys, [keys, vexpr.Tup([fl, fr])], scalar=False, combined=True)
+        runner.stats.add(stage, "device join: per-side partition+sort+fold, hash build+probe of the group keys" + how,
+                         "left=%d right=%d left groups=%d right groups=%d rows=%d" % (len(lk), len(rk), len(gk_l), len(gk_r), len(keys)))
+        return out
+    # ---- product with a unique right side --------------------------------------------------------------------
+    if left_outer or not bool(getattr(red, "many", False)):
+        return None
+    how = ""
+    if dist.active():
+        lk, lv = _exchange_raw(runner, lk, lv)
+        rk, rv = _exchange_raw(runner, rk, rv)
+        how = " [rank %d/%d: both sides exchanged by key owner]" % dist.world()
+    build = ctx.kv_from_columns(rk, np.asarray(rv).view(np.uint64))
+    try:
+        cnt = ctx.kv_from_columns(rk, np.ones(len(rk), dtype=np.int64)).sort_reduce(dev.OP_COUNT, dev.KEY_MIX)
+        unique = len(cnt) == len(rk)
+        cnt.free()
+        if dist.active():
+            unique = dist.all_reduce_sum_int([0 if unique else 1])[0] == 0
+        if not unique:
+            raise NotLowerable("product join: the right side has duplicate keys")
+        probe = ctx.kv_from_columns(lk, np.asarray(lv).view(np.uint64))
+        try:
+            vals, hit = build.hash_probe(probe)
+            try:
+                _pk, pr = vals.columns()
+            finally:
+                vals.free()
+        finally:
+            probe.free()
+    finally:
+        build.free()
+    hit = hit.astype(bool)
+    keys = lk[hit]
+    out = Frame(keys, [keys, vexpr.Tup([np.asarray(lv)[hit], pr.view(rv.dtype)[hit]])], scalar=False, combined=False)
+    runner.stats.add(stage, "device join: broadcast hash build + probe (unique right keys)" + how,
+                     "left=%d right=%d rows=%d" % (len(lk), len(rk), len(keys)))
+    return out
 
 
 # ---- sinks ---------------------------------------------------------------------------------------------------

@@ -599,3 +599,56 @@ def test_crlf_gzip_inputs_agree_with_the_reference(path_kind, monkeypatch, tmp_p
             assert got == exp, (layout, src)
             if path_kind == "scan-plumbing" and layout == "gz-only" and "count" in src:
                 assert any("device text tokenise+combine" in h for _s, h, _d in runner_mod.LAST_STATS.stages), src
+
+
+def test_lowered_join_idioms_agree_with_the_reference(monkeypatch):
+    """Columnar reduce-side joins (plan._lower_join): per-side folds (inner and left), and itertools.product over a
+    right side with unique keys (many=True) — vs the reference's InnerJoin / LeftJoin (base.py:264-315). Joins whose
+    aggregate is not an idiom, or whose right side has duplicate keys under product, take the generic path and
+    must agree as well."""
+    import itertools
+    import numpy as np
+    from fake_device import FakeCtx
+    from dampr_b200 import Dampr, settings, plan
+    from dampr_b200 import runner as runner_mod
+    from dampr_b200.inputs import ArrayKVInput
+    rng = random.Random(41)
+    keys = [rng.randint(0, 400) for _ in range(5000)]
+    vals = [rng.randint(-100, 100) for _ in range(5000)]
+    k2 = rng.sample(range(200, 700), 300)          # unique keys, about half of them present on the left
+    v2 = [rng.randint(0, 50) for _ in range(300)]
+    A_ref = "Dampr.memory(recs, partitions=3)"; B_ref = "Dampr.memory(recs2, partitions=2)"
+    A_our = "Dampr.read_input(ArrayKVInput(K, V))"; B_our = "Dampr.read_input(ArrayKVInput(K2, V2))"
+    G = ".group_by(lambda x: x[0], lambda x: x[1])"
+    tmpl = [
+        "{A}" + G + ".join({B}" + G + ").reduce(lambda l, r: (sum(l), len(list(r))))",
+        "{A}" + G + ".join({B}" + G + ").reduce(lambda l, r: (max(l), min(r)))",
+        "{A}" + G + ".join({B}" + G + ").reduce(lambda l, r: (len(list(l)), sum(r)))",
+        "{A}" + G + ".join({B}" + G + ").left_reduce(lambda l, r: (sum(l), len(list(r))))",
+        "{A}" + G + ".join({B}" + G + ").left_reduce(lambda l, r: (min(l), sum(r)))",
+        "{A}" + G + ".join({B}" + G + ").reduce(lambda l, r: itertools.product(l, r), many=True)",
+        "{B}" + G + ".join({A}" + G + ").reduce(lambda l, r: itertools.product(l, r), many=True)",   # duplicate right keys
+        "{A}" + G + ".join({B}" + G + ").reduce(lambda l, r: (sum(l), sorted(r)))",                   # not an idiom
+    ]
+    env = dict(os.environ)
+    env.pop("PYTHONPATH", None)
+    driver = TWO_DRIVER.replace("import sys, json", "import sys, json, itertools")
+    p = subprocess.run([sys.executable, "-c", driver, REF, json.dumps(list(zip(keys, vals))),
+                        json.dumps([t.format(A=A_ref, B=B_ref) for t in tmpl]), json.dumps(list(zip(k2, v2)))],
+                       capture_output=True, text=True, env=env, cwd="/tmp", timeout=600)
+    assert p.returncode == 0, p.stderr[-2000:]
+    ref = json.loads(p.stdout.strip().split("\n")[-1])
+    ns = {"Dampr": Dampr, "ArrayKVInput": ArrayKVInput, "itertools": itertools, "K": np.array(keys, dtype=np.int64),
+          "V": np.array(vals, dtype=np.int64), "K2": np.array(k2, dtype=np.int64), "V2": np.array(v2, dtype=np.int64)}
+    hows = []
+    for t, exp in zip(tmpl, ref):
+        monkeypatch.setattr(runner_mod, "_CTX", {settings.device: FakeCtx()})
+        monkeypatch.setattr(plan, "_BUFFERS", {})
+        got = sorted(repr(x) for x in eval(t.format(A=A_our, B=B_our), ns).run())
+        hows.append([h for _s, h, _d in runner_mod.LAST_STATS.stages])
+        assert got == exp, t
+    for i in range(5):
+        assert any("device join: per-side partition+sort+fold" in h for h in hows[i]), tmpl[i]
+    assert any("device join: broadcast hash build + probe" in h for h in hows[5])
+    for i in (6, 7):
+        assert not any("device join:" in h for h in hows[i]), tmpl[i]

@@ -41,7 +41,8 @@ import test_gpu_workloads as W
 WORKLOADS = ["test_kv_larger_vs_oracle", "test_kv_workloads_match_reference_golden", "test_map_side_join_lowered_to_hash_probe",
              "test_non_lowerable_map_runs_in_forked_workers", "test_non_lowerable_reduce_runs_in_forked_workers",
              "test_non_lowerable_text_falls_back_to_host_map", "test_shim_package_runs_reference_style_script",
-             "test_sort_by_over_binary_records", "test_spill_path_with_capped_arena", "test_text_workloads_larger_vs_oracle"]
+             "test_sort_by_over_binary_records", "test_spill_path_with_capped_arena", "test_text_workloads_larger_vs_oracle",
+             "test_columnar_join_idioms"]
 
 
 @pytest.mark.parametrize("name", WORKLOADS)

@@ -333,3 +333,35 @@ def test_one_cr_line_in_a_large_text_stays_on_the_device(ctx, tmp_path):
     assert Dampr.text(str(p)).len().read() == [n_lines]
     got = Dampr.text(str(p)).flat_map(lambda x: RX.split(x.lower())).count().read()
     assert dict(got) == dict(refsem.termfreq_nonset(data))
+
+
+def test_columnar_join_idioms(ctx):
+    """L.group_by(k, v).join(R.group_by(k, v)).reduce(idiom) over binary kv inputs: per-side folds (inner, left) and
+    itertools.product with a unique right side run as columnar device joins (plan._lower_join) and agree with the
+    oracle's join semantics (refsem.inner_join / left_join, base.py:264-315)."""
+    import itertools
+    lk, lv = gen.kv(1, 60000, 4000)
+    rk0, rv0 = gen.kv(2, 9000, 8000)
+    lk, rk0 = lk.view(np.int64), rk0.view(np.int64)
+    G = lambda ks, vs: Dampr.read_input(ArrayKVInput(ks, vs)).group_by(lambda x: x[0], lambda x: x[1])
+    inner = refsem.inner_join(lk, lv, rk0, rv0)
+    left = refsem.left_join(lk, lv, rk0, rv0)
+    got = dict(G(lk, lv).join(G(rk0, rv0)).reduce(lambda l, r: (sum(l), len(list(r)))).read())
+    assert lowered("device join: per-side partition+sort+fold")
+    assert got == {k: (sum(a), len(b)) for k, (a, b) in inner.items()}
+    got = dict(G(lk, lv).join(G(rk0, rv0)).reduce(lambda l, r: (max(l), min(r))).read())
+    assert got == {k: (max(a), min(b)) for k, (a, b) in inner.items()}
+    got = dict(G(lk, lv).join(G(rk0, rv0)).left_reduce(lambda l, r: (sum(l), sum(r))).read())
+    assert got == {k: (sum(a), sum(b)) for k, (a, b) in left.items()}
+    # product with a dimension table (unique right keys): one row per matching left record
+    uk, first = np.unique(rk0, return_index=True)
+    uv = rv0[first]
+    rows = G(lk, lv).join(G(uk, uv)).reduce(lambda l, r: itertools.product(l, r), many=True).read()
+    assert lowered("device join: broadcast hash build + probe")
+    table = dict(zip(uk.tolist(), uv.tolist()))
+    exp = sorted((int(k), (int(v), table[int(k)])) for k, v in zip(lk.tolist(), lv.tolist()) if int(k) in table)
+    assert sorted(rows) == exp
+    # duplicate right keys: not the idiom's case, the generic join must still agree
+    rows = G(lk[:3000], lv[:3000]).join(G(rk0, rv0)).reduce(lambda l, r: itertools.product(l, r), many=True).read()
+    sub = refsem.inner_join(lk[:3000], lv[:3000], rk0, rv0)
+    assert sorted(rows) == sorted((k, (a, b)) for k, (la, rb) in sub.items() for a in la for b in rb)
