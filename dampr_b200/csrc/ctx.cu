@@ -1,6 +1,9 @@
 // ctx.cu — context, streams, timings, pinned memory, text buffers and kv containers.
 // Replaces the process pool / Queue plumbing of StageRunner.run (reference stagerunner.py:15-43)
 // and the on-disk run files of dataset.py with device-resident buffers.
+#include <fcntl.h>
+#include <unistd.h>
+
 #include <algorithm>
 #include <atomic>
 #include <condition_variable>
@@ -133,9 +136,12 @@ class CopyPool {
     static constexpr size_t PIECE = 1u << 20;
     struct Job {
         char *dst;
-        const char *src;
+        const char *src;   // memory source, or nullptr: read from fd at file offset foff
+        int fd = -1;
+        size_t foff = 0;
         size_t n, pieces;
         std::atomic<size_t> next{0}, left{0};
+        std::atomic<int> failed{0};
     };
 
   public:
@@ -143,15 +149,18 @@ class CopyPool {
         static CopyPool p;
         return p;
     }
-    void run(void *dst, const void *src, size_t n, int threads) {
-        if (threads <= 1 || n < 4 * PIECE) {
+    // returns false if a read from the file came up short
+    bool run(void *dst, const void *src, size_t n, int threads, int fd = -1, size_t foff = 0) {
+        if (src && (threads <= 1 || n < 4 * PIECE)) {
             memcpy(dst, src, n);
-            return;
+            return true;
         }
         std::lock_guard<std::mutex> job_lock(job_mu_);
         auto job = std::make_shared<Job>();
         job->dst = (char *)dst;
         job->src = (const char *)src;
+        job->fd = fd;
+        job->foff = foff;
         job->n = n;
         job->pieces = (n + PIECE - 1) / PIECE;
         job->left.store(job->pieces);
@@ -165,6 +174,7 @@ class CopyPool {
         work(*job);
         std::unique_lock<std::mutex> lk(mu_);
         done_cv_.wait(lk, [&] { return job->left.load() == 0; });
+        return job->failed.load() == 0;
     }
 
   private:
@@ -182,7 +192,19 @@ class CopyPool {
             const size_t i = j.next.fetch_add(1);
             if (i >= j.pieces) break;
             const size_t lo = i * PIECE, len = std::min(PIECE, j.n - lo);
-            memcpy(j.dst + lo, j.src + lo, len);
+            if (j.src) {
+                memcpy(j.dst + lo, j.src + lo, len);
+            } else {
+                size_t got = 0;
+                while (got < len) {
+                    const ssize_t r = pread(j.fd, j.dst + lo + got, len - got, (off_t)(j.foff + lo + got));
+                    if (r <= 0) {
+                        j.failed.store(1);
+                        break;
+                    }
+                    got += (size_t)r;
+                }
+            }
             if (j.left.fetch_sub(1) == 1) {
                 std::lock_guard<std::mutex> lk(mu_);
                 done_cv_.notify_all();
@@ -212,6 +234,9 @@ class CopyPool {
 };
 
 void par_memcpy(void *dst, const void *src, size_t n, int threads) { CopyPool::get().run(dst, src, n, threads); }
+bool par_pread(void *dst, int fd, size_t foff, size_t n, int threads) {
+    return CopyPool::get().run(dst, nullptr, n, std::max(threads, 1), fd, foff);
+}
 
 bool is_pinned(const void *p) {
     cudaPointerAttributes a;
@@ -250,6 +275,26 @@ int staged_h2d(dampr_ctx *ctx, void *dst, const void *src, size_t bytes, cudaStr
         const size_t len = std::min(B, bytes - off);
         CUDA_TRY(ctx, cudaEventSynchronize(ctx->stage_ev[slot]));  // the DMA that last read this slot
         par_memcpy(ctx->stage_slot[slot], (const char *)src + off, len, ctx->host_threads);
+        CUDA_TRY(ctx, cudaMemcpyAsync((char *)dst + off, ctx->stage_slot[slot], len, cudaMemcpyHostToDevice, st));
+        CUDA_TRY(ctx, cudaEventRecord(ctx->stage_ev[slot], st));
+    }
+    return DAMPR_OK;
+}
+
+// file (page cache) -> device: the copy threads pread() 1 MB pieces straight into the page-locked ring, the DMA of
+// a slot overlaps the reads into the next ones
+int staged_file_h2d(dampr_ctx *ctx, void *dst, int fd, size_t foff, size_t bytes, cudaStream_t st) {
+    if (bytes == 0) return DAMPR_OK;
+    int rc = stage_init(ctx);
+    if (rc) return rc;
+    const size_t B = dampr_ctx::STAGE_BYTES;
+    size_t i = 0;
+    for (size_t off = 0; off < bytes; off += B, ++i) {
+        const int slot = (int)(i % dampr_ctx::STAGE_SLOTS);
+        const size_t len = std::min(B, bytes - off);
+        CUDA_TRY(ctx, cudaEventSynchronize(ctx->stage_ev[slot]));  // the DMA that last read this slot
+        if (!par_pread(ctx->stage_slot[slot], fd, foff + off, len, ctx->host_threads))
+            return set_err(ctx, DAMPR_ERR_ARG, "%s", "short read from the input file");
         CUDA_TRY(ctx, cudaMemcpyAsync((char *)dst + off, ctx->stage_slot[slot], len, cudaMemcpyHostToDevice, st));
         CUDA_TRY(ctx, cudaEventRecord(ctx->stage_ev[slot], st));
     }
@@ -503,6 +548,23 @@ int32_t dampr_textbuf_upload(dampr_ctx *ctx, dampr_textbuf *tb, uint64_t off, co
     ARG_CHECK(ctx, off + len <= tb->capacity, "upload exceeds textbuf capacity");
     if (len) {
         int rc = staged_h2d(ctx, tb->text + off, host, len, ctx->copy);
+        if (rc) return rc;
+        if (off + len > tb->uploaded_hi) tb->uploaded_hi = off + len;
+    }
+    CUDA_TRY(ctx, cudaEventRecord(ctx->upload_done, ctx->copy));
+    ctx->upload_pending = true;
+    return DAMPR_OK;
+}
+
+int32_t dampr_textbuf_upload_file(dampr_ctx *ctx, dampr_textbuf *tb, uint64_t off, const char *path,
+                                  uint64_t file_off, uint64_t len) {
+    ARG_CHECK(ctx, ctx && tb && path, "null");
+    ARG_CHECK(ctx, off + len <= tb->capacity, "upload exceeds textbuf capacity");
+    if (len) {
+        const int fd = open(path, O_RDONLY);
+        if (fd < 0) return set_err(ctx, DAMPR_ERR_ARG, "cannot open %s", path);
+        const int rc = staged_file_h2d(ctx, tb->text + off, fd, file_off, len, ctx->copy);
+        close(fd);
         if (rc) return rc;
         if (off + len > tb->uploaded_hi) tb->uploaded_hi = off + len;
     }

@@ -80,6 +80,7 @@ def load_library():
     _sig(lib, "dampr_textbuf_create", vp, u64, pvp)
     _sig(lib, "dampr_textbuf_destroy", vp, vp)
     _sig(lib, "dampr_textbuf_set_length", vp, vp, u64)
+    _sig(lib, "dampr_textbuf_upload_file", vp, vp, u64, C.c_char_p, u64, u64)
     _sig(lib, "dampr_textbuf_upload", vp, vp, u64, vp, u64)
     _sig(lib, "dampr_textbuf_download", vp, vp, u64, vp, u64)
     _sig(lib, "dampr_textbuf_devptr", vp, vp, pu64)
@@ -314,6 +315,12 @@ class TextBuf(object):
         """Async copy of host bytes (numpy uint8 view; pinned for full speed) to text[off:]."""
         length = len(host_u8) if length is None else length
         self.ctx.check(self.ctx.lib.dampr_textbuf_upload(self.ctx.h, self.h, int(off), _ptr(host_u8), int(length)))
+
+    def upload_file(self, off, path, file_off, length):
+        """Async copy of bytes [file_off, file_off + length) of a file to text[off:]: the library's copy threads
+        pread() the page cache into its page-locked ring, slot by slot, ahead of the DMA."""
+        self.ctx.check(self.ctx.lib.dampr_textbuf_upload_file(self.ctx.h, self.h, int(off), os.fsencode(path),
+                                                              int(file_off), int(length)))
 
     def upload_all(self, data):
         """Convenience: whole text from bytes / numpy (blocking)."""

@@ -629,8 +629,6 @@ class TextScan(object):
                     done = base + off
                     counted = self._count_ready(tab, tb, counted, done, total, final=False)
             else:
-                if ring is None:
-                    ring = _pinned_ring(4, chunk)
                 self._upload_file(ctx, tb, p, base, sz, ring, chunk, tab, counted, total)
                 done = base + sz
                 counted = self._counted
@@ -653,58 +651,15 @@ class TextScan(object):
         return counted
 
     def _upload_file(self, ctx, tb, path, base, sz, ring, chunk, tab, counted, total):
-        """page cache -> pinned ring (reader threads) -> device, kernel launches trailing the copies."""
+        """page cache -> the library's page-locked ring (its copy threads pread() 1 MB pieces in parallel) -> device,
+        chunk by chunk, kernel launches trailing the copies (dampr_textbuf_upload_file)."""
         self._counted = counted
-        nslots = len(ring)
-        nchunks = (sz + chunk - 1) // chunk
-        if nchunks == 0:
-            return
-        fd = os.open(path, os.O_RDONLY)
-        try:
-            results = [None] * nchunks
-            events = [threading.Event() for _ in range(nchunks)]
-            slot_free = [threading.Event() for _ in range(nslots)]
-            for e in slot_free:
-                e.set()
-
-            def reader(ci):
-                slot = ci % nslots
-                slot_free[slot].wait()
-                slot_free[slot].clear()
-                off = ci * chunk
-                ln = min(chunk, sz - off)
-                mv = memoryview(ring[slot].array)[:ln]
-                got = 0
-                while got < ln:
-                    r = os.preadv(fd, [mv[got:]], off + got)
-                    if r <= 0:
-                        break
-                    got += r
-                results[ci] = (slot, off, ln)
-                events[ci].set()
-
-            threads = []
-            nthreads = max(1, min(nslots, int(settings.max_processes)))
-            # simple pipeline: launch readers in order, at most nslots in flight
-            started = 0
-            for ci in range(nchunks):
-                while started < nchunks and started < ci + nslots:
-                    t = threading.Thread(target=reader, args=(started,))
-                    t.daemon = True
-                    t.start()
-                    threads.append(t)
-                    started += 1
-                events[ci].wait()
-                slot, off, ln = results[ci]
-                tb.upload(base + off, ring[slot].array[:ln], ln)
-                # the slot may be refilled only after the copy left it
-                ctx.sync_copy_stream()
-                slot_free[slot].set()
-                self._count_ready(tab, tb, self._counted, base + off + ln, total, final=False)
-            for t in threads:
-                t.join()
-        finally:
-            os.close(fd)
+        off = 0
+        while off < sz:
+            ln = min(chunk, sz - off)
+            tb.upload_file(base + off, path, off, ln)
+            off += ln
+            self._count_ready(tab, tb, self._counted, base + off, total, final=False)
 
 
 def _source_key(sources):

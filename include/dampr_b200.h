@@ -101,6 +101,12 @@ int32_t dampr_textbuf_set_length(dampr_ctx *ctx, dampr_textbuf *tb, uint64_t n);
 /* async host->device copy of text bytes [off, off+len) on the copy stream */
 int32_t dampr_textbuf_upload(dampr_ctx *ctx, dampr_textbuf *tb, uint64_t off, const void *host,
                              uint64_t len);
+/* the same from a FILE: bytes [file_off, file_off+len) of `path` -> text[off, off+len). The library's copy
+ * threads pread() the page cache straight into its page-locked ring while the previous slot is in flight to
+ * the device (replaces the open(...).readline loop of TextLineDataset.read, dataset.py:458-476, as the
+ * ingest of the scan). */
+int32_t dampr_textbuf_upload_file(dampr_ctx *ctx, dampr_textbuf *tb, uint64_t off, const char *path,
+                                  uint64_t file_off, uint64_t len);
 /* blocking device->host copy of text bytes [off, off+len) */
 int32_t dampr_textbuf_download(dampr_ctx *ctx, dampr_textbuf *tb, uint64_t off, void *host,
                                uint64_t len);

@@ -242,6 +242,13 @@ class FakeTextBuf(object):
         self.buf[off:off + length] = np.frombuffer(memoryview(host), dtype=np.uint8)[:length] \
             if not isinstance(host, np.ndarray) else host.reshape(-1).view(np.uint8)[:length]
 
+    def upload_file(self, off, path, file_off, length):
+        with open(path, "rb") as f:
+            f.seek(file_off)
+            data = f.read(length)
+        assert len(data) == length
+        self.buf[off:off + length] = np.frombuffer(data, dtype=np.uint8)
+
     def download(self, off, length):
         return self.buf[off:off + length].copy()
 
