@@ -162,6 +162,59 @@ __global__ void probe_lookup_kernel(const ulonglong2 *__restrict__ probe, u64 n,
     }
 }
 
+// ---- compaction of the probe result: matched records only, probe order kept --------------------
+constexpr int HC_THREADS = 512;
+constexpr int HC_TILE = HC_THREADS * 8;
+__global__ void __launch_bounds__(HC_THREADS)
+hits_count_kernel(const u8 *__restrict__ hit, u64 n, u32 *__restrict__ tile_cnt) {
+    __shared__ u32 wsum[HC_THREADS / 32];
+    const u64 t0 = (u64)blockIdx.x * HC_TILE + (u64)threadIdx.x * 8;
+    u32 c = 0;
+    if (t0 + 8 <= n) {
+        const u64 w = *reinterpret_cast<const u64 *>(hit + t0);  // 8 flags (0 / 1) per load
+        c = (u32)__popcll(w & 0x0101010101010101ULL);
+    } else {
+        for (u64 i = t0; i < n && i < t0 + 8; ++i) c += hit[i] ? 1u : 0u;
+    }
+    for (int d = 16; d > 0; d >>= 1) c += __shfl_down_sync(0xFFFFFFFFu, c, d);
+    if ((threadIdx.x & 31) == 0) wsum[threadIdx.x >> 5] = c;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        u32 t = 0;
+        for (int w = 0; w < HC_THREADS / 32; ++w) t += wsum[w];
+        tile_cnt[blockIdx.x] = t;
+    }
+}
+
+__global__ void __launch_bounds__(HC_THREADS)
+hits_compact_kernel(const ulonglong2 *__restrict__ probe, const ulonglong2 *__restrict__ vals,
+                    const u8 *__restrict__ hit, u64 n, const u64 *__restrict__ tile_base,
+                    ulonglong2 *__restrict__ out_probe, ulonglong2 *__restrict__ out_build) {
+    __shared__ u32 wsum[HC_THREADS / 32];
+    const u32 lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const u64 t0 = (u64)blockIdx.x * HC_TILE + (u64)threadIdx.x * 8;
+    u32 flags = 0;
+    for (int k = 0; k < 8; ++k)
+        if (t0 + k < n && hit[t0 + k]) flags |= 1u << k;
+    const u32 c = (u32)__popc(flags);
+    u32 v = c;
+    for (int d = 1; d < 32; d <<= 1) {
+        u32 o = __shfl_up_sync(0xFFFFFFFFu, v, d);
+        if ((int)lane >= d) v += o;
+    }
+    if (lane == 31) wsum[warp] = v;
+    __syncthreads();
+    u32 woff = 0;
+    for (u32 w = 0; w < warp; ++w) woff += wsum[w];
+    u64 pos = tile_base[blockIdx.x] + woff + v - c;
+    for (int k = 0; k < 8; ++k)
+        if (flags & (1u << k)) {
+            out_probe[pos] = probe[t0 + k];
+            out_build[pos] = vals[t0 + k];
+            ++pos;
+        }
+}
+
 // ---- synthetic inputs (same integer algorithm as oracle/gen.py) -------------------------------
 __host__ __device__ __forceinline__ u64 splitmix64(u64 x) {
     x += 0x9E3779B97F4A7C15ULL;
@@ -373,6 +426,69 @@ int32_t dampr_kv_hash_probe(dampr_ctx *ctx, dampr_kv *build, dampr_kv *probe, da
     CUDA_TRY(ctx, cudaGetLastError());
     CUDA_TRY(ctx, cudaMemcpyAsync(out_hit_host, hit.p, probe->n, cudaMemcpyDeviceToHost, ctx->stream));
     CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    return DAMPR_OK;
+}
+
+int32_t dampr_kv_hash_join(dampr_ctx *ctx, dampr_kv *build, dampr_kv *probe, dampr_kv **out_probe,
+                           dampr_kv **out_build) {
+    ARG_CHECK(ctx, ctx && build && probe && out_probe && out_build, "null");
+    CtxScope scope_(ctx);
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    wait_uploads(ctx);
+    *out_probe = *out_build = nullptr;
+    const u64 n = probe->n;
+    if (n == 0) {
+        int rc = dampr_kv_create(ctx, 0, out_probe);
+        if (rc) return rc;
+        return dampr_kv_create(ctx, 0, out_build);
+    }
+    u64 cap = 1024;
+    while (cap < 2 * build->n) cap <<= 1;
+    const u64 ntiles = (n + HC_TILE - 1) / HC_TILE;
+    DevBuf tk, tv, used, hit, vals, tcnt, tbase;
+    CUDA_TRY(ctx, tk.alloc(cap * 8));
+    CUDA_TRY(ctx, tv.alloc(cap * 8));
+    CUDA_TRY(ctx, used.alloc(cap * 4));
+    CUDA_TRY(ctx, hit.alloc(n + 8));
+    CUDA_TRY(ctx, vals.alloc(n * 16));
+    CUDA_TRY(ctx, tcnt.alloc(ntiles * 4));
+    CUDA_TRY(ctx, tbase.alloc((ntiles + 1) * 8));
+    CUDA_TRY(ctx, cudaMemsetAsync(used.p, 0, cap * 4, ctx->stream));
+    CUDA_TRY(ctx, cudaMemsetAsync(ctx->d_scratch, 0, 8, ctx->stream));
+    {
+        ScopedTimer tm(ctx, DAMPR_K_PROBE);
+        if (build->n)
+            probe_build_kernel<<<ctx->num_sms * 4, 256, 0, ctx->stream>>>(build->rec, build->n, (u64 *)tk.p, (u64 *)tv.p,
+                                                                         (u32 *)used.p, cap - 1, ctx->d_scratch);
+        probe_lookup_kernel<<<ctx->num_sms * 8, 256, 0, ctx->stream>>>(probe->rec, n, (const u64 *)tk.p, (const u64 *)tv.p,
+                                                                      (const u32 *)used.p, cap - 1, (ulonglong2 *)vals.p,
+                                                                      (u8 *)hit.p);
+    }
+    {
+        ScopedTimer tm(ctx, DAMPR_K_JOIN);
+        hits_count_kernel<<<(unsigned)ntiles, HC_THREADS, 0, ctx->stream>>>((const u8 *)hit.p, n, (u32 *)tcnt.p);
+        scan_tiles_kernel<<<1, 1024, 0, ctx->stream>>>((const u32 *)tcnt.p, (u64 *)tbase.p, (u32)ntiles);
+    }
+    CUDA_TRY(ctx, cudaGetLastError());
+    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->h_scratch, (u64 *)tbase.p + ntiles, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    const u64 m = ctx->h_scratch[0];
+    int rc = dampr_kv_create(ctx, m, out_probe);
+    if (rc) return rc;
+    rc = dampr_kv_create(ctx, m, out_build);
+    if (rc) {
+        dampr_kv_destroy(ctx, *out_probe);
+        *out_probe = nullptr;
+        return rc;
+    }
+    (*out_probe)->n = (*out_build)->n = m;
+    if (m) {
+        ScopedTimer tm(ctx, DAMPR_K_JOIN);
+        hits_compact_kernel<<<(unsigned)ntiles, HC_THREADS, 0, ctx->stream>>>(probe->rec, (const ulonglong2 *)vals.p,
+                                                                            (const u8 *)hit.p, n, (const u64 *)tbase.p,
+                                                                            (*out_probe)->rec, (*out_build)->rec);
+    }
+    CUDA_TRY(ctx, cudaGetLastError());
     return DAMPR_OK;
 }
 

@@ -115,6 +115,7 @@ def load_library():
     _sig(lib, "dampr_kv_merge_ranges", vp, vp, vp, i32, i32, i32, pvp)
     _sig(lib, "dampr_kv_sort_reduce", vp, vp, i32, i32, pvp)
     _sig(lib, "dampr_kv_join_ranges", vp, vp, vp, i32, vp, u64, pu64)
+    _sig(lib, "dampr_kv_hash_join", vp, vp, vp, pvp, pvp)
     _sig(lib, "dampr_kv_hash_probe", vp, vp, vp, pvp, vp)
     _sig(lib, "dampr_kv_partition_by_owner", vp, vp, i32, pvp, vp)
     _sig(lib, "dampr_synth_text", vp, vp, u64, u64, vp, vp, u32, vp, pu64)
@@ -537,6 +538,13 @@ class KV(object):
         hit = np.empty(len(probe), dtype=np.uint8)
         self.ctx.check(self.ctx.lib.dampr_kv_hash_probe(self.ctx.h, self.h, probe.h, C.byref(h), _ptr(hit)))
         return KV(self.ctx, None, handle=h), hit
+
+    def hash_join(self, probe):
+        """self = build side (unique keys). Returns (matched probe records KV, (key, build value) KV), compacted on
+        the device in probe order."""
+        hp, hb = C.c_void_p(), C.c_void_p()
+        self.ctx.check(self.ctx.lib.dampr_kv_hash_join(self.ctx.h, self.h, probe.h, C.byref(hp), C.byref(hb)))
+        return KV(self.ctx, None, handle=hp), KV(self.ctx, None, handle=hb)
 
     def partition_by_owner(self, n_dest):
         h = C.c_void_p()

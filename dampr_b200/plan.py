@@ -891,6 +891,8 @@ def _lower_kv_map(runner, stage, inputs):
         kind = lowering.binop_kind(binop)
         if kind not in _FOLD_OPS or vals.dtype not in (np.int64, np.uint64):
             return None
+        if vals.dtype == np.uint64 and len(vals) and int(vals.max()) >= (1 << 63):
+            return None   # the device folds are signed 64-bit: values >= 2^63 would compare / add as negatives
         if kind == lowering.ADD and n and _may_overflow(vals):
             raise NotLowerable("64-bit sum could overflow (SURVEY B12)")
         op = dev.OP_COUNT if (count_only and kind == lowering.ADD) else _FOLD_OPS[kind]
@@ -1434,7 +1436,8 @@ def _lower_reduce(runner, stage, inputs):
             opmap = {lowering.SUM: dev.OP_SUM_I64, lowering.COUNT: dev.OP_COUNT, lowering.MIN: dev.OP_MIN_I64,
                      lowering.MAX: dev.OP_MAX_I64}
             keys, vals = fr.raw()
-            if kind in opmap and vals.dtype.kind in "iu" and not (kind == lowering.SUM and len(vals) and _may_overflow(vals)):
+            if kind in opmap and vals.dtype.kind in "iu" and not (kind == lowering.SUM and len(vals) and _may_overflow(vals)) \
+                    and not (vals.dtype == np.uint64 and len(vals) and int(vals.max()) >= (1 << 63)):
                 rk, rv, how = _device_group(runner, keys, vals, opmap[kind], dev.KEY_MIX)
                 rk = rk.view(keys.dtype)
                 out = Frame(rk, [rk, rv.view(np.int64)], scalar=False, combined=True)
@@ -1519,23 +1522,28 @@ def _lower_join(runner, stage, inputs):
         build = ctx.kv_from_columns(gk_r, gv_r)
         probe = ctx.kv_from_columns(gk_l, gv_l)
         try:
-            vals, hit = build.hash_probe(probe)
-            try:
-                _pk, fr = vals.columns()
-            finally:
-                vals.free()
+            if left_outer:
+                vals, hit = build.hash_probe(probe)
+                try:
+                    _pk, fr = vals.columns()
+                finally:
+                    vals.free()
+                keys = gk_l.view(lk.dtype)
+                fl = gv_l.view(np.int64)
+                fr = np.where(hit.astype(bool), fr.view(np.int64), 0)   # sum / len of an empty right group
+            else:
+                # matched groups are compacted on the device: only the joined rows come back
+                ml, mr = build.hash_join(probe)
+                try:
+                    keys, fl = ml.columns()
+                    _k2, fr = mr.columns()
+                finally:
+                    ml.free()
+                    mr.free()
+                keys, fl, fr = keys.view(lk.dtype), fl.view(np.int64), fr.view(np.int64)
         finally:
             build.free()
             probe.free()
-        hit = hit.astype(bool)
-        if left_outer:
-            keys = gk_l.view(lk.dtype)
-            fl = gv_l.view(np.int64)
-            fr = np.where(hit, fr.view(np.int64), 0)   # sum / len of an empty right group
-        else:
-            keys = gk_l.view(lk.dtype)[hit]
-            fl = gv_l.view(np.int64)[hit]
-            fr = fr.view(np.int64)[hit]
         out = Frame(keys, [keys, vexpr.Tup([fl, fr])], scalar=False, combined=True)
         runner.stats.add(stage, "device join: per-side partition+sort+fold, hash build+probe of the group keys" + how,
                          "left=%d right=%d left groups=%d right groups=%d rows=%d" % (len(lk), len(rk), len(gk_l), len(gk_r), len(keys)))
@@ -1559,18 +1567,19 @@ def _lower_join(runner, stage, inputs):
             raise NotLowerable("product join: the right side has duplicate keys")
         probe = ctx.kv_from_columns(lk, np.asarray(lv).view(np.uint64))
         try:
-            vals, hit = build.hash_probe(probe)
+            ml, mr = build.hash_join(probe)   # matched rows compacted on the device, probe order kept
             try:
-                _pk, pr = vals.columns()
+                keys, plv = ml.columns()
+                _k2, prv = mr.columns()
             finally:
-                vals.free()
+                ml.free()
+                mr.free()
         finally:
             probe.free()
     finally:
         build.free()
-    hit = hit.astype(bool)
-    keys = lk[hit]
-    out = Frame(keys, [keys, vexpr.Tup([np.asarray(lv)[hit], pr.view(rv.dtype)[hit]])], scalar=False, combined=False)
+    keys = keys.view(lk.dtype)
+    out = Frame(keys, [keys, vexpr.Tup([plv.view(lv.dtype), prv.view(rv.dtype)])], scalar=False, combined=False)
     runner.stats.add(stage, "device join: broadcast hash build + probe (unique right keys)" + how,
                      "left=%d right=%d rows=%d" % (len(lk), len(rk), len(keys)))
     return out

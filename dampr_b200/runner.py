@@ -401,7 +401,12 @@ def _numeric_column(vals, kind):
         return None, None
     t = type(vals[0])
     if t is int or t is bool:
-        if not all(type(v) is int or type(v) is bool for v in vals):
+        # bools fold like ints under +, but min / max / first / last must hand a bool back (max(True, False) is True,
+        # not 1): only all-int columns go to the device for those
+        if kind == lowering.ADD:
+            if not all(type(v) is int or type(v) is bool for v in vals):
+                return None, None
+        elif not all(type(v) is int for v in vals):
             return None, None
         try:
             col = np.fromiter(vals, dtype=np.int64, count=len(vals))
@@ -416,6 +421,8 @@ def _numeric_column(vals, kind):
         if not all(type(v) is float for v in vals):
             return None, None
         col = np.fromiter(vals, dtype=np.float64, count=len(vals))
+        if kind in (lowering.MIN, lowering.MAX) and (np.isnan(col).any() or (np.signbit(col) & (col == 0.0)).any()):
+            return None, None   # Python's min / max with NaN or -0.0 depend on argument order: host fold
         op = {lowering.ADD: dev.OP_SUM_F64, lowering.MIN: dev.OP_MIN_F64, lowering.MAX: dev.OP_MAX_F64,
               lowering.FIRST: dev.OP_FIRST, lowering.LAST: dev.OP_LAST}[kind]
         return col, op

@@ -284,6 +284,13 @@ int32_t dampr_kv_join_ranges(dampr_ctx *ctx, dampr_kv *left_sorted, dampr_kv *ri
 int32_t dampr_kv_hash_probe(dampr_ctx *ctx, dampr_kv *build, dampr_kv *probe, dampr_kv **out_vals,
                             uint8_t *out_hit_host);
 
+/* the same join with the result compacted ON THE DEVICE: out_probe[i] / out_build[i] = the i-th probe record that
+ * found a partner (probe order kept) and (its key, the partner's build value). Inner join of a fact table with a
+ * dimension table (PJoin.reduce with many=True over unique right keys, dampr.py:780-802) without a row of the
+ * misses ever leaving the device. Both outputs are created. */
+int32_t dampr_kv_hash_join(dampr_ctx *ctx, dampr_kv *build, dampr_kv *probe, dampr_kv **out_probe,
+                           dampr_kv **out_build);
+
 /* split a kv by destination rank: owner = mix(key) % n_dest; produces destination-contiguous
  * records in `out` and counts[n_dest] on the host. The payload then moves with one all-to-all
  * (torch.distributed/NCCL over NVLink) — replaces DefaultShuffler.shuffle (base.py:416-433). */

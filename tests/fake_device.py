@@ -149,6 +149,16 @@ class FakeKV(object):
         out.n = len(pk)
         return out, hit.astype(np.uint8)
 
+    def hash_join(self, probe):
+        """dampr_kv_hash_join: the probe records that found a partner, and (key, build value), in probe order"""
+        vals, hit = self.hash_probe(probe)
+        m = hit.astype(bool)
+        a, b = FakeKV(self.ctx, max(1, int(m.sum()))), FakeKV(self.ctx, max(1, int(m.sum())))
+        a.rec[:int(m.sum())] = probe.rec[:probe.n][m]
+        b.rec[:int(m.sum())] = vals.rec[:vals.n][m]
+        a.n = b.n = int(m.sum())
+        return a, b
+
     def group_offsets(self):
         k = self.rec[:self.n, 0]
         heads = np.flatnonzero(np.concatenate(([True], k[1:] != k[:-1]))) if len(k) else np.zeros(0, dtype=np.int64)

@@ -393,3 +393,23 @@ def test_reduce_by_key_single_pass(ctx):
     for k, got in zip(gk.tolist(), gv.view(np.float64).tolist()):
         sel = fl[keys == k]
         assert abs(got - math.fsum(sel.tolist())) <= 4 * len(sel) * 2.0 ** -53 * float(np.abs(sel).sum())
+
+
+def test_hash_join_compacts_on_the_device(ctx):
+    """dampr_kv_hash_join: the probe records with a partner and (key, build value), in probe order"""
+    bk = np.unique(gen.kv(3, 20000, 50000)[0])
+    bv = np.arange(len(bk), dtype=np.int64)
+    for n in (0, 1, 4095, 4096, 100000, 1_000_000):
+        pk, pv = gen.kv(4, n, 50000)
+        B = ctx.kv_from_columns(bk, bv)
+        P = ctx.kv_from_columns(pk, pv)
+        ml, mr = B.hash_join(P)
+        table = dict(zip(bk.tolist(), bv.tolist()))
+        m = np.array([k in table for k in pk.tolist()], dtype=bool)
+        lk, lv = ml.columns()
+        rk, rv = mr.columns()
+        assert np.array_equal(lk, pk[m]) and np.array_equal(lv.view(np.int64), pv[m])
+        assert np.array_equal(rk, pk[m])
+        assert np.array_equal(rv.view(np.int64), np.array([table[k] for k in pk[m].tolist()], dtype=np.int64))
+        for x in (B, P, ml, mr):
+            x.free()

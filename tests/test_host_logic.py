@@ -528,3 +528,18 @@ def test_frame_general_lowering_with_a_numpy_device():
     # a guard trips (possible int64 overflow): not lowered
     big = plan.Frame(words, [words, np.full(n, 1 << 61, dtype=np.int64)], scalar=False)
     assert plan._lower_frame_general(Runner, stage([Op("map", lambda tc: tc[1] * 4)]), big) is None
+
+
+def test_device_fold_guards_keep_python_semantics():
+    """bools folded with min / max / first / last stay bools (host fold), float min / max with NaN or -0.0
+    stay on the host, uint64 values >= 2^63 are not handed to the signed device folds."""
+    import numpy as np
+    from dampr_b200 import lowering, runner
+    col, op = runner._numeric_column([True, False, True], lowering.MAX)
+    assert col is None
+    col, op = runner._numeric_column([True, 2, False], lowering.ADD)
+    assert col is not None and col.tolist() == [1, 2, 0]
+    assert runner._numeric_column([1.0, float("nan")], lowering.MIN)[0] is None
+    assert runner._numeric_column([0.0, -0.0], lowering.MAX)[0] is None
+    assert runner._numeric_column([1.5, -2.0], lowering.MAX)[0] is not None
+    assert runner._numeric_column([3, 4], lowering.MIN)[0] is not None
