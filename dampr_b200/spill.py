@@ -120,24 +120,39 @@ def external_group(ctx, chunk_iter, n_records, op=None, xform=dev.KEY_MIX):
     # bucket b holds mix64(key) in [b * 2^64 / P, (b + 1) * 2^64 / P)
     splitters = np.array([(b << 64) // n_buckets for b in range(1, n_buckets)], dtype=np.uint64)
     buckets = [[] for _ in range(n_buckets)]
-    stats = {"buckets": n_buckets, "batches": 0, "spilled_bytes": 0, "arena_bytes": arena}
+    stats = {"buckets": n_buckets, "batches": 0, "spilled_bytes": 0, "arena_bytes": arena,
+             "seconds": {"upload": 0.0, "sort": 0.0, "download": 0.0, "cut": 0.0, "merge_upload": 0.0, "merge": 0.0,
+                         "merge_download": 0.0}}
+    sec = stats["seconds"]
     op2 = dev.OP_SUM_I64 if op == dev.OP_COUNT else op   # partial counts are added up
+    import time as _time
 
     def flush_batch(kchunks, vchunks):
+        t0 = _time.perf_counter()
         kv = _upload_chunks(ctx, kchunks, vchunks)
+        t1 = _time.perf_counter()
         try:
             if op is None:
                 kv.sort(xform)
+                ctx.sync()
+                t2 = _time.perf_counter()
                 recs = kv.records()
             else:
                 red = kv.sort_reduce(op, xform, sorted_run=True)
+                ctx.sync()
+                t2 = _time.perf_counter()
                 try:
                     recs = red.records()
                 finally:
                     red.free()
         finally:
             kv.free()
+        t3 = _time.perf_counter()
+        sec["upload"] += t1 - t0
+        sec["sort"] += t2 - t1
+        sec["download"] += t3 - t2
         cuts = _lazy_cuts(recs[:, 0], splitters, _mix64)
+        sec["cut"] += _time.perf_counter() - t3
         edges = [0] + cuts.tolist() + [len(recs)]
         for b in range(n_buckets):
             if edges[b + 1] > edges[b]:
@@ -168,26 +183,35 @@ def external_group(ctx, chunk_iter, n_records, op=None, xform=dev.KEY_MIX):
         if len(runs) == 1:   # one sorted (folded) run: nothing to merge
             out.append((runs[0][:, 0].copy(), runs[0][:, 1].copy()))
             continue
-        out.extend(_merge_runs(ctx, runs, xform, -1 if op is None else op2, per_batch))
+        out.extend(_merge_runs(ctx, runs, xform, -1 if op is None else op2, per_batch, sec))
     return out, stats
 
 
-def _merge_runs(ctx, runs, xform, op, per_batch):
+def _merge_runs(ctx, runs, xform, op, per_batch, sec=None):
     """[(keys, vals)] — the k-way merge (+ fold, op >= 0) of sorted host runs on the device. Runs that do not
     fit the arena together (a skewed bucket) are merged in key-range slices: the runs are cut at sampled
     splitters so that every slice fits, and the slices come out in key order."""
     total = sum(len(r) for r in runs)
     if total <= per_batch:
+        import time as _time
+        t0 = _time.perf_counter()
         kv = _upload_runs(ctx, runs)
+        t1 = _time.perf_counter()
         try:
             offs = np.concatenate(([0], np.cumsum([len(r) for r in runs]))).astype(np.uint64)
             m = ctx.kv_merge_ranges(kv, offs, xform, op)
+            ctx.sync()
         finally:
             kv.free()
+        t2 = _time.perf_counter()
         try:
             k, v = m.columns()
         finally:
             m.free()
+        if sec is not None:
+            sec["merge_upload"] += t1 - t0
+            sec["merge"] += t2 - t1
+            sec["merge_download"] += _time.perf_counter() - t2
         return [(k, v)]
     dom = (lambda k: _mix64(k)) if xform == dev.KEY_MIX else (lambda k: _order_domain(k, xform))
     rng = np.random.default_rng(len(runs))
