@@ -60,6 +60,12 @@ struct dampr_ctx {
     size_t h_pin_bytes[2] = {0, 0};
     cudaEvent_t h_pin_ev[2] = {nullptr, nullptr};  // last transfer that used the slot
     bool h_pin_busy[2] = {false, false};
+    // two alternating device staging blocks of dampr_kv_upload_columns (a block taken from the pool would make
+    // every call wait for the previous call's interleave kernel: no overlap of host copies and DMA)
+    void *up_tmp[2] = {nullptr, nullptr};
+    size_t up_tmp_bytes[2] = {0, 0};
+    cudaEvent_t up_tmp_ev[2] = {nullptr, nullptr};
+    int up_tmp_next = 0;
 };
 
 // Host <-> device copies that stay at PCIe speed for pageable host memory: the bytes go through the

@@ -394,6 +394,8 @@ int32_t dampr_ctx_destroy(dampr_ctx *ctx) {
     for (int i = 0; i < 2; ++i) {
         if (ctx->h_pin[i]) cudaFreeHost(ctx->h_pin[i]);
         if (ctx->h_pin_ev[i]) cudaEventDestroy(ctx->h_pin_ev[i]);
+        if (ctx->up_tmp[i]) cudaFree(ctx->up_tmp[i]);
+        if (ctx->up_tmp_ev[i]) cudaEventDestroy(ctx->up_tmp_ev[i]);
     }
     for (int i = 0; i < dampr_ctx::STAGE_SLOTS; ++i) {
         if (ctx->stage_slot[i]) cudaFreeHost(ctx->stage_slot[i]);

@@ -321,18 +321,25 @@ int32_t dampr_kv_upload_columns(dampr_ctx *ctx, dampr_kv *kv, uint64_t off, cons
     ARG_CHECK(ctx, off + count <= kv->capacity, "upload exceeds kv capacity");
     CUDA_TRY(ctx, cudaSetDevice(ctx->device));
     if (count) {
-        u64 *tmp = (u64 *)pool_alloc(ctx, count * 16);
-        ARG_CHECK(ctx, tmp != nullptr, "device allocation failed");
+        const int slot = ctx->up_tmp_next;
+        ctx->up_tmp_next ^= 1;
+        if (!ctx->up_tmp_ev[slot]) CUDA_TRY(ctx, cudaEventCreateWithFlags(&ctx->up_tmp_ev[slot], cudaEventDisableTiming));
+        CUDA_TRY(ctx, cudaEventSynchronize(ctx->up_tmp_ev[slot]));  // the interleave kernel that last read this block
+        if (ctx->up_tmp_bytes[slot] < count * 16) {
+            if (ctx->up_tmp[slot]) cudaFree(ctx->up_tmp[slot]);
+            ctx->up_tmp[slot] = nullptr;
+            ctx->up_tmp_bytes[slot] = 0;
+            CUDA_TRY(ctx, cudaMalloc(&ctx->up_tmp[slot], count * 16));
+            ctx->up_tmp_bytes[slot] = count * 16;
+        }
+        u64 *tmp = (u64 *)ctx->up_tmp[slot];
         int rc = staged_h2d(ctx, tmp, keys, count * 8, ctx->copy);
         if (rc == DAMPR_OK && vals) rc = staged_h2d(ctx, tmp + count, vals, count * 8, ctx->copy);
-        if (rc) {
-            pool_free(ctx, tmp);
-            return rc;
-        }
+        if (rc) return rc;
         ctx->launches++;
         interleave_kernel<<<ctx->num_sms * 4, 256, 0, ctx->copy>>>(tmp, vals ? tmp + count : nullptr, kv->rec + off, count);
         CUDA_TRY(ctx, cudaGetLastError());
-        pool_free(ctx, tmp);
+        CUDA_TRY(ctx, cudaEventRecord(ctx->up_tmp_ev[slot], ctx->copy));
     }
     if (off + count > kv->n) kv->n = off + count;
     CUDA_TRY(ctx, cudaEventRecord(ctx->upload_done, ctx->copy));
