@@ -891,11 +891,12 @@ leaf_sort_kernel(const ulonglong2 *__restrict__ data, ulonglong2 *__restrict__ o
             // sort only: the records stay in registers; each one computes its final position and leaves
             // directly (no gather pass over shared memory, no inverse key transform)
             u32 slot[L_IPT];
-            leaf_bin_records(s, n, ch.bin_shift, ch.bin_base, slot);
+            const bool heavy = leaf_bin_records(s, n, ch.bin_shift, ch.bin_base, slot);
+            if (heavy) leaf_sort_heavy_bins(s, n);
 #pragma unroll
             for (int k = 0; k < L_IPT; ++k) {
                 const u32 i = tid + k * L_THREADS;
-                if (i < n) out[ch.start + leaf_final_pos<false>(s, n, i, slot[k])] = rr[k];
+                if (i < n) out[ch.start + leaf_final_pos<false>(s, n, i, slot[k], heavy)] = rr[k];
             }
             __syncthreads();
             continue;

@@ -9,6 +9,7 @@ constexpr int L_THREADS = 512;
 constexpr int L_CAP = 4096;    // records per leaf CTA
 constexpr int L_BINS = 8192;   // counting-sort bins
 constexpr int L_IPT = L_CAP / L_THREADS;  // 8
+constexpr int L_HEAVY = 32;    // bins above this population are sorted by a warp when they hold one key
 
 constexpr int CL = 8;           // CTAs per leaf cluster
 constexpr int CF = 256;         // fine bins of the in-cluster exchange
@@ -88,7 +89,7 @@ __device__ __forceinline__ u32 block_excl_scan(LeafSmem &s, u32 x, u32 *total) {
 // value is the record's (arbitrary) slot inside its bin, exclusive scan of the bin counts (s.cnt then holds the
 // bin starts), every record's index dropped into its bin's range of s.ord. slot[k] = bin << 16 | slot for the
 // thread's records i = tid + k * L_THREADS. Ends with a barrier.
-__device__ __forceinline__ void leaf_bin_records(LeafSmem &s, u32 n, int bin_shift, u64 bin_base, u32 (&slot)[L_IPT]) {
+__device__ __forceinline__ bool leaf_bin_records(LeafSmem &s, u32 n, int bin_shift, u64 bin_base, u32 (&slot)[L_IPT]) {
     const u32 tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     {
         uint4 *z = reinterpret_cast<uint4 *>(s.cnt);  // 8 counters per 16-byte store
@@ -110,6 +111,7 @@ __device__ __forceinline__ void leaf_bin_records(LeafSmem &s, u32 n, int bin_shi
     }
     __syncthreads();
     // exclusive scan of cnt[0..L_BINS): 16 bins per thread
+    bool heavy = false;
     {
         u32 loc[16];
         u32 sum = 0;
@@ -122,6 +124,7 @@ __device__ __forceinline__ void leaf_bin_records(LeafSmem &s, u32 n, int bin_shi
                 loc[2 * k] = w[k] & 0xFFFFu;
                 loc[2 * k + 1] = w[k] >> 16;
                 sum += loc[2 * k] + loc[2 * k + 1];
+                heavy |= (loc[2 * k] > (u32)L_HEAVY) | (loc[2 * k + 1] > (u32)L_HEAVY);
             }
         }
         u32 v = sum;
@@ -147,11 +150,74 @@ __device__ __forceinline__ void leaf_bin_records(LeafSmem &s, u32 n, int bin_shi
         c4[0] = make_uint4(w[0], w[1], w[2], w[3]);
         c4[1] = make_uint4(w[4], w[5], w[6], w[7]);
     }
-    __syncthreads();
+    heavy = __syncthreads_or(heavy ? 1 : 0) != 0;
 #pragma unroll
     for (int k = 0; k < L_IPT; ++k) {
         const u32 i = tid + k * L_THREADS;
         if (i < n) s.ord[s.cnt[slot[k] >> 16] + (slot[k] & 0xFFFFu)] = (u16)i;
+    }
+    __syncthreads();
+    return heavy;
+}
+
+// Heavy bins (many records of ONE key: duplicate-heavy inputs) would cost every member a walk over the whole
+// bin. A warp checks that the bin holds a single key and, if so, sorts the bin's record indices through a
+// presence bitmap (O(members + 128)); the bin is flagged and its members take their rank by binary search.
+// Scratch: the cluster-exchange fields, unused outside the cluster leaf (s.aux = 16 bitmaps, s.fh = flags).
+__device__ __forceinline__ void leaf_sort_heavy_bins(LeafSmem &s, u32 n) {
+    const u32 tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    u32 *flags = s.fh;                                                    // L_BINS bits
+    u32 *bm = reinterpret_cast<u32 *>(s.aux) + warp * (L_CAP / 32);       // L_CAP bits per warp
+    static_assert(sizeof(s.fh) * 8 >= L_BINS && sizeof(s.aux) >= (L_THREADS / 32) * (L_CAP / 8), "scratch too small");
+    if (tid < L_BINS / 32) flags[tid] = 0;
+    __syncthreads();
+    constexpr u32 BPW = L_BINS / (L_THREADS / 32);  // bins per warp
+    for (u32 b = warp * BPW; b < (warp + 1) * BPW; b += 32) {
+        const u32 st = s.cnt[b + lane];
+        const u32 en = (b + lane + 1 < (u32)L_BINS) ? s.cnt[b + lane + 1] : n;
+        u32 hm = __ballot_sync(0xFFFFFFFFu, en - st > (u32)L_HEAVY);
+        while (hm) {
+            const u32 l = (u32)__ffs(hm) - 1u;
+            hm &= hm - 1;
+            const u32 hst = __shfl_sync(0xFFFFFFFFu, st, l), hen = __shfl_sync(0xFFFFFFFFu, en, l);
+            const u64 k0 = s.sk[s.ord[hst]];
+            bool eq = true;
+            for (u32 j = hst + lane; j < hen; j += 32) eq &= s.sk[s.ord[j]] == k0;
+            if (!__all_sync(0xFFFFFFFFu, eq)) continue;  // several keys share the bin: the member walk handles it
+            for (u32 w = lane; w < (u32)(L_CAP / 32); w += 32) bm[w] = 0;
+            __syncwarp();
+            for (u32 j = hst + lane; j < hen; j += 32) {
+                const u32 x = s.ord[j];
+                atomicOr(&bm[x >> 5], 1u << (x & 31));
+            }
+            __syncwarp();
+            constexpr int WPL = L_CAP / 32 / 32;
+            u32 words[WPL];
+            u32 cl = 0;
+#pragma unroll
+            for (int k = 0; k < WPL; ++k) {
+                words[k] = bm[lane * WPL + k];
+                cl += __popc(words[k]);
+            }
+            u32 v = cl;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                u32 o = __shfl_up_sync(0xFFFFFFFFu, v, d);
+                if ((int)lane >= d) v += o;
+            }
+            u32 pos = hst + v - cl;
+#pragma unroll
+            for (int k = 0; k < WPL; ++k) {
+                u32 wd = words[k];
+                while (wd) {
+                    const u32 bit = __ffs(wd) - 1;
+                    wd &= wd - 1;
+                    s.ord[pos++] = (u16)((lane * WPL + k) * 32 + bit);
+                }
+            }
+            __syncwarp();
+            if (lane == 0) atomicOr(&flags[(b + l) >> 5], 1u << ((b + l) & 31));
+        }
     }
     __syncthreads();
 }
@@ -160,11 +226,21 @@ __device__ __forceinline__ void leaf_bin_records(LeafSmem &s, u32 n, int bin_shi
 // the tie-break being the record's smem index (input position) or, in the cluster leaf, its index inside the
 // chunk (s.aux)
 template <bool HAS_AUX>
-__device__ __forceinline__ u32 leaf_final_pos(const LeafSmem &s, u32 n, u32 i, u32 slotinfo) {
+__device__ __forceinline__ u32 leaf_final_pos(const LeafSmem &s, u32 n, u32 i, u32 slotinfo, bool heavy = false) {
     const u32 bin = slotinfo >> 16;
     const u32 st = s.cnt[bin];
     const u32 en = (bin + 1 < L_BINS) ? s.cnt[bin + 1] : n;
     u32 r = 0;
+    if (!HAS_AUX && heavy && en - st > (u32)L_HEAVY && ((s.fh[bin >> 5] >> (bin & 31)) & 1u)) {
+        // single-key bin whose indices a warp sorted (leaf_sort_heavy_bins): rank = lower bound of my index
+        u32 lo = st, hi = en;
+        while (lo < hi) {
+            const u32 mid = (lo + hi) >> 1;
+            if (s.ord[mid] < i) lo = mid + 1;
+            else hi = mid;
+        }
+        return lo;
+    }
     if (en - st > 1) {
         const u64 ki = s.sk[i];
         const u32 ti = HAS_AUX ? s.aux[i] : i;
@@ -183,11 +259,13 @@ template <bool HAS_AUX>
 __device__ __forceinline__ void leaf_sort_core(LeafSmem &s, u32 n, int bin_shift, u64 bin_base) {
     const u32 tid = threadIdx.x;
     u32 slot[L_IPT];
-    leaf_bin_records(s, n, bin_shift, bin_base, slot);
+    bool heavy = leaf_bin_records(s, n, bin_shift, bin_base, slot);
+    if (HAS_AUX) heavy = false;
+    if (heavy) leaf_sort_heavy_bins(s, n);
 #pragma unroll
     for (int k = 0; k < L_IPT; ++k) {
         const u32 i = tid + k * L_THREADS;
-        if (i < n) s.fin[leaf_final_pos<HAS_AUX>(s, n, i, slot[k])] = (u16)i;
+        if (i < n) s.fin[leaf_final_pos<HAS_AUX>(s, n, i, slot[k], heavy)] = (u16)i;
     }
     __syncthreads();
 }

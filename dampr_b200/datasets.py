@@ -90,11 +90,14 @@ class RecordsDataset(Dataset):
     """Stage output on the host path: parallel lists of keys and values, already in the order the
     device sort produced (key order for orderable keys), equal keys adjacent."""
 
-    def __init__(self, keys, values, codes=None, codec=None):
+    def __init__(self, keys, values, codes=None, codec=None, replicated=False):
         self.keys = keys
         self.values = values
         self.codes = codes    # numpy uint64 per record (device sort key) or None
         self.codec = codec    # keycodec.Codec used for `codes`
+        # under torch.distributed: True when every rank holds this same (global) result, e.g. a line count
+        # summed over the ranks; False = this rank's shard of an owner-partitioned result
+        self.replicated = replicated
 
     def __len__(self):
         return len(self.keys)

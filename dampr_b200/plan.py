@@ -799,15 +799,15 @@ def _lower_map(runner, stage, inputs, si):
             if scan.nbytes == 0:
                 # no bytes, no chunks, no count record: len() of an empty text input is an empty collection in
                 # the reference (dampr.py:245-275), not [0]
-                return RecordsDataset([], [])
-            return RecordsDataset([1], [scan.n_lines])
+                return RecordsDataset([], [], replicated=True)
+            return RecordsDataset([1], [scan.n_lines], replicated=True)
         if isinstance(ds, (Frame, RecordsDataset)):
             n = len(ds)
             if dist.active():
                 # results are owner-partitioned over the ranks: the length is the sum of the shards
                 n = int(dist.all_reduce_sum_int([n])[0])
             runner.stats.add(stage, "frame length", "records=%d" % n)
-            return RecordsDataset([1], [n])
+            return RecordsDataset([1], [n], replicated=True)
         return None
     kv = _lower_kv_map(runner, stage, inputs)
     if kv is not None:

@@ -117,8 +117,9 @@ class B200Runner(object):
             inputs = [data[s] for s in stage.inputs]
             t_stage = time.perf_counter()
             lowered = plan.try_lower(self, stage, inputs, si, data)
+            replicated = False
             if lowered is None and dist.active():
-                self._check_distributed_generic(stage, inputs)
+                replicated = self._check_distributed_generic(stage, inputs)
             if lowered is not None:
                 out = lowered
             elif isinstance(stage, GMap):
@@ -129,6 +130,8 @@ class B200Runner(object):
                 out = self._sink_generic(stage, inputs)
             else:
                 raise TypeError("unknown stage type %r" % (stage,))
+            if replicated and isinstance(out, RecordsDataset):
+                out.replicated = True
             data[stage.output] = out
             self.stats.ms.append((str(stage.output), 1e3 * (time.perf_counter() - t_stage)))
             if not isinstance(stage, GSink):
@@ -158,19 +161,28 @@ class B200Runner(object):
         folds, the frame length). A stage that falls back to the host path would silently work on this rank's
         shard (frames are owner-partitioned) or, for an original input, on the whole input on every rank. The
         only host stages that stay correct are record-wise ones over rank-local results: a plain map / filter
-        chain (no combiner, no supplementary input) and the sink, which writes rank-numbered parts."""
+        chain (no combiner; supplementary map-side-join inputs only when replicated) and the sink, which writes
+        rank-numbered parts; and any
+        deterministic stage over REPLICATED results (a global count every rank holds, e.g. the fold of len()),
+        whose output is then replicated too (returns True). A replicated result is sunk by rank 0 alone."""
         from . import plan
-        local = all(isinstance(d, (plan.Frame, RecordsDataset)) for d in inputs) and \
+        if inputs and all(isinstance(d, RecordsDataset) and d.replicated for d in inputs) and \
+                not any(src in self.graph.inputs for src in stage.inputs):
+            return True
+        def is_rep(d):
+            return isinstance(d, RecordsDataset) and d.replicated
+        # the main input is this rank's shard; supplementary inputs (map-side join tables) must be whole
+        local = isinstance(inputs[0], (plan.Frame, RecordsDataset)) and all(is_rep(d) for d in inputs[1:]) and \
             not any(src in self.graph.inputs for src in stage.inputs)
         recordwise = isinstance(stage, GSink) or (
-            isinstance(stage, GMap) and len(inputs) == 1 and
+            isinstance(stage, GMap) and
             not isinstance(stage.combiner, ops.PartialReduceCombiner) and
-            isinstance(stage.mapper, (ops.Map, ops.FusedMapper)) and
-            not isinstance(stage.mapper, (ops.MapCrossJoin, ops.MapAllJoin)))
+            isinstance(stage.mapper, (ops.Map, ops.FusedMapper, ops.MapCrossJoin, ops.MapAllJoin)))
         if not (local and recordwise):
             raise DistributedUnsupported(
                 "stage %s is not lowered to the device and cannot run under torch.distributed (world size %d): "
                 "only lowered stages exchange records between ranks; run it on one GPU" % (stage, dist.world()[1]))
+        return False
 
     # ---- device helpers ---------------------------------------------------------------------
     def device_order(self, codes):
@@ -348,6 +360,8 @@ class B200Runner(object):
         n = 0
         # one process per GPU: results are rank-local, part numbers follow the rank like the lowered sink's
         first = 4096 * dist.world()[0] if dist.active() else 0
+        if dist.active() and getattr(main, "replicated", False) and dist.world()[0] != 0:
+            main = EmptyDataset()  # every rank holds the same records: rank 0 writes them
         for i, ch in enumerate(_chunks_of(main)):
             fname = os.path.join(path, "part-%d" % (first + i))
             with open(fname, "w", encoding="utf-8") as f:

@@ -310,6 +310,41 @@ def test_low_cardinality_keys_hot_runs(ctx):
         check_sort(ctx, keys, vals, dev.KEY_MIX)
 
 
+@pytest.mark.parametrize("n,nk", [(3000, 40), (4096, 1), (4096, 100), (2_000_000, 30_000), (1_000_000, 12_000)])
+def test_duplicate_heavy_leaf_bins(ctx, n, nk):
+    """K << N: a leaf chunk's bins hold 30..300 records of one key each (leaf.cuh leaf_sort_heavy_bins: a warp
+    sorts a single-key bin's record indices through a bitmap) next to bins that several keys share (member walk);
+    order among equal keys must stay the input order, through sort, sort+reduce and the merge tiles."""
+    rng = np.random.default_rng(n + nk)
+    base = rng.integers(0, 1 << 62, size=nk).astype(np.uint64)
+    base[: max(1, nk // 10)] = np.arange(max(1, nk // 10), dtype=np.uint64)  # neighbours that share a bin
+    keys = base[rng.integers(0, nk, size=n)]
+    vals = np.arange(n, dtype=np.int64)
+    for xf in (dev.KEY_RAW, dev.KEY_MIX):
+        check_sort(ctx, keys, vals, xf)
+    u, first = np.unique(keys, return_index=True)
+    last = n - 1 - np.unique(keys[::-1], return_index=True)[1]
+    for op, exp in ((dev.OP_FIRST, first), (dev.OP_LAST, last)):
+        kv = ctx.kv_from_columns(keys, vals)
+        red = kv.sort_reduce(op, dev.KEY_RAW)
+        rk, rv = red.columns()
+        assert np.array_equal(rk, u) and np.array_equal(rv.view(np.int64), exp)
+        red.free()
+    if n >= 1_000_000:
+        half = n // 2
+        runs = []
+        for lo, hi in ((0, half), (half, n)):
+            r = ctx.kv_from_columns(keys[lo:hi], vals[lo:hi])
+            r.sort(dev.KEY_RAW)
+            runs.append(r)
+        out = ctx.kv_merge(runs, dev.KEY_RAW)
+        mk, mv = out.columns()
+        order = np.argsort(keys, kind="stable")
+        assert np.array_equal(mk, keys[order]) and np.array_equal(mv.view(np.int64), vals[order])
+        for x in runs + [out]:
+            x.free()
+
+
 def _merge_oracle(runs_k, runs_v, xf):
     """stable k-way merge = stable sort of the concatenation in run order (heapq.merge, dataset.py:571-579)"""
     ak, av = np.concatenate(runs_k), np.concatenate(runs_v)
