@@ -86,6 +86,30 @@ WORKER = textwrap.dedent("""
             got.extend(l.strip() for l in f if l.strip())
     assert got == [str(len(merged))], got
 
+    # reduce-side joins: both sides exchanged by key owner, folds joined on the owner; product with a unique right
+    import itertools
+    lk, lv = gen.kv(1, 30000, 2000)
+    rk, rv = gen.kv(2, 4000, 3000)
+    lk, rk = lk.view(np.int64), rk.view(np.int64)
+    G = lambda ks, vs: Dampr.read_input(ArrayKVInput(ks, vs)).group_by(lambda x: x[0], lambda x: x[1])
+    inner = refsem.inner_join(lk, lv, rk, rv)
+    left = refsem.left_join(lk, lv, rk, rv)
+    got, _ = gathered(G(lk, lv).join(G(rk, rv)).reduce(lambda l, r: (sum(l), len(list(r)))).read())
+    assert any("device join" in how and "all-to-all" in how for _s, how, _d in runner_mod.LAST_STATS.stages), runner_mod.LAST_STATS.stages
+    assert got == {k: (sum(a), len(b)) for k, (a, b) in inner.items()}
+    got, _ = gathered(G(lk, lv).join(G(rk, rv)).left_reduce(lambda l, r: (sum(l), sum(r))).read())
+    assert got == {k: (sum(a), sum(b)) for k, (a, b) in left.items()}
+    uk, first = np.unique(rk, return_index=True)
+    uv = rv[first]
+    rows = G(lk, lv).join(G(uk, uv)).reduce(lambda l, r: itertools.product(l, r), many=True).read()
+    assert any("device join" in how and "exchanged" in how for _s, how, _d in runner_mod.LAST_STATS.stages), \
+        runner_mod.LAST_STATS.stages
+    allrows = [None] * world
+    tdist.all_gather_object(allrows, list(rows))
+    table = dict(zip(uk.tolist(), uv.tolist()))
+    exp = sorted((int(k), (int(v), table[int(k)])) for k, v in zip(lk.tolist(), lv.tolist()) if int(k) in table)
+    assert sorted(x for p in allrows for x in p) == exp
+
     # a host stage that needs the whole input refuses loudly instead of folding this rank's view
     try:
         Dampr.memory(list(range(100))).group_by(lambda x: x %% 7).reduce(lambda k, it: sorted(it)).read()

@@ -84,6 +84,39 @@ def main():
             assert k not in merged
             merged[k] = v
     assert merged == refsem.group_sum(keys, vals), "kv sums differ from the oracle"
+    # reduce-side joins (BASELINE config 5): both sides exchanged by the owner of the key (one Splitter for both
+    # sides, base.py:264-283), per-side folds joined on the owner; product against a unique right side
+    import itertools
+    lk, lv = gen.kv(1, 300_000, 20_000)
+    rk, rv = gen.kv(2, 40_000, 30_000)
+    lk, rk = lk.view(np.int64), rk.view(np.int64)
+    G = lambda ks, vs: Dampr.read_input(ArrayKVInput(ks, vs)).group_by(lambda x: x[0], lambda x: x[1])
+    inner = refsem.inner_join(lk, lv, rk, rv)
+    left = refsem.left_join(lk, lv, rk, rv)
+
+    def gathered(mine):
+        dist.all_gather_object(parts, list(mine))
+        merged = {}
+        for p in parts:
+            for k, v in p:
+                assert k not in merged, "join key %r on two ranks" % (k,)
+                merged[k] = v
+        return merged
+    got = gathered(G(lk, lv).join(G(rk, rv)).reduce(lambda l, r: (sum(l), len(list(r)))).read())
+    assert any("device join" in how and "all-to-all" in how for _s, how, _d in runner_mod.LAST_STATS.stages), \
+        runner_mod.LAST_STATS.stages
+    assert got == {k: (sum(a), len(b)) for k, (a, b) in inner.items()}, "inner join folds differ from the oracle"
+    got = gathered(G(lk, lv).join(G(rk, rv)).left_reduce(lambda l, r: (sum(l), sum(r))).read())
+    assert got == {k: (sum(a), sum(b)) for k, (a, b) in left.items()}, "left join folds differ from the oracle"
+    uk, first = np.unique(rk, return_index=True)
+    uv = rv[first]
+    rows = G(lk, lv).join(G(uk, uv)).reduce(lambda l, r: itertools.product(l, r), many=True).read()
+    assert any("device join" in how and "exchanged" in how for _s, how, _d in runner_mod.LAST_STATS.stages), \
+        runner_mod.LAST_STATS.stages
+    dist.all_gather_object(parts, list(rows))
+    table = dict(zip(uk.tolist(), uv.tolist()))
+    exp = sorted((int(k), (int(v), table[int(k)])) for k, v in zip(lk.tolist(), lv.tolist()) if int(k) in table)
+    assert sorted(x for p in parts for x in p) == exp, "product join rows differ from the oracle"
     dist.barrier()
     if rank == 0:
         print("mgpu_check ok: world=%d terms=%d lines=%d" % (world, len(exp), exp_lines))
