@@ -54,7 +54,10 @@ struct dampr_ctx {
     static constexpr size_t STAGE_BYTES = 32u << 20;
     void *stage_slot[STAGE_SLOTS] = {nullptr, nullptr, nullptr, nullptr};
     cudaEvent_t stage_ev[STAGE_SLOTS] = {nullptr, nullptr, nullptr, nullptr};
-    int host_threads = 4;
+    unsigned stage_next = 0;   // ring position of the uploads, carried over from call to call
+    void *dstage_slot[STAGE_SLOTS] = {nullptr, nullptr, nullptr, nullptr};   // the downloads' own ring
+    cudaEvent_t dstage_ev[STAGE_SLOTS] = {nullptr, nullptr, nullptr, nullptr};
+
     // page-locked scratch (descriptor uploads / small downloads that must not synchronise the stream)
     void *h_pin[2] = {nullptr, nullptr};
     size_t h_pin_bytes[2] = {0, 0};
@@ -75,6 +78,9 @@ struct dampr_ctx {
 // staged_d2h returns when `dst` holds the data.
 int staged_h2d(dampr_ctx *ctx, void *dst, const void *src, size_t bytes, cudaStream_t st);
 int staged_d2h(dampr_ctx *ctx, void *dst, const void *src, size_t bytes, cudaStream_t st);
+int staged_h2d_columns(dampr_ctx *ctx, void *dst_records, const u64 *keys, const u64 *vals, size_t count, cudaStream_t st);
+bool host_is_pinned(const void *p);
+extern int g_host_threads_cap;
 
 struct dampr_textbuf {
     u8 *alloc;      // device allocation

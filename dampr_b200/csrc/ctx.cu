@@ -125,6 +125,7 @@ void pool_trim(dampr_ctx *ctx, size_t keep_bytes) {
     }
 }
 int g_text_ctas = 4;
+int g_host_threads_cap = 16;   // copy threads per staged transfer (dampr_set_option "host_threads")
 
 // ---- staged transfers ---------------------------------------------------------------------------
 namespace {
@@ -137,6 +138,8 @@ class CopyPool {
     struct Job {
         char *dst;
         const char *src;   // memory source, or nullptr: read from fd at file offset foff
+        const char *src2 = nullptr;  // interleave mode: dst records = (src u64[i], src2 u64[i]); n = bytes of dst
+        bool interleave = false;
         int fd = -1;
         size_t foff = 0;
         size_t n, pieces;
@@ -150,8 +153,9 @@ class CopyPool {
         return p;
     }
     // returns false if a read from the file came up short
-    bool run(void *dst, const void *src, size_t n, int threads, int fd = -1, size_t foff = 0) {
-        if (src && (threads <= 1 || n < 4 * PIECE)) {
+    bool run(void *dst, const void *src, size_t n, int threads, int fd = -1, size_t foff = 0, const void *src2 = nullptr,
+             bool interleave = false) {
+        if (src && !interleave && (threads <= 1 || n < 4 * PIECE)) {
             memcpy(dst, src, n);
             return true;
         }
@@ -159,6 +163,8 @@ class CopyPool {
         auto job = std::make_shared<Job>();
         job->dst = (char *)dst;
         job->src = (const char *)src;
+        job->src2 = (const char *)src2;
+        job->interleave = interleave;
         job->fd = fd;
         job->foff = foff;
         job->n = n;
@@ -192,7 +198,24 @@ class CopyPool {
             const size_t i = j.next.fetch_add(1);
             if (i >= j.pieces) break;
             const size_t lo = i * PIECE, len = std::min(PIECE, j.n - lo);
-            if (j.src) {
+            if (j.interleave) {
+                // PIECE is a multiple of 16: records [lo / 16, (lo + len) / 16)
+                u64 *__restrict d = reinterpret_cast<u64 *>(j.dst + lo);
+                const u64 *__restrict k = reinterpret_cast<const u64 *>(j.src) + lo / 16;
+                const size_t cnt = len / 16;
+                if (j.src2) {
+                    const u64 *__restrict v = reinterpret_cast<const u64 *>(j.src2) + lo / 16;
+                    for (size_t i = 0; i < cnt; ++i) {
+                        d[2 * i] = k[i];
+                        d[2 * i + 1] = v[i];
+                    }
+                } else {
+                    for (size_t i = 0; i < cnt; ++i) {
+                        d[2 * i] = k[i];
+                        d[2 * i + 1] = 0;
+                    }
+                }
+            } else if (j.src) {
                 memcpy(j.dst + lo, j.src + lo, len);
             } else {
                 size_t got = 0;
@@ -234,6 +257,9 @@ class CopyPool {
 };
 
 void par_memcpy(void *dst, const void *src, size_t n, int threads) { CopyPool::get().run(dst, src, n, threads); }
+void par_interleave(void *dst_records, const void *keys, const void *vals, size_t count, int threads) {
+    CopyPool::get().run(dst_records, keys, count * 16, std::max(threads, 1), -1, 0, vals, true);
+}
 bool par_pread(void *dst, int fd, size_t foff, size_t n, int threads) {
     return CopyPool::get().run(dst, nullptr, n, std::max(threads, 1), fd, foff);
 }
@@ -252,13 +278,23 @@ int stage_init(dampr_ctx *ctx) {
     for (int i = 0; i < dampr_ctx::STAGE_SLOTS; ++i) {
         CUDA_TRY(ctx, cudaHostAlloc(&ctx->stage_slot[i], dampr_ctx::STAGE_BYTES, cudaHostAllocDefault));
         CUDA_TRY(ctx, cudaEventCreateWithFlags(&ctx->stage_ev[i], cudaEventDisableTiming));
+        // downloads have a ring of their own: an upload (another host thread, the copy stream) and a download
+        // (the compute stream) may be in flight together (spill.py overlaps the next batch's upload)
+        CUDA_TRY(ctx, cudaHostAlloc(&ctx->dstage_slot[i], dampr_ctx::STAGE_BYTES, cudaHostAllocDefault));
+        CUDA_TRY(ctx, cudaEventCreateWithFlags(&ctx->dstage_ev[i], cudaEventDisableTiming));
     }
-    unsigned hw = std::thread::hardware_concurrency();
-    ctx->host_threads = (int)std::max(2u, std::min(16u, hw / 4));
     return DAMPR_OK;
 }
 
+// copy threads per staged transfer: a quarter of the hardware threads, at most the "host_threads" option
+int copy_threads() {
+    static const unsigned hw = std::max(4u, std::thread::hardware_concurrency());
+    return (int)std::max(2u, std::min((unsigned)g_host_threads_cap, hw / 4));
+}
+
 }  // namespace
+
+bool host_is_pinned(const void *p) { return is_pinned(p); }
 
 int staged_h2d(dampr_ctx *ctx, void *dst, const void *src, size_t bytes, cudaStream_t st) {
     if (bytes == 0) return DAMPR_OK;
@@ -269,13 +305,33 @@ int staged_h2d(dampr_ctx *ctx, void *dst, const void *src, size_t bytes, cudaStr
     int rc = stage_init(ctx);
     if (rc) return rc;
     const size_t B = dampr_ctx::STAGE_BYTES;
-    size_t i = 0;
-    for (size_t off = 0; off < bytes; off += B, ++i) {
-        const int slot = (int)(i % dampr_ctx::STAGE_SLOTS);
+    for (size_t off = 0; off < bytes; off += B) {
+        // the ring position carries over from call to call: a caller that uploads slot-sized chunks one call at
+        // a time still fills the next slot while the previous one is on the wire
+        const int slot = (int)(ctx->stage_next++ % dampr_ctx::STAGE_SLOTS);
         const size_t len = std::min(B, bytes - off);
         CUDA_TRY(ctx, cudaEventSynchronize(ctx->stage_ev[slot]));  // the DMA that last read this slot
-        par_memcpy(ctx->stage_slot[slot], (const char *)src + off, len, ctx->host_threads);
+        par_memcpy(ctx->stage_slot[slot], (const char *)src + off, len, copy_threads());
         CUDA_TRY(ctx, cudaMemcpyAsync((char *)dst + off, ctx->stage_slot[slot], len, cudaMemcpyHostToDevice, st));
+        CUDA_TRY(ctx, cudaEventRecord(ctx->stage_ev[slot], st));
+    }
+    return DAMPR_OK;
+}
+
+// (keys[i], vals[i]) columns in pageable host memory -> 16-byte records on the device: the copy threads interleave
+// the two columns while they fill the page-locked ring (the same memory traffic as the plain staging copy), so no
+// device staging block and no interleave kernel are needed
+int staged_h2d_columns(dampr_ctx *ctx, void *dst_records, const u64 *keys, const u64 *vals, size_t count, cudaStream_t st) {
+    if (count == 0) return DAMPR_OK;
+    int rc = stage_init(ctx);
+    if (rc) return rc;
+    const size_t R = dampr_ctx::STAGE_BYTES / 16;   // records per slot
+    for (size_t off = 0; off < count; off += R) {
+        const int slot = (int)(ctx->stage_next++ % dampr_ctx::STAGE_SLOTS);
+        const size_t len = std::min(R, count - off);
+        CUDA_TRY(ctx, cudaEventSynchronize(ctx->stage_ev[slot]));
+        par_interleave(ctx->stage_slot[slot], keys + off, vals ? vals + off : nullptr, len, copy_threads());
+        CUDA_TRY(ctx, cudaMemcpyAsync((char *)dst_records + off * 16, ctx->stage_slot[slot], len * 16, cudaMemcpyHostToDevice, st));
         CUDA_TRY(ctx, cudaEventRecord(ctx->stage_ev[slot], st));
     }
     return DAMPR_OK;
@@ -288,12 +344,11 @@ int staged_file_h2d(dampr_ctx *ctx, void *dst, int fd, size_t foff, size_t bytes
     int rc = stage_init(ctx);
     if (rc) return rc;
     const size_t B = dampr_ctx::STAGE_BYTES;
-    size_t i = 0;
-    for (size_t off = 0; off < bytes; off += B, ++i) {
-        const int slot = (int)(i % dampr_ctx::STAGE_SLOTS);
+    for (size_t off = 0; off < bytes; off += B) {
+        const int slot = (int)(ctx->stage_next++ % dampr_ctx::STAGE_SLOTS);
         const size_t len = std::min(B, bytes - off);
         CUDA_TRY(ctx, cudaEventSynchronize(ctx->stage_ev[slot]));  // the DMA that last read this slot
-        if (!par_pread(ctx->stage_slot[slot], fd, foff + off, len, ctx->host_threads))
+        if (!par_pread(ctx->stage_slot[slot], fd, foff + off, len, copy_threads()))
             return set_err(ctx, DAMPR_ERR_ARG, "%s", "short read from the input file");
         CUDA_TRY(ctx, cudaMemcpyAsync((char *)dst + off, ctx->stage_slot[slot], len, cudaMemcpyHostToDevice, st));
         CUDA_TRY(ctx, cudaEventRecord(ctx->stage_ev[slot], st));
@@ -313,19 +368,18 @@ int staged_d2h(dampr_ctx *ctx, void *dst, const void *src, size_t bytes, cudaStr
     const size_t B = dampr_ctx::STAGE_BYTES;
     const size_t nchunks = (bytes + B - 1) / B;
     const size_t S = dampr_ctx::STAGE_SLOTS;
-    // a slot may still be the source of an earlier upload's DMA
-    for (size_t s = 0; s < S; ++s) CUDA_TRY(ctx, cudaEventSynchronize(ctx->stage_ev[s]));
+    // (the download ring is only ever used by this function, which drains every slot before it returns)
     for (size_t i = 0; i < nchunks + S - 1; ++i) {
         if (i >= S - 1) {  // drain chunk i-(S-1) before its slot is refilled by chunk i+1
             const size_t j = i - (S - 1);
             const size_t off = j * B, len = std::min(B, bytes - off);
-            CUDA_TRY(ctx, cudaEventSynchronize(ctx->stage_ev[j % S]));
-            par_memcpy((char *)dst + off, ctx->stage_slot[j % S], len, ctx->host_threads);
+            CUDA_TRY(ctx, cudaEventSynchronize(ctx->dstage_ev[j % S]));
+            par_memcpy((char *)dst + off, ctx->dstage_slot[j % S], len, copy_threads());
         }
         if (i < nchunks) {
             const size_t off = i * B, len = std::min(B, bytes - off);
-            CUDA_TRY(ctx, cudaMemcpyAsync(ctx->stage_slot[i % S], (const char *)src + off, len, cudaMemcpyDeviceToHost, st));
-            CUDA_TRY(ctx, cudaEventRecord(ctx->stage_ev[i % S], st));
+            CUDA_TRY(ctx, cudaMemcpyAsync(ctx->dstage_slot[i % S], (const char *)src + off, len, cudaMemcpyDeviceToHost, st));
+            CUDA_TRY(ctx, cudaEventRecord(ctx->dstage_ev[i % S], st));
         }
     }
     return DAMPR_OK;
@@ -400,6 +454,8 @@ int32_t dampr_ctx_destroy(dampr_ctx *ctx) {
     for (int i = 0; i < dampr_ctx::STAGE_SLOTS; ++i) {
         if (ctx->stage_slot[i]) cudaFreeHost(ctx->stage_slot[i]);
         if (ctx->stage_ev[i]) cudaEventDestroy(ctx->stage_ev[i]);
+        if (ctx->dstage_slot[i]) cudaFreeHost(ctx->dstage_slot[i]);
+        if (ctx->dstage_ev[i]) cudaEventDestroy(ctx->dstage_ev[i]);
     }
     cudaStreamDestroy(ctx->stream);
     cudaStreamDestroy(ctx->copy);

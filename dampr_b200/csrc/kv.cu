@@ -1769,6 +1769,11 @@ int32_t dampr_set_option(const char *name, int64_t value) {
         g_text_ctas = (int)value;
         return DAMPR_OK;
     }
+    if (!strcmp(name, "host_threads")) {
+        if (value < 1 || value > 256) return DAMPR_ERR_ARG;
+        g_host_threads_cap = (int)value;
+        return DAMPR_OK;
+    }
     if (!strcmp(name, "text_kernel")) {
         if (value != 1 && value != 2) return DAMPR_ERR_ARG;
         g_text_kernel = (int)value;

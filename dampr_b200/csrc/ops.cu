@@ -320,7 +320,11 @@ int32_t dampr_kv_upload_columns(dampr_ctx *ctx, dampr_kv *kv, uint64_t off, cons
     ARG_CHECK(ctx, ctx && kv && (keys || count == 0), "null");
     ARG_CHECK(ctx, off + count <= kv->capacity, "upload exceeds kv capacity");
     CUDA_TRY(ctx, cudaSetDevice(ctx->device));
-    if (count) {
+    if (count && count * 8 >= (8u << 20) && !host_is_pinned(keys) && !(vals && host_is_pinned(vals))) {
+        // pageable columns: the copy threads interleave them on their way into the page-locked ring
+        int rc = staged_h2d_columns(ctx, kv->rec + off, (const u64 *)keys, (const u64 *)vals, count, ctx->copy);
+        if (rc) return rc;
+    } else if (count) {
         const int slot = ctx->up_tmp_next;
         ctx->up_tmp_next ^= 1;
         if (!ctx->up_tmp_ev[slot]) CUDA_TRY(ctx, cudaEventCreateWithFlags(&ctx->up_tmp_ev[slot], cudaEventDisableTiming));

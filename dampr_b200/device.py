@@ -482,6 +482,13 @@ class KV(object):
         self.ctx.check(self.ctx.lib.dampr_kv_download_columns(self.ctx.h, self.h, 0, _ptr(keys), _ptr(vals), n))
         return keys, vals
 
+    def columns_into(self, keys, vals):
+        """Download into caller-provided contiguous uint64 arrays of len(self) elements (no allocation)."""
+        n = len(self)
+        assert keys.dtype == np.uint64 and vals.dtype == np.uint64 and len(keys) == n and len(vals) == n
+        assert keys.flags.c_contiguous and vals.flags.c_contiguous
+        self.ctx.check(self.ctx.lib.dampr_kv_download_columns(self.ctx.h, self.h, 0, _ptr(keys), _ptr(vals), n))
+
     def decode_words(self, mode, width=32):
         """Keys are token codes: 'S<width>' array decoded on the device (hashed codes -> b'')."""
         n = len(self)

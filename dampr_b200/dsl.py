@@ -236,7 +236,11 @@ class PMap(PBase):
             for _score, x in heapq.nlargest(k, cands):
                 yield x, 1
 
-        return self.partition_map(_map_topk).partition_reduce(_reduce_topk).map(lambda kv: kv[0])
+        # the descriptor lets the planner take the candidates of a columnar frame with one device sort of the
+        # scores (plan._lower_topk); every other input runs _map_topk as written
+        sm = ops.StreamMapper(_map_topk)
+        sm.op = Op("topk", value, k)
+        return self.custom_mapper(sm).partition_reduce(_reduce_topk).map(lambda kv: kv[0])
 
     def join(self, other):
         assert isinstance(other, PBase)

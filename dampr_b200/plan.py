@@ -998,15 +998,18 @@ def _device_group(runner, keys, vals, op, xform):
             red.free()
         return rk, rv, " [rank %d/%d: local fold, all-to-all, owner fold]" % (r, w)
     if n and spill.needs_spill(ctx, n):
-        step = 1 << 22
+        step = 1 << 24
         chunks = ((keys[i:i + step], vals[i:i + step]) for i in range(0, n, step))
         if op is None and xform != dev.KEY_MIX:
             samp = keys[np.random.default_rng(0).integers(0, n, size=min(n, 1 << 16))]
             pieces, st = spill.external_sort(ctx, chunks, n, xform, samp)
         else:
             pieces, st = spill.external_group(ctx, chunks, n, op, xform if op is None else dev.KEY_MIX)
-        rk = np.concatenate([p[0] for p in pieces]) if pieces else np.zeros(0, dtype=np.uint64)
-        rv = np.concatenate([p[1] for p in pieces]) if pieces else np.zeros(0, dtype=np.uint64)
+        if len(pieces) == 1:    # external_group writes its result columns in place: nothing to concatenate
+            rk, rv = pieces[0]
+        else:
+            rk = np.concatenate([p[0] for p in pieces]) if pieces else np.zeros(0, dtype=np.uint64)
+            rv = np.concatenate([p[1] for p in pieces]) if pieces else np.zeros(0, dtype=np.uint64)
         runner.stats.spill = st
         return rk, rv, " [spilled: %d buckets, %d batches, arena %d MB]" % (
             st["buckets"], st["batches"], st["arena_bytes"] >> 20)
@@ -1030,12 +1033,74 @@ def _numeric(col):
     return isinstance(col, np.ndarray) and col.dtype.kind in "iuf" and col.dtype.itemsize == 8
 
 
+def _lower_topk(runner, stage, frame, op):
+    """topk(k, value) over a columnar frame (dampr.py:621-652): value = +-x[i] / +-x on a numeric column. One
+    device sort of (score, row) finds the k-th largest score; the rows at or above it (a superset of the answer
+    when scores tie at the boundary) become the candidates, cut to k by the reference's own (value(x), x) tuple
+    order on the host. Emits what map_topk emits: (1, (value(x), x)) for the surviving rows — the stage's
+    partition_reduce (heapq.nlargest over all candidates) then runs unchanged on at most k records."""
+    import heapq
+    value, k = op.fn, op.fn2
+    if dist.active() or not isinstance(k, int) or isinstance(k, bool) or stage.combiner is not None:
+        return None
+    kp = lowering.projection(value)
+    if kp is None:
+        return None
+    if kp[0] == "field" and not frame.scalar and kp[1] < len(frame.cols):
+        col = frame.cols[kp[1]]
+    elif kp[0] == "ident" and frame.scalar:
+        col = frame.cols[0]
+    else:
+        return None
+    if isinstance(col, DictCol):
+        col = col.materialize()
+    if not _numeric(col) or col.dtype.kind not in "if" or (col.dtype.kind == "f" and np.isnan(col).any()):
+        return None   # NaN scores make the heap order depend on the arrival order
+    n = frame.n
+    if k <= 0 or n == 0:
+        runner.stats.add(stage, "device top-k candidates", "records=%d k=%d candidates=0" % (n, k))
+        return RecordsDataset([], [])
+    sign = kp[2]
+    if col.dtype.kind == "f":
+        if sign < 0 and (col == 0).any():
+            return None   # -0.0 == 0.0 but the codes differ
+        score = (col * sign) if sign < 0 else col
+        codes, xf = score.view(np.uint64), dev.KEY_F64
+    else:
+        c64 = col.astype(np.int64)
+        if sign < 0 and len(c64) and int(c64.min()) == -(1 << 63):
+            return None
+        score = -c64 if sign < 0 else c64
+        codes, xf = score.view(np.uint64), dev.KEY_I64
+    if n > k:
+        kv = runner.ctx.kv_from_columns(codes, np.arange(n, dtype=np.uint64))
+        try:
+            kv.sort(xf)
+            sk, perm = kv.columns()
+        finally:
+            kv.free()
+        sk = sk.view(score.dtype)
+        lo = int(np.searchsorted(sk, sk[n - k], side="left"))   # every row tied with the k-th largest score
+        cand = np.sort(perm[lo:].view(np.int64))
+    else:
+        cand = np.arange(n, dtype=np.int64)
+    rows = frame.take(cand).values()
+    scored = [(value(x), x) for x in rows]
+    if len(scored) > k:
+        scored = heapq.nlargest(k, scored)
+    runner.stats.add(stage, "device top-k candidates (one sort of the scores; ties cut by the tuple order on the host)",
+                     "records=%d k=%d candidates=%d" % (n, k, len(cand)))
+    return RecordsDataset([1] * len(scored), scored)
+
+
 def _lower_frame_map(runner, stage, frame):
     """sort_by(+-x[i]) / sort_by(+-x) over a frame."""
     ks = _opkinds(stage.mapper)
     if ks is None:
         return None
     kinds = [k for k, _ in ks]
+    if kinds == ["topk"]:
+        return _lower_topk(runner, stage, frame, ks[0][1])
     if kinds == ["keyed"] and stage.combiner is None:
         op = ks[0][1]
         if not lowering.is_identity(op.fn2):

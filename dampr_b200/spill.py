@@ -40,21 +40,72 @@ def arena_bytes(ctx):
 
 
 RECORD_FOOTPRINT = 48  # bytes of device memory per record during a sort: data + ping-pong + output
+# ... and while the next batch is uploaded next to the one being sorted (pass 1 / pass 2 overlap)
+RECORD_FOOTPRINT_OVERLAPPED = 64
 
 
 def needs_spill(ctx, n_records):
     return n_records * RECORD_FOOTPRINT > arena_bytes(ctx)
 
 
-def _upload_chunks(ctx, kchunks, vchunks):
-    """One device kv from column chunks, uploaded back to back (no host-side concatenation)."""
-    kv = ctx.kv(max(1, sum(len(k) for k in kchunks)))
-    off = 0
-    for k, v in zip(kchunks, vchunks):
-        kv.upload_columns(off, k, v)
-        off += len(k)
-    ctx.sync()
-    return kv
+def _batches(chunk_iter, per_batch):
+    """Regroup (keys, vals) column chunks into batches of at most per_batch records: lists of (k, v) slices."""
+    pend, pend_n = [], 0
+    for keys, vals in chunk_iter:
+        pos = 0
+        while pos < len(keys):
+            take = min(len(keys) - pos, per_batch - pend_n)
+            pend.append((np.asarray(keys[pos:pos + take]).view(np.uint64), np.asarray(vals[pos:pos + take]).view(np.uint64)))
+            pend_n += take
+            pos += take
+            if pend_n >= per_batch:
+                yield pend
+                pend, pend_n = [], 0
+    if pend_n:
+        yield pend
+
+
+class _Upload(object):
+    """One device kv being filled by a host thread while the caller keeps the device busy with the previous
+    batch: PCIe is full duplex and the staged copies release the GIL, so the upload of batch i+1 runs next to the
+    sort and the download of batch i. The kv is allocated by the CALLER's thread (the device block pool is not
+    thread-safe); the thread only stages and enqueues copies on the copy stream (its own page-locked ring)."""
+
+    def __init__(self, ctx, parts, columns):
+        import threading
+        self.ctx = ctx
+        self.n = sum(len(p[0]) if columns else len(p) for p in parts)
+        self.kv = ctx.kv(max(1, self.n))
+        self.err = None
+        self.seconds = 0.0
+
+        def work():
+            import time as _time
+            t0 = _time.perf_counter()
+            try:
+                off = 0
+                for p in parts:
+                    if columns:
+                        self.kv.upload_columns(off, p[0], p[1])
+                        off += len(p[0])
+                    else:
+                        self.kv.upload(off, p, len(p))
+                        off += len(p)
+            except BaseException as e:   # re-raised by wait()
+                self.err = e
+            self.seconds = _time.perf_counter() - t0
+        self.th = threading.Thread(target=work, name="dampr-spill-upload")
+        self.th.start()
+
+    def wait(self):
+        """The filled kv (all copies complete)."""
+        self.th.join()
+        if self.err is not None:
+            self.kv.free()
+            raise self.err
+        sync = getattr(self.ctx, "sync_copy_stream", None) or self.ctx.sync
+        sync()
+        return self.kv
 
 
 def _upload_runs(ctx, runs):
@@ -66,6 +117,60 @@ def _upload_runs(ctx, runs):
         off += len(r)
     ctx.sync()
     return kv
+
+
+def _pipelined(ctx, items, columns):
+    """(tag, filled kv, upload seconds) for every (tag, parts) of `items` — parts = a list of column chunks
+    (columns=True) or of record runs, or None for an item that needs no device copy (kv is None then) — the
+    upload of the next item overlapping whatever the consumer does with the current one."""
+    it = iter(items)
+    cur = next(it, None)
+    up = _Upload(ctx, cur[1], columns) if cur is not None and cur[1] is not None else None
+    while cur is not None:
+        kv = up.wait() if up is not None else None
+        sec = up.seconds if up is not None else 0.0
+        nxt = next(it, None)
+        try:
+            up = _Upload(ctx, nxt[1], columns) if nxt is not None and nxt[1] is not None else None
+        except BaseException:
+            if kv is not None:
+                kv.free()
+            raise
+        try:
+            yield cur[0], kv, sec
+        except BaseException:
+            if up is not None:
+                try:
+                    up.wait().free()
+                except BaseException:
+                    pass
+            raise
+        cur = nxt
+
+
+class _OutCols(object):
+    """Result columns of a spill pipeline, written in place: one allocation sized for the worst case (untouched
+    pages cost nothing), filled piece by piece straight from the device downloads — no concatenation at the end."""
+
+    def __init__(self, cap):
+        self.k = np.empty(max(1, cap), dtype=np.uint64)
+        self.v = np.empty(max(1, cap), dtype=np.uint64)
+        self.n = 0
+
+    def take_kv(self, kv):
+        g = len(kv)
+        if g:
+            kv.columns_into(self.k[self.n:self.n + g], self.v[self.n:self.n + g])
+            self.n += g
+
+    def take_records(self, recs):
+        g = len(recs)
+        self.k[self.n:self.n + g] = recs[:, 0]
+        self.v[self.n:self.n + g] = recs[:, 1]
+        self.n += g
+
+    def pieces(self):
+        return [(self.k[:self.n], self.v[:self.n])]
 
 
 def _mix64(x):
@@ -110,9 +215,12 @@ def external_group(ctx, chunk_iter, n_records, op=None, xform=dev.KEY_MIX):
             SORTED RUN per batch (SortedWriter, dataset.py:162-164);
     pass 2  one bucket at a time: its runs go back to the device and are k-way merged (+ folded) in one read
             and one write (dampr_kv_merge_ranges, csrc/merge.cu) — MergeDataset.read (dataset.py:571-579)
-            + PartialReduceCombiner (base.py:393-402) — instead of being sorted again."""
+            + PartialReduceCombiner (base.py:393-402) — instead of being sorted again.
+    In both passes the upload of the next batch / bucket runs on a host thread next to the device work and the
+    download of the current one (_pipelined): PCIe carries both directions at once."""
+    import time as _time
     arena = arena_bytes(ctx)
-    per_batch = max(1 << 16, arena // RECORD_FOOTPRINT)
+    per_batch = max(1 << 16, arena // RECORD_FOOTPRINT_OVERLAPPED)
     n_buckets = max(2, int(np.ceil(1.3 * n_records / float(per_batch))))
     mixed = xform == dev.KEY_MIX
     if not mixed:
@@ -121,26 +229,21 @@ def external_group(ctx, chunk_iter, n_records, op=None, xform=dev.KEY_MIX):
     splitters = np.array([(b << 64) // n_buckets for b in range(1, n_buckets)], dtype=np.uint64)
     buckets = [[] for _ in range(n_buckets)]
     stats = {"buckets": n_buckets, "batches": 0, "spilled_bytes": 0, "arena_bytes": arena,
-             "seconds": {"upload": 0.0, "sort": 0.0, "download": 0.0, "cut": 0.0, "merge_upload": 0.0, "merge": 0.0,
-                         "merge_download": 0.0}}
+             "seconds": {"upload_thread": 0.0, "sort_download": 0.0, "cut": 0.0, "pass1_wall": 0.0,
+                         "merge_upload_thread": 0.0, "merge_download": 0.0, "pass2_wall": 0.0}}
     sec = stats["seconds"]
     op2 = dev.OP_SUM_I64 if op == dev.OP_COUNT else op   # partial counts are added up
-    import time as _time
-
-    def flush_batch(kchunks, vchunks):
-        t0 = _time.perf_counter()
-        kv = _upload_chunks(ctx, kchunks, vchunks)
+    t_pass = _time.perf_counter()
+    spilled = 0
+    for _tag, kv, up_s in _pipelined(ctx, ((None, b) for b in _batches(chunk_iter, per_batch)), True):
+        sec["upload_thread"] += up_s
         t1 = _time.perf_counter()
         try:
             if op is None:
                 kv.sort(xform)
-                ctx.sync()
-                t2 = _time.perf_counter()
                 recs = kv.records()
             else:
                 red = kv.sort_reduce(op, xform, sorted_run=True)
-                ctx.sync()
-                t2 = _time.perf_counter()
                 try:
                     recs = red.records()
                 finally:
@@ -148,9 +251,7 @@ def external_group(ctx, chunk_iter, n_records, op=None, xform=dev.KEY_MIX):
         finally:
             kv.free()
         t3 = _time.perf_counter()
-        sec["upload"] += t1 - t0
-        sec["sort"] += t2 - t1
-        sec["download"] += t3 - t2
+        sec["sort_download"] += t3 - t1
         cuts = _lazy_cuts(recs[:, 0], splitters, _mix64)
         sec["cut"] += _time.perf_counter() - t3
         edges = [0] + cuts.tolist() + [len(recs)]
@@ -159,32 +260,61 @@ def external_group(ctx, chunk_iter, n_records, op=None, xform=dev.KEY_MIX):
                 buckets[b].append(recs[edges[b]:edges[b + 1]])
         stats["batches"] += 1
         stats["spilled_bytes"] += recs.nbytes
+        spilled += len(recs)
+    sec["pass1_wall"] = _time.perf_counter() - t_pass
 
-    pend_k, pend_v, pend_n = [], [], 0
-    for keys, vals in chunk_iter:
-        pos = 0
-        while pos < len(keys):
-            take = min(len(keys) - pos, per_batch - pend_n)
-            pend_k.append(keys[pos:pos + take])
-            pend_v.append(np.asarray(vals[pos:pos + take]).view(np.uint64))
-            pend_n += take
-            pos += take
-            if pend_n >= per_batch:
-                flush_batch(pend_k, pend_v)
-                pend_k, pend_v, pend_n = [], [], 0
-    if pend_n:
-        flush_batch(pend_k, pend_v)
+    t_pass = _time.perf_counter()
+    out = _OutCols(spilled)
+    _merge_buckets(ctx, buckets, xform, -1 if op is None else op2, per_batch, out, sec)
+    sec["pass2_wall"] = _time.perf_counter() - t_pass
+    return out.pieces(), stats
 
-    out = []
-    for b in range(n_buckets):
-        runs, buckets[b] = buckets[b], None
-        if not runs:
-            continue
-        if len(runs) == 1:   # one sorted (folded) run: nothing to merge
-            out.append((runs[0][:, 0].copy(), runs[0][:, 1].copy()))
-            continue
-        out.extend(_merge_runs(ctx, runs, xform, -1 if op is None else op2, per_batch, sec))
-    return out, stats
+
+def _merge_buckets(ctx, buckets, xform, op, per_batch, out, sec=None):
+    """Pass 2: the runs of every bucket, in bucket order, merged (+ folded, op >= 0) on the device into `out`.
+    Buckets whose runs fit the arena together are pipelined (the next bucket's runs upload while this one is
+    merged and downloaded); a bucket of one run is already final; an oversized (skewed) bucket is cut into key
+    range slices (_merge_runs)."""
+    import time as _time
+
+    def items():
+        for b in range(len(buckets)):
+            runs, buckets[b] = buckets[b], None
+            if not runs:
+                continue
+            total = sum(len(r) for r in runs)
+            if len(runs) > 1 and total <= per_batch:
+                yield ("merge", runs), runs
+            else:
+                yield ("host", runs), None
+
+    for (kind, runs), kv, up_s in _pipelined(ctx, items(), False):
+        if kind == "merge":
+            t1 = _time.perf_counter()
+            try:
+                offs = np.concatenate(([0], np.cumsum([len(r) for r in runs]))).astype(np.uint64)
+                m = ctx.kv_merge_ranges(kv, offs, xform, op)
+            finally:
+                kv.free()
+            try:
+                out.take_kv(m)
+            finally:
+                m.free()
+            if sec is not None:
+                sec["merge_upload_thread"] += up_s
+                sec["merge_download"] += _time.perf_counter() - t1
+        elif len(runs) == 1:   # one sorted (folded) run: nothing to merge
+            out.take_records(runs[0])
+        else:
+            for k, v in _merge_runs(ctx, runs, xform, op, per_batch):
+                _take_cols(out, k, v)
+
+
+def _take_cols(out, k, v):
+    g = len(k)
+    out.k[out.n:out.n + g] = k
+    out.v[out.n:out.n + g] = np.asarray(v).view(np.uint64)
+    out.n += g
 
 
 def _merge_runs(ctx, runs, xform, op, per_batch, sec=None):
@@ -193,25 +323,16 @@ def _merge_runs(ctx, runs, xform, op, per_batch, sec=None):
     splitters so that every slice fits, and the slices come out in key order."""
     total = sum(len(r) for r in runs)
     if total <= per_batch:
-        import time as _time
-        t0 = _time.perf_counter()
         kv = _upload_runs(ctx, runs)
-        t1 = _time.perf_counter()
         try:
             offs = np.concatenate(([0], np.cumsum([len(r) for r in runs]))).astype(np.uint64)
             m = ctx.kv_merge_ranges(kv, offs, xform, op)
-            ctx.sync()
         finally:
             kv.free()
-        t2 = _time.perf_counter()
         try:
             k, v = m.columns()
         finally:
             m.free()
-        if sec is not None:
-            sec["merge_upload"] += t1 - t0
-            sec["merge"] += t2 - t1
-            sec["merge_download"] += _time.perf_counter() - t2
         return [(k, v)]
     dom = (lambda k: _mix64(k)) if xform == dev.KEY_MIX else (lambda k: _order_domain(k, xform))
     rng = np.random.default_rng(len(runs))
@@ -281,7 +402,7 @@ def external_sort(ctx, chunk_iter, n_records, xform, sample_keys, _depth=0):
     (keys uint64[], vals 8-byte[]) chunks in input order; sample_keys is a random sample of the keys.
     Returns (pieces, stats): pieces = [(keys, vals)] in ascending key order."""
     arena = arena_bytes(ctx)
-    per_batch = max(1 << 16, arena // RECORD_FOOTPRINT)
+    per_batch = max(1 << 16, arena // RECORD_FOOTPRINT_OVERLAPPED)
     n_buckets = max(2, int(np.ceil(1.3 * n_records / float(per_batch))))
     samp = np.unique(_order_domain(np.asarray(sample_keys).view(np.uint64), xform))
     # a splitter is never the smallest sampled key, so the range below the first splitter is not empty
@@ -292,8 +413,7 @@ def external_sort(ctx, chunk_iter, n_records, xform, sample_keys, _depth=0):
     sizes = [0] * nb
     stats = {"buckets": nb, "batches": 0, "spilled_bytes": 0, "arena_bytes": arena}
 
-    def flush_batch(kchunks, vchunks):
-        kv = _upload_chunks(ctx, kchunks, vchunks)
+    for _tag, kv, _up_s in _pipelined(ctx, ((None, bt) for bt in _batches(chunk_iter, per_batch)), True):
         try:
             kv.sort(xform)
             recs = kv.records()
@@ -307,21 +427,6 @@ def external_sort(ctx, chunk_iter, n_records, xform, sample_keys, _depth=0):
                 sizes[b] += edges[b + 1] - edges[b]
         stats["batches"] += 1
         stats["spilled_bytes"] += recs.nbytes
-
-    pend_k, pend_v, pend_n = [], [], 0
-    for keys, vals in chunk_iter:
-        pos = 0
-        while pos < len(keys):
-            take = min(len(keys) - pos, per_batch - pend_n)
-            pend_k.append(np.asarray(keys[pos:pos + take]).view(np.uint64))
-            pend_v.append(np.asarray(vals[pos:pos + take]).view(np.uint64))
-            pend_n += take
-            pos += take
-            if pend_n >= per_batch:
-                flush_batch(pend_k, pend_v)
-                pend_k, pend_v, pend_n = [], [], 0
-    if pend_n:
-        flush_batch(pend_k, pend_v)
 
     out = []
     for b in range(nb):

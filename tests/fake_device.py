@@ -54,6 +54,10 @@ class FakeKV(object):
     def columns(self):
         return self.rec[:self.n, 0].copy(), self.rec[:self.n, 1].copy()
 
+    def columns_into(self, keys, vals):
+        keys[:] = self.rec[:self.n, 0]
+        vals[:] = self.rec[:self.n, 1]
+
     def partition_by_owner(self, nb):
         own = self._order(self.rec[:self.n, 0], 1) % np.uint64(nb)
         o = np.argsort(own, kind="stable")

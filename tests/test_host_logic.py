@@ -543,3 +543,28 @@ def test_device_fold_guards_keep_python_semantics():
     assert runner._numeric_column([0.0, -0.0], lowering.MAX)[0] is None
     assert runner._numeric_column([1.5, -2.0], lowering.MAX)[0] is not None
     assert runner._numeric_column([3, 4], lowering.MIN)[0] is not None
+
+
+def test_topk_over_a_frame_takes_its_candidates_with_one_device_sort(monkeypatch):
+    """topk(k, value) over a columnar frame (plan._lower_topk, dampr.py:621-652): the k largest by the reference's
+    (value(x), x) tuple order, ties at the boundary included; NaN scores and non-projection value functions fall
+    back to the generic partition_map."""
+    import heapq
+    from dampr_b200 import Dampr, settings, plan
+    from dampr_b200 import runner as runner_mod
+    from dampr_b200.inputs import ArrayKVInput
+    monkeypatch.setattr(runner_mod, "_CTX", {settings.device: _FakeCtx()})
+    rng = np.random.default_rng(3)
+    keys = rng.integers(0, 5000, size=60000).astype(np.int64)
+    vals = rng.integers(0, 4, size=60000).astype(np.int64)    # few distinct sums: many ties
+    base = Dampr.read_input(ArrayKVInput(keys, vals)).a_group_by(lambda x: x[0], lambda x: x[1]).sum()
+    rows = base.read()
+    for k in (0, 1, 7, 100, 6000):
+        for value in (lambda x: x[1], lambda x: -x[1], lambda x: x[0]):
+            got = base.topk(k, value).read()
+            assert any("top-k" in how for _s, how, _d in runner_mod.LAST_STATS.stages)
+            exp = [x for _s, x in heapq.nlargest(k, [(value(x), x) for x in rows])]
+            assert sorted(got) == sorted(exp), k
+    got = base.topk(5, lambda x: x[1] * 2 + x[0]).read()   # not a projection: host path, same answer
+    assert not any("top-k" in how for _s, how, _d in runner_mod.LAST_STATS.stages)
+    assert sorted(got) == sorted(x for _s, x in heapq.nlargest(5, [(x[1] * 2 + x[0], x) for x in rows]))
