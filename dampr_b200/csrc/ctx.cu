@@ -148,9 +148,11 @@ class CopyPool {
     };
 
   public:
-    static CopyPool &get() {
-        static CopyPool p;
-        return p;
+    // two pools: uploads (0) and downloads (1) may run at the same time (spill.py overlaps them), each with its
+    // own threads, so the host copies of the two PCIe directions do not queue behind each other
+    static CopyPool &get(int which = 0) {
+        static CopyPool p[2];
+        return p[which & 1];
     }
     // returns false if a read from the file came up short
     bool run(void *dst, const void *src, size_t n, int threads, int fd = -1, size_t foff = 0, const void *src2 = nullptr,
@@ -256,7 +258,7 @@ class CopyPool {
     bool stop_ = false;
 };
 
-void par_memcpy(void *dst, const void *src, size_t n, int threads) { CopyPool::get().run(dst, src, n, threads); }
+void par_memcpy(void *dst, const void *src, size_t n, int threads, int pool = 0) { CopyPool::get(pool).run(dst, src, n, threads); }
 void par_interleave(void *dst_records, const void *keys, const void *vals, size_t count, int threads) {
     CopyPool::get().run(dst_records, keys, count * 16, std::max(threads, 1), -1, 0, vals, true);
 }
@@ -374,7 +376,7 @@ int staged_d2h(dampr_ctx *ctx, void *dst, const void *src, size_t bytes, cudaStr
             const size_t j = i - (S - 1);
             const size_t off = j * B, len = std::min(B, bytes - off);
             CUDA_TRY(ctx, cudaEventSynchronize(ctx->dstage_ev[j % S]));
-            par_memcpy((char *)dst + off, ctx->dstage_slot[j % S], len, copy_threads());
+            par_memcpy((char *)dst + off, ctx->dstage_slot[j % S], len, copy_threads(), 1);
         }
         if (i < nchunks) {
             const size_t off = i * B, len = std::min(B, bytes - off);
@@ -551,6 +553,25 @@ int32_t dampr_host_alloc(uint64_t nbytes, void **out) {
 int32_t dampr_host_free(void *p) {
     if (!p) return DAMPR_OK;
     return cudaFreeHost(p) == cudaSuccess ? DAMPR_OK : DAMPR_ERR_CUDA;
+}
+
+// Page-lock memory the caller owns (the spill run buffer, spill.py): transfers from / to it then go straight over
+// PCIe instead of through the staging ring and the copy threads.
+int32_t dampr_host_register(void *p, uint64_t nbytes) {
+    if (!p || !nbytes) return DAMPR_ERR_ARG;
+    cudaError_t e = cudaHostRegister(p, nbytes, cudaHostRegisterDefault);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return e == cudaErrorMemoryAllocation ? DAMPR_ERR_NOMEM : DAMPR_ERR_CUDA;
+    }
+    return DAMPR_OK;
+}
+
+int32_t dampr_host_unregister(void *p) {
+    if (!p) return DAMPR_OK;
+    cudaError_t e = cudaHostUnregister(p);
+    if (e != cudaSuccess) cudaGetLastError();
+    return e == cudaSuccess ? DAMPR_OK : DAMPR_ERR_CUDA;
 }
 
 // ---- text buffers -------------------------------------------------------------------------

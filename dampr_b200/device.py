@@ -77,6 +77,8 @@ def load_library():
     _sig(lib, "dampr_ctx_stream", vp, pu64)
     _sig(lib, "dampr_host_alloc", u64, pvp)
     _sig(lib, "dampr_host_free", vp)
+    _sig(lib, "dampr_host_register", vp, u64)
+    _sig(lib, "dampr_host_unregister", vp)
     _sig(lib, "dampr_textbuf_create", vp, u64, pvp)
     _sig(lib, "dampr_textbuf_destroy", vp, vp)
     _sig(lib, "dampr_textbuf_set_length", vp, vp, u64)
@@ -170,6 +172,16 @@ class PinnedBuffer(object):
             self.free()
         except Exception:
             pass
+
+
+def host_register(arr):
+    """Page-lock the memory of a C-contiguous numpy array (cudaHostRegister). True on success; the caller must
+    host_unregister() before the array is released."""
+    return load_library().dampr_host_register(_ptr(arr), int(arr.nbytes)) == 0
+
+
+def host_unregister(arr):
+    load_library().dampr_host_unregister(_ptr(arr))
 
 
 class Ctx(object):
@@ -472,6 +484,13 @@ class KV(object):
         """Download as an (n, 2) uint64 array."""
         n = len(self)
         out = np.empty((n, 2), dtype=np.uint64)
+        self.ctx.check(self.ctx.lib.dampr_kv_download(self.ctx.h, self.h, 0, _ptr(out), n))
+        return out
+
+    def records_into(self, out):
+        """Download into a caller-provided contiguous (len(self), 2) uint64 array (no allocation)."""
+        n = len(self)
+        assert out.dtype == np.uint64 and out.shape == (n, 2) and out.flags.c_contiguous
         self.ctx.check(self.ctx.lib.dampr_kv_download(self.ctx.h, self.h, 0, _ptr(out), n))
         return out
 

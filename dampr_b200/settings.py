@@ -40,6 +40,10 @@ ingest_chunk_bytes = 64 << 20
 text_table_log2 = 21  # grows (x4) and the scan re-runs when it overflows or fills beyond 50 %
 # device arena in bytes available to one sort before it spills runs (None = no cap)
 device_arena_bytes = None
+# the host buffer that holds the spilled runs of one job is kept for the next job when it is at most this large
+# (its pages are then already mapped: no page faults on the way out, nothing to unmap at the end);
+# spill.release_host_arena() returns it to the OS
+host_spill_cache_bytes = 96 << 30
 # build of the tokenise kernel the scans start with: CTAs per SM it is sized for (4, 3 or 2; lines with more
 # distinct tokens than a build remembers are retried on the 2-CTA build, see plan.TextScan.run)
 text_kernel_ctas = 4

@@ -148,6 +148,54 @@ def _pipelined(ctx, items, columns):
         cur = nxt
 
 
+_HOST_ARENA = {"buf": None, "leased": False}
+
+
+class _RunArena(object):
+    """Host memory for the sorted runs one job spills (pass 1 writes them back to back, pass 2 reads them). The
+    buffer is leased from a process-wide cache (settings.host_spill_cache_bytes): a second job finds its pages
+    already mapped — no page faults while the downloads land, no unmapping of tens of GB at the end. A nested
+    lease (external_sort splitting a skewed range of runs that live in the arena) gets a buffer of its own."""
+
+    def __init__(self, n_records):
+        n_records = max(1, int(n_records))
+        self.cached = False
+        buf = _HOST_ARENA["buf"]
+        if not _HOST_ARENA["leased"]:
+            if buf is None or len(buf) < n_records:
+                _HOST_ARENA["buf"] = buf = None   # drop the old one before the new one is mapped
+                buf = np.empty((n_records, 2), dtype=np.uint64)
+                if buf.nbytes <= int(settings.host_spill_cache_bytes or 0):
+                    _HOST_ARENA["buf"] = buf
+            self.cached = _HOST_ARENA["buf"] is buf
+            _HOST_ARENA["leased"] = self.cached
+        else:
+            buf = np.empty((n_records, 2), dtype=np.uint64)
+        self.buf, self.pos = buf, 0
+
+    def take(self, kv):
+        """Download a device kv as the next run; returns the (n, 2) view."""
+        n = len(kv)
+        if self.pos + n > len(self.buf):
+            raise RuntimeError("spill arena overflow: %d + %d > %d" % (self.pos, n, len(self.buf)))
+        out = self.buf[self.pos:self.pos + n]
+        if n:
+            kv.records_into(out)
+        self.pos += n
+        return out
+
+    def release(self):
+        if self.cached:
+            _HOST_ARENA["leased"] = False
+        self.buf = None
+
+
+def release_host_arena():
+    """Return the cached run buffer to the OS."""
+    if not _HOST_ARENA["leased"]:
+        _HOST_ARENA["buf"] = None
+
+
 class _OutCols(object):
     """Result columns of a spill pipeline, written in place: one allocation sized for the worst case (untouched
     pages cost nothing), filled piece by piece straight from the device downloads — no concatenation at the end."""
@@ -235,17 +283,30 @@ def external_group(ctx, chunk_iter, n_records, op=None, xform=dev.KEY_MIX):
     op2 = dev.OP_SUM_I64 if op == dev.OP_COUNT else op   # partial counts are added up
     t_pass = _time.perf_counter()
     spilled = 0
+    arena_host = _RunArena(n_records)
+    try:
+        return _external_group_passes(ctx, chunk_iter, per_batch, n_buckets, splitters, buckets, stats, op, op2, xform,
+                                      arena_host)
+    finally:
+        arena_host.release()
+
+
+def _external_group_passes(ctx, chunk_iter, per_batch, n_buckets, splitters, buckets, stats, op, op2, xform, arena_host):
+    import time as _time
+    sec = stats["seconds"]
+    t_pass = _time.perf_counter()
+    spilled = 0
     for _tag, kv, up_s in _pipelined(ctx, ((None, b) for b in _batches(chunk_iter, per_batch)), True):
         sec["upload_thread"] += up_s
         t1 = _time.perf_counter()
         try:
             if op is None:
                 kv.sort(xform)
-                recs = kv.records()
+                recs = arena_host.take(kv)
             else:
                 red = kv.sort_reduce(op, xform, sorted_run=True)
                 try:
-                    recs = red.records()
+                    recs = arena_host.take(red)
                 finally:
                     red.free()
         finally:
@@ -412,11 +473,19 @@ def external_sort(ctx, chunk_iter, n_records, xform, sample_keys, _depth=0):
     buckets = [[] for _ in range(nb)]
     sizes = [0] * nb
     stats = {"buckets": nb, "batches": 0, "spilled_bytes": 0, "arena_bytes": arena}
+    arena_host = _RunArena(n_records)
+    try:
+        return _external_sort_passes(ctx, chunk_iter, per_batch, nb, splitters, buckets, sizes, stats, xform, _depth,
+                                     arena_host)
+    finally:
+        arena_host.release()
 
+
+def _external_sort_passes(ctx, chunk_iter, per_batch, nb, splitters, buckets, sizes, stats, xform, _depth, arena_host):
     for _tag, kv, _up_s in _pipelined(ctx, ((None, bt) for bt in _batches(chunk_iter, per_batch)), True):
         try:
             kv.sort(xform)
-            recs = kv.records()
+            recs = arena_host.take(kv)
         finally:
             kv.free()
         cuts = _lazy_cuts(recs[:, 0], splitters, lambda k: _order_domain(k, xform))

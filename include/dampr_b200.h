@@ -90,6 +90,10 @@ int32_t dampr_ctx_stream(dampr_ctx *ctx, uint64_t *out_stream);
 /* ---- pinned host memory (spill ring / ingest staging) -------------------------------- */
 int32_t dampr_host_alloc(uint64_t nbytes, void **out);
 int32_t dampr_host_free(void *p);
+/* page-lock / release memory the caller allocated (the host buffer of spilled runs: MaxMemoryWriter's run files,
+ * dataset.py:190-262, live in host memory here); copies from / to registered memory skip the staging ring */
+int32_t dampr_host_register(void *p, uint64_t nbytes);
+int32_t dampr_host_unregister(void *p);
 
 /* ---- text ingest: replaces TextInput.chunks (inputs.py:48-56) + TextLineDataset.read
  *      (dataset.py:458-476): byte ranges of a file with the line-ownership rule ---------- */

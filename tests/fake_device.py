@@ -54,6 +54,10 @@ class FakeKV(object):
     def columns(self):
         return self.rec[:self.n, 0].copy(), self.rec[:self.n, 1].copy()
 
+    def records_into(self, out):
+        out[:] = self.rec[:self.n]
+        return out
+
     def columns_into(self, keys, vals):
         keys[:] = self.rec[:self.n, 0]
         vals[:] = self.rec[:self.n, 1]

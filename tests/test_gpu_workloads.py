@@ -251,6 +251,29 @@ def test_sort_by_over_binary_records(ctx):
         settings.device_arena_bytes = old
 
 
+def test_topk_over_frames(ctx, tmp_path):
+    """topk(k, value) over word counts (the usual 'most frequent words' tail of a word count) and over kv folds:
+    candidates by one device sort of the scores, the reference's (value(x), x) tuple order decides ties."""
+    import heapq
+    data = gen.text(99, 20000, vocab=gen.make_vocab(3000), cdf=gen.make_cdf(3000))
+    p = tmp_path / "c.txt"
+    p.write_bytes(data)
+    counts = Dampr.text(str(p)).flat_map(lambda x: x.split()).count()
+    rows = counts.read()
+    for k in (1, 10, 500, 100000):
+        got = counts.topk(k, lambda x: x[1]).read()
+        assert lowered("device top-k candidates")
+        assert sorted(got) == sorted(x for _s, x in heapq.nlargest(k, [(x[1], x) for x in rows]))
+    got = counts.topk(25, lambda x: -x[1]).read()   # the rarest words: thousands of ties at count 1
+    assert sorted(got) == sorted(x for _s, x in heapq.nlargest(25, [(-x[1], x) for x in rows]))
+    keys, vals = gen.kv(5, 300_000, 40_000)
+    sums = Dampr.read_input(ArrayKVInput(keys, vals)).a_group_by(lambda x: x[0], lambda x: x[1]).sum()
+    srows = sums.read()
+    got = sums.topk(100, lambda x: x[1]).read()
+    assert lowered("device top-k candidates")
+    assert sorted(got) == sorted(x for _s, x in heapq.nlargest(100, [(x[1], x) for x in srows]))
+
+
 def test_gzip_text_inputs_are_lowered(ctx, tmp_path):
     """A .gz text file (one unsplittable chunk in the reference, inputs.py:43-46) is inflated on the host
     and goes through the same device tokenise+combine pass as plain text."""

@@ -17,12 +17,15 @@ def main():
     n = int(float(sys.argv[1]) * 1e6) if len(sys.argv) > 1 else 625_000_000
     settings.device_arena_bytes = int(float(sys.argv[2]) * (1 << 30)) if len(sys.argv) > 2 else (3276 << 20)
     ctx = runner_mod.get_ctx()
+    if os.environ.get("DAMPR_HOST_THREADS"):
+        from dampr_b200 import device as dev
+        dev.set_option("host_threads", int(os.environ["DAMPR_HOST_THREADS"]))
     kv = ctx.synth_kv(7, n, n // 4)
     keys, vals = kv.columns()
     kv.free()
     vals = vals.view(np.int64)
     total = int(vals.sum())
-    for rep in range(2):
+    for rep in range(3):
         t0 = time.time()
         res = Dampr.read_input(ArrayKVInput(keys, vals)).group_by(lambda x: x[0], lambda x: x[1]).reduce(lambda k, it: sum(it)).run()
         wall = time.time() - t0
