@@ -120,6 +120,10 @@ def load_library():
     _sig(lib, "dampr_kv_hash_join", vp, vp, vp, pvp, pvp)
     _sig(lib, "dampr_kv_hash_probe", vp, vp, vp, pvp, vp)
     _sig(lib, "dampr_kv_partition_by_owner", vp, vp, i32, pvp, vp)
+    _sig(lib, "dampr_comm_unique_id", vp, u32)
+    _sig(lib, "dampr_comm_create", vp, i32, i32, vp, u32, pvp)
+    _sig(lib, "dampr_comm_destroy", vp)
+    _sig(lib, "dampr_kv_all_to_all", vp, vp, vp, vp, i32, pvp, vp, vp)
     _sig(lib, "dampr_synth_text", vp, vp, u64, u64, vp, vp, u32, vp, pu64)
     _sig(lib, "dampr_synth_kv", vp, vp, u64, u64, u64)
     _lib = lib
@@ -145,6 +149,9 @@ def _ptr(a):
         return None
     assert a.flags["C_CONTIGUOUS"]
     return a.ctypes.data_as(C.c_void_p)
+
+
+COMM_ID_BYTES = 128
 
 
 class PinnedBuffer(object):
@@ -212,6 +219,9 @@ class Ctx(object):
 
     def close(self):
         if self.h is not None:
+            if getattr(self, "comm", None) is not None:
+                self.lib.dampr_comm_destroy(self.comm)
+                self.comm = None
             self.lib.dampr_ctx_destroy(self.h)
             self.h = None
 
@@ -294,6 +304,38 @@ class Ctx(object):
         self.check(self.lib.dampr_kv_merge_ranges(self.h, kv.h, offs.ctypes.data_as(C.c_void_p), len(offs) - 1,
                                                   int(xform), int(op), C.byref(h)))
         return KV(self, None, handle=h)
+
+    # ---- the shuffle exchange inside the C-ABI (csrc/comm.cu) --------------------------------------------
+    @staticmethod
+    def comm_unique_id():
+        """128 bytes rank 0 creates and every rank passes to comm_create (ncclGetUniqueId)."""
+        buf = (C.c_uint8 * COMM_ID_BYTES)()
+        if load_library().dampr_comm_unique_id(buf, COMM_ID_BYTES):
+            raise DeviceError("NCCL is not available (dampr_comm_unique_id)")
+        return bytes(buf)
+
+    def comm_create(self, rank, world, unique_id):
+        """This context's NCCL communicator (one per process / GPU); kept on the context."""
+        assert len(unique_id) >= COMM_ID_BYTES
+        idb = (C.c_uint8 * len(unique_id)).from_buffer_copy(unique_id)
+        h = C.c_void_p()
+        self.check(self.lib.dampr_comm_create(self.h, int(rank), int(world), idb, len(unique_id), C.byref(h)))
+        self.comm, self.comm_world = h, int(world)
+        return h
+
+    def kv_all_to_all(self, kv, header=None):
+        """Every record to the owner of its key (owner = mix(key) % world). Returns (received KV, offsets, headers):
+        the records of source rank s are recv[offsets[s]:offsets[s+1]] in the order rank s held them; headers is
+        the (world, len(header)) int64 matrix of every rank's header values (None without a header)."""
+        assert getattr(self, "comm", None) is not None, "comm_create first"
+        w = self.comm_world
+        hdr = np.ascontiguousarray(header if header is not None else [], dtype=np.int64)
+        allh = np.zeros((w, max(1, len(hdr))), dtype=np.int64)
+        offs = np.zeros(w + 1, dtype=np.uint64)
+        h = C.c_void_p()
+        self.check(self.lib.dampr_kv_all_to_all(self.h, self.comm, kv.h, _ptr(hdr) if len(hdr) else None, len(hdr),
+                                                C.byref(h), _ptr(offs), _ptr(allh) if len(hdr) else None))
+        return KV(self, None, handle=h), offs, (allh[:, :len(hdr)] if len(hdr) else None)
 
     def synth_kv(self, seed, n, n_keys):
         kv = KV(self, n)
@@ -487,11 +529,12 @@ class KV(object):
         self.ctx.check(self.ctx.lib.dampr_kv_download(self.ctx.h, self.h, 0, _ptr(out), n))
         return out
 
-    def records_into(self, out):
-        """Download into a caller-provided contiguous (len(self), 2) uint64 array (no allocation)."""
-        n = len(self)
-        assert out.dtype == np.uint64 and out.shape == (n, 2) and out.flags.c_contiguous
-        self.ctx.check(self.ctx.lib.dampr_kv_download(self.ctx.h, self.h, 0, _ptr(out), n))
+    def records_into(self, out, off=0):
+        """Download records [off, off + len(out)) into a caller-provided contiguous (m, 2) uint64 array."""
+        m = len(out)
+        assert out.dtype == np.uint64 and out.ndim == 2 and out.shape[1] == 2 and out.flags.c_contiguous
+        assert off + m <= len(self)
+        self.ctx.check(self.ctx.lib.dampr_kv_download(self.ctx.h, self.h, int(off), _ptr(out), m))
         return out
 
     def columns(self):

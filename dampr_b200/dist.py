@@ -4,7 +4,10 @@ The reference moves map output to the reducers through files and a multiprocessi
 (DefaultShuffler.shuffle, base.py:416-433; StageRunner.run, stagerunner.py:15-43).  Here every rank
 partitions its (already map-side combined) records by owner = mix64(key) % world on the device
 (dampr_kv_partition_by_owner writes destination-contiguous send buffers, so no pack kernel precedes
-the collective) and ONE variable-size all-to-all moves the payload; a counts all-to-all precedes it.
+the collective) and grouped NCCL send/recv move the payload; an all-gather of the counts (plus a small header:
+line counts, flags) precedes it — all inside ONE C-ABI call (shuffle_kv -> dampr_kv_all_to_all, csrc/comm.cu).
+torch.distributed is the launcher-facing bootstrap (rank / world, the NCCL unique id, object gathers of the rare
+host-side strings); the helpers below (exchange_counts, all_to_all_bytes) remain for host-side tests.
 Only the shuffle exchanges data: inputs are sharded by byte range, results stay on their owner.
 """
 import numpy as np
@@ -73,22 +76,24 @@ def all_gather_objects(obj):
     return out
 
 
-def shuffle_kv(ctx, kv):
-    """Exchange a device kv so that every key lives on its owner rank. Returns (received kv, offsets): the
-    records of source rank s are recv[offsets[s]:offsets[s+1]]. The split by owner is stable, so a kv that is
-    key-sorted arrives as one SORTED RUN per source rank — the input of the k-way merge (csrc/merge.cu)."""
-    import torch
-    _rank, n = world()
-    parts, counts = kv.partition_by_owner(n)
-    ctx.sync()
-    recv_counts = exchange_counts(counts)
-    total = int(recv_counts.sum())
-    out = ctx.kv(max(1, total))
-    out.set_size(total)
-    send_t = device_bytes(parts.devptr(), int(counts.sum()) * 16)
-    recv_t = device_bytes(out.devptr(), total * 16)
-    all_to_all_bytes(send_t, counts, recv_t, recv_counts)
-    torch.cuda.synchronize()
-    parts.free()
-    offsets = np.concatenate(([0], np.cumsum(recv_counts))).astype(np.uint64)
-    return out, offsets
+def _comm(ctx):
+    """The context's NCCL communicator of the C-ABI exchange (csrc/comm.cu), created on first use: rank 0 makes
+    the unique id, torch.distributed (already the launcher's bootstrap) hands it to every rank."""
+    if getattr(ctx, "comm", None) is None:
+        import torch.distributed as dist
+        rank, n = world()
+        box = [ctx.comm_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(box, src=0)
+        ctx.comm_create(rank, n, box[0])
+    return ctx.comm
+
+
+def shuffle_kv(ctx, kv, header=None):
+    """Exchange a device kv so that every key lives on its owner rank. Returns (received kv, offsets, headers):
+    the records of source rank s are recv[offsets[s]:offsets[s+1]]. The split by owner is stable, so a kv that
+    is key-sorted arrives as one SORTED RUN per source rank — the input of the k-way merge (csrc/merge.cu).
+    `header`: a few int64 values of this rank that travel with the counts (one all-gather); headers[s] is rank
+    s's row. The whole exchange is ONE C-ABI call (dampr_kv_all_to_all: partition by owner, counts + header
+    all-gather, grouped NCCL send/recv between the kv buffers) with a single host synchronisation."""
+    _comm(ctx)
+    return ctx.kv_all_to_all(kv, header)

@@ -518,11 +518,23 @@ class TextScan(object):
             ws = keycodes.decode_table(codes[hs], reps[hs], self.mode,
                                        lambda off, ln: tb.download(off, ln).tobytes())
             hashed_words = dict(zip(codes[hs].tolist(), ws))
-        lines, empty, anybad, any_hashed, any_cr, any_fb = dist.all_reduce_sum_int(
-            [int(st["lines"]), int(st["empty"]), 1 if bad else 0, len(hashed_words), 1 if flags & dev.TF_CR else 0,
-             int(st.get("fallback", 0))])
+        # the local table as ONE SORTED RUN, one exchange (dampr_kv_all_to_all: the line counts and flags of every
+        # rank travel with the record counts, so the scan needs no collective of its own), then the owner merges
+        # the sorted runs of all source ranks and folds equal keys while merging (MergeDataset.read + the
+        # combiner, dataset.py:571-579, base.py:393-402): one read + one write instead of a second sort
+        header = [int(st["lines"]), int(st["empty"]), 1 if bad else 0, len(hashed_words), 1 if flags & dev.TF_CR else 0,
+                  int(st.get("fallback", 0))]
+        local = tab.to_kv() if not bad else ctx.kv(1)   # a rank that cannot lower still takes part in the exchange
+        try:
+            if not bad:
+                local.sort(dev.KEY_MIX)
+            recv, offs, heads = dist.shuffle_kv(ctx, local, header)
+        finally:
+            local.free()
+        lines, empty, anybad, any_hashed, any_cr, any_fb = [int(x) for x in np.asarray(heads).sum(axis=0).tolist()]
         self.has_cr = bool(any_cr)
         if anybad:
+            recv.free()
             raise RuntimeError("distributed text scan cannot be lowered on every rank (flags=%d); the "
                                "host-map path is single-process only" % flags)
         merged = {}
@@ -530,13 +542,6 @@ class TextScan(object):
             for c, w in d.items():
                 if merged.setdefault(c, w) != w:
                     raise RuntimeError("64-bit key-code collision between two long tokens across ranks")
-        # the local table as ONE SORTED RUN, one exchange, then the owner merges the sorted runs of all source
-        # ranks and folds equal keys while merging (MergeDataset.read + the combiner, dataset.py:571-579,
-        # base.py:393-402): one read + one write of the received records instead of a second sort
-        local = tab.to_kv()
-        local.sort(dev.KEY_MIX)
-        recv, offs = dist.shuffle_kv(ctx, local)
-        local.free()
         red = ctx.kv_merge_ranges(recv, offs, dev.KEY_MIX, dev.OP_SUM_I64)
         recv.free()
         codes, counts = red.columns()
@@ -560,7 +565,7 @@ class TextScan(object):
         # per-line fallback across ranks: every rank tokenises the lines its shard handed back; the counts of all
         # ranks are added up, a token goes to the rank whose table already holds it, otherwise to rank 0
         self.host_lines = 0
-        if any_fb:   # (known from the all-reduce above: no extra collective when no rank handed lines back)
+        if any_fb:   # (known from the exchange's header: no extra collective when no rank handed lines back)
             extra, extra_empty, extra_lines = self._host_lines(tb, tab, st)
             tot = dist.all_reduce_sum_int([extra_lines, extra_empty])
             self.host_lines = int(tot[0])
@@ -987,7 +992,7 @@ def _device_group(runner, keys, vals, op, xform):
             part = kv.sort_reduce(op, dev.KEY_MIX, sorted_run=True)
         finally:
             kv.free()
-        recv, offs = dist.shuffle_kv(ctx, part)   # `part` is sorted by the mixed key: sorted runs arrive
+        recv, offs, _h = dist.shuffle_kv(ctx, part)   # `part` is sorted by the mixed key: sorted runs arrive
         part.free()
         op2 = dev.OP_SUM_I64 if op == dev.OP_COUNT else op
         red = ctx.kv_merge_ranges(recv, offs, dev.KEY_MIX, op2)   # runs in rank order: FIRST / LAST keep their meaning
@@ -1536,7 +1541,7 @@ def _exchange_raw(runner, keys, vals):
     lo, hi = n * r // w, n * (r + 1) // w
     kv = ctx.kv_from_columns(keys[lo:hi], np.asarray(vals[lo:hi]).view(np.uint64))
     try:
-        recv, _offs = dist.shuffle_kv(ctx, kv)
+        recv, _offs, _h = dist.shuffle_kv(ctx, kv)
     finally:
         kv.free()
     try:

@@ -301,6 +301,26 @@ int32_t dampr_kv_hash_join(dampr_ctx *ctx, dampr_kv *build, dampr_kv *probe, dam
 int32_t dampr_kv_partition_by_owner(dampr_ctx *ctx, dampr_kv *kv, int32_t n_dest, dampr_kv **out,
                                     uint64_t *counts_host);
 
+/* ---- S1 across GPUs: the shuffle exchange inside the C-ABI (SURVEY §8(b) kv_all_to_all) --------------------
+ * One process per GPU. dampr_comm_unique_id on rank 0 -> the host runtime hands the bytes to every rank (any
+ * bootstrap it has: torch.distributed, MPI, a file) -> dampr_comm_create on every rank (ncclCommInitRank).
+ * dampr_kv_all_to_all replaces DefaultShuffler.shuffle (base.py:416-433) + the per-partition run files the
+ * reducers read (stagerunner.py:269-282): every record goes to the rank that owns its key
+ * (owner = mix(key) % world, the same function on every rank = one Splitter for all inputs, base.py:264-283).
+ * *out = this rank's records, those of source rank s at [out_offsets[s], out_offsets[s+1]) in the order rank s
+ * held them (a key-sorted input arrives as world sorted runs: the input of dampr_kv_merge_ranges).
+ * header / headers_all: n_header (<= 64) int64 values per rank, all-gathered with the counts (row s of
+ * headers_all = rank s's header) so that line counts / flags need no collective of their own.
+ * NCCL is bound at run time (dlopen libnccl.so.2); without it these calls fail, nothing else does. */
+typedef struct dampr_comm dampr_comm;
+#define DAMPR_COMM_ID_BYTES 128
+int32_t dampr_comm_unique_id(uint8_t *out_id, uint32_t cap);
+int32_t dampr_comm_create(dampr_ctx *ctx, int32_t rank, int32_t world, const uint8_t *id, uint32_t id_bytes,
+                          dampr_comm **out);
+int32_t dampr_comm_destroy(dampr_comm *comm);
+int32_t dampr_kv_all_to_all(dampr_ctx *ctx, dampr_comm *comm, dampr_kv *kv, const int64_t *header,
+                            int32_t n_header, dampr_kv **out, uint64_t *out_offsets, int64_t *headers_all);
+
 /* ---- synthetic inputs (bench/test tooling; deterministic, same algorithm as oracle/gen.py) */
 int32_t dampr_synth_text(dampr_ctx *ctx, dampr_textbuf *tb, uint64_t seed, uint64_t n_lines,
                          const uint8_t *vocab_bytes, const uint32_t *vocab_off, uint32_t vocab_n,

@@ -54,8 +54,8 @@ class FakeKV(object):
     def columns(self):
         return self.rec[:self.n, 0].copy(), self.rec[:self.n, 1].copy()
 
-    def records_into(self, out):
-        out[:] = self.rec[:self.n]
+    def records_into(self, out, off=0):
+        out[:] = self.rec[off:off + len(out)]
         return out
 
     def columns_into(self, keys, vals):

@@ -27,8 +27,8 @@ WORKER = textwrap.dedent("""
     runner_mod._CTX = {settings.device: FakeCtx()}
     out_root = os.environ["DAMPR_TEST_OUT"]
 
-    def host_shuffle(ctx, kv):
-        # dist.shuffle_kv with host buffers (the product moves device memory over NCCL)
+    def host_shuffle(ctx, kv, header=None):
+        # dist.shuffle_kv with host buffers (the product does all of this in one C-ABI call over NCCL)
         parts, counts = kv.partition_by_owner(world)
         recv_counts = D.exchange_counts(counts)
         total = int(recv_counts.sum())
@@ -36,7 +36,8 @@ WORKER = textwrap.dedent("""
         recv = torch.empty(total * 16, dtype=torch.uint8)
         D.all_to_all_bytes(send, counts, recv, recv_counts)
         out = ctx.kv_from_records(recv.numpy().view(np.uint64).reshape(-1, 2))
-        return out, np.concatenate(([0], np.cumsum(recv_counts))).astype(np.uint64)
+        heads = np.asarray(D.all_gather_objects(list(header)), dtype=np.int64) if header is not None else None
+        return out, np.concatenate(([0], np.cumsum(recv_counts))).astype(np.uint64), heads
     D.shuffle_kv = host_shuffle
 
     def gathered(mine):

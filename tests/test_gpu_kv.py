@@ -226,6 +226,26 @@ def test_partition_by_owner(ctx):
         assert np.array_equal(counts, np.bincount(owner, minlength=nd).astype(np.uint64))
 
 
+def test_all_to_all_world1_through_the_c_abi(ctx):
+    """dampr_kv_all_to_all on a one-rank communicator (csrc/comm.cu; the 2-GPU path is tests/test_gpu_multi.py):
+    NCCL binds at run time, the counts + header row comes back, the payload is the stable split by owner."""
+    keys, vals = gen.kv(9, 200_000, 30_000)
+    kv = ctx.kv_from_columns(keys, vals)
+    if getattr(ctx, "comm", None) is None:
+        ctx.comm_create(0, 1, ctx.comm_unique_id())
+    out, offs, heads = ctx.kv_all_to_all(kv, header=[7, -3, 1 << 40])
+    assert offs.tolist() == [0, len(keys)] and heads.tolist() == [[7, -3, 1 << 40]]
+    k2, v2 = out.columns()
+    assert np.array_equal(k2, keys.view(np.uint64)) and np.array_equal(v2, vals.view(np.uint64))
+    assert len(kv) == len(keys)          # the input is left alone
+    out.free()
+    empty = ctx.kv(1)
+    out, offs, heads = ctx.kv_all_to_all(empty)
+    assert offs.tolist() == [0, 0] and heads is None and len(out) == 0
+    for x in (kv, empty, out):
+        x.free()
+
+
 def test_synth_kv_matches_numpy(ctx):
     kv = ctx.kv(10000)
     ctx.check(ctx.lib.dampr_synth_kv(ctx.h, kv.h, 42, 10000, 777))

@@ -94,7 +94,8 @@ def config4(out):
         plan._may_overflow(vals)
         t_ovf = time.time() - t0
         runs = []
-        for label in ("cold", "warm (host run buffer kept from the first job)"):
+        for label in ("cold", "second job (host run buffer kept; its page-locking finishes in the background)",
+                      "third job (host run buffer kept and page-locked)"):
             t0 = time.time()
             res = Dampr.read_input(ArrayKVInput(keys, vals)).group_by(lambda x: x[0], lambda x: x[1]) \
                 .reduce(lambda k, it: sum(it)).run()
