@@ -301,8 +301,12 @@ bool host_is_pinned(const void *p) { return is_pinned(p); }
 int staged_h2d(dampr_ctx *ctx, void *dst, const void *src, size_t bytes, cudaStream_t st) {
     if (bytes == 0) return DAMPR_OK;
     if (bytes < (8u << 20) || is_pinned(src)) {
-        CUDA_TRY(ctx, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, st));
-        return DAMPR_OK;
+        // (a range that straddles two separately page-locked regions, or the end of one, is refused with
+        // cudaErrorInvalidValue at enqueue time: such a copy goes through the ring like pageable memory)
+        const cudaError_t e = cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, st);
+        if (e == cudaSuccess) return DAMPR_OK;
+        if (e != cudaErrorInvalidValue) CUDA_TRY(ctx, e);
+        cudaGetLastError();
     }
     int rc = stage_init(ctx);
     if (rc) return rc;
@@ -361,9 +365,13 @@ int staged_file_h2d(dampr_ctx *ctx, void *dst, int fd, size_t foff, size_t bytes
 int staged_d2h(dampr_ctx *ctx, void *dst, const void *src, size_t bytes, cudaStream_t st) {
     if (bytes == 0) return DAMPR_OK;
     if (bytes < (8u << 20) || is_pinned(dst)) {
-        CUDA_TRY(ctx, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, st));
-        CUDA_TRY(ctx, cudaStreamSynchronize(st));
-        return DAMPR_OK;
+        const cudaError_t e = cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, st);
+        if (e == cudaSuccess) {
+            CUDA_TRY(ctx, cudaStreamSynchronize(st));
+            return DAMPR_OK;
+        }
+        if (e != cudaErrorInvalidValue) CUDA_TRY(ctx, e);
+        cudaGetLastError();   // straddles page-locked regions: through the ring
     }
     int rc = stage_init(ctx);
     if (rc) return rc;

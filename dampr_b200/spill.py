@@ -149,20 +149,16 @@ def _pipelined(ctx, items, columns):
 
 
 _HOST_ARENA = {"buf": None, "leased": False, "chunks": [], "reg": 0, "thread": None}
-_REG_STEP = (1 << 30) // 16     # records per cudaHostRegister call (1 GiB)
 
 
 def _register_prefix(buf, upto):
-    """Page-lock buf[:upto] 1 GiB at a time (background thread, after the job that touched those pages)."""
+    """Page-lock buf[reg:upto] (background thread, after the job that touched those pages) as ONE region: a copy
+    may not straddle two registrations (the library sends such a copy through its staging ring instead)."""
     done = _HOST_ARENA["reg"]
-    while done < upto and _HOST_ARENA["buf"] is buf:
-        hi = min(upto, done + _REG_STEP)
-        chunk = buf[done:hi]
-        if not dev.host_register(chunk):
-            break
-        _HOST_ARENA["chunks"].append((done, hi))
-        done = hi
-        _HOST_ARENA["reg"] = done
+    if done < upto and _HOST_ARENA["buf"] is buf:
+        if dev.host_register(buf[done:upto]):
+            _HOST_ARENA["chunks"].append((done, upto))
+            _HOST_ARENA["reg"] = upto
 
 
 def _drop_cached_arena():

@@ -226,6 +226,32 @@ def test_partition_by_owner(ctx):
         assert np.array_equal(counts, np.bincount(owner, minlength=nd).astype(np.uint64))
 
 
+def test_copies_that_straddle_page_locked_regions(ctx):
+    """A host range that crosses two separately registered regions (or the end of one) cannot be copied directly
+    (cudaErrorInvalidValue): the library sends it through its staging ring (spill.py's run buffer is page-locked
+    piecewise). Downloads and uploads, both ends registered, one end registered, none."""
+    n = 3_000_000   # 48 MB
+    keys, vals = gen.kv(13, n, n)
+    kv = ctx.kv_from_columns(keys, vals)
+    want = kv.records()
+    buf = np.zeros((n, 2), dtype=np.uint64)
+    assert dev.host_register(buf[:n // 3]) and dev.host_register(buf[n // 3: 2 * n // 3])
+    try:
+        for lo, hi in ((0, n), (0, n // 3), (n // 6, n // 2), (n // 2, n), (2 * n // 3, n)):
+            buf[:] = 0
+            kv.records_into(buf[lo:hi], lo)
+            assert np.array_equal(buf[lo:hi], want[lo:hi]), (lo, hi)
+            back = ctx.kv(hi - lo)
+            back.upload(0, buf[lo:hi], hi - lo)
+            ctx.sync()
+            assert np.array_equal(back.records(), want[lo:hi]), (lo, hi)
+            back.free()
+    finally:
+        dev.host_unregister(buf[:n // 3])
+        dev.host_unregister(buf[n // 3: 2 * n // 3])
+    kv.free()
+
+
 def test_all_to_all_world1_through_the_c_abi(ctx):
     """dampr_kv_all_to_all on a one-rank communicator (csrc/comm.cu; the 2-GPU path is tests/test_gpu_multi.py):
     NCCL binds at run time, the counts + header row comes back, the payload is the stable split by owner."""
