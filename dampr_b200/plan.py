@@ -960,6 +960,28 @@ class LazyKVFrame(Frame):
         self._keys, self._cols, self._done, self.n = None, [[]], True, 0
 
 
+class _Background(object):
+    """fn(*args) on a host thread (numpy reductions release the GIL); result() joins."""
+
+    def __init__(self, fn, *args):
+        import threading
+        self._out, self._err = None, None
+
+        def work():
+            try:
+                self._out = fn(*args)
+            except BaseException as e:
+                self._err = e
+        self._th = threading.Thread(target=work, name="dampr-background")
+        self._th.start()
+
+    def result(self):
+        self._th.join()
+        if self._err is not None:
+            raise self._err
+        return self._out
+
+
 def _may_overflow(vals):
     """Cheap bound for Python-int semantics: n * max|v| must stay far below 2^63."""
     n = len(vals)
@@ -1506,9 +1528,20 @@ def _lower_reduce(runner, stage, inputs):
             opmap = {lowering.SUM: dev.OP_SUM_I64, lowering.COUNT: dev.OP_COUNT, lowering.MIN: dev.OP_MIN_I64,
                      lowering.MAX: dev.OP_MAX_I64}
             keys, vals = fr.raw()
-            if kind in opmap and vals.dtype.kind in "iu" and not (kind == lowering.SUM and len(vals) and _may_overflow(vals)) \
+            from . import spill as _spill
+            # the overflow bound scans every value: on an input large enough to spill (tens of GB) it runs
+            # on a host thread NEXT TO the device pipeline and vetoes the result afterwards, instead of in front of it
+            late = kind == lowering.SUM and vals.dtype.kind in "iu" and len(vals) and _spill.needs_spill(runner.ctx, len(vals)) \
+                and not dist.active()
+            if kind in opmap and vals.dtype.kind in "iu" and not (kind == lowering.SUM and len(vals) and not late and _may_overflow(vals)) \
                     and not (vals.dtype == np.uint64 and len(vals) and int(vals.max()) >= (1 << 63)):
-                rk, rv, how = _device_group(runner, keys, vals, opmap[kind], dev.KEY_MIX)
+                chk = _Background(_may_overflow, vals) if late else None
+                try:
+                    rk, rv, how = _device_group(runner, keys, vals, opmap[kind], dev.KEY_MIX)
+                finally:
+                    overflow = chk.result() if chk is not None else False
+                if overflow:
+                    raise NotLowerable("64-bit sum could overflow (SURVEY B12)")
                 rk = rk.view(keys.dtype)
                 out = Frame(rk, [rk, rv.view(np.int64)], scalar=False, combined=True)
                 runner.stats.add(stage, "device kv partition+sort+segmented-reduce (fused group_by + reduce)" + how,

@@ -207,6 +207,14 @@ def test_spill_path_with_capped_arena(ctx):
         assert got == refsem.group_sum(keys, vals)
         got = dict(src.count(lambda x: x[0]).read())
         assert got == refsem.group_count(keys)
+        # sums that leave the 64-bit range: the overflow bound is evaluated next to the spill pipeline (a host
+        # thread) and vetoes its result afterwards — the answer must still be Python's exact integers
+        big = np.full(300_000, (1 << 62) - 5, dtype=np.int64)
+        bk = (np.arange(300_000) % 1000).astype(np.int64)
+        got = dict(Dampr.read_input(ArrayKVInput(bk, big)).group_by(lambda x: x[0], lambda x: x[1])
+                   .reduce(lambda k, it: sum(it)).read())
+        assert not lowered("[spilled:")
+        assert got == {k: 300 * ((1 << 62) - 5) for k in range(1000)}
     finally:
         settings.device_arena_bytes = old
 
