@@ -437,6 +437,7 @@ def kv_extras(ctx_unused, args):
     guarded("kv_merge_reduce_8runs_1e8_K=1e7", lambda: kv_bench.merge_case(ctx, 100_000_000, 10_000_000, 8, dev.OP_SUM_I64))
     guarded("kv_reduce_by_key_sorted_1e8_K=1e7", lambda: kv_bench.reduce_sorted_case(ctx, 100_000_000, 10_000_000))
     guarded("config2_e2e", lambda: kv_bench.config2_e2e(ctx))
+    guarded("config4_scaled", lambda: kv_bench.config4_scaled(ctx))
     guarded("config5", lambda: kv_bench.config5(ctx))
     guarded("config5_dsl", lambda: kv_bench.config5_dsl(ctx))
     return extra

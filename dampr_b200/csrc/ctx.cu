@@ -11,6 +11,9 @@
 #include <mutex>
 #include <thread>
 
+#if defined(__SSE2__)
+#include <emmintrin.h>
+#endif
 #include "common.cuh"
 
 int g_text_kernel = 2;
@@ -207,7 +210,20 @@ class CopyPool {
                 const size_t cnt = len / 16;
                 if (j.src2) {
                     const u64 *__restrict v = reinterpret_cast<const u64 *>(j.src2) + lo / 16;
-                    for (size_t i = 0; i < cnt; ++i) {
+                    size_t i = 0;
+#if defined(__SSE2__)
+                    // two records per step; streaming stores: the slot is written once and read by the DMA engine,
+                    // so no read-for-ownership of the destination lines (32 instead of 48 bytes of memory traffic
+                    // per record). The slots are 4 KB aligned, the columns 8-byte aligned.
+                    for (; i + 2 <= cnt; i += 2) {
+                        const __m128i kk = _mm_loadu_si128(reinterpret_cast<const __m128i *>(k + i));
+                        const __m128i vv = _mm_loadu_si128(reinterpret_cast<const __m128i *>(v + i));
+                        _mm_stream_si128(reinterpret_cast<__m128i *>(d + 2 * i), _mm_unpacklo_epi64(kk, vv));
+                        _mm_stream_si128(reinterpret_cast<__m128i *>(d + 2 * i + 2), _mm_unpackhi_epi64(kk, vv));
+                    }
+                    _mm_sfence();
+#endif
+                    for (; i < cnt; ++i) {
                         d[2 * i] = k[i];
                         d[2 * i + 1] = v[i];
                     }

@@ -376,7 +376,10 @@ class PReduce(PBase):
                     seen.add(fv)
                     out.append(v)
             return out
-        return self.reduce(_uniq)
+        red = ops.KeyedReduce(_uniq)
+        red.op = Op("unique", key)   # plan._lower_unique: numeric kv records, identity key
+        source, pmer = self.pmer._add_reducer([self.source], red)
+        return PMap(source, pmer)
 
     def join(self, other):
         assert isinstance(other, PBase)

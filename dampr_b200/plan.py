@@ -1513,11 +1513,75 @@ def _inline(fn, depth=0):
 
 
 # ---- reduce stages ----------------------------------------------------------------------------------------
+def _device_perm(runner, codes, xf, payload=None):
+    """Stable device sort of 64-bit codes under `xf`; returns the payload (default: the positions) in sorted order."""
+    n = len(codes)
+    kv = runner.ctx.kv_from_columns(codes, np.arange(n, dtype=np.uint64) if payload is None else payload)
+    try:
+        kv.sort(xf)
+        _k, perm = kv.columns()
+    finally:
+        kv.free()
+    return perm.view(np.int64)
+
+
+def _lower_unique(runner, stage, fr):
+    """group_by(k, v).unique() over binary kv records (dampr.py:727-746): per key, the distinct values in the
+    order of their first appearance. Three stable device sorts and linear host passes over the columns:
+      by key                      -> the records of every key, in input order;
+      by value, then by key       -> equal (key, value) pairs adjacent, earliest first => the first occurrence of
+                                     every distinct pair is the head of its run;
+    the by-key order filtered to first occurrences is the answer. The value lists are Python lists (the
+    reducer's return type), built per group at the end."""
+    from . import spill
+    keys, vals = fr.raw()
+    n = len(keys)
+    if dist.active() or n == 0 or spill.needs_spill(runner.ctx, 2 * n):
+        return None
+    if vals.dtype.kind == "f":
+        if np.isnan(vals).any() or (np.signbit(vals) & (vals == 0)).any():
+            return None   # NaN != NaN keeps every NaN; -0.0 == 0.0 are one value: leave those to the set()
+        vxf = dev.KEY_F64
+    elif vals.dtype.kind in "iu" and vals.dtype.itemsize == 8:
+        vxf = _key_xform_for(vals)
+    else:
+        return None
+    kxf = _key_xform_for(keys)
+    ku, vu = keys.view(np.uint64), vals.view(np.uint64)
+    by_key = _device_perm(runner, ku, kxf)
+    p1 = _device_perm(runner, vu, vxf)
+    p2 = _device_perm(runner, ku[p1], kxf, p1.view(np.uint64))
+    k2, v2 = ku[p2], vu[p2]
+    head = np.empty(n, dtype=np.bool_)
+    head[0] = True
+    np.logical_or(k2[1:] != k2[:-1], v2[1:] != v2[:-1], out=head[1:])
+    first = np.zeros(n, dtype=np.bool_)
+    first[p2[head]] = True
+    sel = by_key[first[by_key]]
+    ks, vs = keys[sel], vals[sel]
+    cut = np.flatnonzero(ks[1:] != ks[:-1]) + 1
+    starts = np.concatenate(([0], cut))
+    ends = np.concatenate((cut, [len(ks)]))
+    vl = vs.tolist()
+    lists = [vl[a:b] for a, b in zip(starts.tolist(), ends.tolist())]
+    gk = ks[starts]
+    out = Frame(gk, [gk, lists], scalar=False, combined=True)
+    runner.stats.add(stage, "device unique: three stable sorts (by key; by value then key), first occurrences kept in input order",
+                     "records=%d groups=%d distinct pairs=%d" % (n, len(gk), len(ks)))
+    return out
+
+
 def _lower_reduce(runner, stage, inputs):
     red = stage.reducer
     if len(inputs) == 1 and isinstance(inputs[0], Frame):
         fr = inputs[0]
         binop = getattr(red, "binop", None)
+        uop = getattr(red, "op", None)
+        if isinstance(red, ops.KeyedReduce) and uop is not None and uop.kind == "unique" and lowering.is_identity(uop.fn) \
+                and isinstance(fr, LazyKVFrame) and not fr._done:
+            out = _lower_unique(runner, stage, fr)
+            if out is not None:
+                return out
         if isinstance(red, ops.KeyedReduce) and binop is not None and fr.combined and fr.scalar:
             # fully combined on the map side: the fold of a one-element group is the element
             out = Frame(fr.keys, [fr.keys, fr.cols[0]], scalar=False, combined=True)

@@ -282,6 +282,28 @@ def test_topk_over_frames(ctx, tmp_path):
     assert sorted(got) == sorted(x for _s, x in heapq.nlargest(100, [(x[1], x) for x in srows]))
 
 
+def test_unique_over_kv_records(ctx):
+    """group_by(k, v).unique(): three stable device sorts, first occurrences kept in input order."""
+    rng = np.random.default_rng(8)
+    n = 400_000
+    keys = rng.integers(0, 30_000, size=n).astype(np.int64)
+    vals = rng.integers(-50, 50, size=n).astype(np.int64)
+    got = dict(Dampr.read_input(ArrayKVInput(keys, vals)).group_by(lambda x: x[0], lambda x: x[1]).unique().read())
+    assert lowered("device unique")
+    exp = {}
+    for k, v in zip(keys.tolist(), vals.tolist()):
+        seen = exp.setdefault(k, {})
+        seen.setdefault(v, None)
+    assert got == {k: list(d) for k, d in exp.items()}
+    fvals = (vals / 8.0).astype(np.float64) + 0.125
+    got = dict(Dampr.read_input(ArrayKVInput(keys.view(np.uint64), fvals)).group_by(lambda x: x[0], lambda x: x[1]).unique().read())
+    assert lowered("device unique")
+    exp = {}
+    for k, v in zip(keys.tolist(), fvals.tolist()):
+        exp.setdefault(k, {}).setdefault(v, None)
+    assert got == {k: list(d) for k, d in exp.items()}
+
+
 def test_gzip_text_inputs_are_lowered(ctx, tmp_path):
     """A .gz text file (one unsplittable chunk in the reference, inputs.py:43-46) is inflated on the host
     and goes through the same device tokenise+combine pass as plain text."""

@@ -568,3 +568,40 @@ def test_topk_over_a_frame_takes_its_candidates_with_one_device_sort(monkeypatch
     got = base.topk(5, lambda x: x[1] * 2 + x[0]).read()   # not a projection: host path, same answer
     assert not any("top-k" in how for _s, how, _d in runner_mod.LAST_STATS.stages)
     assert sorted(got) == sorted(x for _s, x in heapq.nlargest(5, [(x[1] * 2 + x[0], x) for x in rows]))
+
+
+def test_unique_over_kv_records_keeps_first_appearance_order(monkeypatch):
+    """group_by(k, v).unique() over binary kv records (plan._lower_unique, dampr.py:727-746): per key the distinct
+    values in first-appearance order, Python ints / floats; NaN values and key functions stay on the host."""
+    from dampr_b200 import Dampr, settings
+    from dampr_b200 import runner as runner_mod
+    from dampr_b200.inputs import ArrayKVInput
+    monkeypatch.setattr(runner_mod, "_CTX", {settings.device: _FakeCtx()})
+    rng = np.random.default_rng(3)
+
+    def ref(keys, vals):
+        d = {}
+        for k, v in zip(keys.tolist(), vals.tolist()):
+            seen = d.setdefault(k, [])
+            if v not in seen:
+                seen.append(v)
+        return d
+
+    def lowered():
+        return any("device unique" in how for _s, how, _d in runner_mod.LAST_STATS.stages)
+    for kd, vd in ((np.int64, np.int64), (np.uint64, np.float64), (np.int64, np.uint64)):
+        keys = rng.integers(0, 500, size=20000).astype(kd)
+        vals = (rng.integers(-20, 40, size=20000) if vd != np.uint64 else rng.integers(0, 40, size=20000)).astype(vd)
+        if vd == np.float64:
+            vals = vals / 4.0 + 0.25
+        got = dict(Dampr.read_input(ArrayKVInput(keys, vals)).group_by(lambda x: x[0], lambda x: x[1]).unique().read())
+        assert lowered()
+        assert got == ref(keys, vals)
+        assert all(type(x) is (float if vd == np.float64 else int) for l in got.values() for x in l)
+    vals = rng.integers(-20, 40, size=20000).astype(np.float64)
+    vals[5] = float("nan")
+    vals[6] = -0.0
+    got = dict(Dampr.read_input(ArrayKVInput(keys, vals)).group_by(lambda x: x[0], lambda x: x[1]).unique().read())
+    assert not lowered()
+    Dampr.read_input(ArrayKVInput(keys, vals)).group_by(lambda x: x[0], lambda x: x[1]).unique(lambda v: v % 3).read()
+    assert not lowered()

@@ -181,6 +181,48 @@ def config2_e2e(ctx):
             "checks": "sum of group sums == sum of values, groups <= K", "ok": bool(ok)}
 
 
+def config4_scaled(ctx):
+    """BASELINE config 4 at 1/5 scale (the full 50 GB run takes minutes with its input generation and checks:
+    tools/scale_check.py config4, profiles/r02_config4_three_jobs.json): group_by(k, v).reduce(sum) over 10 GB of
+    records (6.25e8, K = N/4) in host numpy columns with the device arena capped at 3.2 GB, so the job spills:
+    12 batches -> sorted, pre-folded runs per key range in the host run buffer -> K5 merge per bucket. Three jobs:
+    cold, second (run buffer kept), third (run buffer page-locked)."""
+    from dampr_b200 import Dampr, settings, spill
+    from dampr_b200 import runner as runner_mod
+    from dampr_b200.inputs import ArrayKVInput
+    n = 625_000_000
+    kv = ctx.synth_kv(7, n, n // 4)
+    keys, vals = kv.columns()
+    kv.free()
+    vals = vals.view(np.int64)
+    total = int(vals.sum())
+    old = settings.device_arena_bytes
+    settings.device_arena_bytes = 3276 << 20
+    spill.release_host_arena()
+    runs = []
+    try:
+        for label in ("cold", "second job", "third job (run buffer page-locked)"):
+            t0 = time.perf_counter()
+            res = Dampr.read_input(ArrayKVInput(keys, vals)).group_by(lambda x: x[0], lambda x: x[1]) \
+                .reduce(lambda k, it: sum(it)).run()
+            sec = time.perf_counter() - t0
+            fr = res.datasets
+            ok = int(np.asarray(fr.cols[1]).sum()) == total
+            st = getattr(runner_mod.LAST_STATS, "spill", None) or {}
+            runs.append({"run": label, "wall_s": round(sec, 3), "MB_per_s": round(16.0 * n / sec / 1e6, 1), "groups": int(len(fr)),
+                         "ok": bool(ok), "batches": st.get("batches"), "buckets": st.get("buckets"),
+                         "spilled_bytes": st.get("spilled_bytes"),
+                         "seconds": {k: round(v, 3) for k, v in (st.get("seconds") or {}).items()}})
+            del res, fr
+    finally:
+        settings.device_arena_bytes = old
+        spill.release_host_arena()
+    return {"what": "config 4 at 1/5 scale: group_by.reduce(sum) over 10 GB of host records through a 3.2 GB device arena "
+                    "(spill path: sorted runs per batch -> host run buffer -> K5 merge per bucket)",
+            "records": n, "arena_bytes": 3276 << 20, "runs": runs, "MB_per_s": runs[-1]["MB_per_s"],
+            "ok": all(r["ok"] for r in runs), "full_size": "profiles/r02_config4_three_jobs.json"}
+
+
 def config5(ctx):
     """BASELINE config 5 at the C-ABI, device-resident: 20 GB (1.25e9) x 2 GB (1.25e8, unique keys) records,
     ~50 % of the left keys match: broadcast hash build + probe, and sort-merge join ranges."""
