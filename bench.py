@@ -217,7 +217,7 @@ def reference_procs(ncores):
             if c <= ncores and c not in cands:
                 cands.append(c)
         saved = REF_TIMEOUT
-        REF_TIMEOUT = 25
+        REF_TIMEOUT = 12   # a count that works needs 1-2 s for the 8 MB sample
         try:
             for c in cands:
                 try:
