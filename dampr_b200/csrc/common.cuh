@@ -81,6 +81,7 @@ int staged_d2h(dampr_ctx *ctx, void *dst, const void *src, size_t bytes, cudaStr
 int staged_h2d_columns(dampr_ctx *ctx, void *dst_records, const u64 *keys, const u64 *vals, size_t count, cudaStream_t st);
 bool host_is_pinned(const void *p);
 extern int g_host_threads_cap;
+extern int g_file_cufile, g_cufile_threads;
 
 struct dampr_textbuf {
     u8 *alloc;      // device allocation

@@ -1,6 +1,8 @@
 // ctx.cu — context, streams, timings, pinned memory, text buffers and kv containers.
 // Replaces the process pool / Queue plumbing of StageRunner.run (reference stagerunner.py:15-43)
 // and the on-disk run files of dataset.py with device-resident buffers.
+#include <cufile.h>
+#include <dlfcn.h>
 #include <fcntl.h>
 #include <unistd.h>
 
@@ -128,6 +130,8 @@ void pool_trim(dampr_ctx *ctx, size_t keep_bytes) {
     }
 }
 int g_text_ctas = 4;
+int g_file_cufile = 0;         // 1: file ingest through cuFile (GPUDirect Storage) instead of the page-locked ring
+int g_cufile_threads = 8;
 int g_host_threads_cap = 16;   // copy threads per staged transfer (dampr_set_option "host_threads")
 
 // ---- staged transfers ---------------------------------------------------------------------------
@@ -659,11 +663,120 @@ int32_t dampr_textbuf_upload(dampr_ctx *ctx, dampr_textbuf *tb, uint64_t off, co
     return DAMPR_OK;
 }
 
+// ---- GPUDirect Storage ingest (cuFile), opt-in: dampr_set_option("file_cufile", 1) ---------------------------
+// libcufile is bound at run time. cuFileRead moves file bytes to device memory without the page-locked ring: by
+// DMA from the NVMe controller where the nvidia-fs driver and an O_DIRECT-capable file system are present, through
+// cuFile's own bounce buffers ("compatibility mode") elsewhere. Several host threads issue disjoint 16 MB reads.
+namespace {
+
+struct CuFileApi {
+    void *lib = nullptr;
+    CUfileError_t (*DriverOpen)() = nullptr;
+    CUfileError_t (*HandleRegister)(CUfileHandle_t *, CUfileDescr_t *) = nullptr;
+    void (*HandleDeregister)(CUfileHandle_t) = nullptr;
+    ssize_t (*Read)(CUfileHandle_t, void *, size_t, off_t, off_t) = nullptr;
+    bool driver_open = false;
+    std::string why;
+};
+
+CuFileApi *cufile_api() {
+    static CuFileApi api;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        const char *names[] = {"libcufile.so.0", "libcufile.so", "/usr/local/cuda/targets/x86_64-linux/lib/libcufile.so.0"};
+        for (const char *n : names) {
+            api.lib = dlopen(n, RTLD_NOW);
+            if (api.lib) break;
+        }
+        if (!api.lib) {
+            api.why = "libcufile.so.0 not found";
+            return;
+        }
+        api.DriverOpen = reinterpret_cast<decltype(api.DriverOpen)>(dlsym(api.lib, "cuFileDriverOpen"));
+        api.HandleRegister = reinterpret_cast<decltype(api.HandleRegister)>(dlsym(api.lib, "cuFileHandleRegister"));
+        api.HandleDeregister = reinterpret_cast<decltype(api.HandleDeregister)>(dlsym(api.lib, "cuFileHandleDeregister"));
+        api.Read = reinterpret_cast<decltype(api.Read)>(dlsym(api.lib, "cuFileRead"));
+        if (!api.DriverOpen || !api.HandleRegister || !api.HandleDeregister || !api.Read) {
+            api.why = "cuFile symbols missing";
+            api.lib = nullptr;
+            return;
+        }
+        const CUfileError_t e = api.DriverOpen();
+        if (e.err != CU_FILE_SUCCESS) {
+            api.why = "cuFileDriverOpen failed (" + std::to_string((int)e.err) + ")";
+            api.lib = nullptr;
+            return;
+        }
+        api.driver_open = true;
+    });
+    return api.lib ? &api : nullptr;
+}
+
+int cufile_h2d(dampr_ctx *ctx, void *dst, const char *path, size_t foff, size_t bytes) {
+    CuFileApi *a = cufile_api();
+    if (!a) {
+        return set_err(ctx, DAMPR_ERR_CUDA, "cuFile is not available: %s", "dlopen / cuFileDriverOpen failed");
+    }
+    int fd = open(path, O_RDONLY | O_DIRECT);
+    if (fd < 0) fd = open(path, O_RDONLY);
+    if (fd < 0) return set_err(ctx, DAMPR_ERR_ARG, "cannot open %s", path);
+    CUfileDescr_t descr;
+    memset(&descr, 0, sizeof descr);
+    descr.handle.fd = fd;
+    descr.type = CU_FILE_HANDLE_TYPE_OPAQUE_FD;
+    CUfileHandle_t fh;
+    CUfileError_t e = a->HandleRegister(&fh, &descr);
+    if (e.err != CU_FILE_SUCCESS) {
+        close(fd);
+        return set_err(ctx, DAMPR_ERR_CUDA, "cuFileHandleRegister failed for %s", path);
+    }
+    const size_t PIECE = 16u << 20;
+    const size_t pieces = (bytes + PIECE - 1) / PIECE;
+    const int nthreads = (int)std::max<size_t>(1, std::min<size_t>(pieces, (size_t)g_cufile_threads));
+    std::atomic<size_t> next{0};
+    std::atomic<int> failed{0};
+    const int device = ctx->device;
+    auto work = [&] {
+        cudaSetDevice(device);
+        for (;;) {
+            const size_t i = next.fetch_add(1);
+            if (i >= pieces || failed.load()) break;
+            const size_t lo = i * PIECE, len = std::min(PIECE, bytes - lo);
+            size_t got = 0;
+            while (got < len) {
+                const ssize_t r = a->Read(fh, dst, len - got, (off_t)(foff + lo + got), (off_t)(lo + got));
+                if (r <= 0) {
+                    failed.store(1);
+                    break;
+                }
+                got += (size_t)r;
+            }
+        }
+    };
+    std::vector<std::thread> th;
+    for (int t = 1; t < nthreads; ++t) th.emplace_back(work);
+    work();
+    for (auto &t : th) t.join();
+    a->HandleDeregister(fh);
+    close(fd);
+    if (failed.load()) return set_err(ctx, DAMPR_ERR_CUDA, "cuFileRead failed on %s", path);
+    return DAMPR_OK;
+}
+
+}  // namespace
+
 int32_t dampr_textbuf_upload_file(dampr_ctx *ctx, dampr_textbuf *tb, uint64_t off, const char *path,
                                   uint64_t file_off, uint64_t len) {
     ARG_CHECK(ctx, ctx && tb && path, "null");
     ARG_CHECK(ctx, off + len <= tb->capacity, "upload exceeds textbuf capacity");
-    if (len) {
+    if (len && g_file_cufile) {
+        CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+        // earlier uploads into this buffer travel on the copy stream; cuFileRead is not stream-ordered
+        CUDA_TRY(ctx, cudaStreamSynchronize(ctx->copy));
+        const int rc = cufile_h2d(ctx, tb->text + off, path, file_off, len);
+        if (rc) return rc;
+        if (off + len > tb->uploaded_hi) tb->uploaded_hi = off + len;
+    } else if (len) {
         const int fd = open(path, O_RDONLY);
         if (fd < 0) return set_err(ctx, DAMPR_ERR_ARG, "cannot open %s", path);
         const int rc = staged_file_h2d(ctx, tb->text + off, fd, file_off, len, ctx->copy);

@@ -1769,6 +1769,16 @@ int32_t dampr_set_option(const char *name, int64_t value) {
         g_text_ctas = (int)value;
         return DAMPR_OK;
     }
+    if (!strcmp(name, "file_cufile")) {
+        if (value != 0 && value != 1) return DAMPR_ERR_ARG;
+        g_file_cufile = (int)value;
+        return DAMPR_OK;
+    }
+    if (!strcmp(name, "cufile_threads")) {
+        if (value < 1 || value > 64) return DAMPR_ERR_ARG;
+        g_cufile_threads = (int)value;
+        return DAMPR_OK;
+    }
     if (!strcmp(name, "host_threads")) {
         if (value < 1 || value > 256) return DAMPR_ERR_ARG;
         g_host_threads_cap = (int)value;

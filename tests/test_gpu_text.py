@@ -255,3 +255,35 @@ def test_fallback_list_overflow_sets_the_scan_wide_flag(ctx, text_kernel):
     data = "é\n".encode() * 70000      # more bad lines than the list holds (and than a warp region may isolate)
     _, st = run_count(ctx, data, dev.TOK_NONWORD_LOWER_SET, verify=False)
     assert st["flags"] & dev.TF_NONASCII
+
+
+def test_upload_file_through_cufile_matches_the_ring(ctx, tmp_path):
+    """The opt-in cuFile ingest (dampr_set_option("file_cufile", 1), csrc/ctx.cu): the same bytes land in the text
+    buffer as through the page-locked ring; token counts agree. Skipped where libcufile cannot be opened."""
+    data = gen.text(31, 30000, V=5000)
+    p = tmp_path / "c.txt"
+    p.write_bytes(data)
+    tb = ctx.textbuf(len(data))
+    tb.set_length(len(data))
+    tb.upload_file(0, str(p), 0, len(data))
+    ctx.sync()
+    want = tb.download(0, len(data)).tobytes()
+    assert want == data
+    dev.set_option("file_cufile", 1)
+    try:
+        tb2 = ctx.textbuf(len(data))
+        tb2.set_length(len(data))
+        try:
+            tb2.upload_file(0, str(p), 0, len(data))
+        except dev.DeviceError as e:
+            if "cuFile" in str(e):
+                pytest.skip("cuFile unavailable here: %s" % e)
+            raise
+        ctx.sync()
+        assert tb2.download(0, len(data)).tobytes() == data
+        # an unaligned window of the file into an unaligned offset
+        tb2.upload_file(1003, str(p), 777, 50001)
+        ctx.sync()
+        assert tb2.download(1003, 50001).tobytes() == data[777:777 + 50001]
+    finally:
+        dev.set_option("file_cufile", 0)
