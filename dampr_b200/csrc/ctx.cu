@@ -717,18 +717,32 @@ int cufile_h2d(dampr_ctx *ctx, void *dst, const char *path, size_t foff, size_t 
     if (!a) {
         return set_err(ctx, DAMPR_ERR_CUDA, "cuFile is not available: %s", "dlopen / cuFileDriverOpen failed");
     }
-    int fd = open(path, O_RDONLY | O_DIRECT);
-    if (fd < 0) fd = open(path, O_RDONLY);
-    if (fd < 0) return set_err(ctx, DAMPR_ERR_ARG, "cannot open %s", path);
-    CUfileDescr_t descr;
-    memset(&descr, 0, sizeof descr);
-    descr.handle.fd = fd;
-    descr.type = CU_FILE_HANDLE_TYPE_OPAQUE_FD;
+    // O_DIRECT first (what GPUDirect Storage wants); a file system that refuses it, or whose registration fails
+    // with it, gets a second try with a plain descriptor (cuFile's compatibility mode)
+    int fd = -1;
     CUfileHandle_t fh;
-    CUfileError_t e = a->HandleRegister(&fh, &descr);
-    if (e.err != CU_FILE_SUCCESS) {
-        close(fd);
-        return set_err(ctx, DAMPR_ERR_CUDA, "cuFileHandleRegister failed for %s", path);
+    int last_err = 0;
+    bool registered = false;
+    for (int attempt = 0; attempt < 2 && !registered; ++attempt) {
+        fd = open(path, attempt == 0 ? (O_RDONLY | O_DIRECT) : O_RDONLY);
+        if (fd < 0) continue;
+        CUfileDescr_t descr;
+        memset(&descr, 0, sizeof descr);
+        descr.handle.fd = fd;
+        descr.type = CU_FILE_HANDLE_TYPE_OPAQUE_FD;
+        const CUfileError_t e = a->HandleRegister(&fh, &descr);
+        if (e.err == CU_FILE_SUCCESS) {
+            registered = true;
+        } else {
+            last_err = (int)e.err;
+            close(fd);
+            fd = -1;
+        }
+    }
+    if (!registered) {
+        char b[64];
+        snprintf(b, sizeof b, "CUfileOpError %d", last_err);
+        return set_err(ctx, DAMPR_ERR_CUDA, "cuFileHandleRegister failed (%s): this file system is not served by cuFile", b);
     }
     const size_t PIECE = 16u << 20;
     const size_t pieces = (bytes + PIECE - 1) / PIECE;
