@@ -59,6 +59,7 @@ constexpr int HOT_L = 32;  // (tile, bucket) runs longer than this are sorted by
 constexpr u64 C_NMAX = 27500;   // records per cluster chunk (8 x 4096 minus slack for bin granularity)
 constexpr u64 C_TARGET = 25000; // planned average segment size when the cluster leaf is in use
 constexpr u64 S_TARGET = 2600;  // planned average segment size for single-CTA leaves
+int g_kv_leaf_target = (int)S_TARGET;   // (dampr_set_option "kv_leaf_target": experiments with more, smaller segments)
 
 struct Piece {
     u64 start, end;
@@ -1455,7 +1456,7 @@ static int sort_range(dampr_ctx *ctx, ulonglong2 *cur, ulonglong2 *alt, u64 star
     // are packed into shared leaf chunks) and skewed inputs need the resolution. With the table scatter the
     // first level takes 12 bits whenever the key has them (its fast path wants buckets >= records per tile);
     // further levels (more than ~1.1e8 records) use the ballot scatter with at most 10 bits each.
-    int total_bits = bits_for(n, use_cluster ? C_TARGET : S_TARGET);
+    int total_bits = bits_for(n, use_cluster ? C_TARGET : (u64)g_kv_leaf_target);
     if (total_bits > 0) total_bits = std::max(total_bits, 8);
     total_bits = std::min(top, total_bits);
     std::vector<int> lev_bits;
@@ -1767,6 +1768,11 @@ int32_t dampr_set_option(const char *name, int64_t value) {
     if (!strcmp(name, "text_ctas")) {
         if (value < 2 || value > 4) return DAMPR_ERR_ARG;
         g_text_ctas = (int)value;
+        return DAMPR_OK;
+    }
+    if (!strcmp(name, "kv_leaf_target")) {
+        if (value < 64 || value > (int64_t)L_CAP) return DAMPR_ERR_ARG;
+        g_kv_leaf_target = (int)value;
         return DAMPR_OK;
     }
     if (!strcmp(name, "file_cufile")) {

@@ -22,6 +22,10 @@
 #include <functional>
 #include <thread>
 
+#include <charconv>
+#include <cmath>
+#include <limits>
+
 #include "common.cuh"
 
 namespace {
@@ -939,6 +943,90 @@ struct IntDicts {
     std::vector<int32_t> kinds;
     std::vector<const void *> aux, aux2;
 };
+// repr(float) of CPython (float_repr_style 'short': PyOS_double_to_string(x, 'r', 0, Py_DTSF_ADD_DOT_0), i.e. the
+// shortest digit string that round-trips, laid out in fixed notation when -4 < decpt <= 16 and with an exponent of
+// at least two digits otherwise) — what print(value) / sink_tsv write for a float (dampr.py:521-529). The digits
+// come from std::to_chars (shortest round-trip, like David Gay's dtoa mode 0 that CPython uses). Returns the length
+// (<= 24).
+static int format_py_float(double v, char *out) {
+    if (v != v) {
+        memcpy(out, "nan", 3);
+        return 3;
+    }
+    int n = 0;
+    if (std::signbit(v)) {
+        out[n++] = '-';
+        v = -v;
+    }
+    if (v == std::numeric_limits<double>::infinity()) {
+        memcpy(out + n, "inf", 3);
+        return n + 3;
+    }
+    if (v == 0.0) {
+        memcpy(out + n, "0.0", 3);
+        return n + 3;
+    }
+    char tmp[40];
+    const auto r = std::to_chars(tmp, tmp + sizeof tmp, v, std::chars_format::scientific);
+    // tmp = d[.ddd]e(+|-)XX[X]
+    char digits[24];
+    int k = 0;
+    const char *p = tmp;
+    while (p < r.ptr && *p != 'e') {
+        if (*p != '.') digits[k++] = *p;
+        ++p;
+    }
+    ++p;  // 'e'
+    const bool eneg = (*p == '-');
+    ++p;
+    int e10 = 0;
+    while (p < r.ptr) e10 = e10 * 10 + (*p++ - '0');
+    if (eneg) e10 = -e10;
+    const int decpt = e10 + 1;
+    if (decpt > -4 && decpt <= 16) {
+        if (decpt <= 0) {
+            out[n++] = '0';
+            out[n++] = '.';
+            for (int i = 0; i < -decpt; ++i) out[n++] = '0';
+            memcpy(out + n, digits, k);
+            n += k;
+        } else if (decpt < k) {
+            memcpy(out + n, digits, decpt);
+            n += decpt;
+            out[n++] = '.';
+            memcpy(out + n, digits + decpt, k - decpt);
+            n += k - decpt;
+        } else {
+            memcpy(out + n, digits, k);
+            n += k;
+            for (int i = 0; i < decpt - k; ++i) out[n++] = '0';
+            out[n++] = '.';
+            out[n++] = '0';
+        }
+    } else {
+        out[n++] = digits[0];
+        if (k > 1) {
+            out[n++] = '.';
+            memcpy(out + n, digits + 1, k - 1);
+            n += k - 1;
+        }
+        out[n++] = 'e';
+        int ex = decpt - 1;
+        out[n++] = ex < 0 ? '-' : '+';
+        if (ex < 0) ex = -ex;
+        if (ex >= 100) {
+            out[n++] = (char)('0' + ex / 100);
+            ex %= 100;
+            out[n++] = (char)('0' + ex / 10);
+            out[n++] = (char)('0' + ex % 10);
+        } else {
+            out[n++] = (char)('0' + ex / 10);
+            out[n++] = (char)('0' + ex % 10);
+        }
+    }
+    return n;
+}
+
 static void lower_int_dicts(int ncols, const int32_t *kinds, const uint32_t *widths, const void *const *aux,
                             const void *const *aux2, IntDicts &d) {
     d.kinds.assign(kinds, kinds + ncols);
@@ -947,6 +1035,37 @@ static void lower_int_dicts(int ncols, const int32_t *kinds, const uint32_t *wid
     d.blobs.resize(ncols);
     d.offs.resize(ncols);
     for (int c = 0; c < ncols; ++c) {
+        if (kinds[c] == 3) {
+            // dictionary of float64 values: ptr = u32 inv[n], aux = double values[m], widths = m -> kind 1 with
+            // Python's repr of every distinct value, formatted here (a few threads for large dictionaries)
+            const double *vals = (const double *)aux[c];
+            const u32 m = widths[c];
+            auto &blob = d.blobs[c];
+            auto &off = d.offs[c];
+            std::vector<char> slots((size_t)m * 24 + 24);
+            std::vector<u8> lens((size_t)m + 1);
+            const unsigned hw = std::thread::hardware_concurrency();
+            const int T = (int)std::max<u32>(1, std::min<u32>(std::min(hw, 8u), m / 4096));
+            auto work = [&](int t) {
+                const u32 lo = (u32)((u64)m * t / T), hi = (u32)((u64)m * (t + 1) / T);
+                for (u32 j = lo; j < hi; ++j) lens[j] = (u8)format_py_float(vals[j], slots.data() + (size_t)j * 24);
+            };
+            {
+                std::vector<std::thread> th;
+                for (int t = 1; t < T; ++t) th.emplace_back(work, t);
+                work(0);
+                for (auto &x : th) x.join();
+            }
+            off.resize((size_t)m + 1);
+            off[0] = 0;
+            for (u32 j = 0; j < m; ++j) off[j + 1] = off[j] + lens[j];
+            blob.resize((size_t)off[m] + 1);
+            for (u32 j = 0; j < m; ++j) memcpy(blob.data() + off[j], slots.data() + (size_t)j * 24, lens[j]);
+            d.kinds[c] = 1;
+            d.aux[c] = blob.data();
+            d.aux2[c] = off.data();
+            continue;
+        }
         if (kinds[c] != 2) continue;
         const int64_t *vals = (const int64_t *)aux[c];
         const u32 m = widths[c];
@@ -1042,6 +1161,13 @@ static u64 join_rows_fast(const JoinArgs &a, u64 lo, u64 hi, u8 *out) {
     return (u64)(p - out);
 }
 }  // namespace
+
+// repr(float) of n values into 24-byte slots (lens[i] bytes used each): the formatter of the float dictionaries
+extern "C" int32_t dampr_host_format_f64(const double *vals, uint64_t n, uint8_t *slots, uint8_t *lens) {
+    if ((!vals || !slots || !lens) && n) return DAMPR_ERR_ARG;
+    for (uint64_t i = 0; i < n; ++i) lens[i] = (uint8_t)format_py_float(vals[i], (char *)slots + i * 24);
+    return DAMPR_OK;
+}
 
 extern "C" int32_t dampr_host_join_tsv(uint64_t n, int32_t ncols, const int32_t *kinds, const void *const *ptrs,
                                        const uint32_t *widths, const void *const *aux, const void *const *aux2,

@@ -77,6 +77,7 @@ def load_library():
     _sig(lib, "dampr_ctx_stream", vp, pu64)
     _sig(lib, "dampr_host_alloc", u64, pvp)
     _sig(lib, "dampr_host_free", vp)
+    _sig(lib, "dampr_host_format_f64", vp, u64, vp, vp)
     _sig(lib, "dampr_host_register", vp, u64)
     _sig(lib, "dampr_host_unregister", vp)
     _sig(lib, "dampr_textbuf_create", vp, u64, pvp)
@@ -656,11 +657,15 @@ def host_join_tsv(columns, prefix=None, first=0, max_files=16):
             ptrs[c] = arr.ctypes.data
             keep.append(arr)
             m = len(arr)
-        elif isinstance(col[1], np.ndarray):   # (inv, int64 values): formatted natively
+        elif isinstance(col[1], np.ndarray):   # (inv, int64 | float64 values): formatted natively
             inv, vals = col
             inv = np.ascontiguousarray(inv, dtype=np.uint32)
-            vals = np.ascontiguousarray(vals, dtype=np.int64)
-            kinds[c], widths[c] = 2, len(vals)
+            if vals.dtype == np.float64:       # Python's repr(float) of every distinct value (kind 3)
+                vals = np.ascontiguousarray(vals)
+                kinds[c], widths[c] = 3, len(vals)
+            else:
+                vals = np.ascontiguousarray(vals, dtype=np.int64)
+                kinds[c], widths[c] = 2, len(vals)
             ptrs[c], aux[c] = inv.ctypes.data, vals.ctypes.data
             keep.extend([inv, vals])
             m = len(inv)

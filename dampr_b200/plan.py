@@ -1757,8 +1757,10 @@ def _sink_column(col):
     """A frame column in the form dampr_host_join_tsv takes: an 'S' array, or (inv, [bytes per distinct
     value]) with Python's own str() of every distinct value (exact float repr); None if unsupported."""
     if isinstance(col, DictCol):
-        if isinstance(col.uniq, np.ndarray) and col.uniq.dtype == np.int64:
-            return (col.inv, col.uniq)   # decimal text of the distinct ints is produced natively
+        if isinstance(col.uniq, np.ndarray) and col.uniq.dtype in (np.int64, np.float64):
+            # decimal text of the distinct ints / Python's repr of the distinct floats is produced natively
+            # (dampr_host_format_f64: bit-for-bit repr(float), tests/test_host_logic.py)
+            return (col.inv, col.uniq)
         u = col.uniq.tolist() if isinstance(col.uniq, np.ndarray) else col.uniq
         return (col.inv, [str(x).encode("utf-8") for x in u])
     if isinstance(col, np.ndarray):
@@ -1766,7 +1768,7 @@ def _sink_column(col):
             return col
         if col.dtype.kind in "iuf":
             uniq, inv = unique_inverse(col)
-            if uniq.dtype == np.int64:
+            if uniq.dtype in (np.int64, np.float64):
                 return (inv, uniq)
             return (inv, [str(x).encode("utf-8") for x in uniq.tolist()])
         return None

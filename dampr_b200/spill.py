@@ -161,35 +161,6 @@ def _register_prefix(buf, upto):
             _HOST_ARENA["reg"] = upto
 
 
-def _prefault(buf, threads=4, step=256 << 20):
-    """Map the pages of a fresh buffer ahead of the downloads that will land in it (first job only: a download into
-    unmapped pages runs at 18 GB/s here, into mapped ones at 39): a few daemon threads walk the buffer front to back
-    with madvise(MADV_POPULATE_WRITE), each taking every `threads`-th block. Purely an optimisation — where the
-    call is not available (Linux < 5.14) nothing happens and the copy threads take the page faults as before."""
-    import ctypes
-    import threading
-    try:
-        libc = ctypes.CDLL(None, use_errno=True)
-        madvise = libc.madvise
-    except Exception:
-        return
-    madvise.argtypes = [ctypes.c_void_p, ctypes.c_size_t, ctypes.c_int]
-    base, nbytes = buf.ctypes.data, buf.nbytes
-    lo = (base + 4095) & ~4095
-    hi = (base + nbytes) & ~4095
-    if hi - lo < step:
-        return
-
-    def work(t):
-        pos = lo + t * step
-        while pos < hi and _HOST_ARENA["buf"] is buf:
-            if madvise(pos, min(step, hi - pos), 23) != 0:    # MADV_POPULATE_WRITE
-                return
-            pos += threads * step
-    for t in range(threads):
-        threading.Thread(target=work, args=(t,), name="dampr-spill-prefault", daemon=True).start()
-
-
 def _drop_cached_arena():
     th = _HOST_ARENA["thread"]
     buf = _HOST_ARENA["buf"]
@@ -223,8 +194,6 @@ class _RunArena(object):
                 buf = np.empty((n_records, 2), dtype=np.uint64)
                 if buf.nbytes <= int(settings.host_spill_cache_bytes or 0):
                     _HOST_ARENA["buf"] = buf
-                if self.real_device:
-                    _prefault(buf)
             elif _HOST_ARENA["thread"] is not None:
                 _HOST_ARENA["thread"].join()
                 _HOST_ARENA["thread"] = None

@@ -183,6 +183,10 @@ int32_t dampr_kv_decode_words(dampr_ctx *ctx, dampr_kv *kv, int32_t mode, uint32
  * u32 inv[n] into a dictionary of strings aux[c] (bytes) / aux2[c] (u32 offsets[m+1]); kinds[c] == 2:
  * the same with a dictionary of int64 values aux[c][widths[c]], written in decimal.
  * out == NULL computes *out_len only. Pure host code, no device work. */
+/* Python's repr(float) of n doubles into 24-byte slots (lens[i] bytes used): what print(value) writes for a float
+ * (SinkWriter.add_record dataset.py:264-282; sink_tsv dampr.py:521-529). The join / sink entry points below take
+ * float dictionaries directly (kind 3: ptrs = u32 inv[n], aux = double values[m], widths = m). */
+int32_t dampr_host_format_f64(const double *vals, uint64_t n, uint8_t *slots, uint8_t *lens);
 int32_t dampr_host_join_tsv(uint64_t n, int32_t ncols, const int32_t *kinds, const void *const *ptrs,
                             const uint32_t *widths, const void *const *aux, const void *const *aux2,
                             uint8_t *out, uint64_t cap, uint64_t *out_len);

@@ -605,3 +605,32 @@ def test_unique_over_kv_records_keeps_first_appearance_order(monkeypatch):
     assert not lowered()
     Dampr.read_input(ArrayKVInput(keys, vals)).group_by(lambda x: x[0], lambda x: x[1]).unique(lambda v: v % 3).read()
     assert not lowered()
+
+
+def test_native_float_repr_is_pythons_repr():
+    """dampr_host_format_f64 (the formatter behind the float dictionaries of the native sink): bit-for-bit
+    repr(float) — shortest round-trip digits, fixed notation for -4 < decpt <= 16, two-digit exponents, '.0',
+    signed zeros, inf / nan — on edge cases, the tf-idf value range and random bit patterns."""
+    lib = dev.load_library()
+    rng = np.random.default_rng(1)
+    cases = [0.0, -0.0, 1.0, -1.0, 0.1, 1e16, 1e15, 123456789012345678.0, 1234567890123456.0, 9999999999999998.0, 1e-4, 1e-5,
+             0.0001234, 1.5e-7, 5e-324, 2.2250738585072014e-308, 1.7976931348623157e308, float("inf"), float("-inf"),
+             float("nan"), 1e22, 1e23, 1e100, 1e-100, 123.456, 0.30000000000000004, 2.5, 100.0, 1e21, 12345678901234567890.0]
+    cases += [math.log(1 + 1e8 / d) for d in range(1, 5000)]
+    cases += (rng.random(50000) * 10.0 ** rng.integers(-30, 30, size=50000)).tolist()
+    vals = np.concatenate([np.array(cases, dtype=np.float64), rng.integers(0, 1 << 64, size=200000, dtype=np.uint64).view(np.float64)])
+    n = len(vals)
+    slots = np.zeros(n * 24, dtype=np.uint8)
+    lens = np.zeros(n, dtype=np.uint8)
+    assert lib.dampr_host_format_f64(vals.ctypes.data_as(ctypes.c_void_p), n, slots.ctypes.data_as(ctypes.c_void_p),
+                                     lens.ctypes.data_as(ctypes.c_void_p)) == 0
+    blob = slots.tobytes()
+    for i, v in enumerate(vals.tolist()):
+        assert blob[i * 24:i * 24 + int(lens[i])].decode() == repr(v), (v, i)
+    # through the join: a float dictionary column next to an int dictionary and a fixed-width string column
+    inv = rng.integers(0, 1000, size=5000).astype(np.uint32)
+    fu = np.array([math.log(1 + 1e6 / (j + 1)) for j in range(1000)], dtype=np.float64)
+    iu = np.arange(1000, dtype=np.int64) * 7 - 50
+    words = np.array([("w%d" % j).encode() for j in inv.tolist()], dtype="S8")
+    rows = dev.host_join_tsv([words, (inv, iu), (inv, fu)]).tobytes().decode().split("\n")[:-1]
+    assert rows == ["w%d\t%d\t%r" % (j, iu[j], float(fu[j])) for j in inv.tolist()]
