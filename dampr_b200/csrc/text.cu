@@ -1290,18 +1290,44 @@ extern "C" int32_t dampr_host_unique_small(const int64_t *col, uint64_t n, uint6
                                            uint64_t *n_big) {
     if (!col || !uniq || !n_uniq || !inv || !n_big || table == 0 || table > (1ULL << 26) || n >= (1ULL << 32))
         return DAMPR_ERR_ARG;
+    // three passes, the two over the rows split over a few threads: (1) mark the values present (and the smallest
+    // row holding each), collect the rows outside the table; (2) rank the marked values in ascending order;
+    // (3) look every row's rank up
     std::vector<u32> rank(table, 0);
-    std::vector<u32> first(first_row ? table : 0);
+    std::vector<u32> first(first_row ? table : 0, 0xFFFFFFFFu);
+    const unsigned hw = std::thread::hardware_concurrency();
+    const int T = (int)std::max<u64>(1, std::min<u64>(std::min(hw, 8u), n / 65536));
+    std::vector<std::vector<std::pair<int64_t, u64>>> bigs((size_t)T);
+    auto mark = [&](int t) {
+        const u64 lo = n * t / T, hi = n * (t + 1) / T;
+        auto &big = bigs[(size_t)t];
+        for (u64 i = lo; i < hi; ++i) {
+            const int64_t v = col[i];
+            if (v >= 0 && (u64)v < table) {
+                if (!rank[(u64)v]) rank[(u64)v] = 1;   // (every writer stores the same value)
+                if (first_row) {
+                    u32 *f = &first[(u64)v];
+                    u32 cur = __atomic_load_n(f, __ATOMIC_RELAXED);
+                    while ((u32)i < cur && !__atomic_compare_exchange_n(f, &cur, (u32)i, true, __ATOMIC_RELAXED, __ATOMIC_RELAXED)) {
+                    }
+                }
+            } else {
+                big.emplace_back(v, i);
+            }
+        }
+    };
+    {
+        std::vector<std::thread> th;
+        for (int t = 1; t < T; ++t) th.emplace_back(mark, t);
+        mark(0);
+        for (auto &x : th) x.join();
+    }
     u64 nb = 0;
-    for (u64 i = 0; i < n; ++i) {
-        const int64_t v = col[i];
-        if (v >= 0 && (u64)v < table) {
-            if (first_row && !rank[(u64)v]) first[(u64)v] = (u32)i;
-            rank[(u64)v] = 1;
-        } else {
-            if (nb >= big_cap) return DAMPR_ERR_ARG;
-            big_vals[nb] = v;
-            big_rows[nb] = i;
+    for (auto &big : bigs) {
+        if (nb + big.size() > big_cap) return DAMPR_ERR_ARG;
+        for (auto &pr : big) {
+            big_vals[nb] = pr.first;
+            big_rows[nb] = pr.second;
             ++nb;
         }
     }
@@ -1313,9 +1339,18 @@ extern "C" int32_t dampr_host_unique_small(const int64_t *col, uint64_t n, uint6
             rank[v] = (u32)m++;
         }
     }
-    for (u64 i = 0; i < n; ++i) {
-        const int64_t v = col[i];
-        if (v >= 0 && (u64)v < table) inv[i] = rank[(u64)v];
+    auto look = [&](int t) {
+        const u64 lo = n * t / T, hi = n * (t + 1) / T;
+        for (u64 i = lo; i < hi; ++i) {
+            const int64_t v = col[i];
+            if (v >= 0 && (u64)v < table) inv[i] = rank[(u64)v];
+        }
+    };
+    {
+        std::vector<std::thread> th;
+        for (int t = 1; t < T; ++t) th.emplace_back(look, t);
+        look(0);
+        for (auto &x : th) x.join();
     }
     *n_uniq = m;
     *n_big = nb;

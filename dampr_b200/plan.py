@@ -1357,19 +1357,33 @@ def _lower_cross(runner, stage, inputs):
         else:
             uniq, inv, rep = dict_cache.get(dep[0]) or unique_inverse_rows(col)
             dict_cache[dep[0]] = (uniq, inv, rep)
-        # representative rows, gathered column-wise (no per-cell Python dispatch)
-        rep_cols = [_gather(c, rep) for c in outer.cols]
-        res = []
         direct = getattr(cross, "swapped_of", None)
         pick = ci if e.op == "tuple" else None
-        if direct is not None:   # cross_right's argument swap, without the extra call per value
-            for row in zip(*rep_cols):
-                r = direct(row, inner)
-                res.append(r if pick is None else r[pick])
-        else:
-            for row in zip(*rep_cols):
-                r = cross(inner, row)
-                res.append(r if pick is None else r[pick])
+
+        def evaluate(rep_cols):
+            out = []
+            if direct is not None:   # cross_right's argument swap, without the extra call per value
+                for row in zip(*rep_cols):
+                    r = direct(row, inner)
+                    out.append(r if pick is None else r[pick])
+            else:
+                for row in zip(*rep_cols):
+                    r = cross(inner, row)
+                    out.append(r if pick is None else r[pick])
+            return out
+        # representative rows, gathered column-wise (no per-cell Python dispatch). This component reads only the
+        # fields in `dep`: the other fields of the representative rows are placeholders (no gather, no string
+        # decoding of thousands of keys nobody looks at). The user's function still evaluates its other
+        # components on them; if one of those chokes on a placeholder the full rows are used instead.
+        m = len(rep)
+        res = None
+        if pick is not None and len(outer.cols) > len(dep):
+            try:
+                res = evaluate([_gather(c, rep) if j in dep else [None] * m for j, c in enumerate(outer.cols)])
+            except Exception:
+                res = None
+        if res is None:
+            res = evaluate([_gather(c, rep) for c in outer.cols])
         kinds = set(type(x) for x in res)
         if kinds == {float}:
             res = np.array(res, dtype=np.float64)

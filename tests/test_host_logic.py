@@ -634,3 +634,24 @@ def test_native_float_repr_is_pythons_repr():
     words = np.array([("w%d" % j).encode() for j in inv.tolist()], dtype="S8")
     rows = dev.host_join_tsv([words, (inv, iu), (inv, fu)]).tobytes().decode().split("\n")[:-1]
     assert rows == ["w%d\t%d\t%r" % (j, iu[j], float(fu[j])) for j in inv.tolist()]
+
+
+def test_cross_components_with_placeholder_rows_fall_back_when_needed(monkeypatch):
+    """plan._lower_cross evaluates a component that reads one field on representative rows whose OTHER fields are
+    placeholders; when another component of the user's function cannot digest a placeholder (None + 1) the full
+    rows are used — the results are Python's either way."""
+    from dampr_b200 import Dampr, settings
+    from dampr_b200 import runner as runner_mod
+    from dampr_b200.inputs import ArrayKVInput
+    monkeypatch.setattr(runner_mod, "_CTX", {settings.device: _FakeCtx()})
+    rng = np.random.default_rng(5)
+    keys = rng.integers(0, 3000, size=40000).astype(np.int64)
+    vals = rng.integers(1, 9, size=40000).astype(np.int64)
+    sums = Dampr.read_input(ArrayKVInput(keys, vals)).a_group_by(lambda x: x[0], lambda x: x[1]).sum()
+    rows = sums.read()
+    n = len(rows)
+    got = sums.cross_right(sums.len(), lambda kv, total: (kv[0] + 1, kv[1], math.log(1 + float(total) / kv[1]))).read()
+    assert any("frame cross" in how for _s, how, _d in runner_mod.LAST_STATS.stages)
+    assert sorted(got) == sorted((k + 1, v, math.log(1 + float(n) / v)) for k, v in rows)
+    got = sums.cross_right(sums.len(), lambda kv, total: (kv[0], kv[1], math.log(1 + float(total) / kv[1]))).read()
+    assert sorted(got) == sorted((k, v, math.log(1 + float(n) / v)) for k, v in rows)
