@@ -4,6 +4,7 @@
 #include <stdint.h>
 #include <stdio.h>
 #include <string.h>
+#include <mutex>
 #include <string>
 #include <unordered_map>
 #include <vector>
@@ -55,6 +56,7 @@ struct dampr_ctx {
     void *stage_slot[STAGE_SLOTS] = {nullptr, nullptr, nullptr, nullptr};
     cudaEvent_t stage_ev[STAGE_SLOTS] = {nullptr, nullptr, nullptr, nullptr};
     unsigned stage_next = 0;   // ring position of the uploads, carried over from call to call
+    std::mutex stage_mu, dstage_mu;   // one staged transfer per ring at a time (the spill path uploads from a second host thread)
     void *dstage_slot[STAGE_SLOTS] = {nullptr, nullptr, nullptr, nullptr};   // the downloads' own ring
     cudaEvent_t dstage_ev[STAGE_SLOTS] = {nullptr, nullptr, nullptr, nullptr};
 

@@ -296,8 +296,11 @@ bool is_pinned(const void *p) {
 }
 
 int stage_init(dampr_ctx *ctx) {
-    if (ctx->stage_slot[0]) return DAMPR_OK;
+    static std::mutex init_mu;   // (an uploading thread and the main thread may both arrive here first)
+    std::lock_guard<std::mutex> lk(init_mu);
+    if (ctx->dstage_ev[dampr_ctx::STAGE_SLOTS - 1]) return DAMPR_OK;
     for (int i = 0; i < dampr_ctx::STAGE_SLOTS; ++i) {
+        if (ctx->stage_slot[i]) continue;
         CUDA_TRY(ctx, cudaHostAlloc(&ctx->stage_slot[i], dampr_ctx::STAGE_BYTES, cudaHostAllocDefault));
         CUDA_TRY(ctx, cudaEventCreateWithFlags(&ctx->stage_ev[i], cudaEventDisableTiming));
         // downloads have a ring of their own: an upload (another host thread, the copy stream) and a download
@@ -330,6 +333,7 @@ int staged_h2d(dampr_ctx *ctx, void *dst, const void *src, size_t bytes, cudaStr
     }
     int rc = stage_init(ctx);
     if (rc) return rc;
+    std::lock_guard<std::mutex> ring(ctx->stage_mu);
     const size_t B = dampr_ctx::STAGE_BYTES;
     for (size_t off = 0; off < bytes; off += B) {
         // the ring position carries over from call to call: a caller that uploads slot-sized chunks one call at
@@ -351,6 +355,7 @@ int staged_h2d_columns(dampr_ctx *ctx, void *dst_records, const u64 *keys, const
     if (count == 0) return DAMPR_OK;
     int rc = stage_init(ctx);
     if (rc) return rc;
+    std::lock_guard<std::mutex> ring(ctx->stage_mu);
     const size_t R = dampr_ctx::STAGE_BYTES / 16;   // records per slot
     for (size_t off = 0; off < count; off += R) {
         const int slot = (int)(ctx->stage_next++ % dampr_ctx::STAGE_SLOTS);
@@ -369,6 +374,7 @@ int staged_file_h2d(dampr_ctx *ctx, void *dst, int fd, size_t foff, size_t bytes
     if (bytes == 0) return DAMPR_OK;
     int rc = stage_init(ctx);
     if (rc) return rc;
+    std::lock_guard<std::mutex> ring(ctx->stage_mu);
     const size_t B = dampr_ctx::STAGE_BYTES;
     for (size_t off = 0; off < bytes; off += B) {
         const int slot = (int)(ctx->stage_next++ % dampr_ctx::STAGE_SLOTS);
@@ -395,6 +401,7 @@ int staged_d2h(dampr_ctx *ctx, void *dst, const void *src, size_t bytes, cudaStr
     }
     int rc = stage_init(ctx);
     if (rc) return rc;
+    std::lock_guard<std::mutex> ring(ctx->dstage_mu);
     const size_t B = dampr_ctx::STAGE_BYTES;
     const size_t nchunks = (bytes + B - 1) / B;
     const size_t S = dampr_ctx::STAGE_SLOTS;

@@ -655,3 +655,40 @@ def test_cross_components_with_placeholder_rows_fall_back_when_needed(monkeypatc
     assert sorted(got) == sorted((k + 1, v, math.log(1 + float(n) / v)) for k, v in rows)
     got = sums.cross_right(sums.len(), lambda kv, total: (kv[0], kv[1], math.log(1 + float(total) / kv[1]))).read()
     assert sorted(got) == sorted((k, v, math.log(1 + float(n) / v)) for k, v in rows)
+
+
+def test_spill_pipeline_propagates_upload_errors_and_releases_the_run_buffer():
+    """The next batch is uploaded by a host thread (spill._Upload): an error there must surface in the caller, leave
+    no thread behind and give the process-wide run buffer back."""
+    from dampr_b200 import settings, spill
+    ctx = _FakeCtx()
+    old = settings.device_arena_bytes
+    settings.device_arena_bytes = 1 << 20
+    rng = np.random.default_rng(0)
+    keys = rng.integers(0, 1000, size=200000).astype(np.uint64)
+    vals = np.ones(200000, dtype=np.int64)
+    orig = _FakeKV.upload_columns
+    try:
+        for fail_at in (1, 2, 4):
+            calls = {"n": 0}
+
+            def boom(self, off, k, v):
+                calls["n"] += 1
+                if calls["n"] == fail_at:
+                    raise RuntimeError("upload failed")
+                return orig(self, off, k, v)
+            _FakeKV.upload_columns = boom
+            with pytest.raises(RuntimeError, match="upload failed"):
+                spill.external_group(ctx, iter([(keys, vals)]), len(keys), dev.OP_SUM_I64, dev.KEY_MIX)
+            assert spill._HOST_ARENA["leased"] is False
+        _FakeKV.upload_columns = orig
+        pieces, st = spill.external_group(ctx, iter([(keys, vals)]), len(keys), dev.OP_SUM_I64, dev.KEY_MIX)
+        got = dict(zip(np.concatenate([p[0] for p in pieces]).tolist(), np.concatenate([p[1] for p in pieces]).view(np.int64).tolist()))
+        exp = {}
+        for k in keys.tolist():
+            exp[k] = exp.get(k, 0) + 1
+        assert got == exp and st["batches"] == 4
+    finally:
+        _FakeKV.upload_columns = orig
+        settings.device_arena_bytes = old
+        spill.release_host_arena()
