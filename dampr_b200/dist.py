@@ -26,21 +26,6 @@ def world():
     return dist.get_rank(), dist.get_world_size()
 
 
-class _DeviceMemory(object):
-    """Expose library-owned device memory to torch through __cuda_array_interface__."""
-
-    def __init__(self, ptr, nbytes):
-        self.__cuda_array_interface__ = {"shape": (int(nbytes),), "typestr": "|u1", "data": (int(ptr), False),
-                                         "version": 2}
-
-
-def device_bytes(ptr, nbytes):
-    import torch
-    if nbytes == 0:
-        return torch.empty(0, dtype=torch.uint8, device="cuda")
-    return torch.as_tensor(_DeviceMemory(ptr, nbytes), device="cuda")
-
-
 def exchange_counts(counts):
     """counts[d] = records this rank sends to rank d -> recv[s] = records rank s sends here."""
     import torch
