@@ -265,11 +265,12 @@ part_scatter_kernel(const ulonglong2 *__restrict__ in, ulonglong2 *__restrict__ 
     for (u32 p = pb; p < pe; ++p) {
         const Piece pc = pieces ? pieces[p] : uniform_piece(p, ustart, un, uR);
         for (u32 b = tid; b < nb; b += P_THREADS) s.run_off[b] = piece_off[(u64)p * nb + b];
+        // the per-warp histograms are cleared here for the first tile and, for every later one, next to the
+        // stores of the tile before it (they are dead once the records are staged): no barrier of their own
+        for (u32 i = tid; i < P_WARPS * nb; i += P_THREADS) (&s.warp_hist[0][0])[(i / nb) * P1_MAX_NB + (i % nb)] = 0;
         __syncthreads();
         for (u64 t0 = pc.start; t0 < pc.end; t0 += P_TILE) {
             const u32 tn = (u32)min((u64)P_TILE, pc.end - t0);
-            for (u32 i = tid; i < P_WARPS * nb; i += P_THREADS) (&s.warp_hist[0][0])[(i / nb) * P1_MAX_NB + (i % nb)] = 0;
-            __syncthreads();
             ulonglong2 rec[P_ROUNDS];
             u32 dig[P_ROUNDS];
             u32 rnk[P_ROUNDS];
@@ -360,22 +361,31 @@ part_scatter_kernel(const ulonglong2 *__restrict__ in, ulonglong2 *__restrict__ 
             if (USE_TMA) fence_proxy_async();
             __syncthreads();
             if (USE_TMA) {
+                // the thread that sends a bucket's run also advances the bucket's cursor: no pass (and no
+                // barrier) of its own for that
                 for (u32 b = tid; b < nb; b += P_THREADS) {
-                    u32 c = s.tile_cnt[b];
-                    if (c) tma_store_1d(out + s.run_off[b], &s.stage[s.local_base[b]], c * 16u);
+                    const u32 c = s.tile_cnt[b];
+                    if (c) {
+                        const u64 ro = s.run_off[b];
+                        tma_store_1d(out + ro, &s.stage[s.local_base[b]], c * 16u);
+                        s.run_off[b] = ro + c;
+                    }
                 }
                 tma_store_commit();
+                for (u32 i = tid; i < P_WARPS * nb; i += P_THREADS) (&s.warp_hist[0][0])[(i / nb) * P1_MAX_NB + (i % nb)] = 0;
                 tma_store_wait_read();
+                __syncthreads();
             } else {
                 for (u32 j = tid; j < tn; j += P_THREADS) {
                     ulonglong2 rc = s.stage[j];
                     u32 d = digit_of(rc.x, ds);
                     out[s.run_off[d] + (j - s.local_base[d])] = rc;
                 }
+                for (u32 i = tid; i < P_WARPS * nb; i += P_THREADS) (&s.warp_hist[0][0])[(i / nb) * P1_MAX_NB + (i % nb)] = 0;
+                __syncthreads();
+                for (u32 b = tid; b < nb; b += P_THREADS) s.run_off[b] += s.tile_cnt[b];
+                __syncthreads();
             }
-            __syncthreads();
-            for (u32 b = tid; b < nb; b += P_THREADS) s.run_off[b] += s.tile_cnt[b];
-            __syncthreads();
         }
     }
     if (USE_TMA) tma_store_wait_all();
