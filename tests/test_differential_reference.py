@@ -653,3 +653,55 @@ def test_lowered_join_idioms_agree_with_the_reference(monkeypatch):
     assert any("device join: broadcast hash build + probe" in h for h in hows[5])
     for i in (6, 7):
         assert not any("device join:" in h for h in hows[i]), tmpl[i]
+
+
+def test_lowered_topk_unique_prefix_agree_with_the_reference(monkeypatch):
+    """The lowerings added for SURVEY §8(f)2 — topk over a frame (plan._lower_topk), group_by(...).unique() over kv
+    records (plan._lower_unique), prefix / suffix / map_keys through the frame map — against the reference's own
+    topk (dampr.py:621-652), unique (:727-746) and prefix / suffix (:310-340) on the same records. unique()'s value
+    order inside a group is the reference's merge order, which depends on its worker scheduling: one input
+    partition keeps it the input order, which is what the lowering produces."""
+    import numpy as np
+    from fake_device import FakeCtx
+    from dampr_b200 import Dampr, settings, plan
+    from dampr_b200 import runner as runner_mod
+    from dampr_b200.inputs import ArrayKVInput
+    rng = random.Random(77)
+    keys = [rng.randint(0, 300) for _ in range(6000)]
+    vals = [rng.randint(-40, 40) for _ in range(6000)]
+    A_ref = "Dampr.memory(recs, partitions=1)"
+    A_our = "Dampr.read_input(ArrayKVInput(K, V))"
+    G = ".group_by(lambda x: x[0], lambda x: x[1])"
+    S = ".a_group_by(lambda x: x[0], lambda x: x[1]).sum()"
+    tmpl = [
+        "{A}" + S + ".topk(7, lambda x: x[1])",
+        "{A}" + S + ".topk(40, lambda x: -x[1])",
+        "{A}" + S + ".topk(1000, lambda x: x[0])",          # k larger than the frame
+        "{A}" + S + ".topk(5, lambda x: x[1] * 2 - x[0])",  # not a projection: host heap
+        "{A}" + G + ".unique()",
+        "{A}" + G + ".unique(lambda v: v % 3)",              # key function: host reducer over device-grouped records
+        "{A}" + S + ".prefix(lambda x: x[1] % 10)",
+        "{A}" + S + ".suffix(lambda x: x[0] + x[1])",
+        "{A}" + S + ".map_keys(lambda k: k * 2).map_values(lambda v: v - 1)",
+    ]
+    env = dict(os.environ)
+    env.pop("PYTHONPATH", None)
+    p = subprocess.run([sys.executable, "-c", TWO_DRIVER, REF, json.dumps(list(zip(keys, vals))),
+                        json.dumps([t.format(A=A_ref) for t in tmpl]), json.dumps([])],
+                       capture_output=True, text=True, env=env, cwd="/tmp", timeout=600)
+    assert p.returncode == 0, p.stderr[-2000:]
+    ref = json.loads(p.stdout.strip().split("\n")[-1])
+    ns = {"Dampr": Dampr, "ArrayKVInput": ArrayKVInput, "K": np.array(keys, dtype=np.int64), "V": np.array(vals, dtype=np.int64)}
+    hows = []
+    for t, exp in zip(tmpl, ref):
+        monkeypatch.setattr(runner_mod, "_CTX", {settings.device: FakeCtx()})
+        monkeypatch.setattr(plan, "_BUFFERS", {})
+        got = sorted(repr(x) for x in eval(t.format(A=A_our), ns).run())
+        hows.append([h for _s, h, _d in runner_mod.LAST_STATS.stages])
+        assert got == exp, t
+    for i in (0, 1, 2):
+        assert any("device top-k candidates" in h for h in hows[i]), tmpl[i]
+    assert not any("device top-k" in h for h in hows[3])
+    assert any("device unique" in h for h in hows[4]) and not any("device unique" in h for h in hows[5])
+    for i in (6, 7, 8):
+        assert any("frame map/filter evaluated column-at-a-time" in h for h in hows[i]), (tmpl[i], hows[i])
