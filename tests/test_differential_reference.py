@@ -182,7 +182,7 @@ def more_pipelines(seed, n):
             base+".group_by(lambda x: x %% %d).reduce(lambda k, it: sum(it)).join(%s.group_by(lambda x: x %% %d + 1).reduce(lambda k, it: max(it))).left_reduce(lambda l, r: (list(l), list(r)))"%(m,other,m),
             base+".group_by(lambda x: x %% %d).join(%s.group_by(lambda x: x %% %d)).reduce(lambda l, r: (sorted(l), sorted(r)))"%(m,other,m),
             base+".group_by(lambda x: x %% %d).join(%s.group_by(lambda x: x %% %d)).reduce(lambda l, r: (lambda ll, rr: [a*b for a in ll for b in rr[:2]])(sorted(l), sorted(r)), many=True)"%(m,other,m),
-            base+".group_by(lambda x: x %% %d).unique(lambda v: v %% 2)"%m,
+            "Dampr.memory(items, partitions=1).group_by(lambda x: x %% %d).unique(lambda v: v %% 2)"%m,   # (one input partition: with several, which value unique() sees first depends on the reference's worker scheduling)
             base+".prefix(lambda x: x %% %d).suffix(lambda x: x[0] + 1)"%m,
             base+".cross_left(%s.filter(lambda x: x %% 17 == 0), lambda a, b: (a, b))"%other,
             base+".cross_set(%s, lambda b, table: (b, b in table), agg=set)"%other,
