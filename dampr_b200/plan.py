@@ -898,10 +898,19 @@ def _lower_kv_map(runner, stage, inputs):
             return None
         if vals.dtype == np.uint64 and len(vals) and int(vals.max()) >= (1 << 63):
             return None   # the device folds are signed 64-bit: values >= 2^63 would compare / add as negatives
-        if kind == lowering.ADD and n and _may_overflow(vals):
+        # the overflow bound of a sum scans every value (numpy, GIL released): on a large input it runs on a host
+        # thread next to the upload + device fold and vetoes the result afterwards
+        late = kind == lowering.ADD and n >= _LATE_OVERFLOW_MIN and not count_only and not dist.active()
+        if kind == lowering.ADD and n and not late and _may_overflow(vals):
             raise NotLowerable("64-bit sum could overflow (SURVEY B12)")
         op = dev.OP_COUNT if (count_only and kind == lowering.ADD) else _FOLD_OPS[kind]
-        rk, rv, how = _device_group(runner, keys, vals, op, dev.KEY_MIX)
+        chk = _Background(_may_overflow, vals) if late else None
+        try:
+            rk, rv, how = _device_group(runner, keys, vals, op, dev.KEY_MIX)
+        finally:
+            overflow = chk.result() if chk is not None else False
+        if overflow:
+            raise NotLowerable("64-bit sum could overflow (SURVEY B12)")
         f = Frame(rk.view(keys.dtype), [rv.view(np.int64)], scalar=True, combined=True)
         runner.stats.add(stage, "device kv partition+sort+segmented-reduce" + how, "records=%d groups=%d" % (n, len(rk)))
         return f
@@ -958,6 +967,9 @@ class LazyKVFrame(Frame):
     def delete(self):
         self._rk = self._rv = None
         self._keys, self._cols, self._done, self.n = None, [[]], True, 0
+
+
+_LATE_OVERFLOW_MIN = 1 << 24   # records from which the overflow bound of a sum runs next to the device work
 
 
 class _Background(object):

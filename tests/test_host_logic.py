@@ -692,3 +692,23 @@ def test_spill_pipeline_propagates_upload_errors_and_releases_the_run_buffer():
         _FakeKV.upload_columns = orig
         settings.device_arena_bytes = old
         spill.release_host_arena()
+
+
+def test_overflow_bound_evaluated_next_to_the_device_work_still_vetoes(monkeypatch):
+    """a_group_by(...).sum() over many records checks the 64-bit overflow bound on a host thread while the device
+    folds (plan._lower_kv_map); sums that leave the 64-bit range must still come back as Python's exact integers
+    (host path), sums that do not are the device's."""
+    from dampr_b200 import Dampr, settings, plan
+    from dampr_b200 import runner as runner_mod
+    from dampr_b200.inputs import ArrayKVInput
+    monkeypatch.setattr(runner_mod, "_CTX", {settings.device: _FakeCtx()})
+    monkeypatch.setattr(plan, "_LATE_OVERFLOW_MIN", 1000)
+    keys = (np.arange(6000) % 50).astype(np.int64)
+    big = np.full(6000, (1 << 62) - 3, dtype=np.int64)
+    got = dict(Dampr.read_input(ArrayKVInput(keys, big)).a_group_by(lambda x: x[0], lambda x: x[1]).sum().read())
+    assert got == {k: 120 * ((1 << 62) - 3) for k in range(50)}
+    assert not any("segmented-reduce" in how for _s, how, _d in runner_mod.LAST_STATS.stages)
+    small = np.arange(6000, dtype=np.int64)
+    got = dict(Dampr.read_input(ArrayKVInput(keys, small)).a_group_by(lambda x: x[0], lambda x: x[1]).sum().read())
+    assert got == {k: int(small[keys == k].sum()) for k in range(50)}
+    assert any("segmented-reduce" in how for _s, how, _d in runner_mod.LAST_STATS.stages)
