@@ -1551,7 +1551,7 @@ def _device_perm(runner, codes, xf, payload=None):
     return perm.view(np.int64)
 
 
-def _lower_unique(runner, stage, fr):
+def _lower_unique(runner, stage, fr, key_fn=None):
     """group_by(k, v).unique() over binary kv records (dampr.py:727-746): per key, the distinct values in the
     order of their first appearance. Three stable device sorts and linear host passes over the columns:
       by key                      -> the records of every key, in input order;
@@ -1564,16 +1564,35 @@ def _lower_unique(runner, stage, fr):
     n = len(keys)
     if dist.active() or n == 0 or spill.needs_spill(runner.ctx, 2 * n):
         return None
-    if vals.dtype.kind == "f":
-        if np.isnan(vals).any() or (np.signbit(vals) & (vals == 0)).any():
+    if vals.dtype.itemsize != 8 or vals.dtype.kind not in "iuf":
+        return None
+    # what makes two values "the same": key(v) — the identity, or a straight-line numeric expression evaluated
+    # column-at-a-time with CPython's results (vexpr)
+    fv = vals
+    if key_fn is not None and not lowering.is_identity(key_fn):
+        ke = _inline(key_fn)
+        if ke is None:
+            return None
+        try:
+            fv = vexpr.evaluate(ke, [vals], True, n)
+        except vexpr.NotVec:
+            return None
+        if isinstance(fv, vexpr.Const):
+            fv = vexpr.broadcast(fv, n)
+        if not isinstance(fv, np.ndarray) or fv.dtype.kind not in "iufb" or len(fv) != n:
+            return None
+        if fv.dtype.kind == "b":
+            fv = fv.astype(np.int64)     # True == 1, False == 0 (and hash alike)
+        elif fv.dtype.itemsize != 8:
+            return None
+    if fv.dtype.kind == "f":
+        if np.isnan(fv).any() or (np.signbit(fv) & (fv == 0)).any():
             return None   # NaN != NaN keeps every NaN; -0.0 == 0.0 are one value: leave those to the set()
         vxf = dev.KEY_F64
-    elif vals.dtype.kind in "iu" and vals.dtype.itemsize == 8:
-        vxf = _key_xform_for(vals)
     else:
-        return None
+        vxf = _key_xform_for(fv)
     kxf = _key_xform_for(keys)
-    ku, vu = keys.view(np.uint64), vals.view(np.uint64)
+    ku, vu = keys.view(np.uint64), np.ascontiguousarray(fv).view(np.uint64)
     by_key = _device_perm(runner, ku, kxf)
     p1 = _device_perm(runner, vu, vxf)
     p2 = _device_perm(runner, ku[p1], kxf, p1.view(np.uint64))
@@ -1603,9 +1622,9 @@ def _lower_reduce(runner, stage, inputs):
         fr = inputs[0]
         binop = getattr(red, "binop", None)
         uop = getattr(red, "op", None)
-        if isinstance(red, ops.KeyedReduce) and uop is not None and uop.kind == "unique" and lowering.is_identity(uop.fn) \
+        if isinstance(red, ops.KeyedReduce) and uop is not None and uop.kind == "unique" \
                 and isinstance(fr, LazyKVFrame) and not fr._done:
-            out = _lower_unique(runner, stage, fr)
+            out = _lower_unique(runner, stage, fr, uop.fn)
             if out is not None:
                 return out
         if isinstance(red, ops.KeyedReduce) and binop is not None and fr.combined and fr.scalar:

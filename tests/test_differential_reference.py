@@ -679,7 +679,8 @@ def test_lowered_topk_unique_prefix_agree_with_the_reference(monkeypatch):
         "{A}" + S + ".topk(1000, lambda x: x[0])",          # k larger than the frame
         "{A}" + S + ".topk(5, lambda x: x[1] * 2 - x[0])",  # not a projection: host heap
         "{A}" + G + ".unique()",
-        "{A}" + G + ".unique(lambda v: v % 3)",              # key function: host reducer over device-grouped records
+        "{A}" + G + ".unique(lambda v: v % 3)",              # numeric key function: evaluated column-at-a-time
+        "{A}" + G + ".unique(lambda v: str(v)[-1])",          # not numeric: host reducer over device-grouped records
         "{A}" + S + ".prefix(lambda x: x[1] % 10)",
         "{A}" + S + ".suffix(lambda x: x[0] + x[1])",
         "{A}" + S + ".map_keys(lambda k: k * 2).map_values(lambda v: v - 1)",
@@ -702,6 +703,7 @@ def test_lowered_topk_unique_prefix_agree_with_the_reference(monkeypatch):
     for i in (0, 1, 2):
         assert any("device top-k candidates" in h for h in hows[i]), tmpl[i]
     assert not any("device top-k" in h for h in hows[3])
-    assert any("device unique" in h for h in hows[4]) and not any("device unique" in h for h in hows[5])
-    for i in (6, 7, 8):
+    assert any("device unique" in h for h in hows[4]) and any("device unique" in h for h in hows[5])
+    assert not any("device unique" in h for h in hows[6])
+    for i in (7, 8, 9):
         assert any("frame map/filter evaluated column-at-a-time" in h for h in hows[i]), (tmpl[i], hows[i])

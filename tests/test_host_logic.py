@@ -572,7 +572,7 @@ def test_topk_over_a_frame_takes_its_candidates_with_one_device_sort(monkeypatch
 
 def test_unique_over_kv_records_keeps_first_appearance_order(monkeypatch):
     """group_by(k, v).unique() over binary kv records (plan._lower_unique, dampr.py:727-746): per key the distinct
-    values in first-appearance order, Python ints / floats; NaN values and key functions stay on the host."""
+    values in first-appearance order, Python ints / floats; NaN values and non-numeric key functions stay on the host."""
     from dampr_b200 import Dampr, settings
     from dampr_b200 import runner as runner_mod
     from dampr_b200.inputs import ArrayKVInput
@@ -603,8 +603,23 @@ def test_unique_over_kv_records_keeps_first_appearance_order(monkeypatch):
     vals[6] = -0.0
     got = dict(Dampr.read_input(ArrayKVInput(keys, vals)).group_by(lambda x: x[0], lambda x: x[1]).unique().read())
     assert not lowered()
-    Dampr.read_input(ArrayKVInput(keys, vals)).group_by(lambda x: x[0], lambda x: x[1]).unique(lambda v: v % 3).read()
-    assert not lowered()
+    # a vectorisable key function: "the same" = equal key(v); the first v of every class is kept
+    ivals = rng.integers(-20, 40, size=20000).astype(np.int64)
+
+    def ref_by(keys, vals, f):
+        d, seen = {}, {}
+        for k, v in zip(keys.tolist(), vals.tolist()):
+            if f(v) not in seen.setdefault(k, set()):
+                seen[k].add(f(v))
+                d.setdefault(k, []).append(v)
+        return d
+    for f in (lambda v: v % 3, lambda v: v > 5, lambda v: v * 0.5, lambda v: -v):
+        got = dict(Dampr.read_input(ArrayKVInput(keys, ivals)).group_by(lambda x: x[0], lambda x: x[1]).unique(f).read())
+        assert lowered()
+        assert got == ref_by(keys, ivals, f)
+    got = dict(Dampr.read_input(ArrayKVInput(keys, ivals)).group_by(lambda x: x[0], lambda x: x[1]).unique(lambda v: str(v)[0]).read())
+    assert not lowered()   # not a numeric expression: the host reducer over device-grouped records
+    assert got == ref_by(keys, ivals, lambda v: str(v)[0])
 
 
 def test_native_float_repr_is_pythons_repr():
