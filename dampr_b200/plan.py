@@ -1216,9 +1216,11 @@ def _lower_frame_general(runner, stage, frame):
     ks = _opkinds(stage.mapper)
     if not ks or frame.n == 0 or dist.active():   # frames are rank-local under torch.distributed
         return None
-    body, last = ks, None
+    body, last, topk_op = ks, None, None
     if ks[-1][0] == "keyed":
         body, last = ks[:-1], ks[-1][1]
+    elif ks[-1][0] == "topk":       # map / filter chain fused in front of a topk: evaluate it, then take the candidates
+        body, topk_op = ks[:-1], ks[-1][1]
     keys, cols, scalar, n = frame.keys, list(frame.cols), frame.scalar, frame.n
     try:
         for kind, op in body:
@@ -1243,6 +1245,8 @@ def _lower_frame_general(runner, stage, frame):
                     return None
             else:
                 return None
+        if topk_op is not None:
+            return _lower_topk(runner, stage, Frame(keys, cols, scalar), topk_op)
         if last is None:
             out = Frame(keys, cols, scalar)
             runner.stats.add(stage, "frame map/filter evaluated column-at-a-time", "records=%d" % n)

@@ -678,6 +678,8 @@ def test_lowered_topk_unique_prefix_agree_with_the_reference(monkeypatch):
         "{A}" + S + ".topk(40, lambda x: -x[1])",
         "{A}" + S + ".topk(1000, lambda x: x[0])",          # k larger than the frame
         "{A}" + S + ".topk(5, lambda x: x[1] * 2 - x[0])",  # not a projection: host heap
+        "{A}" + S + ".map(lambda x: x[1]).topk(9)",                                   # a map fused in front of the topk
+        "{A}" + S + ".filter(lambda x: x[0] % 2 == 0).map(lambda x: (x[1], x[0])).topk(6, lambda x: -x[0])",
         "{A}" + G + ".unique()",
         "{A}" + G + ".unique(lambda v: v % 3)",              # numeric key function: evaluated column-at-a-time
         "{A}" + G + ".unique(lambda v: str(v)[-1])",          # not numeric: host reducer over device-grouped records
@@ -703,7 +705,9 @@ def test_lowered_topk_unique_prefix_agree_with_the_reference(monkeypatch):
     for i in (0, 1, 2):
         assert any("device top-k candidates" in h for h in hows[i]), tmpl[i]
     assert not any("device top-k" in h for h in hows[3])
-    assert any("device unique" in h for h in hows[4]) and any("device unique" in h for h in hows[5])
-    assert not any("device unique" in h for h in hows[6])
-    for i in (7, 8, 9):
+    for i in (4, 5):
+        assert any("device top-k candidates" in h for h in hows[i]), (tmpl[i], hows[i])
+    assert any("device unique" in h for h in hows[6]) and any("device unique" in h for h in hows[7])
+    assert not any("device unique" in h for h in hows[8])
+    for i in (9, 10, 11):
         assert any("frame map/filter evaluated column-at-a-time" in h for h in hows[i]), (tmpl[i], hows[i])
