@@ -295,6 +295,19 @@ def test_unique_over_kv_records(ctx):
         seen = exp.setdefault(k, {})
         seen.setdefault(v, None)
     assert got == {k: list(d) for k, d in exp.items()}
+    # numeric key functions (evaluated column-at-a-time, then the same three sorts) and a topk behind a fused map
+    for f in (lambda v: v % 7, lambda v: v * 0.25, lambda v: v > 0):
+        got = dict(Dampr.read_input(ArrayKVInput(keys, vals)).group_by(lambda x: x[0], lambda x: x[1]).unique(f).read())
+        assert lowered("device unique")
+        exp = {}
+        for k, v in zip(keys.tolist(), vals.tolist()):
+            exp.setdefault(k, {}).setdefault(f(v), v)
+        assert got == {k: list(d.values()) for k, d in exp.items()}
+    import heapq
+    sums = Dampr.read_input(ArrayKVInput(keys, vals)).a_group_by(lambda x: x[0], lambda x: x[1]).sum()
+    got = sums.filter(lambda x: x[0] % 2 == 0).map(lambda x: x[1]).topk(20).read()
+    assert lowered("device top-k candidates")
+    assert sorted(got) == sorted(heapq.nlargest(20, [v for k, v in sums.read() if k % 2 == 0]))
     fvals = (vals / 8.0).astype(np.float64) + 0.125
     got = dict(Dampr.read_input(ArrayKVInput(keys.view(np.uint64), fvals)).group_by(lambda x: x[0], lambda x: x[1]).unique().read())
     assert lowered("device unique")
