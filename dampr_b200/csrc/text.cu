@@ -1160,6 +1160,39 @@ static u64 join_rows_fast(const JoinArgs &a, u64 lo, u64 hi, u8 *out) {
     }
     return (u64)(p - out);
 }
+// rows with a byte string in front of every column and a row ending instead of the TSV tabs / newline (JSON lines:
+// pre = {"[\"", "\", ", ", "}, row_end = "]\n"): same cells, same dictionaries
+struct RowFmt {
+    std::vector<std::string> pre;
+    std::string row_end;
+};
+static u64 join_rows_fmt(const JoinArgs &a, const RowFmt &f, u64 lo, u64 hi, u8 *out) {
+    u8 *p = out;
+    for (u64 i = lo; i < hi; ++i) {
+        for (int c = 0; c < a.ncols; ++c) {
+            const std::string &pre = f.pre[(size_t)c];
+            memcpy(p, pre.data(), pre.size());
+            p += pre.size();
+            if (a.kinds[c] == 0) {
+                const u32 width = a.widths[c];
+                const u8 *w = (const u8 *)a.ptrs[c] + i * width;
+                u32 len = 0;
+                while (len < width && w[len]) ++len;
+                memcpy(p, w, len);
+                p += len;
+            } else {
+                const u32 j = ((const u32 *)a.ptrs[c])[i];
+                const u32 *off = (const u32 *)a.aux2[c];
+                const u32 len = off[j + 1] - off[j];
+                memcpy(p, (const u8 *)a.aux[c] + off[j], len);
+                p += len;
+            }
+        }
+        memcpy(p, f.row_end.data(), f.row_end.size());
+        p += f.row_end.size();
+    }
+    return (u64)(p - out);
+}
 }  // namespace
 
 // repr(float) of n values into 24-byte slots (lens[i] bytes used each): the formatter of the float dictionaries
@@ -1205,10 +1238,10 @@ extern "C" int32_t dampr_host_join_tsv(uint64_t n, int32_t ncols, const int32_t 
 // large outputs are split by row range into up to max_files files `<prefix><first_index + j>`, each
 // formatted and written by its own thread (the reference writes one part file per sink job as well:
 // SinkStageRunner.sink stagerunner.py:165-189, SinkWriter dataset.py:264-282).
-extern "C" int32_t dampr_host_sink_tsv(const char *prefix, uint32_t first_index, uint32_t max_files, uint64_t n,
-                                       int32_t ncols, const int32_t *kinds, const void *const *ptrs,
-                                       const uint32_t *widths, const void *const *aux, const void *const *aux2,
-                                       uint64_t *out_len, uint32_t *n_files) {
+static int32_t sink_rows(const char *prefix, uint32_t first_index, uint32_t max_files, uint64_t n,
+                         int32_t ncols, const int32_t *kinds, const void *const *ptrs,
+                         const uint32_t *widths, const void *const *aux, const void *const *aux2,
+                         uint64_t *out_len, uint32_t *n_files, const RowFmt *fmt) {
     if (!prefix || !kinds || !ptrs || !out_len || !n_files || ncols < 1 || ncols > 16 || max_files < 1)
         return DAMPR_ERR_ARG;
     IntDicts idc;
@@ -1219,6 +1252,10 @@ extern "C" int32_t dampr_host_sink_tsv(const char *prefix, uint32_t first_index,
     JoinArgs a{n, ncols, kinds, ptrs, widths, aux, aux2};
     // longest possible row: fixed widths + the longest string of every dictionary + separators
     u64 max_row = (u64)ncols;
+    if (fmt) {
+        max_row = fmt->row_end.size();
+        for (auto &x : fmt->pre) max_row += x.size();
+    }
     for (int c = 0; c < ncols; ++c) {
         if (kinds[c] == 0) {
             max_row += widths[c];
@@ -1251,7 +1288,7 @@ extern "C" int32_t dampr_host_sink_tsv(const char *prefix, uint32_t first_index,
             close(fd);
             return;
         }
-        const u64 len = (hi > lo) ? join_rows_fast(a, lo, hi, buf) : 0;
+        const u64 len = (hi > lo) ? (fmt ? join_rows_fmt(a, *fmt, lo, hi, buf) : join_rows_fast(a, lo, hi, buf)) : 0;
         u64 done = 0;
         while (done < len) {
             ssize_t w = write(fd, buf + done, len - done);
@@ -1276,6 +1313,28 @@ extern "C" int32_t dampr_host_sink_tsv(const char *prefix, uint32_t first_index,
     *out_len = total;
     *n_files = (u32)T;
     return bad.load() ? DAMPR_ERR_ARG : DAMPR_OK;
+}
+
+extern "C" int32_t dampr_host_sink_tsv(const char *prefix, uint32_t first_index, uint32_t max_files, uint64_t n,
+                                       int32_t ncols, const int32_t *kinds, const void *const *ptrs,
+                                       const uint32_t *widths, const void *const *aux, const void *const *aux2,
+                                       uint64_t *out_len, uint32_t *n_files) {
+    return sink_rows(prefix, first_index, max_files, n, ncols, kinds, ptrs, widths, aux, aux2, out_len, n_files, nullptr);
+}
+
+// The same part files with a byte string in front of every column (col_pre[c], NUL-terminated, may be empty) and
+// row_end instead of the newline: no separators of its own. sink_json's lines (SinkWriter.add_record over
+// json.dumps(value), dampr.py:531-539) are this with pre = `["`, `", `, `, ` ... and row_end = `]\n`.
+extern "C" int32_t dampr_host_sink_fmt(const char *prefix, uint32_t first_index, uint32_t max_files, uint64_t n,
+                                       int32_t ncols, const int32_t *kinds, const void *const *ptrs,
+                                       const uint32_t *widths, const void *const *aux, const void *const *aux2,
+                                       const char *const *col_pre, const char *row_end, uint64_t *out_len,
+                                       uint32_t *n_files) {
+    if (!col_pre || !row_end || ncols < 1 || ncols > 16) return DAMPR_ERR_ARG;
+    RowFmt f;
+    for (int c = 0; c < ncols; ++c) f.pre.emplace_back(col_pre[c] ? col_pre[c] : "");
+    f.row_end = row_end;
+    return sink_rows(prefix, first_index, max_files, n, ncols, kinds, ptrs, widths, aux, aux2, out_len, n_files, &f);
 }
 
 // Sorted distinct values + inverse index of a non-negative int64 column (the dictionary encoding of a

@@ -101,6 +101,8 @@ def load_library():
     _sig(lib, "dampr_host_join_tsv", u64, i32, vp, vp, vp, vp, vp, vp, u64, pu64)
     _sig(lib, "dampr_host_sink_tsv", C.c_char_p, C.c_uint32, C.c_uint32, u64, i32, vp, vp, vp, vp, vp, pu64,
          C.POINTER(C.c_uint32))
+    _sig(lib, "dampr_host_sink_fmt", C.c_char_p, C.c_uint32, C.c_uint32, u64, i32, vp, vp, vp, vp, vp, vp, C.c_char_p, pu64,
+         C.POINTER(C.c_uint32))
     _sig(lib, "dampr_host_unique_small", vp, u64, u64, vp, pu64, vp, vp, vp, vp, u64, pu64)
     _sig(lib, "dampr_kv_create", vp, u64, pvp)
     _sig(lib, "dampr_kv_destroy", vp, vp)
@@ -635,7 +637,7 @@ class KV(object):
             pass
 
 
-def host_join_tsv(columns, prefix=None, first=0, max_files=16):
+def host_join_tsv(columns, prefix=None, first=0, max_files=16, col_pre=None, row_end=None):
     """Rows of tab-separated text from columns (native host loop). Each column is either a numpy
     'S<w>' array (NUL-padded fixed-width strings), a pair (inv uint32 array, list of bytes) or a pair
     (inv uint32 array, int64 array of the distinct values). With `prefix` the rows are written to part files prefix<first>, prefix<first+1>, ... (row ranges, one
@@ -685,8 +687,14 @@ def host_join_tsv(columns, prefix=None, first=0, max_files=16):
     out_len = C.c_uint64(0)
     if prefix is not None:
         nf = C.c_uint32(0)
-        rc = lib.dampr_host_sink_tsv(os.fsencode(prefix), int(first), int(max_files), n, k, kinds, ptrs, widths,
-                                     aux, aux2, C.byref(out_len), C.byref(nf))
+        if col_pre is not None:
+            # formatted rows (sink_json): a byte string in front of every column, row_end instead of the newline
+            pre = (C.c_char_p * k)(*[bytes(x) for x in col_pre])
+            rc = lib.dampr_host_sink_fmt(os.fsencode(prefix), int(first), int(max_files), n, k, kinds, ptrs, widths,
+                                         aux, aux2, pre, bytes(row_end), C.byref(out_len), C.byref(nf))
+        else:
+            rc = lib.dampr_host_sink_tsv(os.fsencode(prefix), int(first), int(max_files), n, k, kinds, ptrs, widths,
+                                         aux, aux2, C.byref(out_len), C.byref(nf))
         if rc:
             raise DeviceError("dampr_host_sink_tsv(%r) failed (%d)" % (prefix, rc))
         return ["%s%d" % (prefix, first + j) for j in range(nf.value)]

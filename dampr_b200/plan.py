@@ -16,6 +16,7 @@ Lowered pipelines and the reference code they replace:
 """
 import logging
 import math
+import json
 import os
 import re
 import threading
@@ -1210,6 +1211,38 @@ def _fold_column(runner, kcodes, xf, vals, kind):
     return rk, rv.view(vals.dtype), how
 
 
+def _apply_chain(frame, body):
+    """A fused map / filter chain ([(kind, Op)]) over a frame, evaluated column-at-a-time (vexpr: CPython's exact
+    results); the resulting Frame, or None when a step is not vectorisable (or a filter leaves nothing: the host
+    path then produces the empty result). May raise vexpr.NotVec."""
+    keys, cols, scalar, n = frame.keys, list(frame.cols), frame.scalar, frame.n
+    for kind, op in body:
+        if kind == "identity":
+            continue
+        e = _inline(op.fn)
+        if e is None:
+            return None
+        v = vexpr.evaluate(e, cols, scalar, n)
+        if kind == "map":
+            if isinstance(v, vexpr.Tup):
+                cols, scalar = [vexpr.broadcast(c, n) for c in v.items], False
+            else:
+                cols, scalar = [vexpr.broadcast(v, n)], True
+        elif kind == "filter":
+            if not (isinstance(v, np.ndarray) and v.dtype == np.bool_):
+                return None   # truthiness of a non-boolean: host path
+            idx = np.flatnonzero(v)
+            tmp = Frame(keys, cols, scalar).take(idx)
+            keys, cols, n = tmp.keys, tmp.cols, len(idx)
+            if n == 0:
+                return None
+        else:
+            return None
+    out = Frame(keys, cols, scalar)
+    out.n = n
+    return out
+
+
 def _lower_frame_general(runner, stage, frame):
     """map / filter chains and keyed folds over a frame whose lambdas evaluate column-at-a-time
     (vexpr): the stages after an aggregation in examples/word-stats.py:24-37, mean(), map_values() ..."""
@@ -1221,30 +1254,11 @@ def _lower_frame_general(runner, stage, frame):
         body, last = ks[:-1], ks[-1][1]
     elif ks[-1][0] == "topk":       # map / filter chain fused in front of a topk: evaluate it, then take the candidates
         body, topk_op = ks[:-1], ks[-1][1]
-    keys, cols, scalar, n = frame.keys, list(frame.cols), frame.scalar, frame.n
     try:
-        for kind, op in body:
-            if kind == "identity":
-                continue
-            e = _inline(op.fn)
-            if e is None:
-                return None
-            v = vexpr.evaluate(e, cols, scalar, n)
-            if kind == "map":
-                if isinstance(v, vexpr.Tup):
-                    cols, scalar = [vexpr.broadcast(c, n) for c in v.items], False
-                else:
-                    cols, scalar = [vexpr.broadcast(v, n)], True
-            elif kind == "filter":
-                if not (isinstance(v, np.ndarray) and v.dtype == np.bool_):
-                    return None   # truthiness of a non-boolean: host path
-                idx = np.flatnonzero(v)
-                tmp = Frame(keys, cols, scalar).take(idx)
-                keys, cols, n = tmp.keys, tmp.cols, len(idx)
-                if n == 0:
-                    return None
-            else:
-                return None
+        chained = _apply_chain(frame, body)
+        if chained is None:
+            return None
+        keys, cols, scalar, n = chained.keys, list(chained.cols), chained.scalar, chained.n
         if topk_op is not None:
             return _lower_topk(runner, stage, Frame(keys, cols, scalar), topk_op)
         if last is None:
@@ -1829,6 +1843,60 @@ def _sink_column(col):
     return None
 
 
+def _json_columns(fr):
+    """sink_json over a frame (json.dumps(value) per record, dampr.py:531-539): the columns in the form the native
+    row writer takes plus the byte strings it puts in front of every column and at the end of a row — `["w", 3, 1.5]`
+    for tuple rows, the bare value for scalar rows. Strings of an 'S' column go out as they are between quotes when
+    they are printable ASCII without '"' and '\\' (what json.dumps would write); dictionary strings are escaped
+    per distinct value by json.dumps itself; ints in decimal; floats by repr() — json.dumps does the same for
+    finite floats. Anything else (non-finite floats, bools, None, nested tuples) -> None: the host sink."""
+    cols, kinds = [], []
+    for c in fr.cols:
+        if isinstance(c, DictCol):
+            u = c.uniq
+            if isinstance(u, np.ndarray) and u.dtype == np.int64:
+                cols.append((c.inv, u)); kinds.append("n")
+            elif isinstance(u, np.ndarray) and u.dtype == np.float64:
+                if not np.isfinite(u).all():
+                    return None
+                cols.append((c.inv, u)); kinds.append("n")
+            elif isinstance(u, list) and all(type(x) is str for x in u):
+                cols.append((c.inv, [json.dumps(x).encode("ascii") for x in u])); kinds.append("n")
+            else:
+                return None
+        elif isinstance(c, np.ndarray) and c.dtype.kind == "S":
+            b = np.ascontiguousarray(c).view(np.uint8)
+            if ((b != 0) & ((b < 0x20) | (b > 0x7e) | (b == 0x22) | (b == 0x5c))).any():
+                return None
+            cols.append(c); kinds.append("s")
+        elif isinstance(c, np.ndarray) and c.dtype in (np.int64, np.float64):
+            if c.dtype == np.float64 and not np.isfinite(c).all():
+                return None
+            sc = _sink_column(c)
+            if sc is None:
+                return None
+            cols.append(sc); kinds.append("n")
+        elif isinstance(c, list) and all(type(x) is str for x in c):
+            uniq = sorted(set(c))
+            idx = {w: i for i, w in enumerate(uniq)}
+            inv = np.fromiter((idx[w] for w in c), dtype=np.uint32, count=len(c))
+            cols.append((inv, [json.dumps(w).encode("ascii") for w in uniq])); kinds.append("n")
+        else:
+            return None
+    pre = []
+    for i, k in enumerate(kinds):
+        p = b""
+        if i == 0:
+            p += b"" if fr.scalar else b"["
+        else:
+            p += (b'"' if kinds[i - 1] == "s" else b"") + b", "
+        if k == "s":
+            p += b'"'
+        pre.append(p)
+    end = (b'"' if kinds[-1] == "s" else b"") + (b"" if fr.scalar else b"]") + b"\n"
+    return cols, pre, end
+
+
 def _lower_sink(runner, stage, inputs):
     if len(inputs) != 1 or not isinstance(inputs[0], Frame):
         return None
@@ -1836,12 +1904,28 @@ def _lower_sink(runner, stage, inputs):
     parts = _parts(stage.mapper)
     from .dsl import _tsv_line
     cols = None
+    col_pre = row_end = None
+    ks = _opkinds(stage.mapper)
+    if ks and len(ks) > 1 and fr.n and not dist.active():
+        # a map / filter chain fused in front of the formatting step (x.map(f).sink_tsv(...)): evaluated
+        # column-at-a-time first; what is left is the one-part case below
+        try:
+            fr2 = _apply_chain(fr, ks[:-1])
+        except vexpr.NotVec:
+            fr2 = None
+        if fr2 is None:
+            return None
+        fr, parts = fr2, parts[-1:]
     if len(parts) == 1 and getattr(parts[0], "op", None) is not None:
         op = parts[0].op
         if op.kind == "map" and op.fn is _tsv_line and not fr.scalar:
             cols = [_sink_column(c) for c in fr.cols]
         elif op.kind == "identity" and fr.scalar:
             cols = [_sink_column(fr.cols[0])]
+        elif op.kind == "map" and op.fn is json.dumps:
+            js = _json_columns(fr)    # sink_json: one JSON value (an array for tuple rows) per line
+            if js is not None:
+                cols, col_pre, row_end = js
     if cols is None or any(c is None for c in cols):
         return None
     os.makedirs(stage.path, exist_ok=True)
@@ -1849,7 +1933,8 @@ def _lower_sink(runner, stage, inputs):
     first = 16 * dist.world()[0] if dist.active() else 0
     prefix = os.path.join(stage.path, "part-")
     if fr.n:
-        names = dev.host_join_tsv(cols, prefix=prefix, first=first)   # formatted and written by native threads
+        # formatted and written by native threads
+        names = dev.host_join_tsv(cols, prefix=prefix, first=first, col_pre=col_pre, row_end=row_end)
     else:
         names = ["%s%d" % (prefix, first)]
         open(names[0], "wb").close()

@@ -198,6 +198,14 @@ int32_t dampr_host_sink_tsv(const char *prefix, uint32_t first_index, uint32_t m
                             int32_t ncols, const int32_t *kinds, const void *const *ptrs,
                             const uint32_t *widths, const void *const *aux, const void *const *aux2,
                             uint64_t *out_len, uint32_t *n_files);
+/* the same part files with col_pre[c] (NUL-terminated, may be empty) written in front of column c and row_end in
+ * place of the newline, no separators of its own: the lines of sink_json (json.dumps(value) per record,
+ * dampr.py:531-539) are col_pre = `["`, `", `, `, ` ... and row_end = `]\n` */
+int32_t dampr_host_sink_fmt(const char *prefix, uint32_t first_index, uint32_t max_files, uint64_t n,
+                            int32_t ncols, const int32_t *kinds, const void *const *ptrs,
+                            const uint32_t *widths, const void *const *aux, const void *const *aux2,
+                            const char *const *col_pre, const char *row_end, uint64_t *out_len,
+                            uint32_t *n_files);
 /* dictionary encoding of an int64 column (host helper of the frame layer): values in [0, table) are
  * ranked through a presence table -> uniq[0..*n_uniq) ascending and inv[i]; other values are handed
  * back in big_vals / big_rows (at most big_cap, else the call fails) and their inv[] is untouched.

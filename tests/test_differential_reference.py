@@ -686,6 +686,8 @@ def test_lowered_topk_unique_prefix_agree_with_the_reference(monkeypatch):
         "{A}" + S + ".prefix(lambda x: x[1] % 10)",
         "{A}" + S + ".suffix(lambda x: x[0] + x[1])",
         "{A}" + S + ".map_keys(lambda k: k * 2).map_values(lambda v: v - 1)",
+        "{A}" + S + ".map(lambda x: (x[0], x[1], x[1] / 7.0)).sink_json(__import__('tempfile').mkdtemp())",
+        "{A}" + S + ".map(lambda x: x[1] * 0.5).sink_json(__import__('tempfile').mkdtemp())",
     ]
     env = dict(os.environ)
     env.pop("PYTHONPATH", None)
@@ -711,3 +713,5 @@ def test_lowered_topk_unique_prefix_agree_with_the_reference(monkeypatch):
     assert not any("device unique" in h for h in hows[8])
     for i in (9, 10, 11):
         assert any("frame map/filter evaluated column-at-a-time" in h for h in hows[i]), (tmpl[i], hows[i])
+    for i in (12, 13):
+        assert any("native frame sink" in h for h in hows[i]), (tmpl[i], hows[i])

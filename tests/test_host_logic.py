@@ -727,3 +727,56 @@ def test_overflow_bound_evaluated_next_to_the_device_work_still_vetoes(monkeypat
     got = dict(Dampr.read_input(ArrayKVInput(keys, small)).a_group_by(lambda x: x[0], lambda x: x[1]).sum().read())
     assert got == {k: int(small[keys == k].sum()) for k in range(50)}
     assert any("segmented-reduce" in how for _s, how, _d in runner_mod.LAST_STATS.stages)
+
+
+def test_sink_json_over_frames_is_json_dumps_per_record(monkeypatch, tmp_path):
+    """sink_json over a frame (plan._json_columns + dampr_host_sink_fmt): every line is json.dumps(value) — arrays
+    for tuple rows, quoted strings, decimal ints, repr floats; values the native writer does not take (strings that
+    need escaping in an 'S' column, non-finite floats) go through the host sink and give the same lines."""
+    import json
+    from fake_device import FakeTextCtx, FakePinned
+    from dampr_b200 import Dampr, settings, plan
+    from dampr_b200 import runner as runner_mod
+    from dampr_b200.inputs import ArrayKVInput
+    monkeypatch.setattr(runner_mod, "_CTX", {settings.device: FakeTextCtx()})
+    monkeypatch.setattr(plan, "_pinned_ring", lambda n, b: [FakePinned(b) for _ in range(n)])
+    monkeypatch.setattr(plan, "_BUFFERS", {})
+
+    def lines_of(d):
+        out = []
+        for fn in sorted(os.listdir(d)):
+            with open(os.path.join(d, fn)) as f:
+                out.extend(l.rstrip("\n") for l in f)
+        return out
+
+    def native():
+        return any("native frame sink" in how for _s, how, _d in runner_mod.LAST_STATS.stages)
+    data = gen.text(5, 3000, V=800)
+    p = tmp_path / "c.txt"
+    p.write_bytes(data)
+    counts = Dampr.text(str(p)).flat_map(lambda x: x.split()).count()
+    rows = counts.read()
+    n = len(rows)
+    idf = counts.cross_right(counts.len(), lambda df, total: (df[0], df[1], math.log(1 + float(total) / df[1])))
+    idf.sink_json(str(tmp_path / "j1")).run()
+    assert native()
+    assert sorted(lines_of(str(tmp_path / "j1"))) == sorted(json.dumps((w, c, math.log(1 + float(n) / c))) for w, c in rows)
+    counts.sink_json(str(tmp_path / "j2")).run()
+    assert native()
+    assert sorted(lines_of(str(tmp_path / "j2"))) == sorted(json.dumps((w, c)) for w, c in rows)
+    counts.map(lambda x: x[0]).sink_json(str(tmp_path / "j3")).run()       # scalar string rows
+    assert sorted(lines_of(str(tmp_path / "j3"))) == sorted(json.dumps(w) for w, _c in rows)
+    # tokens with a quote / a backslash: not what the native writer copies verbatim -> host sink, same lines
+    q = tmp_path / "q.txt"
+    q.write_bytes(b'say "hi" to\\\\ back\\\\slash "hi"\\nplain words only\\n')
+    qc = Dampr.text(str(q)).flat_map(lambda x: x.split()).count()
+    qc.sink_json(str(tmp_path / "j4")).run()
+    assert not native()
+    assert sorted(lines_of(str(tmp_path / "j4"))) == sorted(json.dumps(r) for r in qc.read())
+    # non-finite floats: json.dumps writes NaN / Infinity
+    keys = np.arange(6, dtype=np.int64)
+    vals = np.array([1, 2, 0, 4, 5, 6], dtype=np.int64)
+    fr = Dampr.read_input(ArrayKVInput(keys, vals)).a_group_by(lambda x: x[0], lambda x: x[1]).sum()
+    inf = fr.map(lambda x: (x[0], x[1] * 1e308 * 10))
+    inf.sink_json(str(tmp_path / "j5")).run()
+    assert sorted(lines_of(str(tmp_path / "j5"))) == sorted(json.dumps(r) for r in inf.read())
