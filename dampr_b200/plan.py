@@ -1843,6 +1843,37 @@ def _sink_column(col):
     return None
 
 
+def _tuple_repr_columns(fr):
+    """sink(path) over tuple rows: print(value) writes str(tuple) = "('w', 3, 1.5)" — the repr of every element.
+    'S' strings go out between single quotes when they are printable ASCII without quotes and backslashes (what
+    repr(str) writes for them), ints in decimal, floats by repr (any float: repr is what print uses). Other cells
+    -> None: the host sink."""
+    cols, kinds = [], []
+    for c in fr.cols:
+        if isinstance(c, DictCol) and isinstance(c.uniq, np.ndarray) and c.uniq.dtype in (np.int64, np.float64):
+            cols.append((c.inv, c.uniq)); kinds.append("n")
+        elif isinstance(c, np.ndarray) and c.dtype.kind == "S":
+            b = np.ascontiguousarray(c).view(np.uint8)
+            if ((b != 0) & ((b < 0x20) | (b > 0x7e) | (b == 0x22) | (b == 0x27) | (b == 0x5c))).any():
+                return None
+            cols.append(c); kinds.append("s")
+        elif isinstance(c, np.ndarray) and c.dtype in (np.int64, np.float64):
+            sc = _sink_column(c)
+            if sc is None:
+                return None
+            cols.append(sc); kinds.append("n")
+        else:
+            return None
+    pre = []
+    for i, k in enumerate(kinds):
+        p = b"(" if i == 0 else (b"'" if kinds[i - 1] == "s" else b"") + b", "
+        if k == "s":
+            p += b"'"
+        pre.append(p)
+    end = (b"'" if kinds[-1] == "s" else b"") + (b",)" if len(kinds) == 1 else b")") + b"\n"
+    return cols, pre, end
+
+
 def _json_columns(fr):
     """sink_json over a frame (json.dumps(value) per record, dampr.py:531-539): the columns in the form the native
     row writer takes plus the byte strings it puts in front of every column and at the end of a row — `["w", 3, 1.5]`
@@ -1906,26 +1937,37 @@ def _lower_sink(runner, stage, inputs):
     cols = None
     col_pre = row_end = None
     ks = _opkinds(stage.mapper)
-    if ks and len(ks) > 1 and fr.n and not dist.active():
-        # a map / filter chain fused in front of the formatting step (x.map(f).sink_tsv(...)): evaluated
-        # column-at-a-time first; what is left is the one-part case below
-        try:
-            fr2 = _apply_chain(fr, ks[:-1])
-        except vexpr.NotVec:
-            fr2 = None
-        if fr2 is None:
+    if not ks:
+        return None
+    # the last step formats (sink_tsv's / sink_json's map, or nothing: print(value)); whatever is fused in front of
+    # it (x.map(f).sink(...)) is a map / filter chain, evaluated column-at-a-time first
+    last_kind, last_op = ks[-1]
+    if last_kind == "identity" or (last_kind == "map" and (last_op.fn is _tsv_line or last_op.fn is json.dumps)):
+        chain, fmt = ks[:-1], last_op
+    else:
+        chain, fmt = ks, None
+    if any(k != "identity" for k, _o in chain):
+        if not fr.n or dist.active():
             return None
-        fr, parts = fr2, parts[-1:]
-    if len(parts) == 1 and getattr(parts[0], "op", None) is not None:
-        op = parts[0].op
-        if op.kind == "map" and op.fn is _tsv_line and not fr.scalar:
+        try:
+            fr = _apply_chain(fr, chain)
+        except vexpr.NotVec:
+            fr = None
+        if fr is None:
+            return None
+    if fmt is not None and fmt.kind == "map" and fmt.fn is _tsv_line:
+        if not fr.scalar:
             cols = [_sink_column(c) for c in fr.cols]
-        elif op.kind == "identity" and fr.scalar:
-            cols = [_sink_column(fr.cols[0])]
-        elif op.kind == "map" and op.fn is json.dumps:
-            js = _json_columns(fr)    # sink_json: one JSON value (an array for tuple rows) per line
-            if js is not None:
-                cols, col_pre, row_end = js
+    elif fmt is not None and fmt.kind == "map" and fmt.fn is json.dumps:
+        js = _json_columns(fr)    # sink_json: one JSON value (an array for tuple rows) per line
+        if js is not None:
+            cols, col_pre, row_end = js
+    elif fr.scalar:
+        cols = [_sink_column(fr.cols[0])]
+    else:
+        tp = _tuple_repr_columns(fr)   # sink(path) of tuple rows: print(value) writes repr(tuple)
+        if tp is not None:
+            cols, col_pre, row_end = tp
     if cols is None or any(c is None for c in cols):
         return None
     os.makedirs(stage.path, exist_ok=True)

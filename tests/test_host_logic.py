@@ -768,7 +768,7 @@ def test_sink_json_over_frames_is_json_dumps_per_record(monkeypatch, tmp_path):
     assert sorted(lines_of(str(tmp_path / "j3"))) == sorted(json.dumps(w) for w, _c in rows)
     # tokens with a quote / a backslash: not what the native writer copies verbatim -> host sink, same lines
     q = tmp_path / "q.txt"
-    q.write_bytes(b'say "hi" to\\\\ back\\\\slash "hi"\\nplain words only\\n')
+    q.write_bytes(b'say "hi" to\\ back\\slash "hi"\nplain words only\n')
     qc = Dampr.text(str(q)).flat_map(lambda x: x.split()).count()
     qc.sink_json(str(tmp_path / "j4")).run()
     assert not native()
@@ -780,3 +780,46 @@ def test_sink_json_over_frames_is_json_dumps_per_record(monkeypatch, tmp_path):
     inf = fr.map(lambda x: (x[0], x[1] * 1e308 * 10))
     inf.sink_json(str(tmp_path / "j5")).run()
     assert sorted(lines_of(str(tmp_path / "j5"))) == sorted(json.dumps(r) for r in inf.read())
+
+
+def test_plain_sink_of_tuple_rows_is_print_of_the_tuple(monkeypatch, tmp_path):
+    """sink(path) over tuple rows (plan._tuple_repr_columns): every line is str(value) = repr of the tuple, written by
+    the native row writer; strings with quotes fall back to the host sink and give the same lines."""
+    from fake_device import FakeTextCtx, FakePinned
+    from dampr_b200 import Dampr, settings, plan
+    from dampr_b200 import runner as runner_mod
+    monkeypatch.setattr(runner_mod, "_CTX", {settings.device: FakeTextCtx()})
+    monkeypatch.setattr(plan, "_pinned_ring", lambda n, b: [FakePinned(b) for _ in range(n)])
+    monkeypatch.setattr(plan, "_BUFFERS", {})
+
+    def lines_of(d):
+        out = []
+        for fn in sorted(os.listdir(d)):
+            with open(os.path.join(d, fn)) as f:
+                out.extend(l.rstrip("\n") for l in f)
+        return out
+
+    def native():
+        return any("native frame sink" in how for _s, how, _d in runner_mod.LAST_STATS.stages)
+    data = gen.text(6, 2500, V=700)
+    p = tmp_path / "c.txt"
+    p.write_bytes(data)
+    counts = Dampr.text(str(p)).flat_map(lambda x: x.split()).count()
+    rows = counts.read()
+    counts.sink(str(tmp_path / "s1")).run()
+    assert native()
+    assert sorted(lines_of(str(tmp_path / "s1"))) == sorted(str(r) for r in rows)
+    n = len(rows)
+    idf = counts.cross_right(counts.len(), lambda df, total: (df[0], df[1], math.log(1 + float(total) / df[1])))
+    idf.sink(str(tmp_path / "s2")).run()
+    assert native()
+    assert sorted(lines_of(str(tmp_path / "s2"))) == sorted(str((w, c, math.log(1 + float(n) / c))) for w, c in rows)
+    counts.map(lambda x: (x[1],)).sink(str(tmp_path / "s3")).run()       # 1-tuples: "(3,)"
+    assert native()
+    assert sorted(lines_of(str(tmp_path / "s3"))) == sorted(str((c,)) for _w, c in rows)
+    q = tmp_path / "q.txt"
+    q.write_bytes(b"it's a \"quoted\" line\nplain words only\n")
+    qc = Dampr.text(str(q)).flat_map(lambda x: x.split()).count()
+    qc.sink(str(tmp_path / "s4")).run()
+    assert not native()
+    assert sorted(lines_of(str(tmp_path / "s4"))) == sorted(str(r) for r in qc.read())
