@@ -807,6 +807,12 @@ def _lower_map(runner, stage, inputs, si):
                 # the reference (dampr.py:245-275), not [0]
                 return RecordsDataset([], [], replicated=True)
             return RecordsDataset([1], [scan.n_lines], replicated=True)
+        kvc = _kv_columns(ds)
+        if kvc is not None:
+            # binary (key, value) records: the input is the same on every rank, its length needs no pass at all
+            n = len(kvc[0])
+            runner.stats.add(stage, "record count of a columnar input", "records=%d" % n)
+            return RecordsDataset([1], [n], replicated=True) if n else RecordsDataset([], [], replicated=True)
         if isinstance(ds, (Frame, RecordsDataset)):
             n = len(ds)
             if dist.active():
@@ -818,6 +824,18 @@ def _lower_map(runner, stage, inputs, si):
     kv = _lower_kv_map(runner, stage, inputs)
     if kv is not None:
         return kv
+    if len(inputs) == 1 and not isinstance(inputs[0], Frame) and not dist.active():
+        # binary (key, value) records under a stage _lower_kv_map does not take (a map / filter chain in front of the
+        # fold, mean(), topk ...): the two columns are a frame of (key, value) rows, and whatever a frame can do
+        # column-at-a-time applies — no per-record Python over hundreds of millions of records
+        kvc = _kv_columns(inputs[0])
+        if kvc is not None and len(kvc[0]):
+            fr = Frame(None, [kvc[0], kvc[1]], scalar=False)
+            out = _lower_frame_map(runner, stage, fr)
+            if out is None:
+                out = _lower_frame_general(runner, stage, fr)
+            if out is not None:
+                return out
     if len(inputs) == 1 and isinstance(inputs[0], Frame):
         out = _lower_frame_map(runner, stage, inputs[0])
         if out is None and not isinstance(inputs[0], LazyKVFrame):

@@ -715,3 +715,51 @@ def test_lowered_topk_unique_prefix_agree_with_the_reference(monkeypatch):
         assert any("frame map/filter evaluated column-at-a-time" in h for h in hows[i]), (tmpl[i], hows[i])
     for i in (12, 13):
         assert any("native frame sink" in h for h in hows[i]), (tmpl[i], hows[i])
+
+
+def test_chains_over_binary_kv_inputs_agree_with_the_reference(monkeypatch):
+    """Stages over binary (key, value) inputs that are more than a bare keyed fold — a map / filter chain in front of
+    it, mean(), topk, a plain map, len() — run column-at-a-time on the two input columns (plan._lower_map: the kv
+    input as a frame of (key, value) rows). Same records through the reference as Dampr.memory tuples."""
+    import numpy as np
+    from fake_device import FakeCtx
+    from dampr_b200 import Dampr, settings, plan
+    from dampr_b200 import runner as runner_mod
+    from dampr_b200.inputs import ArrayKVInput
+    rng = random.Random(99)
+    keys = [rng.randint(0, 200) for _ in range(5000)]
+    vals = [rng.randint(-30, 60) for _ in range(5000)]
+    A_ref = "Dampr.memory(recs, partitions=3)"
+    A_our = "Dampr.read_input(ArrayKVInput(K, V))"
+    tmpl = [
+        "{A}.len()",
+        "{A}.mean(lambda x: x[0], lambda x: x[1])",
+        "{A}.filter(lambda x: x[1] > 0).count(lambda x: x[0])",
+        "{A}.map(lambda x: (x[0] % 10, x[1] * 2)).a_group_by(lambda x: x[0], lambda x: x[1]).sum()",
+        "{A}.filter(lambda x: x[0] % 3 == 1).map(lambda x: (x[0], x[1] - 1)).fold_by(lambda x: x[0], max, lambda x: x[1])",
+        "{A}.topk(6, lambda x: x[1])",
+        "{A}.topk(4, lambda x: -x[0])",
+        "{A}.map(lambda x: x[0] * 1000 + x[1])",
+        "{A}.filter(lambda x: x[1] == 7).map(lambda x: x[0])",
+        "{A}.map(lambda x: (x[1], x[0])).sort_by(lambda x: x[0])",
+        "{A}.a_group_by(lambda x: x[0] % 5, lambda x: x[1]).reduce(min)",
+        "{A}.map(lambda x: x[1] / 4.0).a_group_by(lambda x: 1).reduce(max)",
+    ]
+    env = dict(os.environ)
+    env.pop("PYTHONPATH", None)
+    p = subprocess.run([sys.executable, "-c", TWO_DRIVER, REF, json.dumps(list(zip(keys, vals))),
+                        json.dumps([t.format(A=A_ref) for t in tmpl]), json.dumps([])],
+                       capture_output=True, text=True, env=env, cwd="/tmp", timeout=600)
+    assert p.returncode == 0, p.stderr[-2000:]
+    ref = json.loads(p.stdout.strip().split("\n")[-1])
+    ns = {"Dampr": Dampr, "ArrayKVInput": ArrayKVInput, "K": np.array(keys, dtype=np.int64), "V": np.array(vals, dtype=np.int64)}
+    hows = []
+    for t, exp in zip(tmpl, ref):
+        monkeypatch.setattr(runner_mod, "_CTX", {settings.device: FakeCtx()})
+        monkeypatch.setattr(plan, "_BUFFERS", {})
+        got = sorted(repr(x) for x in eval(t.format(A=A_our), ns).run())
+        hows.append([h for _s, h, _d in runner_mod.LAST_STATS.stages])
+        assert got == exp, t
+    assert any("record count of a columnar input" in h for h in hows[0])
+    for i in range(1, 10):
+        assert not any(h.startswith("host-map") for h in hows[i][:1]), (tmpl[i], hows[i])
