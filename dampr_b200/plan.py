@@ -1308,7 +1308,7 @@ def _lower_frame_general(runner, stage, frame):
                 rcols = [np.array([r]) for r in res]
                 okeys, how = np.array([kv.v]), " [one group, folded on the host]"
             else:
-                if not (isinstance(kv, np.ndarray) and kv.dtype == np.int64):
+                if not (isinstance(kv, np.ndarray) and kv.dtype in (np.int64, np.uint64)):
                     return None   # float / string keys: equality is not bit equality
                 rk = None
                 rcols = []
@@ -1328,7 +1328,7 @@ def _lower_frame_general(runner, stage, frame):
                         raise NotLowerable("component folds disagree on the groups")
                     rk = rk2
                     rcols.append(rv)
-                okeys = rk.view(np.int64)
+                okeys = rk.view(kv.dtype)
             val = vexpr.Tup(rcols) if isinstance(vv, vexpr.Tup) else rcols[0]
             out = Frame(okeys, [val], scalar=True, combined=True)
             runner.stats.add(stage, "frame keyed fold: columns evaluated on the host, groups folded on the device" + how,
