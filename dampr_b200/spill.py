@@ -13,7 +13,10 @@ Here the spill trigger is the device arena (settings.device_arena_bytes, default
   pass 2  one bucket at a time: host -> device, k-way merge of its runs (+ segmented reduce) in one read and
           one write (csrc/merge.cu), results streamed back.  A key lives in exactly one bucket, so buckets are
           independent, exactly like the reference's reduce partitions.
-PCIe traffic: 2 x 16 B per record each way; the device never holds more than one batch / bucket.
+PCIe traffic: 2 x 16 B per record each way. The device holds the batch / bucket being worked on and the NEXT one,
+which a host thread uploads meanwhile (_Upload / _pipelined: its own stream, staging ring and copy threads), so
+both PCIe directions are busy; the runs live in one process-wide host buffer (_RunArena) that is kept between
+jobs and page-locked in the background once a job has touched it; results are written in place (_OutCols).
 Grouping order (mixed-key order inside a bucket, buckets in owner order) is unobservable in results
 (SURVEY "Result-order contract").
 
